@@ -1,0 +1,550 @@
+"""CPU oracle for the DenseCap inference hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This file is a CPU restatement of the reference algorithm (jcjohnson/densecap @ 7c32170,
+Lua/Torch7).  It is the *checker* for the CUDA path: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs
+may import it.  Nothing under ``densecap_b200/`` imports it and the product path has no
+CPU fallback.
+
+Every function cites the reference file:line it restates (paths relative to
+/root/reference).  Box/index arithmetic is numpy fp32 with the reference's operation
+order (one rounding per Torch tensor op, no FMA); dense contractions (conv / linear)
+use torch-CPU fp32 (oneDNN / MKL) because the reference's own summation order
+(THNN im2col + BLAS sgemm) is unspecified.
+
+PARITY PINNING:
+  * pinned by the reference's own known-answer tests (see tests/test_oracle_golden.py):
+      nms (test/nms_test.lua:9-95), BoxToAffine (test/BoxToAffine_test.lua:14-44),
+      ApplyBoxTransform (test/ApplyBoxTransform_test.lua:12-35), anchor/transform
+      composition + row order (test/MakeBoxes_test.lua:47-234 through the equivalence
+      stated by test/MakeAnchors_test.lua:17-44), ReshapeBoxFeatures strides
+      (test/ReshapeBoxFeatures_test.lua:33-58), Apply/Invert round trip
+      (test/InvertBoxTransform_test.lua:15-58).
+  * "parity unpinned" (third-party arithmetic that is NOT under /root/reference and
+    has no numeric known-answer test there; restated from the published algorithm):
+      stnbhwd AffineGridGeneratorBHWD / BilinearSamplerBHWD  (sampler_* below),
+      torch-rnn nn.LSTM gate order / layout                   (lstm_step below),
+      torch/nn SpatialConvolution / SpatialMaxPooling(ceil) / Linear numerics.
+    The reference itself (Lua/Torch7) cannot run in this environment (no th/luajit).
+"""
+from __future__ import annotations
+
+import math
+import numpy as np
+
+f32 = np.float32
+
+
+def _f(x):
+    return np.asarray(x, dtype=np.float32)
+
+
+# ----------------------------------------------------------------------------------------
+# exp as the reference's CPU path sees it: glibc expf is correctly rounded in all but
+# ~1e-8 of cases, which is what exp-in-double-then-round gives.  The CUDA kernels use the
+# same recipe ((float)exp((double)x)) so both sides agree bit for bit.
+# ----------------------------------------------------------------------------------------
+def exp_f32(x):
+    return np.exp(np.asarray(x, dtype=np.float64)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------
+# densecap/modules/MakeAnchors.lua:40-67
+# ----------------------------------------------------------------------------------------
+def make_anchors(N, H, W, x0, y0, sx, sy, anchors):
+    """anchors: (2,k) widths/heights.  Returns (N,4k,H,W) fp32, channel 4a+{0:xc,1:yc,2:w,3:h}."""
+    anchors = _f(anchors)
+    k = anchors.shape[1]
+    xc = np.arange(W, dtype=np.float32) * f32(sx) + f32(x0)      # :mul(sx):add(x0)
+    yc = np.arange(H, dtype=np.float32) * f32(sy) + f32(y0)
+    out = np.empty((N, k, 4, H, W), np.float32)
+    out[:, :, 0] = xc[None, None, None, :]
+    out[:, :, 1] = yc[None, None, :, None]
+    out[:, :, 2] = anchors[0][None, :, None, None]
+    out[:, :, 3] = anchors[1][None, :, None, None]
+    return out.reshape(N, 4 * k, H, W)
+
+
+# ----------------------------------------------------------------------------------------
+# densecap/modules/ReshapeBoxFeatures.lua:24-33   (row r = (a*H + y)*W + x)
+# ----------------------------------------------------------------------------------------
+def reshape_box_features(x, k):
+    N, kD, H, W = x.shape
+    D = kD // k
+    return np.ascontiguousarray(x.reshape(N, k, D, H, W).transpose(0, 1, 3, 4, 2)).reshape(N, k * H * W, D)
+
+
+# densecap/modules/ReshapeBoxFeatures.lua:36-44
+def reshape_box_features_backward(grad_out, k, H, W):
+    N, _, D = grad_out.shape
+    return np.ascontiguousarray(grad_out.reshape(N, k, H, W, D).transpose(0, 1, 4, 2, 3)).reshape(N, k * D, H, W)
+
+
+# ----------------------------------------------------------------------------------------
+# densecap/modules/ApplyBoxTransform.lua:63-90
+# ----------------------------------------------------------------------------------------
+def apply_box_transform(boxes, trans):
+    b = _f(boxes).reshape(-1, 4)
+    t = _f(trans).reshape(-1, 4)
+    out = np.empty_like(b)
+    out[:, 0] = t[:, 0] * b[:, 2] + b[:, 0]          # cmul(tx, wa):add(xa)  (two roundings)
+    out[:, 1] = t[:, 1] * b[:, 3] + b[:, 1]
+    out[:, 2] = exp_f32(t[:, 2]) * b[:, 2]           # exp(tw):cmul(wa)
+    out[:, 3] = exp_f32(t[:, 3]) * b[:, 3]
+    return out.reshape(np.shape(boxes))
+
+
+# densecap/modules/ApplyBoxTransform.lua:93-128
+def apply_box_transform_backward(boxes, trans, out, grad_out):
+    b = _f(boxes).reshape(-1, 4); t = _f(trans).reshape(-1, 4)
+    o = _f(out).reshape(-1, 4); g = _f(grad_out).reshape(-1, 4)
+    gb = np.zeros_like(b); gt = np.zeros_like(t)
+    gt[:, 0] = g[:, 0] * b[:, 2]
+    gt[:, 1] = g[:, 1] * b[:, 3]
+    gt[:, 2] = o[:, 2] * g[:, 2]
+    gt[:, 3] = o[:, 3] * g[:, 3]
+    gb[:, 0] = g[:, 0]
+    gb[:, 1] = g[:, 1]
+    gb[:, 2] = exp_f32(t[:, 2]) * g[:, 2] + t[:, 0] * g[:, 0]
+    gb[:, 3] = exp_f32(t[:, 3]) * g[:, 3] + t[:, 1] * g[:, 1]
+    return gb.reshape(np.shape(boxes)), gt.reshape(np.shape(trans))
+
+
+# ----------------------------------------------------------------------------------------
+# densecap/modules/InvertBoxTransform.lua:36-60
+# ----------------------------------------------------------------------------------------
+def invert_box_transform(anchor_boxes, target_boxes):
+    a = _f(anchor_boxes); t = _f(target_boxes)
+    out = np.empty_like(t)
+    out[:, 0] = (t[:, 0] - a[:, 0]) / a[:, 2]
+    out[:, 1] = (t[:, 1] - a[:, 1]) / a[:, 3]
+    out[:, 2] = np.log((t[:, 2] / a[:, 2]).astype(np.float64)).astype(np.float32)
+    out[:, 3] = np.log((t[:, 3] / a[:, 3]).astype(np.float64)).astype(np.float32)
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# densecap/box_utils.lua:270-298   x1 = xc - (w-1)/2 ; x2 = xc + (w-1)/2
+# ----------------------------------------------------------------------------------------
+def xcycwh_to_x1y1x2y2(boxes):
+    b = _f(boxes)
+    xc, yc, w, h = b[..., 0], b[..., 1], b[..., 2], b[..., 3]
+    ret = np.empty_like(b)
+    half_w = (w + f32(-1)) / f32(2.0)
+    half_h = (h + f32(-1)) / f32(2.0)
+    ret[..., 0] = half_w * f32(-1) + xc
+    ret[..., 2] = half_w + xc
+    ret[..., 1] = half_h * f32(-1) + yc
+    ret[..., 3] = half_h + yc
+    return ret
+
+
+# densecap/box_utils.lua:382-410   xc = (x0+x1)/2 ; w = x1 - x0   (NOT the inverse of the above)
+def x1y1x2y2_to_xcycwh(boxes):
+    b = _f(boxes)
+    x0, y0, x1, y1 = b[..., 0], b[..., 1], b[..., 2], b[..., 3]
+    out = np.empty_like(b)
+    out[..., 0] = (x0 + x1) / f32(2.0)
+    out[..., 1] = (y0 + y1) / f32(2.0)
+    out[..., 2] = x1 - x0
+    out[..., 3] = y1 - y0
+    return out
+
+
+# densecap/box_utils.lua:311-380 (xywh helpers used by run_model.lua:79)
+def x1y1x2y2_to_xywh(boxes):
+    b = _f(boxes)
+    out = np.empty_like(b)
+    out[..., 0] = b[..., 0]
+    out[..., 1] = b[..., 1]
+    out[..., 2] = (b[..., 2] - b[..., 0]) + f32(1)
+    out[..., 3] = (b[..., 3] - b[..., 1]) + f32(1)
+    return out
+
+
+def xcycwh_to_xywh(boxes):
+    return x1y1x2y2_to_xywh(xcycwh_to_x1y1x2y2(boxes))
+
+
+# ----------------------------------------------------------------------------------------
+# densecap/box_utils.lua:486-523  clip_boxes(boxes, bounds, 'xcycwh')
+# ----------------------------------------------------------------------------------------
+def clip_boxes(boxes, x_min, y_min, x_max, y_max, fmt="xcycwh"):
+    shape = np.shape(boxes)
+    if fmt == "xcycwh":
+        c = xcycwh_to_x1y1x2y2(boxes).reshape(-1, 4)
+    elif fmt == "x1y1x2y2":
+        c = _f(boxes).reshape(-1, 4).copy()
+    else:
+        raise ValueError('Unrecognized box format "%s"' % fmt)
+    c[:, 0] = np.clip(c[:, 0], f32(x_min), f32(x_max - 1))
+    c[:, 1] = np.clip(c[:, 1], f32(y_min), f32(y_max - 1))
+    c[:, 2] = np.clip(c[:, 2], f32(x_min + 1), f32(x_max))
+    c[:, 3] = np.clip(c[:, 3], f32(y_min + 1), f32(y_max))
+    valid = (c[:, 2] > c[:, 0]) & (c[:, 3] > c[:, 1])
+    if fmt == "xcycwh":
+        c = x1y1x2y2_to_xcycwh(c)
+    return c.reshape(shape), valid.astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------------------
+# densecap/box_utils.lua:154-256   greedy NMS; returns 1-based int64 indices, best first.
+# Sort: reference uses TH's unstable ascending quicksort on CPU float (:185) and pops from
+# the end; the oracle DEFINES the tie rule as a stable ascending sort, i.e. among equal
+# scores the HIGHER index is picked first.
+# ----------------------------------------------------------------------------------------
+def nms(boxes_scores, overlap, max_boxes=None):
+    bs = _f(boxes_scores)
+    if bs.size == 0:
+        return np.zeros((0,), np.int64)
+    x1, y1, x2, y2, s = bs[:, 0], bs[:, 1], bs[:, 2], bs[:, 3], bs[:, 4]
+    area = ((x2 - x1) + f32(1.0)) * ((y2 - y1) + f32(1.0))
+    I = np.argsort(s, kind="stable")                     # ascending
+    thr = f32(overlap)
+    pick = []
+    while (max_boxes is None or len(pick) < max_boxes) and I.size > 0:
+        i = I[-1]
+        pick.append(i)
+        if I.size == 1:
+            break
+        I = I[:-1]
+        xx1 = np.maximum(x1[I], x1[i]); xx2 = np.minimum(x2[I], x2[i])
+        yy1 = np.maximum(y1[I], y1[i]); yy2 = np.minimum(y2[I], y2[i])
+        w = np.maximum((xx2 - xx1) + f32(1.0), f32(0))
+        h = np.maximum((yy2 - yy1) + f32(1.0), f32(0))
+        inter = w * h
+        union = (area[I] + area[i]) - inter
+        with np.errstate(divide="ignore", invalid="ignore"):
+            iou = inter / union
+        I = I[iou <= thr]                                  # NaN -> dropped, as torch le()
+    return np.asarray(pick, np.int64) + 1
+
+
+# ----------------------------------------------------------------------------------------
+# densecap/modules/BoxToAffine.lua:69-93      (H, W = IMAGE size)
+# ----------------------------------------------------------------------------------------
+def box_to_affine(boxes, H, W):
+    b = _f(boxes)
+    B = b.shape[0]
+    th = np.zeros((B, 2, 3), np.float32)
+    th[:, 1, 2] = (b[:, 0] * f32(2) + f32(-1 - W)) / f32(W - 1)
+    th[:, 0, 2] = (b[:, 1] * f32(2) + f32(-1 - H)) / f32(H - 1)
+    th[:, 1, 1] = b[:, 2] / f32(W)
+    th[:, 0, 0] = b[:, 3] / f32(H)
+    return th
+
+
+# densecap/modules/BoxToAffine.lua:96-118
+def box_to_affine_backward(grad_theta, H, W):
+    g = _f(grad_theta)
+    gi = np.zeros((g.shape[0], 4), np.float32)
+    gi[:, 0] = g[:, 1, 2] * f32(2 / (W - 1))
+    gi[:, 1] = g[:, 0, 2] * f32(2 / (H - 1))
+    gi[:, 2] = g[:, 1, 1] * f32(1 / W)
+    gi[:, 3] = g[:, 0, 0] * f32(1 / H)
+    return gi
+
+
+# ----------------------------------------------------------------------------------------
+# [3P, parity unpinned] qassemoquab/stnbhwd AffineGridGeneratorBHWD(HH, WW)
+#   call site densecap/modules/BilinearRoiPooling.lua:52 ; SURVEY.md Appendix B1.
+#   baseGrid[i][j] = (y_i, x_j, 1), y_i = -1 + (i-1)/(HH-1)*2 (Lua double -> float tensor);
+#   grid[b] = baseGrid . theta[b]^T  -> last dim (gy, gx).
+# ----------------------------------------------------------------------------------------
+def affine_grid(theta, HH, WW):
+    th = _f(theta)
+    ys = np.array([-1 + (i / (HH - 1)) * 2 for i in range(HH)], np.float64).astype(np.float32)
+    xs = np.array([-1 + (j / (WW - 1)) * 2 for j in range(WW)], np.float64).astype(np.float32)
+    Y = ys[None, :, None]; X = xs[None, None, :]
+    gy = (th[:, 0, 0, None, None] * Y + th[:, 0, 1, None, None] * X) + th[:, 0, 2, None, None]
+    gx = (th[:, 1, 0, None, None] * Y + th[:, 1, 1, None, None] * X) + th[:, 1, 2, None, None]
+    return np.stack([gy, gx], axis=-1).astype(np.float32)          # (B,HH,WW,2)
+
+
+# ----------------------------------------------------------------------------------------
+# [3P, parity unpinned] stnbhwd BilinearSamplerBHWD_updateOutput
+#   call site densecap/modules/BatchBilinearSamplerBHWD.lua:104-122 ; SURVEY.md App. B2.
+# ----------------------------------------------------------------------------------------
+def bilinear_sample(feats_hwc, grids):
+    """feats_hwc (H,W,C) fp32, grids (B,HH,WW,2) (y,x) in [-1,1] -> (B,HH,WW,C)."""
+    feats = _f(feats_hwc)
+    H, W, C = feats.shape
+    g = _f(grids)
+    gy, gx = g[..., 0], g[..., 1]
+    xcoord = ((gx + f32(1)) * f32(W - 1)) / f32(2)
+    ycoord = ((gy + f32(1)) * f32(H - 1)) / f32(2)
+    xL = np.floor(xcoord); yT = np.floor(ycoord)
+    wx = f32(1) - (xcoord - xL)
+    wy = f32(1) - (ycoord - yT)
+    xL = xL.astype(np.int64); yT = yT.astype(np.int64)
+
+    def tap(y, x):
+        ok = (x >= 0) & (x <= W - 1) & (y >= 0) & (y <= H - 1)
+        v = feats[np.clip(y, 0, H - 1), np.clip(x, 0, W - 1)]     # (B,HH,WW,C)
+        return np.where(ok[..., None], v, f32(0))
+
+    TL = tap(yT, xL); TR = tap(yT, xL + 1); BL = tap(yT + 1, xL); BR = tap(yT + 1, xL + 1)
+    wx_ = wx[..., None]; wy_ = wy[..., None]
+    omx = f32(1) - wx_; omy = f32(1) - wy_
+    out = (wx_ * wy_) * TL
+    out = out + (omx * wy_) * TR
+    out = out + (wx_ * omy) * BL
+    out = out + (omx * omy) * BR
+    return out.astype(np.float32)
+
+
+# stnbhwd BilinearSamplerBHWD_updateGradInput (App. B2), summed over the batch as in
+# densecap/modules/BatchBilinearSamplerBHWD.lua:125-157.  Accumulates in float64 (gold).
+def bilinear_sample_backward(feats_hwc, grids, grad_out):
+    feats = _f(feats_hwc); H, W, C = feats.shape
+    g = _f(grids); go = _f(grad_out)
+    gy, gx = g[..., 0], g[..., 1]
+    xcoord = ((gx + f32(1)) * f32(W - 1)) / f32(2)
+    ycoord = ((gy + f32(1)) * f32(H - 1)) / f32(2)
+    xL = np.floor(xcoord); yT = np.floor(ycoord)
+    wx = (f32(1) - (xcoord - xL)).astype(np.float64); wy = (f32(1) - (ycoord - yT)).astype(np.float64)
+    xL = xL.astype(np.int64); yT = yT.astype(np.int64)
+    gfeat = np.zeros((H, W, C), np.float64)
+    ggrid = np.zeros(g.shape, np.float64)
+    go64 = go.astype(np.float64)
+    dots = {}
+    for name, (dy, dx, wgt) in {"TL": (0, 0, wx * wy), "TR": (0, 1, (1 - wx) * wy),
+                                "BL": (1, 0, wx * (1 - wy)), "BR": (1, 1, (1 - wx) * (1 - wy))}.items():
+        y = yT + dy; x = xL + dx
+        ok = (x >= 0) & (x <= W - 1) & (y >= 0) & (y <= H - 1)
+        yy = np.clip(y, 0, H - 1); xx = np.clip(x, 0, W - 1)
+        contrib = np.where(ok[..., None], wgt[..., None] * go64, 0.0)
+        np.add.at(gfeat, (yy.reshape(-1), xx.reshape(-1)), contrib.reshape(-1, C))
+        v = np.where(ok[..., None], feats[yy, xx].astype(np.float64), 0.0)
+        dots[name] = (v * go64).sum(-1)
+    ggrid[..., 0] = (-wx * dots["TL"] + wx * dots["BL"] - (1 - wx) * dots["TR"] + (1 - wx) * dots["BR"]) * (H - 1) / 2
+    ggrid[..., 1] = (-wy * dots["TL"] + wy * dots["TR"] - (1 - wy) * dots["BL"] + (1 - wy) * dots["BR"]) * (W - 1) / 2
+    return gfeat.astype(np.float32), ggrid.astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------
+# densecap/modules/BilinearRoiPooling.lua:35-67,84-91
+#   feats (C,H',W') -> transpose HWC ; boxes (B,4) xcycwh in IMAGE coords ; -> (B,C,HH,WW)
+# ----------------------------------------------------------------------------------------
+def bilinear_roi_pooling(feats_chw, boxes, image_h, image_w, HH=7, WW=7, layout="BCHW"):
+    feats_hwc = np.ascontiguousarray(_f(feats_chw).transpose(1, 2, 0))
+    theta = box_to_affine(boxes, image_h, image_w)
+    grids = affine_grid(theta, HH, WW)
+    out = bilinear_sample(feats_hwc, grids)                       # (B,HH,WW,C)
+    if layout == "BHWC":
+        return out
+    return np.ascontiguousarray(out.transpose(0, 3, 1, 2))
+
+
+# ----------------------------------------------------------------------------------------
+# densecap/modules/BoxIoU.lua:40-73  (area = w*h, corners from (w-1)/2, no +1)
+# ----------------------------------------------------------------------------------------
+def box_iou(box1, box2):
+    b1 = _f(box1); b2 = _f(box2)                     # (N,B1,4), (N,B2,4)
+    a1 = (b1[..., 2] * b1[..., 3])[:, :, None]
+    a2 = (b2[..., 2] * b2[..., 3])[:, None, :]
+    l1 = xcycwh_to_x1y1x2y2(b1)[:, :, None, :]
+    l2 = xcycwh_to_x1y1x2y2(b2)[:, None, :, :]
+    x0 = np.maximum(l1[..., 0], l2[..., 0]); y0 = np.maximum(l1[..., 1], l2[..., 1])
+    x1 = np.minimum(l1[..., 2], l2[..., 2]); y1 = np.minimum(l1[..., 3], l2[..., 3])
+    w = np.maximum(x1 - x0, f32(0)); h = np.maximum(y1 - y0, f32(0))
+    inter = w * h
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = (f32(1) / ((a1 - inter) + a2)) * inter          # add(a1,-1,inter):add(a2):pow(-1):cmul(inter)
+    return out.astype(np.float32)
+
+
+# ========================================================================================
+# Dense layers (torch CPU fp32).  [3P, parity unpinned] torch/nn definitions, App. B4.
+# ========================================================================================
+def _torch():
+    import torch
+    return torch
+
+
+def conv2d(x, w, b, pad):
+    torch = _torch()
+    import torch.nn.functional as F
+    y = F.conv2d(torch.from_numpy(_f(x)), torch.from_numpy(_f(w)),
+                 None if b is None else torch.from_numpy(_f(b)), stride=1, padding=pad)
+    return y.numpy()
+
+
+def max_pool2x2(x, ceil_mode=True):
+    torch = _torch()
+    import torch.nn.functional as F
+    return F.max_pool2d(torch.from_numpy(_f(x)), 2, 2, 0, ceil_mode=ceil_mode).numpy()
+
+
+def linear(x, w, b):
+    torch = _torch()
+    y = torch.from_numpy(_f(x)) @ torch.from_numpy(_f(w)).t()
+    if b is not None:
+        y = y + torch.from_numpy(_f(b))
+    return y.numpy()
+
+
+def relu(x):
+    return np.maximum(x, f32(0))
+
+
+VGG16_LAYERS = ["conv1_1", "conv1_2", "P", "conv2_1", "conv2_2", "P",
+                "conv3_1", "conv3_2", "conv3_3", "P", "conv4_1", "conv4_2", "conv4_3", "P",
+                "conv5_1", "conv5_2", "conv5_3"]
+
+
+# densecap/DenseCapModel.lua:61-76 (conv_net1 = layers 1-10, conv_net2 = 11-30; pool5 excluded)
+def vgg_trunk(img, weights, pool_ceil=True, taps=None):
+    x = _f(img)
+    for name in VGG16_LAYERS:
+        if name == "P":
+            x = max_pool2x2(x, pool_ceil)
+        else:
+            x = relu(conv2d(x, weights[name + ".weight"], weights[name + ".bias"], 1))
+        if taps is not None and name != "P":
+            taps[name] = x
+    return x
+
+
+DEFAULT_ANCHORS = np.array([[45, 90], [90, 45], [64, 64], [90, 180], [180, 90], [128, 128],
+                            [181, 362], [362, 181], [256, 256], [362, 724], [724, 362], [512, 512]],
+                           np.float32).T.copy()          # (2,k)   LocalizationLayer.lua:613-618
+FIELD_CENTERS = (8.5, 8.5, 16.0, 16.0)                   # net_utils.lua:106-140 on VGG-16 1..30
+
+
+# densecap/LocalizationLayer.lua:609-690  build_rpn -> {boxes, anchors, trans, scores}
+def rpn_forward(feats, weights, anchors=DEFAULT_ANCHORS, field_centers=FIELD_CENTERS):
+    k = anchors.shape[1]
+    N, C, H, W = feats.shape
+    hid = relu(conv2d(feats, weights["rpn.conv.weight"], weights["rpn.conv.bias"], 1))
+    box_out = conv2d(hid, weights["rpn.box.weight"], weights["rpn.box.bias"], 0)       # (N,4k,H,W)
+    score_out = conv2d(hid, weights["rpn.score.weight"], weights["rpn.score.bias"], 0)  # (N,2k,H,W)
+    x0, y0, sx, sy = field_centers
+    anc = reshape_box_features(make_anchors(N, H, W, x0, y0, sx, sy, anchors), k)
+    trans = reshape_box_features(box_out, k)
+    boxes = apply_box_transform(anc, trans)
+    scores = reshape_box_features(score_out, k)
+    return boxes, anc, trans, scores, hid
+
+
+# densecap/LocalizationLayer.lua:250-363 with rpn outputs given (post-processing only)
+def rpn_postprocess(rpn_boxes, rpn_anchors, rpn_trans, rpn_scores, image_h, image_w,
+                    nms_thresh=0.7, max_proposals=300, clip=True):
+    boxes, anchors, trans, scores = rpn_boxes, rpn_anchors, rpn_trans, rpn_scores
+    valid = None
+    if clip:
+        boxes, valid = clip_boxes(boxes, 1, 1, image_w, image_h, "xcycwh")
+        m = valid.astype(bool)
+        boxes = boxes[:, m]; anchors = anchors[:, m]; trans = trans[:, m]; scores = scores[:, m]
+    x1y1x2y2 = xcycwh_to_x1y1x2y2(boxes)
+    e = exp_f32(scores)
+    pos, neg = e[0, :, 0], e[0, :, 1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        prob = (f32(1) / (pos + neg)) * pos                 # (pos+neg):pow(-1):cmul(pos)
+    bs = np.concatenate([x1y1x2y2[0], prob[:, None]], axis=1)
+    idx = nms(bs, nms_thresh, None if max_proposals == -1 else max_proposals)
+    i0 = idx - 1
+    return {"boxes": boxes[0, i0], "anchors": anchors[0, i0], "trans": trans[0, i0],
+            "scores": scores[0, i0], "prob": prob[i0], "idx": idx, "valid": valid,
+            "all_prob": prob, "all_boxes_x1y1x2y2": x1y1x2y2[0]}
+
+
+def localization_layer_forward_test(feats, weights, image_h, image_w, nms_thresh=0.7,
+                                    max_proposals=300, clip=True, anchors=DEFAULT_ANCHORS,
+                                    field_centers=FIELD_CENTERS, HH=7, WW=7):
+    boxes, anc, trans, scores, _ = rpn_forward(feats, weights, anchors, field_centers)
+    pp = rpn_postprocess(boxes, anc, trans, scores, image_h, image_w, nms_thresh, max_proposals, clip)
+    roi = bilinear_roi_pooling(feats[0], pp["boxes"], image_h, image_w, HH, WW)
+    pp["roi_features"] = roi
+    return pp
+
+
+# densecap/DenseCapModel.lua:87-100,127-162  recognition head (test time)
+def recog_head(roi_features, roi_boxes, weights):
+    B = roi_features.shape[0]
+    x = roi_features.reshape(B, -1)                                   # View: (c,y,x) flatten
+    x = relu(linear(x, weights["fc6.weight"], weights["fc6.bias"]))
+    codes = relu(linear(x, weights["fc7.weight"], weights["fc7.bias"]))
+    obj = linear(codes, weights["obj.weight"], weights["obj.bias"])              # (B,1)
+    trans = linear(codes, weights["boxreg.weight"], weights["boxreg.bias"])      # (B,4)
+    final_boxes = apply_box_transform(roi_boxes, trans)
+    return codes, obj, trans, final_boxes
+
+
+def sigmoid(x):
+    return (1.0 / (1.0 + np.exp(-x.astype(np.float64)))).astype(np.float32)
+
+
+# [3P, parity unpinned] jcjohnson/torch-rnn nn.LSTM step, SURVEY.md App. B3:
+#   weight ((D+H),4H) rows [Wx;Wh], gate blocks [i|f|o|g]
+def lstm_step(x, h, c, W, b):
+    D = x.shape[1]; H = h.shape[1]
+    a = linear(x, W[:D].T, None) + linear(h, W[D:].T, None) + _f(b)[None, :]
+    i = sigmoid(a[:, 0:H]); f = sigmoid(a[:, H:2 * H]); o = sigmoid(a[:, 2 * H:3 * H])
+    g = np.tanh(a[:, 3 * H:4 * H].astype(np.float64)).astype(np.float32)
+    c2 = f * c + i * g
+    h2 = o * np.tanh(c2.astype(np.float64)).astype(np.float32)
+    return h2, c2
+
+
+# densecap/LanguageModel.lua:293-348  LM:sample (greedy argmax), tokens 1-based
+def lm_sample(codes, weights, seq_length, return_logits=False):
+    N = codes.shape[0]
+    Wl = weights["lm.lstm.weight"]; bl = weights["lm.lstm.bias"]
+    H = Wl.shape[1] // 4
+    V1 = weights["lm.vocab.weight"].shape[0]            # V+1
+    START = V1                                           # START = END = V+1  (:32-33)
+    enc = relu(linear(codes, weights["lm.encoder.weight"], weights["lm.encoder.bias"]))
+    h = np.zeros((N, H), np.float32); c = np.zeros((N, H), np.float32)
+    h, c = lstm_step(enc, h, c, Wl, bl)                  # first step: image vector, output ignored (:312-313)
+    seq = np.zeros((N, seq_length), np.int64)
+    logits_all = []
+    for t in range(seq_length):
+        words = np.full((N,), START, np.int64) if t == 0 else seq[:, t - 1]
+        x = _f(weights["lm.lookup.weight"])[words - 1]
+        h, c = lstm_step(x, h, c, Wl, bl)
+        logits = linear(h, weights["lm.vocab.weight"], weights["lm.vocab.bias"])
+        seq[:, t] = np.argmax(logits, axis=1) + 1        # torch.max: first maximal index
+        if return_logits:
+            logits_all.append(logits)
+    if return_logits:
+        return seq, np.stack(logits_all, axis=1)
+    return seq
+
+
+# densecap/LanguageModel.lua:86-103
+def decode_sequence(seq, idx_to_token, end_token):
+    caps = []
+    for row in np.asarray(seq):
+        words = []
+        for idx in row:
+            if idx == end_token or idx == 0:
+                break
+            words.append(idx_to_token[int(idx)])
+        caps.append(" ".join(words))
+    return caps
+
+
+# densecap/DenseCapModel.lua:242-282 (test time)  + forward_test :319-327
+def densecap_forward_test(img, weights, cfg, return_intermediates=False):
+    """img (1,3,H,W) fp32.  cfg: dict(rpn_nms_thresh, final_nms_thresh, num_proposals, seq_length, pool_ceil)."""
+    H, W = img.shape[2], img.shape[3]
+    feats = vgg_trunk(img, weights, cfg.get("pool_ceil", True))
+    ll = localization_layer_forward_test(feats, weights, H, W, cfg.get("rpn_nms_thresh", 0.7),
+                                         cfg.get("num_proposals", 1000), True)
+    codes, obj, trans, final_boxes = recog_head(ll["roi_features"], ll["boxes"], weights)
+    seq = lm_sample(codes, weights, cfg["seq_length"])
+    out = {"objectness_scores": obj, "roi_boxes": ll["boxes"], "final_box_trans": trans,
+           "final_boxes": final_boxes, "seq": seq}
+    thr = cfg.get("final_nms_thresh", 0.3)
+    if thr > 0:
+        bs = np.concatenate([xcycwh_to_x1y1x2y2(final_boxes), obj[:, :1]], axis=1)
+        idx = nms(bs, thr)
+        out["final_idx"] = idx
+        out["final_boxes"] = final_boxes[idx - 1]
+        out["objectness_scores"] = obj[idx - 1]
+        out["seq"] = seq[idx - 1]
+    if return_intermediates:
+        out["feats"] = feats; out["ll"] = ll; out["codes"] = codes
+        out["pre_nms"] = {"final_boxes": final_boxes, "obj": obj, "seq": seq}
+    return out
