@@ -1,0 +1,1071 @@
+// C ABI of libdensecap_b200.so: context, weights, and the orchestration of the DenseCap test-time
+// forward pass (DenseCapModel.lua:242-282) over the kernels in the sibling .cu files.
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+struct Weight {
+  __half* planes = nullptr;     // split planes (hi then lo), K-major
+  size_t plane_elems = 0;
+  float* f32 = nullptr;         // fp32 copy (biases, conv1_1, tiny heads)
+  size_t n_f32 = 0;
+  bool loaded = false;
+};
+
+struct SplitBuf {
+  __half* base = nullptr;
+  size_t cap_elems = 0;         // capacity per plane
+  __half* hi() const { return base; }
+  __half* lo(size_t n) const { return base + n; }   // planes are packed for the CURRENT tensor size n
+};
+
+struct PhaseTimer {
+  std::vector<const char*> names;
+  std::vector<cudaEvent_t> events;   // events[i] marks the START of phase i; last = end
+  bool enabled = false;
+  size_t used = 0;
+};
+
+struct dc_ctx {
+  dc_config cfg;
+  int device = 0;
+  char err[512];
+  int64_t launches = 0;
+  // test args (DenseCapModel.lua:185-191, LocalizationLayer.lua:233-238)
+  float rpn_nms_thresh = 0.7f, final_nms_thresh = 0.3f;
+  int num_proposals = 1000, clip_boxes = 1;
+  // setImageSize protocol
+  int image_h = 0, image_w = 0;
+  bool size_consumed = true;
+  std::map<std::string, Weight> w;
+  std::vector<void*> allocs;
+  // geometry capacity
+  int fh_max = 0, fw_max = 0, A_max = 0, P = 0, B = 0;
+  // buffers
+  SplitBuf act[2], feats, rpn_hidden, roi, fc6o, fc7o, xh;
+  float *rpn_head = nullptr, *codes = nullptr, *obj = nullptr, *trans = nullptr, *boxes_all = nullptr, *gates = nullptr, *cstate = nullptr;
+  float *pp_boxes = nullptr, *pp_x1y1 = nullptr, *pp_prob = nullptr, *roi_boxes = nullptr, *fin_x1y1 = nullptr;
+  int32_t *pp_src = nullptr, *pp_nvalid = nullptr, *pp_blocks = nullptr;
+  int32_t *rpn_idx32 = nullptr, *rpn_count = nullptr, *fin_idx32 = nullptr, *fin_count = nullptr, *tokens = nullptr;
+  int64_t *rpn_idx64 = nullptr, *fin_idx64 = nullptr, *seq64 = nullptr, *fin_seq = nullptr;
+  float *fin_boxes = nullptr, *fin_scores = nullptr;
+  unsigned long long* packed = nullptr;
+  float* anchors_dev = nullptr;
+  float* scratch_f32 = nullptr;      // generic fp32 scratch (HWC features for dc_bilinear_roi_pool, ...)
+  size_t scratch_elems = 0;
+  void* nms_mem = nullptr;
+  NmsWorkspace nms;
+  PhaseTimer timer;
+};
+
+static char g_err[512] = "";
+
+int dc_set_error(dc_ctx* ctx, int code, const char* fmt, ...) {
+  char* dst = ctx ? ctx->err : g_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  if (ctx) strncpy(g_err, ctx->err, sizeof(g_err) - 1);
+  return code;
+}
+void dc_count_launch(dc_ctx* ctx, int n) {
+  if (ctx) ctx->launches += n;
+}
+
+extern "C" const char* dc_last_error(const dc_ctx* ctx) { return ctx ? ctx->err : g_err; }
+extern "C" int dc_version(void) { return 100; }
+extern "C" int64_t dc_kernel_launches(const dc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int dc_config_default(dc_config* c) {
+  if (!c) return dc_set_error(nullptr, DC_E_INVALID, "dc_config_default: null");
+  memset(c, 0, sizeof(*c));
+  const int widths[5] = {64, 128, 256, 512, 512};
+  memcpy(c->widths, widths, sizeof(widths));
+  c->rpn_filters = 256;
+  c->num_anchors = 12;
+  c->fc_dim = 4096;
+  c->pool_hw = 7;
+  c->rnn_size = 512;
+  c->encoding_size = 512;
+  c->vocab_size = 10497;
+  c->seq_length = 15;
+  c->pool_ceil = 1;
+  c->max_batch = 1;
+  c->max_image_h = 600;
+  c->max_image_w = 720;
+  c->max_proposals = 1000;
+  c->engine = DC_ENGINE_TC;
+  c->fuse_pool = 1;
+  // LocalizationLayer.lua:613-618 (stored (2,k): widths then heights)
+  const float aw[12] = {45, 90, 64, 90, 180, 128, 181, 362, 256, 362, 724, 512};
+  const float ah[12] = {90, 45, 64, 180, 90, 128, 362, 181, 256, 724, 362, 512};
+  for (int i = 0; i < 12; ++i) { c->anchors[i] = aw[i]; c->anchors[12 + i] = ah[i]; }
+  c->field_centers[0] = 8.5f; c->field_centers[1] = 8.5f; c->field_centers[2] = 16.f; c->field_centers[3] = 16.f;
+  return DC_OK;
+}
+
+static int pooled(int v, int ceil_mode) { return ceil_mode ? (v + 1) / 2 : v / 2; }
+static void feat_hw(const dc_config& c, int h, int w, int& fh, int& fw) {
+  fh = h; fw = w;
+  for (int i = 0; i < 4; ++i) { fh = pooled(fh, c.pool_ceil); fw = pooled(fw, c.pool_ceil); }
+}
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename T>
+static int dev_alloc(dc_ctx* ctx, T** p, size_t n) {
+  void* q = nullptr;
+  const size_t bytes = align_up((n ? n : 1) * sizeof(T), 256);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) return dc_set_error(ctx, DC_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  cudaMemset(q, 0, bytes);
+  ctx->allocs.push_back(q);
+  *p = (T*)q;
+  return DC_OK;
+}
+static int split_alloc(dc_ctx* ctx, SplitBuf& b, size_t elems) {
+  b.cap_elems = align_up(elems, 64);
+  return dev_alloc(ctx, &b.base, 2 * b.cap_elems);
+}
+
+static const char* kConvNames[13] = {"conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_3",
+                                     "conv4_1", "conv4_2", "conv4_3", "conv5_1", "conv5_2", "conv5_3"};
+static const int kConvStage[13] = {0, 0, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4};
+static const int kPoolAfter[13] = {0, 1, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0, 0};
+
+static int weight_alloc_split(dc_ctx* ctx, const std::string& name, size_t elems) {
+  Weight& w = ctx->w[name];
+  w.plane_elems = align_up(elems, 64);
+  return dev_alloc(ctx, &w.planes, 2 * w.plane_elems);
+}
+static int weight_alloc_f32(dc_ctx* ctx, const std::string& name, size_t n) {
+  Weight& w = ctx->w[name];
+  w.n_f32 = n;
+  return dev_alloc(ctx, &w.f32, n);
+}
+
+extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
+  if (!cfg || !out) return dc_set_error(nullptr, DC_E_INVALID, "dc_create: null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return dc_set_error(nullptr, DC_E_CUDA, "dc_create: no CUDA device available (%s); this library has no CPU fallback",
+                        cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return dc_set_error(nullptr, DC_E_INVALID, "dc_create: device %d out of range (%d devices)", device, ndev);
+  const dc_config& c = *cfg;
+  if (c.num_anchors <= 0 || c.num_anchors > DC_MAX_ANCHORS || c.max_batch <= 0 || c.max_proposals <= 0 || c.pool_hw < 2 ||
+      c.pool_hw * c.pool_hw > 64 || c.seq_length <= 0 || c.vocab_size <= 0)
+    return dc_set_error(nullptr, DC_E_INVALID, "dc_create: invalid configuration");
+  for (int i = 0; i < 5; ++i)
+    if (c.widths[i] <= 0 || c.widths[i] % 64 != 0) return dc_set_error(nullptr, DC_E_UNSUPPORTED, "dc_create: stage widths must be multiples of 64");
+  if (c.rpn_filters % 64 || c.fc_dim % 64 || c.rnn_size % 64 || c.encoding_size % 64)
+    return dc_set_error(nullptr, DC_E_UNSUPPORTED, "dc_create: rpn_filters/fc_dim/rnn_size/encoding_size must be multiples of 64");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return dc_set_error(nullptr, DC_E_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  dc_ctx* ctx = new dc_ctx();
+  ctx->cfg = c;
+  ctx->device = device;
+  ctx->err[0] = 0;
+  ctx->num_proposals = c.max_proposals;
+  int rc = DC_OK;
+#define TRY(x) do { rc = (x); if (rc != DC_OK) { strncpy(g_err, ctx->err, sizeof(g_err) - 1); dc_destroy(ctx); return rc; } } while (0)
+  if (c.engine == DC_ENGINE_TC) TRY(tc_init(ctx));
+  ctx->B = c.max_batch;
+  ctx->P = c.max_proposals;
+  feat_hw(c, c.max_image_h, c.max_image_w, ctx->fh_max, ctx->fw_max);
+  // the feature map of a smaller image with the other aspect ratio must fit too: bound by cells
+  ctx->A_max = c.num_anchors * ctx->fh_max * ctx->fw_max;
+  const size_t B = ctx->B, P = ctx->P;
+  const size_t C5 = c.widths[4], F = c.rpn_filters, fc = c.fc_dim, E = c.encoding_size, H = c.rnn_size, T = c.seq_length;
+  const size_t hw = (size_t)c.pool_hw * c.pool_hw;
+  const size_t cells = (size_t)ctx->fh_max * ctx->fw_max;
+  // largest activation: 64-channel full-resolution map (or wider stage at lower resolution)
+  size_t act_elems = 0;
+  {
+    int h = c.max_image_h, w = c.max_image_w;
+    for (int s = 0; s < 5; ++s) {
+      act_elems = std::max(act_elems, B * (size_t)h * w * c.widths[s]);
+      h = pooled(h, c.pool_ceil); w = pooled(w, c.pool_ceil);
+    }
+  }
+  TRY(split_alloc(ctx, ctx->act[0], act_elems));
+  TRY(split_alloc(ctx, ctx->act[1], act_elems));
+  TRY(split_alloc(ctx, ctx->feats, B * cells * C5));
+  TRY(split_alloc(ctx, ctx->rpn_hidden, B * cells * F));
+  TRY(dev_alloc(ctx, &ctx->rpn_head, B * cells * 6 * c.num_anchors));
+  TRY(split_alloc(ctx, ctx->roi, B * P * hw * C5));
+  TRY(split_alloc(ctx, ctx->fc6o, B * P * fc));
+  TRY(split_alloc(ctx, ctx->fc7o, B * P * fc));
+  TRY(split_alloc(ctx, ctx->xh, B * P * (E + H)));
+  TRY(dev_alloc(ctx, &ctx->codes, B * P * fc));
+  TRY(dev_alloc(ctx, &ctx->obj, B * P));
+  TRY(dev_alloc(ctx, &ctx->trans, B * P * 4));
+  TRY(dev_alloc(ctx, &ctx->boxes_all, B * P * 4));
+  TRY(dev_alloc(ctx, &ctx->gates, B * P * 4 * H));
+  TRY(dev_alloc(ctx, &ctx->cstate, B * P * H));
+  const size_t A = ctx->A_max;
+  TRY(dev_alloc(ctx, &ctx->pp_boxes, B * A * 4));
+  TRY(dev_alloc(ctx, &ctx->pp_x1y1, B * A * 4));
+  TRY(dev_alloc(ctx, &ctx->pp_prob, B * A));
+  TRY(dev_alloc(ctx, &ctx->pp_src, B * A));
+  TRY(dev_alloc(ctx, &ctx->pp_nvalid, B));
+  TRY(dev_alloc(ctx, &ctx->pp_blocks, B * (A / 256 + 2)));
+  TRY(dev_alloc(ctx, &ctx->roi_boxes, B * P * 4));
+  TRY(dev_alloc(ctx, &ctx->fin_x1y1, B * P * 4));
+  TRY(dev_alloc(ctx, &ctx->rpn_idx32, B * P));
+  TRY(dev_alloc(ctx, &ctx->rpn_idx64, B * P));
+  TRY(dev_alloc(ctx, &ctx->rpn_count, B));
+  TRY(dev_alloc(ctx, &ctx->fin_idx32, B * P));
+  TRY(dev_alloc(ctx, &ctx->fin_idx64, B * P));
+  TRY(dev_alloc(ctx, &ctx->fin_count, B));
+  TRY(dev_alloc(ctx, &ctx->tokens, B * P * T));
+  TRY(dev_alloc(ctx, &ctx->seq64, B * P * T));
+  TRY(dev_alloc(ctx, &ctx->fin_seq, B * P * T));
+  TRY(dev_alloc(ctx, &ctx->fin_boxes, B * P * 4));
+  TRY(dev_alloc(ctx, &ctx->fin_scores, B * P));
+  TRY(dev_alloc(ctx, &ctx->packed, B * P));
+  TRY(dev_alloc(ctx, &ctx->anchors_dev, (size_t)2 * c.num_anchors));
+  DC_CHECK_CUDA(ctx, cudaMemcpy(ctx->anchors_dev, c.anchors, sizeof(float) * 2 * c.num_anchors, cudaMemcpyHostToDevice));
+  ctx->scratch_elems = std::max(cells * C5, (size_t)1 << 20);
+  TRY(dev_alloc(ctx, &ctx->scratch_f32, ctx->scratch_elems));
+  const int nms_cap = (int)align_up(std::max(A, P), 64);
+  {
+    char* mem = nullptr;
+    TRY(dev_alloc(ctx, &mem, nms_workspace_bytes(nms_cap)));
+    ctx->nms_mem = mem;
+    nms_workspace_carve(ctx->nms, mem, nms_cap);
+  }
+  // ---- weights ----
+  {
+    int cin = 3;
+    for (int i = 0; i < 13; ++i) {
+      const int cout = c.widths[kConvStage[i]];
+      const std::string n = kConvNames[i];
+      if (i == 0) TRY(weight_alloc_f32(ctx, n + ".weight", (size_t)cout * 27));
+      else TRY(weight_alloc_split(ctx, n + ".weight", (size_t)cout * 9 * cin));
+      TRY(weight_alloc_f32(ctx, n + ".bias", cout));
+      cin = cout;
+    }
+    const int k = c.num_anchors;
+    TRY(weight_alloc_split(ctx, "rpn.conv.weight", F * 9 * C5));
+    TRY(weight_alloc_f32(ctx, "rpn.conv.bias", F));
+    TRY(weight_alloc_split(ctx, "rpn.head.weight", (size_t)6 * k * F));   // rows [0,4k) box, [4k,6k) score
+    TRY(weight_alloc_f32(ctx, "rpn.head.bias", (size_t)6 * k));
+    TRY(weight_alloc_split(ctx, "fc6.weight", fc * hw * C5));
+    TRY(weight_alloc_f32(ctx, "fc6.bias", fc));
+    TRY(weight_alloc_split(ctx, "fc7.weight", fc * fc));
+    TRY(weight_alloc_f32(ctx, "fc7.bias", fc));
+    TRY(weight_alloc_f32(ctx, "obj.weight", fc));
+    TRY(weight_alloc_f32(ctx, "obj.bias", 1));
+    TRY(weight_alloc_f32(ctx, "boxreg.weight", 4 * fc));
+    TRY(weight_alloc_f32(ctx, "boxreg.bias", 4));
+    const size_t V = c.vocab_size;
+    TRY(weight_alloc_split(ctx, "lm.encoder.weight", E * fc));
+    TRY(weight_alloc_f32(ctx, "lm.encoder.bias", E));
+    TRY(weight_alloc_split(ctx, "lm.lookup.weight", (V + 2) * E));
+    TRY(weight_alloc_split(ctx, "lm.lstm.weight", 4 * H * (E + H)));
+    TRY(weight_alloc_f32(ctx, "lm.lstm.bias", 4 * H));
+    TRY(weight_alloc_split(ctx, "lm.vocab.weight", (V + 1) * H));
+    TRY(weight_alloc_f32(ctx, "lm.vocab.bias", V + 1));
+  }
+#undef TRY
+  *out = ctx;
+  return DC_OK;
+}
+
+extern "C" int dc_destroy(dc_ctx* ctx) {
+  if (!ctx) return DC_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (void* p : ctx->allocs) cudaFree(p);
+  for (cudaEvent_t ev : ctx->timer.events) cudaEventDestroy(ev);
+  delete ctx;
+  return DC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static size_t shape_numel(const int64_t* shape, int ndim) {
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
+  return n;
+}
+static bool shape_is(const int64_t* s, int nd, std::initializer_list<int64_t> want) {
+  if ((size_t)nd != want.size()) return false;
+  int i = 0;
+  for (int64_t v : want) if (s[i++] != v) return false;
+  return true;
+}
+
+extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_host, const int64_t* shape, int ndim) {
+  if (!ctx || !name || !data_host || !shape) return dc_set_error(ctx, DC_E_INVALID, "dc_load_weights: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  const dc_config& c = ctx->cfg;
+  const std::string n = name;
+  const size_t numel = shape_numel(shape, ndim);
+  const int64_t C5 = c.widths[4], F = c.rpn_filters, fc = c.fc_dim, E = c.encoding_size, H = c.rnn_size, V = c.vocab_size;
+  const int64_t k = c.num_anchors, hw = (int64_t)c.pool_hw * c.pool_hw;
+  cudaStream_t st = 0;
+  // staging copy of the raw fp32 tensor
+  float* raw = nullptr;
+  auto stage = [&]() -> int {
+    cudaError_t e = cudaMalloc((void**)&raw, numel * sizeof(float));
+    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_NOMEM, "dc_load_weights(%s): staging cudaMalloc failed: %s", name, cudaGetErrorString(e));
+    e = cudaMemcpy(raw, data_host, numel * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(raw); raw = nullptr; return dc_set_error(ctx, DC_E_CUDA, "dc_load_weights(%s): H2D failed: %s", name, cudaGetErrorString(e)); }
+    return DC_OK;
+  };
+  auto finish = [&](int rc) -> int {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (raw) cudaFree(raw);
+    if (rc != DC_OK) return rc;
+    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "dc_load_weights(%s): %s", name, cudaGetErrorString(e));
+    return DC_OK;
+  };
+  auto bad_shape = [&]() { return dc_set_error(ctx, DC_E_INVALID, "dc_load_weights(%s): unexpected shape", name); };
+  auto copy_f32 = [&](const std::string& key, size_t offset, size_t count) -> int {
+    Weight& w = ctx->w[key];
+    if (offset + count > w.n_f32) return bad_shape();
+    DC_CHECK_CUDA(ctx, cudaMemcpy(w.f32 + offset, data_host, count * sizeof(float), cudaMemcpyHostToDevice));
+    w.loaded = true;
+    return DC_OK;
+  };
+
+  // ---- VGG convs ----
+  {
+    int cin = 3;
+    for (int i = 0; i < 13; ++i) {
+      const int cout = c.widths[kConvStage[i]];
+      const std::string base = kConvNames[i];
+      if (n == base + ".weight") {
+        if (!shape_is(shape, ndim, {cout, cin, 3, 3})) return bad_shape();
+        if (i == 0) return copy_f32(n, 0, numel);
+        int rc = stage();
+        if (rc) return rc;
+        Weight& w = ctx->w[n];
+        rc = k_conv_weight_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, cout, cin, st);
+        w.loaded = true;
+        return finish(rc);
+      }
+      if (n == base + ".bias") {
+        if (!shape_is(shape, ndim, {cout})) return bad_shape();
+        return copy_f32(n, 0, numel);
+      }
+      cin = cout;
+    }
+  }
+  if (n == "rpn.conv.weight") {
+    if (!shape_is(shape, ndim, {F, C5, 3, 3})) return bad_shape();
+    int rc = stage();
+    if (rc) return rc;
+    Weight& w = ctx->w[n];
+    rc = k_conv_weight_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, (int)F, (int)C5, st);
+    w.loaded = true;
+    return finish(rc);
+  }
+  if (n == "rpn.conv.bias") { if (!shape_is(shape, ndim, {F})) return bad_shape(); return copy_f32(n, 0, numel); }
+  if (n == "rpn.box.weight" || n == "rpn.score.weight") {
+    const bool box = (n == "rpn.box.weight");
+    const int64_t rows = box ? 4 * k : 2 * k;
+    if (!(shape_is(shape, ndim, {rows, F, 1, 1}) || shape_is(shape, ndim, {rows, F}))) return bad_shape();
+    int rc = stage();
+    if (rc) return rc;
+    Weight& w = ctx->w["rpn.head.weight"];
+    const size_t off = box ? 0 : (size_t)4 * k * F;
+    rc = k_rowmajor_to_split(ctx, raw, w.planes + off, w.planes + w.plane_elems + off, numel, st);
+    w.loaded = true;
+    return finish(rc);
+  }
+  if (n == "rpn.box.bias") { if (!shape_is(shape, ndim, {4 * k})) return bad_shape(); return copy_f32("rpn.head.bias", 0, numel); }
+  if (n == "rpn.score.bias") { if (!shape_is(shape, ndim, {2 * k})) return bad_shape(); return copy_f32("rpn.head.bias", (size_t)4 * k, numel); }
+  if (n == "fc6.weight") {
+    if (!shape_is(shape, ndim, {fc, C5 * hw})) return bad_shape();
+    int rc = stage();
+    if (rc) return rc;
+    Weight& w = ctx->w[n];
+    rc = k_fc6_weight_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, (int)fc, (int)C5, (int)hw, st);
+    w.loaded = true;
+    return finish(rc);
+  }
+  struct RowMajor { const char* name; int64_t rows, cols; };
+  const RowMajor rm[] = {{"fc7.weight", fc, fc}, {"lm.encoder.weight", E, fc}, {"lm.lookup.weight", V + 2, E}, {"lm.vocab.weight", V + 1, H}};
+  for (const RowMajor& r : rm) {
+    if (n == r.name) {
+      if (!shape_is(shape, ndim, {r.rows, r.cols})) return bad_shape();
+      int rc = stage();
+      if (rc) return rc;
+      Weight& w = ctx->w[n];
+      rc = k_rowmajor_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, numel, st);
+      w.loaded = true;
+      return finish(rc);
+    }
+  }
+  if (n == "lm.lstm.weight") {
+    if (!shape_is(shape, ndim, {E + H, 4 * H})) return bad_shape();
+    int rc = stage();
+    if (rc) return rc;
+    Weight& w = ctx->w[n];
+    rc = k_transpose_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, (int)(E + H), (int)(4 * H), st);
+    w.loaded = true;
+    return finish(rc);
+  }
+  struct F32 { const char* name; int64_t n; };
+  const F32 fl[] = {{"fc6.bias", fc}, {"fc7.bias", fc}, {"obj.weight", fc}, {"obj.bias", 1}, {"boxreg.weight", 4 * fc}, {"boxreg.bias", 4},
+                    {"lm.encoder.bias", E}, {"lm.lstm.bias", 4 * H}, {"lm.vocab.bias", V + 1}};
+  for (const F32& f : fl) {
+    if (n == f.name) {
+      if ((int64_t)numel != f.n) return bad_shape();
+      return copy_f32(n, 0, numel);
+    }
+  }
+  return dc_set_error(ctx, DC_E_NOTFOUND, "dc_load_weights: unknown weight name '%s'", name);
+}
+
+extern "C" int dc_set_test_args(dc_ctx* ctx, float rpn_nms_thresh, float final_nms_thresh, int num_proposals, int clip_boxes) {
+  if (!ctx) return dc_set_error(nullptr, DC_E_INVALID, "dc_set_test_args: null ctx");
+  DC_REQUIRE(ctx, num_proposals == -1 || (num_proposals > 0 && num_proposals <= ctx->P), DC_E_INVALID,
+             "num_proposals=%d exceeds the configured max_proposals=%d", num_proposals, ctx->P);
+  ctx->rpn_nms_thresh = rpn_nms_thresh;
+  ctx->final_nms_thresh = final_nms_thresh;
+  ctx->num_proposals = (num_proposals == -1) ? ctx->P : num_proposals;
+  ctx->clip_boxes = clip_boxes ? 1 : 0;
+  return DC_OK;
+}
+
+extern "C" int dc_set_image_size(dc_ctx* ctx, int image_h, int image_w) {
+  if (!ctx) return dc_set_error(nullptr, DC_E_INVALID, "dc_set_image_size: null ctx");
+  DC_REQUIRE(ctx, image_h > 0 && image_w > 0, DC_E_INVALID, "setImageSize: bad size %dx%d", image_h, image_w);
+  ctx->image_h = image_h;
+  ctx->image_w = image_w;
+  ctx->size_consumed = false;
+  return DC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase timing (LocalizationLayer:timeit, LocalizationLayer.lua:219-230)
+// ------------------------------------------------------------------------------------------------
+static void phase_mark(dc_ctx* ctx, const char* name, cudaStream_t st) {
+  PhaseTimer& t = ctx->timer;
+  if (!t.enabled) return;
+  if (t.used == t.events.size()) {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    t.events.push_back(ev);
+    t.names.push_back(name);
+  }
+  t.names[t.used] = name;
+  cudaEventRecord(t.events[t.used], st);
+  ++t.used;
+}
+extern "C" int dc_enable_timing(dc_ctx* ctx, int enable) {
+  if (!ctx) return DC_E_INVALID;
+  ctx->timer.enabled = enable != 0;
+  ctx->timer.used = 0;
+  return DC_OK;
+}
+extern "C" int dc_get_times(dc_ctx* ctx, const char** names_out, float* ms_out, int capacity, int* count_out) {
+  if (!ctx || !count_out) return DC_E_INVALID;
+  PhaseTimer& t = ctx->timer;
+  int n = 0;
+  if (t.used >= 2) {
+    DC_CHECK_CUDA(ctx, cudaEventSynchronize(t.events[t.used - 1]));
+    for (size_t i = 0; i + 1 < t.used && n < capacity; ++i, ++n) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, t.events[i], t.events[i + 1]);
+      if (names_out) names_out[n] = t.names[i];
+      if (ms_out) ms_out[n] = ms;
+    }
+  }
+  *count_out = n;
+  return DC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense-layer helpers (engine dispatch)
+// ------------------------------------------------------------------------------------------------
+static int need_weight(dc_ctx* ctx, const char* name, Weight** out) {
+  auto it = ctx->w.find(name);
+  DC_REQUIRE(ctx, it != ctx->w.end(), DC_E_NOTFOUND, "internal: weight '%s' not registered", name);
+  DC_REQUIRE(ctx, it->second.loaded, DC_E_PROTOCOL, "weight '%s' has not been loaded (dc_load_weights)", name);
+  *out = &it->second;
+  return DC_OK;
+}
+
+static int gemm(dc_ctx* ctx, const __half* a_hi, size_t a_plane, int lda, const Weight& w, int ldb, int M, int N, int K,
+                const GemmEpilogue& ep, cudaStream_t st) {
+  if (ctx->cfg.engine == DC_ENGINE_TC) return k_tc_gemm(ctx, a_hi, a_plane, lda, w.planes, w.plane_elems, ldb, M, N, K, ep, st);
+  return k_simt_gemm(ctx, a_hi, a_hi + a_plane, lda, w.planes, w.planes + w.plane_elems, ldb, M, N, K, ep, st);
+}
+
+// y = relu(conv3x3(x)+b) [+pool]; returns the spatial size of y through oh/ow
+static int conv_layer(dc_ctx* ctx, const __half* x, size_t x_plane, __half* y, int N, int H, int W, int Cin, int Cout, const Weight& wt,
+                      const Weight& bias, int pool_after, __half* pool_tmp, int* oh, int* ow, cudaStream_t st) {
+  const int ceil_mode = ctx->cfg.pool_ceil;
+  const int PH = pooled(H, ceil_mode), PW = pooled(W, ceil_mode);
+  if (ctx->cfg.engine == DC_ENGINE_TC) {
+    const bool fuse = pool_after && ctx->cfg.fuse_pool && ceil_mode;
+    if (fuse) {
+      const size_t yp = (size_t)N * PH * PW * Cout;
+      int rc = k_tc_conv3x3(ctx, x, x_plane, wt.planes, wt.plane_elems, bias.f32, y, y + yp, N, H, W, Cin, Cout, 1, st);
+      *oh = PH; *ow = PW;
+      return rc;
+    }
+    __half* dst = pool_after ? pool_tmp : y;
+    const size_t yp = (size_t)N * H * W * Cout;
+    int rc = k_tc_conv3x3(ctx, x, x_plane, wt.planes, wt.plane_elems, bias.f32, dst, dst + yp, N, H, W, Cin, Cout, 0, st);
+    if (rc) return rc;
+    if (pool_after) {
+      const size_t pp = (size_t)N * PH * PW * Cout;
+      rc = k_maxpool2x2_split(ctx, dst, dst + yp, y, y + pp, N, H, W, Cout, ceil_mode, st);
+      *oh = PH; *ow = PW;
+      return rc;
+    }
+    *oh = H; *ow = W;
+    return DC_OK;
+  }
+  __half* dst = pool_after ? pool_tmp : y;
+  const size_t yp = (size_t)N * H * W * Cout;
+  int rc = k_simt_conv3x3(ctx, x, x + x_plane, wt.planes, wt.planes + wt.plane_elems, bias.f32, dst, dst + yp, N, H, W, Cin, Cout, st);
+  if (rc) return rc;
+  if (pool_after) {
+    const size_t pp = (size_t)N * PH * PW * Cout;
+    rc = k_maxpool2x2_split(ctx, dst, dst + yp, y, y + pp, N, H, W, Cout, ceil_mode, st);
+    *oh = PH; *ow = PW;
+    return rc;
+  }
+  *oh = H; *ow = W;
+  return DC_OK;
+}
+
+// conv_net1 + conv_net2 (DenseCapModel.lua:61-76): img NCHW fp32 -> ctx->feats (split NHWC)
+static int run_trunk(dc_ctx* ctx, const float* img, int N, int H, int W, int* fh, int* fw, cudaStream_t st) {
+  const dc_config& c = ctx->cfg;
+  DC_REQUIRE(ctx, N >= 1 && N <= ctx->B, DC_E_INVALID, "batch %d exceeds max_batch %d", N, ctx->B);
+  DC_REQUIRE(ctx, (size_t)H * W <= (size_t)c.max_image_h * c.max_image_w && H > 0 && W > 0, DC_E_INVALID,
+             "image %dx%d exceeds the configured maximum %dx%d", H, W, c.max_image_h, c.max_image_w);
+  int efh, efw;
+  feat_hw(c, H, W, efh, efw);
+  DC_REQUIRE(ctx, (size_t)efh * efw <= (size_t)ctx->fh_max * ctx->fw_max, DC_E_INVALID, "feature map too large");
+  Weight *w0, *b0;
+  int rc;
+  if ((rc = need_weight(ctx, "conv1_1.weight", &w0))) return rc;
+  if ((rc = need_weight(ctx, "conv1_1.bias", &b0))) return rc;
+  int cur = 0;
+  int h = H, w = W, cin = c.widths[0];
+  {
+    __half* y = ctx->act[0].base;
+    const size_t yp = (size_t)N * H * W * cin;
+    if ((rc = k_conv_first(ctx, img, w0->f32, b0->f32, y, y + yp, N, H, W, cin, st))) return rc;
+  }
+  for (int i = 1; i < 13; ++i) {
+    const int cout = c.widths[kConvStage[i]];
+    Weight *wt, *bs;
+    if ((rc = need_weight(ctx, (std::string(kConvNames[i]) + ".weight").c_str(), &wt))) return rc;
+    if ((rc = need_weight(ctx, (std::string(kConvNames[i]) + ".bias").c_str(), &bs))) return rc;
+    const __half* x = ctx->act[cur].base;
+    const size_t xp = (size_t)N * h * w * cin;
+    int oh, ow;
+    if (i == 12) {
+      // last layer writes straight into the feature buffer (no pool after conv5_3; pool5 is excluded)
+      if ((rc = conv_layer(ctx, x, xp, ctx->feats.base, N, h, w, cin, cout, *wt, *bs, 0, nullptr, &oh, &ow, st))) return rc;
+    } else {
+      const bool unfused_pool = kPoolAfter[i] && !(c.engine == DC_ENGINE_TC && c.fuse_pool && c.pool_ceil);
+      // unfused pool: conv x(cur) -> tmp(other), pool tmp(other) -> y(cur): x is dead by then
+      __half* y = unfused_pool ? ctx->act[cur].base : ctx->act[cur ^ 1].base;
+      __half* tmp = ctx->act[cur ^ 1].base;
+      if ((rc = conv_layer(ctx, x, xp, y, N, h, w, cin, cout, *wt, *bs, kPoolAfter[i], tmp, &oh, &ow, st))) return rc;
+      if (!unfused_pool) cur ^= 1;
+    }
+    h = oh; w = ow; cin = cout;
+  }
+  *fh = h; *fw = w;
+  return DC_OK;
+}
+
+__global__ void identity_idx_kernel(const int32_t* __restrict__ count_in, int P, int32_t* idx32, int64_t* idx64, int32_t* count_out) {
+  const int n = min(*count_in, P);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { idx32[i] = i; idx64[i] = i + 1; }
+  if (threadIdx.x == 0) *count_out = n;
+}
+__global__ void set_count_kernel(int32_t* p, int v) { *p = v; }
+
+// RPN + post-processing + NMS + ROI pooling for image b of the batch (LocalizationLayer.lua:250-363)
+static int run_localization(dc_ctx* ctx, int N, int fh, int fw, int img_h, int img_w, cudaStream_t st) {
+  const dc_config& c = ctx->cfg;
+  const int C5 = c.widths[4], F = c.rpn_filters, k = c.num_anchors;
+  const int cells = fh * fw;
+  const int A = k * cells;
+  DC_REQUIRE(ctx, A <= ctx->A_max, DC_E_INVALID, "feature map %dx%d exceeds capacity", fh, fw);
+  Weight *wc, *bc, *wh, *bh;
+  int rc;
+  if ((rc = need_weight(ctx, "rpn.conv.weight", &wc))) return rc;
+  if ((rc = need_weight(ctx, "rpn.conv.bias", &bc))) return rc;
+  if ((rc = need_weight(ctx, "rpn.head.weight", &wh))) return rc;
+  if ((rc = need_weight(ctx, "rpn.head.bias", &bh))) return rc;
+  phase_mark(ctx, "rpn:forward_test", st);
+  int oh, ow;
+  const size_t fplane = (size_t)N * cells * C5;
+  if ((rc = conv_layer(ctx, ctx->feats.base, fplane, ctx->rpn_hidden.base, N, fh, fw, C5, F, *wc, *bc, 0, nullptr, &oh, &ow, st))) return rc;
+  {
+    GemmEpilogue ep;
+    ep.bias = bh->f32;
+    ep.out_f32 = ctx->rpn_head;
+    ep.ldf = 6 * k;
+    const size_t hplane = (size_t)N * cells * F;
+    if ((rc = gemm(ctx, ctx->rpn_hidden.base, hplane, F, *wh, F, N * cells, 6 * k, F, ep, st))) return rc;
+  }
+  const int P = ctx->P;
+  for (int b = 0; b < N; ++b) {
+    RpnPostOut po;
+    po.boxes_xcycwh = ctx->pp_boxes + (size_t)b * ctx->A_max * 4;
+    po.boxes_x1y1x2y2 = ctx->pp_x1y1 + (size_t)b * ctx->A_max * 4;
+    po.prob = ctx->pp_prob + (size_t)b * ctx->A_max;
+    po.src_row = ctx->pp_src + (size_t)b * ctx->A_max;
+    po.n_valid = ctx->pp_nvalid + b;
+    po.block_counts = ctx->pp_blocks + (size_t)b * (ctx->A_max / 256 + 2);
+    if ((rc = k_rpn_postprocess(ctx, ctx->rpn_head + (size_t)b * cells * 6 * k, 6 * k, fh, fw, k, ctx->anchors_dev, c.field_centers[0],
+                                c.field_centers[1], c.field_centers[2], c.field_centers[3], (float)img_w, (float)img_h, ctx->clip_boxes,
+                                po, st)))
+      return rc;
+  }
+  phase_mark(ctx, "nms", st);
+  for (int b = 0; b < N; ++b) {
+    if ((rc = k_nms(ctx, ctx->pp_x1y1 + (size_t)b * ctx->A_max * 4, 4, ctx->pp_prob + (size_t)b * ctx->A_max, 1, A, ctx->pp_nvalid + b,
+                    ctx->rpn_nms_thresh, ctx->num_proposals, ctx->nms, ctx->rpn_idx64 + (size_t)b * P, ctx->rpn_idx32 + (size_t)b * P,
+                    ctx->rpn_count + b, st)))
+      return rc;
+    if ((rc = k_gather_rows_f32(ctx, ctx->pp_boxes + (size_t)b * ctx->A_max * 4, 4, ctx->rpn_idx32 + (size_t)b * P, ctx->rpn_count + b, P,
+                                ctx->roi_boxes + (size_t)b * P * 4, st)))
+      return rc;
+  }
+  phase_mark(ctx, "roi_pooling:forward_test", st);
+  const int hw = c.pool_hw * c.pool_hw;
+  const size_t rplane = (size_t)N * P * hw * C5;
+  for (int b = 0; b < N; ++b) {
+    const size_t foff = (size_t)b * cells * C5;
+    const size_t roff = (size_t)b * P * hw * C5;
+    if ((rc = k_roi_pool(ctx, ctx->feats.base + foff, ctx->feats.base + fplane + foff, nullptr, C5, fh, fw, ctx->roi_boxes + (size_t)b * P * 4,
+                         ctx->rpn_count + b, P, img_h, img_w, c.pool_hw, c.pool_hw, ctx->roi.base + roff, ctx->roi.base + rplane + roff,
+                         nullptr, 1, st)))
+      return rc;
+  }
+  return DC_OK;
+}
+
+// recognition head on ctx->roi (rows = N*P): fc6, fc7, objectness, box regression, final boxes
+static int run_recog(dc_ctx* ctx, int rows, cudaStream_t st) {
+  const dc_config& c = ctx->cfg;
+  const int C5 = c.widths[4], fc = c.fc_dim, hw = c.pool_hw * c.pool_hw;
+  Weight *w6, *b6, *w7, *b7, *wo, *bo, *wr, *br;
+  int rc;
+  if ((rc = need_weight(ctx, "fc6.weight", &w6))) return rc;
+  if ((rc = need_weight(ctx, "fc6.bias", &b6))) return rc;
+  if ((rc = need_weight(ctx, "fc7.weight", &w7))) return rc;
+  if ((rc = need_weight(ctx, "fc7.bias", &b7))) return rc;
+  if ((rc = need_weight(ctx, "obj.weight", &wo))) return rc;
+  if ((rc = need_weight(ctx, "obj.bias", &bo))) return rc;
+  if ((rc = need_weight(ctx, "boxreg.weight", &wr))) return rc;
+  if ((rc = need_weight(ctx, "boxreg.bias", &br))) return rc;
+  phase_mark(ctx, "recog:fc6", st);
+  const int K6 = hw * C5;
+  const size_t rplane = (size_t)rows * K6;
+  const size_t fplane = (size_t)rows * fc;
+  {
+    GemmEpilogue ep;
+    ep.bias = b6->f32; ep.relu = 1;
+    ep.out_hi = ctx->fc6o.base; ep.out_lo = ctx->fc6o.base + fplane; ep.ldo = fc;
+    if ((rc = gemm(ctx, ctx->roi.base, rplane, K6, *w6, K6, rows, fc, K6, ep, st))) return rc;
+  }
+  phase_mark(ctx, "recog:fc7", st);
+  {
+    GemmEpilogue ep;
+    ep.bias = b7->f32; ep.relu = 1;
+    ep.out_hi = ctx->fc7o.base; ep.out_lo = ctx->fc7o.base + fplane; ep.ldo = fc;
+    ep.out_f32 = ctx->codes; ep.ldf = fc;
+    if ((rc = gemm(ctx, ctx->fc6o.base, fplane, fc, *w7, fc, rows, fc, fc, ep, st))) return rc;
+  }
+  phase_mark(ctx, "recog:heads", st);
+  if ((rc = k_small_heads(ctx, ctx->codes, fc, wo->f32, bo->f32, ctx->obj, rows, fc, 1, st))) return rc;
+  if ((rc = k_small_heads(ctx, ctx->codes, fc, wr->f32, br->f32, ctx->trans, rows, fc, 4, st))) return rc;
+  if ((rc = k_apply_box_transform(ctx, ctx->roi_boxes, ctx->trans, ctx->boxes_all, rows, st))) return rc;
+  return DC_OK;
+}
+
+// LanguageModel:sample on ctx->fc7o (rows), greedy (LanguageModel.lua:293-348)
+static int run_lm(dc_ctx* ctx, int rows, float* logits, cudaStream_t st) {
+  const dc_config& c = ctx->cfg;
+  const int fc = c.fc_dim, E = c.encoding_size, H = c.rnn_size, V = c.vocab_size, T = c.seq_length;
+  Weight *we, *be, *wl, *wlstm, *blstm, *wv, *bv;
+  int rc;
+  if ((rc = need_weight(ctx, "lm.encoder.weight", &we))) return rc;
+  if ((rc = need_weight(ctx, "lm.encoder.bias", &be))) return rc;
+  if ((rc = need_weight(ctx, "lm.lookup.weight", &wl))) return rc;
+  if ((rc = need_weight(ctx, "lm.lstm.weight", &wlstm))) return rc;
+  if ((rc = need_weight(ctx, "lm.lstm.bias", &blstm))) return rc;
+  if ((rc = need_weight(ctx, "lm.vocab.weight", &wv))) return rc;
+  if ((rc = need_weight(ctx, "lm.vocab.bias", &bv))) return rc;
+  phase_mark(ctx, "lm:sample", st);
+  const int ld = E + H;
+  const size_t xplane = (size_t)rows * ld;
+  const size_t fplane = (size_t)rows * fc;
+  __half* xh_hi = ctx->xh.base;
+  __half* xh_lo = ctx->xh.base + xplane;
+  {  // image_encoder: Linear + ReLU (LanguageModel.lua:27-29) -> x half of [x|h]
+    GemmEpilogue ep;
+    ep.bias = be->f32; ep.relu = 1;
+    ep.out_hi = xh_hi; ep.out_lo = xh_lo; ep.ldo = ld; ep.out_col0 = 0;
+    if ((rc = gemm(ctx, ctx->fc7o.base, fplane, fc, *we, fc, rows, E, fc, ep, st))) return rc;
+  }
+  {  // first LSTM step on the encoded image with h0 = c0 = 0: only the Wx rows contribute (K = E)
+    GemmEpilogue ep;
+    ep.bias = blstm->f32;
+    ep.out_f32 = ctx->gates; ep.ldf = 4 * H;
+    if ((rc = gemm(ctx, xh_hi, xplane, ld, *wlstm, ld, rows, 4 * H, E, ep, st))) return rc;
+    if ((rc = k_lstm_pointwise(ctx, ctx->gates, ctx->cstate, xh_hi, xh_lo, ld, E, rows, H, 1, st))) return rc;
+  }
+  for (int t = 0; t < T; ++t) {
+    if ((rc = k_lm_gather_x(ctx, ctx->tokens, T, t, V + 1, wl->planes, wl->planes + wl->plane_elems, E, xh_hi, xh_lo, ld, rows, st))) return rc;
+    {
+      GemmEpilogue ep;
+      ep.bias = blstm->f32;
+      ep.out_f32 = ctx->gates; ep.ldf = 4 * H;
+      if ((rc = gemm(ctx, xh_hi, xplane, ld, *wlstm, ld, rows, 4 * H, ld, ep, st))) return rc;
+    }
+    if ((rc = k_lstm_pointwise(ctx, ctx->gates, ctx->cstate, xh_hi, xh_lo, ld, E, rows, H, 0, st))) return rc;
+    if ((rc = k_argmax_init(ctx, ctx->packed, rows, st))) return rc;
+    {
+      GemmEpilogue ep;
+      ep.bias = bv->f32;
+      ep.argmax = ctx->packed;
+      if (logits) { ep.out_f32 = logits + (size_t)t * (V + 1); ep.ldf = T * (V + 1); }
+      // A = h half of [x|h]
+      if ((rc = gemm(ctx, xh_hi + E, xplane, ld, *wv, H, rows, V + 1, H, ep, st))) return rc;
+    }
+    if ((rc = k_argmax_finish(ctx, ctx->packed, ctx->tokens, T, t, ctx->seq64, T, rows, st))) return rc;
+  }
+  return DC_OK;
+}
+
+// final NMS + selection (DenseCapModel.lua:261-275)
+static int run_final(dc_ctx* ctx, int N, cudaStream_t st) {
+  const int P = ctx->P, T = ctx->cfg.seq_length;
+  int rc;
+  phase_mark(ctx, "final_nms", st);
+  if ((rc = k_xcycwh_to_x1y1x2y2(ctx, ctx->boxes_all, ctx->fin_x1y1, N * P, st))) return rc;
+  for (int b = 0; b < N; ++b) {
+    const size_t o = (size_t)b * P;
+    if (ctx->final_nms_thresh > 0.f) {
+      if ((rc = k_nms(ctx, ctx->fin_x1y1 + o * 4, 4, ctx->obj + o, 1, P, ctx->rpn_count + b, ctx->final_nms_thresh, 0, ctx->nms,
+                      ctx->fin_idx64 + o, ctx->fin_idx32 + o, ctx->fin_count + b, st)))
+        return rc;
+    } else {
+      identity_idx_kernel<<<1, 256, 0, st>>>(ctx->rpn_count + b, P, ctx->fin_idx32 + o, ctx->fin_idx64 + o, ctx->fin_count + b);
+      DC_CHECK_LAUNCH(ctx);
+    }
+    if ((rc = k_final_gather(ctx, ctx->fin_idx32 + o, ctx->fin_count + b, P, ctx->boxes_all + o * 4, ctx->obj + o, ctx->seq64 + o * T, T,
+                             ctx->fin_boxes + o * 4, ctx->fin_scores + o, ctx->fin_seq + o * T, st)))
+      return rc;
+  }
+  return DC_OK;
+}
+
+static void fill_result(dc_ctx* ctx, int N, dc_result* out) {
+  out->batch = N;
+  out->max_proposals = ctx->P;
+  out->num_proposals = ctx->rpn_count;
+  out->num_final = ctx->fin_count;
+  out->final_boxes = ctx->fin_boxes;
+  out->final_scores = ctx->fin_scores;
+  out->final_seq = ctx->fin_seq;
+  out->final_idx = ctx->fin_idx64;
+  out->roi_boxes = ctx->roi_boxes;
+  out->box_trans = ctx->trans;
+  out->all_boxes = ctx->boxes_all;
+  out->all_scores = ctx->obj;
+  out->all_seq = ctx->seq64;
+  out->codes = ctx->codes;
+}
+
+extern "C" int dc_forward_test(dc_ctx* ctx, const float* img, int batch, int image_h, int image_w, dc_result* out, void* stream) {
+  if (!ctx || !img) return dc_set_error(ctx, DC_E_INVALID, "dc_forward_test: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  // DenseCapModel:updateOutput sets the image size itself (DenseCapModel.lua:245-246)
+  if ((rc = dc_set_image_size(ctx, image_h, image_w))) return rc;
+  ctx->timer.used = 0;
+  phase_mark(ctx, "conv_trunk", st);
+  int fh, fw;
+  if ((rc = run_trunk(ctx, img, batch, image_h, image_w, &fh, &fw, st))) return rc;
+  ctx->size_consumed = true;
+  if ((rc = run_localization(ctx, batch, fh, fw, image_h, image_w, st))) return rc;
+  const int rows = batch * ctx->P;
+  if ((rc = run_recog(ctx, rows, st))) return rc;
+  if ((rc = run_lm(ctx, rows, nullptr, st))) return rc;
+  if ((rc = run_final(ctx, batch, st))) return rc;
+  phase_mark(ctx, "end", st);
+  if (out) fill_result(ctx, batch, out);
+  return DC_OK;
+}
+
+extern "C" int dc_forward_test_host(dc_ctx* ctx, const float* img_host, int batch, int image_h, int image_w, int32_t* num_final_host,
+                                    float* final_boxes_host, float* final_scores_host, int64_t* final_seq_host) {
+  if (!ctx || !img_host) return dc_set_error(ctx, DC_E_INVALID, "dc_forward_test_host: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  DC_REQUIRE(ctx, batch >= 1 && batch <= ctx->B, DC_E_INVALID, "batch %d exceeds max_batch %d", batch, ctx->B);
+  const size_t n = (size_t)batch * 3 * image_h * image_w;
+  // dedicated device staging buffer for the host image, sized on first use
+  static thread_local float* staging = nullptr;
+  static thread_local size_t staging_elems = 0;
+  if (staging_elems < n) {
+    if (staging) cudaFree(staging);
+    DC_CHECK_CUDA(ctx, cudaMalloc((void**)&staging, n * sizeof(float)));
+    staging_elems = n;
+  }
+  cudaStream_t st = 0;
+  DC_CHECK_CUDA(ctx, cudaMemcpyAsync(staging, img_host, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  dc_result r;
+  int rc = dc_forward_test(ctx, staging, batch, image_h, image_w, &r, st);
+  if (rc) return rc;
+  const size_t rows = (size_t)batch * ctx->P;
+  const int T = ctx->cfg.seq_length;
+  if (num_final_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(num_final_host, r.num_final, batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (final_boxes_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(final_boxes_host, r.final_boxes, rows * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (final_scores_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(final_scores_host, r.final_scores, rows * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (final_seq_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(final_seq_host, r.final_seq, rows * T * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  DC_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+  return DC_OK;
+}
+
+extern "C" int dc_vgg_trunk_forward(dc_ctx* ctx, const float* img, int batch, int image_h, int image_w, float* feats_nchw, void* stream) {
+  if (!ctx || !img || !feats_nchw) return dc_set_error(ctx, DC_E_INVALID, "dc_vgg_trunk_forward: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int fh, fw, rc;
+  if ((rc = run_trunk(ctx, img, batch, image_h, image_w, &fh, &fw, st))) return rc;
+  const int C5 = ctx->cfg.widths[4];
+  const size_t plane = (size_t)batch * fh * fw * C5;
+  return k_split_nhwc_to_nchw(ctx, ctx->feats.base, ctx->feats.base + plane, feats_nchw, batch, C5, fh, fw, st);
+}
+
+extern "C" int dc_localization_forward_test(dc_ctx* ctx, const float* feats_nchw, int feat_h, int feat_w, float* roi_features,
+                                            float* roi_boxes, int64_t* idx, int32_t* num_out, void* stream) {
+  if (!ctx || !feats_nchw) return dc_set_error(ctx, DC_E_INVALID, "dc_localization_forward_test: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  // LocalizationLayer.lua:259-261
+  DC_REQUIRE(ctx, ctx->image_h > 0 && ctx->image_w > 0 && !ctx->size_consumed, DC_E_PROTOCOL,
+             "Must call setImageSize before each forward pass");
+  ctx->size_consumed = true;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dc_config& c = ctx->cfg;
+  const int C5 = c.widths[4];
+  DC_REQUIRE(ctx, (size_t)feat_h * feat_w <= (size_t)ctx->fh_max * ctx->fw_max, DC_E_INVALID, "feature map too large");
+  const size_t plane = (size_t)feat_h * feat_w * C5;
+  int rc;
+  ctx->timer.used = 0;
+  if ((rc = k_nchw_to_split_nhwc(ctx, feats_nchw, ctx->feats.base, ctx->feats.base + plane, 1, C5, feat_h, feat_w, st))) return rc;
+  if ((rc = run_localization(ctx, 1, feat_h, feat_w, ctx->image_h, ctx->image_w, st))) return rc;
+  phase_mark(ctx, "end", st);
+  const int P = ctx->P, hw = c.pool_hw * c.pool_hw;
+  if (roi_features) {
+    const size_t rplane = (size_t)P * hw * C5;
+    if ((rc = k_bhwc_split_to_bchw(ctx, ctx->roi.base, ctx->roi.base + rplane, roi_features, ctx->num_proposals, C5, hw, st))) return rc;
+  }
+  if (roi_boxes) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(roi_boxes, ctx->roi_boxes, (size_t)ctx->num_proposals * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (idx) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(idx, ctx->rpn_idx64, (size_t)ctx->num_proposals * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  if (num_out) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(num_out, ctx->rpn_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return DC_OK;
+}
+
+extern "C" int dc_recog_forward(dc_ctx* ctx, const float* roi_features, const float* roi_boxes, int K, float* codes, float* obj_scores,
+                                float* box_trans, float* final_boxes, void* stream) {
+  if (!ctx || !roi_features || !roi_boxes) return dc_set_error(ctx, DC_E_INVALID, "dc_recog_forward: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  DC_REQUIRE(ctx, K >= 1 && K <= ctx->P * ctx->B, DC_E_INVALID, "K=%d exceeds capacity %d", K, ctx->P * ctx->B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const dc_config& c = ctx->cfg;
+  const int C5 = c.widths[4], hw = c.pool_hw * c.pool_hw, fc = c.fc_dim;
+  int rc;
+  const size_t rplane = (size_t)K * hw * C5;
+  if ((rc = k_bchw_to_split_rows(ctx, roi_features, ctx->roi.base, ctx->roi.base + rplane, K, C5, hw, st))) return rc;
+  DC_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->roi_boxes, roi_boxes, (size_t)K * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ctx->timer.used = 0;
+  if ((rc = run_recog(ctx, K, st))) return rc;
+  if (codes) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(codes, ctx->codes, (size_t)K * fc * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (obj_scores) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(obj_scores, ctx->obj, (size_t)K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (box_trans) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(box_trans, ctx->trans, (size_t)K * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (final_boxes) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(final_boxes, ctx->boxes_all, (size_t)K * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return DC_OK;
+}
+
+extern "C" int dc_lm_sample(dc_ctx* ctx, const float* codes, int K, int64_t* seq, float* logits, void* stream) {
+  if (!ctx || !codes || !seq) return dc_set_error(ctx, DC_E_INVALID, "dc_lm_sample: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  DC_REQUIRE(ctx, K >= 1 && K <= ctx->P * ctx->B, DC_E_INVALID, "K=%d exceeds capacity %d", K, ctx->P * ctx->B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int fc = ctx->cfg.fc_dim, T = ctx->cfg.seq_length;
+  const size_t fplane = (size_t)K * fc;
+  int rc;
+  if ((rc = k_rowmajor_to_split(ctx, codes, ctx->fc7o.base, ctx->fc7o.base + fplane, fplane, st))) return rc;
+  ctx->timer.used = 0;
+  if ((rc = run_lm(ctx, K, logits, st))) return rc;
+  DC_CHECK_CUDA(ctx, cudaMemcpyAsync(seq, ctx->seq64, (size_t)K * T * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  return DC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// leaf operators
+// ------------------------------------------------------------------------------------------------
+extern "C" int dc_make_anchors(float* out, int N, int H, int W, int k, float x0, float y0, float sx, float sy, const float* anchors_host, void* stream) {
+  if (!out || !anchors_host || k <= 0 || k > DC_MAX_ANCHORS) return dc_set_error(nullptr, DC_E_INVALID, "dc_make_anchors: bad argument");
+  float* a = nullptr;
+  if (cudaMalloc((void**)&a, sizeof(float) * 2 * k) != cudaSuccess) return dc_set_error(nullptr, DC_E_NOMEM, "dc_make_anchors: cudaMalloc");
+  cudaMemcpyAsync(a, anchors_host, sizeof(float) * 2 * k, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  int rc = k_make_anchors(nullptr, out, N, H, W, k, x0, y0, sx, sy, a, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(a);
+  return rc;
+}
+extern "C" int dc_reshape_box_features(const float* in, float* out, int N, int k, int D, int H, int W, void* stream) {
+  if (!in || !out) return dc_set_error(nullptr, DC_E_INVALID, "dc_reshape_box_features: null");
+  return k_reshape_box_features(nullptr, in, out, N, k, D, H, W, (cudaStream_t)stream);
+}
+extern "C" int dc_apply_box_transform(const float* boxes, const float* trans, float* out, int n, void* stream) {
+  if (n > 0 && (!boxes || !trans || !out)) return dc_set_error(nullptr, DC_E_INVALID, "dc_apply_box_transform: null");
+  return k_apply_box_transform(nullptr, boxes, trans, out, n, (cudaStream_t)stream);
+}
+extern "C" int dc_invert_box_transform(const float* anchors, const float* targets, float* out, int n, void* stream) {
+  if (n > 0 && (!anchors || !targets || !out)) return dc_set_error(nullptr, DC_E_INVALID, "dc_invert_box_transform: null");
+  return k_invert_box_transform(nullptr, anchors, targets, out, n, (cudaStream_t)stream);
+}
+extern "C" int dc_xcycwh_to_x1y1x2y2(const float* in, float* out, int n, void* stream) {
+  if (n > 0 && (!in || !out)) return dc_set_error(nullptr, DC_E_INVALID, "dc_xcycwh_to_x1y1x2y2: null");
+  return k_xcycwh_to_x1y1x2y2(nullptr, in, out, n, (cudaStream_t)stream);
+}
+extern "C" int dc_x1y1x2y2_to_xcycwh(const float* in, float* out, int n, void* stream) {
+  if (n > 0 && (!in || !out)) return dc_set_error(nullptr, DC_E_INVALID, "dc_x1y1x2y2_to_xcycwh: null");
+  return k_x1y1x2y2_to_xcycwh(nullptr, in, out, n, (cudaStream_t)stream);
+}
+extern "C" int dc_clip_boxes(const float* boxes, float* out, uint8_t* valid, int n, float x_min, float y_min, float x_max, float y_max, void* stream) {
+  if (n > 0 && (!boxes || !out || !valid)) return dc_set_error(nullptr, DC_E_INVALID, "dc_clip_boxes: null");
+  return k_clip_boxes(nullptr, boxes, out, valid, n, x_min, y_min, x_max, y_max, (cudaStream_t)stream);
+}
+extern "C" int dc_objectness_prob(const float* scores, float* prob, int n, void* stream) {
+  if (n > 0 && (!scores || !prob)) return dc_set_error(nullptr, DC_E_INVALID, "dc_objectness_prob: null");
+  return k_objectness_prob(nullptr, scores, prob, n, (cudaStream_t)stream);
+}
+extern "C" int dc_box_to_affine(const float* boxes, float* theta, int B, int image_h, int image_w, void* stream) {
+  if (B > 0 && (!boxes || !theta)) return dc_set_error(nullptr, DC_E_INVALID, "dc_box_to_affine: null");
+  return k_box_to_affine(nullptr, boxes, theta, B, image_h, image_w, (cudaStream_t)stream);
+}
+extern "C" int dc_box_iou(const float* box1, const float* box2, float* out, int B1, int B2, void* stream) {
+  if (B1 > 0 && B2 > 0 && (!box1 || !box2 || !out)) return dc_set_error(nullptr, DC_E_INVALID, "dc_box_iou: null");
+  return k_box_iou(nullptr, box1, box2, out, B1, B2, (cudaStream_t)stream);
+}
+
+extern "C" int dc_nms(dc_ctx* ctx, const float* boxes_scores, int n, float thresh, int max_boxes, int64_t* idx_out, int32_t* count_out, void* stream) {
+  if (!ctx || !count_out || (n > 0 && (!boxes_scores || !idx_out))) return dc_set_error(ctx, DC_E_INVALID, "dc_nms: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  return k_nms(ctx, boxes_scores, 5, boxes_scores + 4, 5, n, nullptr, thresh, max_boxes, ctx->nms, idx_out, nullptr, count_out, (cudaStream_t)stream);
+}
+
+__global__ void chw_to_hwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW) {
+  const size_t total = (size_t)C * HW;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int c = o % C;
+    const size_t p = o / C;
+    out[o] = in[(size_t)c * HW + p];
+  }
+}
+extern "C" int dc_bilinear_roi_pool(dc_ctx* ctx, const float* feats_chw, int C, int feat_h, int feat_w, const float* boxes, int B, int image_h,
+                                    int image_w, int HH, int WW, float* out, int out_layout, void* stream) {
+  if (!ctx || !feats_chw || !boxes || !out) return dc_set_error(ctx, DC_E_INVALID, "dc_bilinear_roi_pool: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)C * feat_h * feat_w;
+  DC_REQUIRE(ctx, n <= ctx->scratch_elems, DC_E_INVALID, "dc_bilinear_roi_pool: feature map larger than the ctx scratch (%zu > %zu)", n, ctx->scratch_elems);
+  // nn.Transpose({1,2},{2,3}) (BilinearRoiPooling.lua:56): CHW -> HWC, done once
+  chw_to_hwc_kernel<<<(unsigned)std::min<size_t>(2048, DC_CEIL_DIV(n, (size_t)256)), 256, 0, st>>>(feats_chw, ctx->scratch_f32, C, feat_h * feat_w);
+  DC_CHECK_LAUNCH(ctx);
+  return k_roi_pool(ctx, nullptr, nullptr, ctx->scratch_f32, C, feat_h, feat_w, boxes, nullptr, B, image_h, image_w, HH, WW, nullptr, nullptr, out,
+                    out_layout, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense test hooks
+// ------------------------------------------------------------------------------------------------
+struct TmpBufs {
+  std::vector<void*> p;
+  ~TmpBufs() { for (void* q : p) cudaFree(q); }
+  template <typename T> T* get(size_t n) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    p.push_back(q);
+    return (T*)q;
+  }
+};
+
+extern "C" int dc_linear(dc_ctx* ctx, const float* x, const float* w, const float* b, float* y, int M, int N, int K, int relu, int engine, void* stream) {
+  if (!ctx || !x || !w || !y) return dc_set_error(ctx, DC_E_INVALID, "dc_linear: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (engine == DC_ENGINE_TC) { int rc = tc_init(ctx); if (rc) return rc; }
+  TmpBufs tmp;
+  const size_t ap = align_up((size_t)M * K, 64), bp = align_up((size_t)N * K, 64);
+  __half* a = tmp.get<__half>(2 * ap);
+  __half* bw = tmp.get<__half>(2 * bp);
+  DC_REQUIRE(ctx, a && bw, DC_E_NOMEM, "dc_linear: temporary allocation failed");
+  int rc;
+  if ((rc = k_rowmajor_to_split(ctx, x, a, a + ap, (size_t)M * K, st))) return rc;
+  if ((rc = k_rowmajor_to_split(ctx, w, bw, bw + bp, (size_t)N * K, st))) return rc;
+  GemmEpilogue ep;
+  ep.bias = b; ep.relu = relu; ep.out_f32 = y; ep.ldf = N;
+  if (engine == DC_ENGINE_TC) rc = k_tc_gemm(ctx, a, ap, K, bw, bp, K, M, N, K, ep, st);
+  else rc = k_simt_gemm(ctx, a, a + ap, K, bw, bw + bp, K, M, N, K, ep, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc) return rc;
+  if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "dc_linear: %s", cudaGetErrorString(e));
+  return DC_OK;
+}
+
+extern "C" int dc_conv3x3_relu(dc_ctx* ctx, const float* x, const float* w, const float* b, float* y, int N, int Cin, int Cout, int H, int W, int pool,
+                               int engine, void* stream) {
+  if (!ctx || !x || !w || !y) return dc_set_error(ctx, DC_E_INVALID, "dc_conv3x3_relu: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (engine == DC_ENGINE_TC) { int rc = tc_init(ctx); if (rc) return rc; }
+  TmpBufs tmp;
+  const size_t xp = align_up((size_t)N * H * W * Cin, 64), wp = align_up((size_t)Cout * 9 * Cin, 64), yp = align_up((size_t)N * H * W * Cout, 64);
+  const int PH = (H + 1) / 2, PW = (W + 1) / 2;
+  const size_t pp = align_up((size_t)N * PH * PW * Cout, 64);
+  __half* xs = tmp.get<__half>(2 * xp);
+  __half* ws = tmp.get<__half>(2 * wp);
+  __half* ys = tmp.get<__half>(2 * yp);
+  __half* ps = tmp.get<__half>(2 * pp);
+  DC_REQUIRE(ctx, xs && ws && ys && ps, DC_E_NOMEM, "dc_conv3x3_relu: temporary allocation failed");
+  int rc;
+  const size_t xn = (size_t)N * H * W * Cin, yn = (size_t)N * H * W * Cout, pn = (size_t)N * PH * PW * Cout;
+  if ((rc = k_nchw_to_split_nhwc(ctx, x, xs, xs + xn, N, Cin, H, W, st))) return rc;
+  if ((rc = k_conv_weight_to_split(ctx, w, ws, ws + wp, Cout, Cin, st))) return rc;
+  if (engine == DC_ENGINE_TC) {
+    if (pool == 2) {        // fused pool epilogue
+      rc = k_tc_conv3x3(ctx, xs, xn, ws, wp, b, ps, ps + pn, N, H, W, Cin, Cout, 1, st);
+    } else {
+      rc = k_tc_conv3x3(ctx, xs, xn, ws, wp, b, ys, ys + yn, N, H, W, Cin, Cout, 0, st);
+      if (!rc && pool) rc = k_maxpool2x2_split(ctx, ys, ys + yn, ps, ps + pn, N, H, W, Cout, 1, st);
+    }
+  } else {
+    rc = k_simt_conv3x3(ctx, xs, xs + xn, ws, ws + wp, b, ys, ys + yn, N, H, W, Cin, Cout, st);
+    if (!rc && pool) rc = k_maxpool2x2_split(ctx, ys, ys + yn, ps, ps + pn, N, H, W, Cout, 1, st);
+  }
+  if (!rc) {
+    if (pool) rc = k_split_nhwc_to_nchw(ctx, ps, ps + pn, y, N, Cout, PH, PW, st);
+    else rc = k_split_nhwc_to_nchw(ctx, ys, ys + yn, y, N, Cout, H, W, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc) return rc;
+  if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "dc_conv3x3_relu: %s", cudaGetErrorString(e));
+  return DC_OK;
+}

@@ -1,0 +1,182 @@
+// Internal shared declarations for libdensecap_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/densecap_b200.h"
+
+// ---------------------------------------------------------------------------------------
+// Activation / operand format used by every dense kernel ("split-fp16 planes"):
+// a fp32 value a is stored as two fp16 numbers hi = rn(a), lo = rn(a - hi); a tensor is two
+// planes [hi plane][lo plane] of identical shape (same bytes as fp32).  a*b is evaluated on
+// the tensor cores as hi*hi + hi*lo + lo*hi with fp32 accumulation (error ~2^-21 relative),
+// which is what lets tcgen05 kind::f16 reproduce the reference's fp32 sgemm results.
+// ---------------------------------------------------------------------------------------
+struct SplitTensor {
+  __half* hi = nullptr;   // plane 0
+  __half* lo = nullptr;   // plane 1 (== hi + plane_elems)
+  size_t plane_elems = 0;
+};
+
+__device__ __forceinline__ void split_f32(float a, __half& hi, __half& lo) {
+  const float c = fminf(fmaxf(a, -65504.f), 65504.f);
+  hi = __float2half_rn(c);
+  const float r = a - __half2float(hi);
+  lo = __float2half_rn(fminf(fmaxf(r, -65504.f), 65504.f));
+}
+__device__ __forceinline__ float join_f32(__half hi, __half lo) {
+  return __half2float(hi) + __half2float(lo);
+}
+
+#define DC_CEIL_DIV(a, b) (((a) + (b) - 1) / (b))
+
+struct dc_ctx;
+int dc_set_error(dc_ctx* ctx, int code, const char* fmt, ...);
+void dc_count_launch(dc_ctx* ctx, int n = 1);
+
+#define DC_CHECK_CUDA(ctx, expr)                                                            \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return dc_set_error((ctx), DC_E_CUDA, "%s failed: %s (%s:%d)", #expr,                 \
+                          cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+  } while (0)
+
+#define DC_CHECK_LAUNCH(ctx)                                                                \
+  do {                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess)                                                                  \
+      return dc_set_error((ctx), DC_E_CUDA, "kernel launch failed: %s (%s:%d)",             \
+                          cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+    dc_count_launch(ctx);                                                                   \
+  } while (0)
+
+#define DC_REQUIRE(ctx, cond, code, ...)                                                    \
+  do {                                                                                      \
+    if (!(cond)) return dc_set_error((ctx), (code), __VA_ARGS__);                           \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// Kernel launchers implemented across the .cu files (all asynchronous on `st`).
+// ---------------------------------------------------------------------------------------
+// box_kernels.cu
+int k_make_anchors(dc_ctx*, float* out, int N, int H, int W, int k, float x0, float y0, float sx, float sy,
+                   const float* anchors_dev, cudaStream_t st);
+int k_reshape_box_features(dc_ctx*, const float* in, float* out, int N, int k, int D, int H, int W, cudaStream_t st);
+int k_apply_box_transform(dc_ctx*, const float* boxes, const float* trans, float* out, int n, cudaStream_t st);
+int k_invert_box_transform(dc_ctx*, const float* anchors, const float* targets, float* out, int n, cudaStream_t st);
+int k_xcycwh_to_x1y1x2y2(dc_ctx*, const float* in, float* out, int n, cudaStream_t st);
+int k_x1y1x2y2_to_xcycwh(dc_ctx*, const float* in, float* out, int n, cudaStream_t st);
+int k_clip_boxes(dc_ctx*, const float* boxes, float* out, uint8_t* valid, int n, float x_min, float y_min,
+                 float x_max, float y_max, cudaStream_t st);
+int k_objectness_prob(dc_ctx*, const float* scores, float* prob, int n, cudaStream_t st);
+int k_box_to_affine(dc_ctx*, const float* boxes, float* theta, int B, int H, int W, cudaStream_t st);
+int k_box_iou(dc_ctx*, const float* b1, const float* b2, float* out, int B1, int B2, cudaStream_t st);
+
+// Fused RPN post-processing (MakeAnchors + ReshapeBoxFeatures + ApplyBoxTransform + clip_boxes +
+// objectness prob + clamp_data compaction).  head: (HW, ld) fp32 rows = pixels, columns
+// [0,4k) box deltas (4a+d), [4k,6k) scores (2a+d).  Outputs are compacted over valid boxes, in
+// row order r=(a*H+y)*W+x.  n_valid (1) int32.
+struct RpnPostOut {
+  float* boxes_xcycwh;   // (A,4)
+  float* boxes_x1y1x2y2; // (A,4)
+  float* prob;           // (A)
+  int32_t* src_row;      // (A) original row r of each compacted box (0-based)
+  int32_t* n_valid;      // (1)
+  int32_t* block_counts; // scratch (>= number of blocks)
+};
+int k_rpn_postprocess(dc_ctx*, const float* head, int ld, int H, int W, int k, const float* anchors_dev,
+                      float x0, float y0, float sx, float sy, float img_w, float img_h, int clip,
+                      RpnPostOut out, cudaStream_t st);
+
+// nms_kernels.cu
+struct NmsWorkspace {
+  uint64_t* keys;        // (cap) sort keys
+  int32_t* order;        // (cap) sorted position -> box index
+  float* sorted_boxes;   // (cap,4) x1y1x2y2 in sorted order
+  uint64_t* mask;        // (cap, ceil(cap/64)) suppression bitmask
+  int cap;               // max boxes
+};
+size_t nms_workspace_bytes(int cap);
+void nms_workspace_carve(NmsWorkspace& ws, void* base, int cap);
+// boxes (n,4) x1y1x2y2 and scores (n) may come from a strided (n,5) array: pass strides in floats.
+// n_dev (optional): device int32 holding the actual n (<= n_max) -- used after compaction.
+int k_nms(dc_ctx*, const float* boxes, int box_stride, const float* scores, int score_stride, int n_max,
+          const int32_t* n_dev, float thresh, int max_boxes, NmsWorkspace ws, int64_t* idx_out,
+          int32_t* idx32_out, int32_t* count_out, cudaStream_t st);
+
+// roi_pool.cu
+// feats: split NHWC planes (hi, lo) of one image (H',W',C) or fp32 HWC (feats_f32 != nullptr).
+int k_roi_pool(dc_ctx*, const __half* feat_hi, const __half* feat_lo, const float* feats_f32, int C, int fh, int fw,
+               const float* boxes, const int32_t* nboxes_dev, int max_boxes, int img_h, int img_w, int HH, int WW,
+               __half* out_hi, __half* out_lo, float* out_f32, int out_layout, cudaStream_t st);
+
+// layout_kernels.cu
+int k_nchw_to_split_nhwc(dc_ctx*, const float* in, __half* hi, __half* lo, int N, int C, int H, int W, cudaStream_t st);
+int k_split_nhwc_to_nchw(dc_ctx*, const __half* hi, const __half* lo, float* out, int N, int C, int H, int W, cudaStream_t st);
+int k_rowmajor_to_split(dc_ctx*, const float* in, __half* hi, __half* lo, size_t n, cudaStream_t st);
+int k_split_to_rowmajor(dc_ctx*, const __half* hi, const __half* lo, float* out, size_t n, cudaStream_t st);
+int k_maxpool2x2_split(dc_ctx*, const __half* ihi, const __half* ilo, __half* ohi, __half* olo, int N, int H, int W, int C,
+                       int ceil_mode, cudaStream_t st);
+// weight re-layout: conv (Cout,Cin,3,3) -> [Cout][(r*3+s)*Cin + ci] split; fc6 (out, C*HH*WW) (c,y,x) -> (y,x,c);
+// lstm ((D+H),4H) -> [4H][D+H]
+int k_conv_weight_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int Cout, int Cin, cudaStream_t st);
+int k_fc6_weight_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int out, int C, int hw, cudaStream_t st);
+int k_transpose_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int rows, int cols, cudaStream_t st);
+// BCHW (K,C,HH,WW) fp32 -> split rows (K, HH*WW*C) in (y,x,c) order
+int k_bchw_to_split_rows(dc_ctx*, const float* in, __half* hi, __half* lo, int K, int C, int hw, cudaStream_t st);
+int k_bhwc_split_to_bchw(dc_ctx*, const __half* hi, const __half* lo, float* out, int K, int C, int hw, cudaStream_t st);
+
+// simt_kernels.cu : fp32 CUDA-core engine on the same split layout
+struct GemmEpilogue {
+  const float* bias = nullptr;    // (N) or null
+  int relu = 0;
+  __half* out_hi = nullptr;       // split output planes (M, ldo) or null
+  __half* out_lo = nullptr;
+  int ldo = 0;                    // row stride (elements) of split output
+  int out_col0 = 0;               // column offset inside the split output row
+  float* out_f32 = nullptr;       // fp32 output (M, ldf) or null
+  int ldf = 0;
+  unsigned long long* argmax = nullptr;  // (M) packed (sortable(value)<<32 | ~col) atomicMax target or null
+};
+int k_simt_gemm(dc_ctx*, const __half* a_hi, const __half* a_lo, int lda, const __half* b_hi, const __half* b_lo, int ldb,
+                int M, int N, int K, GemmEpilogue ep, cudaStream_t st);
+int k_simt_conv3x3(dc_ctx*, const __half* x_hi, const __half* x_lo, const __half* w_hi, const __half* w_lo,
+                   const float* bias, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, cudaStream_t st);
+// conv1_1: NCHW fp32 (N,3,H,W) -> split NHWC (N,H,W,Cout), bias+ReLU fused.  w (Cout,3,3,3) fp32 reference layout.
+int k_conv_first(dc_ctx*, const float* img, const float* w, const float* bias, __half* y_hi, __half* y_lo,
+                 int N, int H, int W, int Cout, cudaStream_t st);
+// small heads: y[m][j] = dot(x[m,:], w[j,:]) + b[j], x fp32 (M,K), w (J,K) fp32, J <= 8
+int k_small_heads(dc_ctx*, const float* x, int ldx, const float* w, const float* b, float* y, int M, int K, int J, cudaStream_t st);
+
+// tc_gemm.cu : tcgen05 engine
+int tc_init(dc_ctx*);   // resolves cuTensorMapEncodeTiled, sets smem attributes
+int k_tc_gemm(dc_ctx*, const __half* a_planes, size_t a_plane_elems, int lda, const __half* b_planes, size_t b_plane_elems, int ldb,
+              int M, int N, int K, GemmEpilogue ep, cudaStream_t st);
+// x: split NHWC (N,H,W,Cin) planes; w: split [Cout][9*Cin]; y: split NHWC (N,H,W,Cout) or pooled (N,ceil(H/2),ceil(W/2),Cout)
+int k_tc_conv3x3(dc_ctx*, const __half* x_planes, size_t x_plane_elems, const __half* w_planes, size_t w_plane_elems,
+                 const float* bias, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, int fuse_pool,
+                 cudaStream_t st);
+
+// lm_kernels.cu
+int k_lm_gather_x(dc_ctx*, const int32_t* tokens, int tok_stride, int t, int start_token, const __half* lut_hi, const __half* lut_lo,
+                  int E, __half* xh_hi, __half* xh_lo, int ld, int M, cudaStream_t st);
+int k_lstm_pointwise(dc_ctx*, const float* gates, float* c, __half* xh_hi, __half* xh_lo, int ld, int col0, int M, int H,
+                     int first, cudaStream_t st);
+int k_argmax_init(dc_ctx*, unsigned long long* packed, int M, cudaStream_t st);
+int k_argmax_finish(dc_ctx*, const unsigned long long* packed, int32_t* tokens, int tok_stride, int t, int64_t* seq64, int T, int M,
+                    cudaStream_t st);
+int k_final_gather(dc_ctx*, const int32_t* idx32, const int32_t* count, int P, const float* boxes, const float* scores,
+                   const int64_t* seq, int T, float* out_boxes, float* out_scores, int64_t* out_seq, cudaStream_t st);
+int k_gather_rows_f32(dc_ctx*, const float* src, int cols, const int32_t* idx32, const int32_t* count, int max_rows, float* dst,
+                      cudaStream_t st);
+int k_fill_u32(dc_ctx*, uint32_t* p, uint32_t v, size_t n, cudaStream_t st);

@@ -1,0 +1,240 @@
+// Layout / format conversion kernels between the reference's tensor layouts (fp32 NCHW, (out,in)
+// Linear weights, ...) and the library's internal "split-fp16 planes" NHWC / K-major layouts.
+#include "common.cuh"
+
+static inline unsigned grid_for(size_t n, int threads = 256, unsigned cap = 148 * 16) {
+  size_t b = DC_CEIL_DIV(n, (size_t)threads);
+  if (b < 1) b = 1;
+  return (unsigned)(b > cap ? cap : b);
+}
+
+// (N,C,H,W) fp32 -> split (N,H,W,C).  32x32 smem transpose tile over (C, HW) per image.
+__global__ void nchw_to_split_nhwc_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* src = in + (size_t)n * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? src[(size_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) {
+      __half h, l;
+      split_f32(tile[threadIdx.x][i], h, l);
+      const size_t o = ((size_t)n * HW + p) * C + c;
+      hi[o] = h;
+      lo[o] = l;
+    }
+  }
+}
+int k_nchw_to_split_nhwc(dc_ctx* ctx, const float* in, __half* hi, __half* lo, int N, int C, int H, int W, cudaStream_t st) {
+  if ((size_t)N * C * H * W == 0) return DC_OK;
+  dim3 grid(DC_CEIL_DIV(H * W, 32), DC_CEIL_DIV(C, 32), N), block(32, 8);
+  nchw_to_split_nhwc_kernel<<<grid, block, 0, st>>>(in, hi, lo, C, H * W);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+
+__global__ void split_nhwc_to_nchw_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ out, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (p < HW && c < C) {
+      const size_t g = ((size_t)n * HW + p) * C + c;
+      v = join_f32(hi[g], lo[g]);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  float* dst = out + (size_t)n * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) dst[(size_t)c * HW + p] = tile[threadIdx.x][i];
+  }
+}
+int k_split_nhwc_to_nchw(dc_ctx* ctx, const __half* hi, const __half* lo, float* out, int N, int C, int H, int W, cudaStream_t st) {
+  if ((size_t)N * C * H * W == 0) return DC_OK;
+  dim3 grid(DC_CEIL_DIV(H * W, 32), DC_CEIL_DIV(C, 32), N), block(32, 8);
+  split_nhwc_to_nchw_kernel<<<grid, block, 0, st>>>(hi, lo, out, C, H * W);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+
+__global__ void rowmajor_to_split_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    __half h, l;
+    split_f32(in[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+int k_rowmajor_to_split(dc_ctx* ctx, const float* in, __half* hi, __half* lo, size_t n, cudaStream_t st) {
+  if (n == 0) return DC_OK;
+  rowmajor_to_split_kernel<<<grid_for(n), 256, 0, st>>>(in, hi, lo, n);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+__global__ void split_to_rowmajor_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = join_f32(hi[i], lo[i]);
+}
+int k_split_to_rowmajor(dc_ctx* ctx, const __half* hi, const __half* lo, float* out, size_t n, cudaStream_t st) {
+  if (n == 0) return DC_OK;
+  split_to_rowmajor_kernel<<<grid_for(n), 256, 0, st>>>(hi, lo, out, n);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+
+// nn.SpatialMaxPooling(2,2,2,2) (ceil mode as emitted by loadcaffe) on split NHWC.  The max of
+// the reconstructed values is selected and its (hi,lo) pair copied, so pooling is exact.
+__global__ void maxpool2x2_split_kernel(const __half* __restrict__ ihi, const __half* __restrict__ ilo, __half* __restrict__ ohi,
+                                        __half* __restrict__ olo, int N, int H, int W, int C, int OH, int OW) {
+  const size_t total = (size_t)N * OH * OW * C;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int c = o % C;
+    size_t r = o / C;
+    const int ox = r % OW; r /= OW;
+    const int oy = r % OH;
+    const int n = r / OH;
+    float best = -INFINITY;
+    __half bh = __float2half(0.f), bl = __float2half(0.f);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int y = oy * 2 + dy, x = ox * 2 + dx;
+        if (y < H && x < W) {
+          const size_t g = (((size_t)n * H + y) * W + x) * C + c;
+          const __half h = ihi[g], l = ilo[g];
+          const float v = join_f32(h, l);
+          if (v > best) { best = v; bh = h; bl = l; }
+        }
+      }
+    ohi[o] = bh;
+    olo[o] = bl;
+  }
+}
+int k_maxpool2x2_split(dc_ctx* ctx, const __half* ihi, const __half* ilo, __half* ohi, __half* olo, int N, int H, int W, int C,
+                       int ceil_mode, cudaStream_t st) {
+  const int OH = ceil_mode ? (H + 1) / 2 : H / 2, OW = ceil_mode ? (W + 1) / 2 : W / 2;
+  const size_t total = (size_t)N * OH * OW * C;
+  if (total == 0) return DC_OK;
+  maxpool2x2_split_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(ihi, ilo, ohi, olo, N, H, W, C, OH, OW);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+
+// conv weight (Cout,Cin,3,3) -> split [Cout][(r*3+s)*Cin + ci]   (K-major B operand of the implicit GEMM)
+__global__ void conv_weight_to_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int Cout, int Cin) {
+  const size_t total = (size_t)Cout * 9 * Cin;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int ci = o % Cin;
+    const int tap = (o / Cin) % 9;
+    const int co = o / ((size_t)9 * Cin);
+    __half h, l;
+    split_f32(w[((size_t)co * Cin + ci) * 9 + tap], h, l);
+    hi[o] = h;
+    lo[o] = l;
+  }
+}
+int k_conv_weight_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, int Cout, int Cin, cudaStream_t st) {
+  const size_t total = (size_t)Cout * 9 * Cin;
+  if (total == 0) return DC_OK;
+  conv_weight_to_split_kernel<<<grid_for(total), 256, 0, st>>>(w, hi, lo, Cout, Cin);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+
+// fc6 weight (out, C*hw) with input order (c, pos) -> split (out, hw*C) with input order (pos, c),
+// so that the BHWC output of the ROI pooling feeds fc6 without the reference's nn.Transpose/View.
+__global__ void fc6_weight_to_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int out, int C, int hw) {
+  const size_t K = (size_t)C * hw;
+  const size_t total = (size_t)out * K;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int c = o % C;
+    const int pos = (o / C) % hw;
+    const size_t row = o / K;
+    __half h, l;
+    split_f32(w[row * K + (size_t)c * hw + pos], h, l);
+    hi[o] = h;
+    lo[o] = l;
+  }
+}
+int k_fc6_weight_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, int out, int C, int hw, cudaStream_t st) {
+  const size_t total = (size_t)out * C * hw;
+  if (total == 0) return DC_OK;
+  fc6_weight_to_split_kernel<<<grid_for(total, 256, 148 * 64), 256, 0, st>>>(w, hi, lo, out, C, hw);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+
+// (rows, cols) fp32 -> split (cols, rows)   (torch-rnn LSTM weight ((D+H),4H) -> [4H][D+H])
+__global__ void transpose_to_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? w[(size_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) {
+      __half h, l;
+      split_f32(tile[threadIdx.x][i], h, l);
+      hi[(size_t)c * rows + r] = h;
+      lo[(size_t)c * rows + r] = l;
+    }
+  }
+}
+int k_transpose_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, int rows, int cols, cudaStream_t st) {
+  if ((size_t)rows * cols == 0) return DC_OK;
+  dim3 grid(DC_CEIL_DIV(cols, 32), DC_CEIL_DIV(rows, 32)), block(32, 8);
+  transpose_to_split_kernel<<<grid, block, 0, st>>>(w, hi, lo, rows, cols);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+
+// (K,C,hw) fp32 BCHW -> split rows (K, hw*C) in (pos, c) order
+__global__ void bchw_to_split_rows_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, int K, int C, int hw) {
+  const size_t total = (size_t)K * C * hw;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int c = o % C;
+    const int pos = (o / C) % hw;
+    const size_t b = o / ((size_t)C * hw);
+    __half h, l;
+    split_f32(in[(b * C + c) * hw + pos], h, l);
+    hi[o] = h;
+    lo[o] = l;
+  }
+}
+int k_bchw_to_split_rows(dc_ctx* ctx, const float* in, __half* hi, __half* lo, int K, int C, int hw, cudaStream_t st) {
+  const size_t total = (size_t)K * C * hw;
+  if (total == 0) return DC_OK;
+  bchw_to_split_rows_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(in, hi, lo, K, C, hw);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+__global__ void bhwc_split_to_bchw_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ out, int K, int C, int hw) {
+  const size_t total = (size_t)K * C * hw;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int pos = o % hw;
+    const int c = (o / hw) % C;
+    const size_t b = o / ((size_t)C * hw);
+    const size_t g = (b * hw + pos) * C + c;
+    out[o] = join_f32(hi[g], lo[g]);
+  }
+}
+int k_bhwc_split_to_bchw(dc_ctx* ctx, const __half* hi, const __half* lo, float* out, int K, int C, int hw, cudaStream_t st) {
+  const size_t total = (size_t)K * C * hw;
+  if (total == 0) return DC_OK;
+  bhwc_split_to_bchw_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(hi, lo, out, K, C, hw);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}

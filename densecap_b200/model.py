@@ -1,0 +1,198 @@
+"""Host-side mirrors of the reference's composite modules for the test-time path:
+nn.LocalizationLayer (densecap/LocalizationLayer.lua), nn.LanguageModel (densecap/LanguageModel.lua)
+and DenseCapModel (densecap/DenseCapModel.lua).  Same method names, argument meaning and protocol
+errors; all compute happens in libdensecap_b200.so on the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .runtime import Context, ptr, stream_ptr, _check_cuda_f32
+from .synth import ModelDims, feature_hw
+
+
+class LocalizationLayer:
+    """nn.LocalizationLayer, test-time forward (LocalizationLayer.lua:250-363).
+
+    forward(cnn_features (1,C,H',W')) -> [roi_features (K,C,HH,WW), roi_boxes (K,4), empty, empty]."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.train = False
+        self.image_height = None
+        self.image_width = None
+        self.setTestArgs()
+
+    def setImageSize(self, image_height, image_width):                 # LocalizationLayer.lua:167-172
+        self.image_height, self.image_width = int(image_height), int(image_width)
+        self.ctx.check(self.ctx._lib.dc_set_image_size(self.ctx.handle, self.image_height, self.image_width))
+
+    def setTestArgs(self, args=None):                                   # LocalizationLayer.lua:233-238
+        args = args or {}
+        self.test_clip_boxes = args.get("clip_boxes", True)
+        self.test_nms_thresh = args.get("nms_thresh", 0.7)
+        self.test_max_proposals = args.get("max_proposals", 300)
+        self._final_thresh = args.get("final_nms_thresh", 0.3)
+        self.ctx.set_test_args(self.test_nms_thresh, self._final_thresh, self.test_max_proposals, self.test_clip_boxes)
+
+    def evaluate(self):
+        self.train = False
+
+    def forward(self, input):
+        if self.train:
+            raise NotImplementedError("training-mode LocalizationLayer is not built yet (SURVEY.md 8a row a18)")
+        f = _check_cuda_f32(input)
+        assert f.dim() == 4 and f.shape[0] == 1, "must have 1 image per batch"
+        dims = self.ctx.dims
+        _, C_, fh, fw = f.shape
+        K = self.ctx.max_proposals if self.test_max_proposals == -1 else self.test_max_proposals
+        roi = torch.empty((K, C_, dims.pool_hw, dims.pool_hw), dtype=torch.float32, device=f.device)
+        boxes = torch.empty((K, 4), dtype=torch.float32, device=f.device)
+        idx = torch.empty((K,), dtype=torch.int64, device=f.device)
+        n = torch.zeros((1,), dtype=torch.int32, device=f.device)
+        # raises DenseCapError(DC_E_PROTOCOL, 'Must call setImageSize before each forward pass') like the assert at :259
+        self.ctx.check(self.ctx._lib.dc_localization_forward_test(self.ctx.handle, ptr(f), fh, fw, ptr(roi), ptr(boxes), ptr(idx), ptr(n),
+                                                                 stream_ptr()))
+        k = int(n.item())
+        self.last_idx = idx[:k]
+        empty = torch.empty((0,), dtype=torch.float32, device=f.device)
+        self.output = [roi[:k], boxes[:k], empty, empty]
+        return self.output
+
+
+class LanguageModel:
+    """nn.LanguageModel, greedy sampling path (LanguageModel.lua:293-348) + decodeSequence (:86-103)."""
+
+    def __init__(self, ctx: Context, idx_to_token=None):
+        self.ctx = ctx
+        d = ctx.dims
+        self.vocab_size = d.vocab_size
+        self.seq_length = d.seq_length
+        self.START_TOKEN = d.vocab_size + 1
+        self.END_TOKEN = d.vocab_size + 1
+        self.NULL_TOKEN = d.vocab_size + 2
+        self.idx_to_token = idx_to_token or {}
+
+    def sample(self, image_vectors, return_logits=False):
+        v = _check_cuda_f32(image_vectors)
+        N = v.shape[0]
+        T = self.seq_length
+        seq = torch.zeros((N, T), dtype=torch.int64, device=v.device)
+        logits = torch.empty((N, T, self.vocab_size + 1), dtype=torch.float32, device=v.device) if return_logits else None
+        self.ctx.check(self.ctx._lib.dc_lm_sample(self.ctx.handle, ptr(v), N, ptr(seq), ptr(logits), stream_ptr()))
+        self.output = seq
+        return (seq, logits) if return_logits else seq
+
+    def forward(self, input):
+        image_vectors, gt_sequence = input
+        if gt_sequence is not None and gt_sequence.numel() > 0:
+            raise NotImplementedError("training-time LanguageModel forward is outside the test-time hot path")
+        return self.sample(image_vectors)
+
+    def decodeSequence(self, seq):
+        captions = []
+        for row in seq.tolist():
+            words = []
+            for idx in row:
+                if idx == self.END_TOKEN or idx == 0:
+                    break
+                words.append(self.idx_to_token.get(idx, str(idx)) if isinstance(self.idx_to_token, dict) else self.idx_to_token[idx - 1])
+            captions.append(" ".join(words))
+        return captions
+
+
+class DenseCapModel:
+    """DenseCapModel test-time API (DenseCapModel.lua:185-191, 242-282, 319-327)."""
+
+    def __init__(self, opt=None, weights=None, device=0, max_batch=1, max_image_hw=(600, 720), engine=_lib.DC_ENGINE_TC,
+                 fuse_pool=True):
+        opt = dict(opt or {})
+        self.opt = opt
+        dims = opt.get("dims") or ModelDims(vocab_size=opt.get("vocab_size", 10497), seq_length=opt.get("seq_length", 15),
+                                            rnn_size=opt.get("rnn_size", 512), encoding_size=opt.get("rnn_encoding_size", 512))
+        self.dims = dims
+        self.opt.setdefault("final_nms_thresh", 0.3)
+        self.ctx = Context(dims, device=device, max_batch=max_batch, max_image_hw=max_image_hw,
+                           max_proposals=opt.get("max_proposals", 1000), engine=engine, fuse_pool=fuse_pool,
+                           pool_ceil=opt.get("pool_ceil", True))
+        self.train = False
+        self.nets = {"localization_layer": LocalizationLayer(self.ctx),
+                     "language_model": LanguageModel(self.ctx, opt.get("idx_to_token"))}
+        self.setTestArgs({})
+        if weights is not None:
+            self.ctx.load_weights(weights)
+
+    def evaluate(self):
+        self.train = False
+
+    def setTestArgs(self, kwargs):
+        self._rpn_nms = kwargs.get("rpn_nms_thresh", 0.7)
+        self.opt["final_nms_thresh"] = kwargs.get("final_nms_thresh", 0.3)
+        self._num_proposals = kwargs.get("num_proposals", 1000)
+        self.ctx.set_test_args(self._rpn_nms, self.opt["final_nms_thresh"], self._num_proposals, True)
+
+    def forward_device(self, input):
+        """Runs the whole test-time forward; returns a dict of torch CUDA tensors that alias ctx-owned
+        buffers (valid until the next forward -- same contract as the reference's self.output)."""
+        x = _check_cuda_f32(input)
+        assert x.dim() == 4 and x.shape[1] == 3, "input must be (N,3,H,W)"
+        N, _, H, W = x.shape
+        res = _lib.DcResult()
+        self.ctx.check(self.ctx._lib.dc_forward_test(self.ctx.handle, ptr(x), N, H, W, C.byref(res), stream_ptr()))
+        return _wrap_result(res, self.dims, x.device)
+
+    def forward(self, input):
+        """DenseCapModel:updateOutput for one image (1,3,H,W): list of the 7 outputs
+        (DenseCapModel.lua:223-241) with [1],[4],[5] NMS-filtered (:272-274)."""
+        assert input.dim() == 4 and input.shape[0] == 1 and input.shape[1] == 3
+        r = self.forward_device(input)
+        K = int(r["num_proposals"][0].item())
+        Kf = int(r["num_final"][0].item())
+        empty = torch.empty((0,), device=input.device)
+        self.output = [r["final_scores"][:Kf].reshape(Kf, 1), r["roi_boxes"][:K], r["box_trans"][:K], r["final_boxes"][:Kf],
+                       r["final_seq"][:Kf], empty, empty]
+        self._last = r
+        return self.output
+
+    def forward_test(self, input):
+        """DenseCapModel:forward_test (DenseCapModel.lua:319-327)."""
+        self.evaluate()
+        out = self.forward(input)
+        captions = self.nets["language_model"].decodeSequence(out[4])
+        return out[3], out[0], captions
+
+
+def _dev_tensor(addr, shape, dtype, device):
+    """Zero-copy torch view of a ctx-owned device buffer through the CUDA array interface."""
+    n = int(np.prod(shape))
+    if n == 0 or not addr:
+        return torch.empty(shape, dtype=dtype, device=device)
+    typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.int64: "<i8"}[dtype]
+
+    class _Holder:
+        __cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(addr), False), "version": 2}
+
+    return torch.as_tensor(_Holder(), device=device)
+
+
+def _wrap_result(res, dims, device):
+    B, P, T = res.batch, res.max_proposals, dims.seq_length
+    rows = B * P
+    return {
+        "num_proposals": _dev_tensor(res.num_proposals, (B,), torch.int32, device),
+        "num_final": _dev_tensor(res.num_final, (B,), torch.int32, device),
+        "final_boxes": _dev_tensor(res.final_boxes, (rows, 4), torch.float32, device),
+        "final_scores": _dev_tensor(res.final_scores, (rows,), torch.float32, device),
+        "final_seq": _dev_tensor(res.final_seq, (rows, T), torch.int64, device),
+        "final_idx": _dev_tensor(res.final_idx, (rows,), torch.int64, device),
+        "roi_boxes": _dev_tensor(res.roi_boxes, (rows, 4), torch.float32, device),
+        "box_trans": _dev_tensor(res.box_trans, (rows, 4), torch.float32, device),
+        "all_boxes": _dev_tensor(res.all_boxes, (rows, 4), torch.float32, device),
+        "all_scores": _dev_tensor(res.all_scores, (rows,), torch.float32, device),
+        "all_seq": _dev_tensor(res.all_seq, (rows, T), torch.int64, device),
+        "codes": _dev_tensor(res.codes, (rows, dims.fc_dim), torch.float32, device),
+        "max_proposals": P,
+    }

@@ -1,0 +1,107 @@
+"""GPU parity of the dense kernels (tcgen05 split-fp16 engine and the fp32 CUDA-core engine)
+against an fp64 torch reference of the same op: y = act(x W^T + b) and 3x3 conv + bias + ReLU
+(+ 2x2 ceil max-pool).  Tolerance: 1e-4 relative to the output scale (BASELINE north_star);
+the split-fp16 scheme is expected to land around 1e-6."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TC, SIMT = 0, 1
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from densecap_b200.runtime import Context
+    from densecap_b200.synth import ModelDims
+    d = ModelDims(widths=(64, 64, 64, 64, 64), fc_dim=64, vocab_size=64, rnn_size=64, encoding_size=64, seq_length=2)
+    c = Context(d, max_image_hw=(64, 64), max_proposals=64, engine=SIMT)
+    yield c
+    c.close()
+
+
+def p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def rel_err(got, ref):
+    scale = ref.abs().max().item() + 1e-30
+    return ((got.double() - ref).abs().max().item()) / scale
+
+
+def run_linear(ctx, M, N, K, relu, engine, seed=0, bias=True):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / np.sqrt(K)).cuda()
+    b = torch.randn(N, generator=g).cuda() if bias else None
+    y = torch.full((M, N), float("nan"), device="cuda")
+    ctx.check(ctx._lib.dc_linear(ctx.handle, p(x), p(w), p(b), p(y), M, N, K, relu, engine, None))
+    ref = x.double() @ w.double().t()
+    if bias:
+        ref = ref + b.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    return y, ref
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (130, 72, 128), (257, 100, 192)])
+def test_simt_linear(ctx, M, N, K):
+    y, ref = run_linear(ctx, M, N, K, 1, SIMT)
+    assert rel_err(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,relu", [(128, 64, 64, 0), (128, 128, 64, 0), (128, 128, 256, 1), (1, 64, 64, 0),
+                                        (300, 200, 512, 1), (1000, 72, 256, 0), (257, 1030, 1024, 0), (1000, 4096, 4096, 1)])
+def test_tc_linear(ctx, M, N, K, relu):
+    y, ref = run_linear(ctx, M, N, K, relu, TC, seed=M + N + K)
+    assert not torch.isnan(y).any(), "output rows left unwritten"
+    e = rel_err(y, ref)
+    assert e < 2e-5, "tcgen05 linear M=%d N=%d K=%d rel err %.3e" % (M, N, K, e)
+
+
+def test_tc_linear_is_fp32_class_accurate(ctx):
+    # the split scheme must beat a single fp16 pass by orders of magnitude
+    y, ref = run_linear(ctx, 256, 256, 2048, 0, TC, seed=7, bias=False)
+    e = rel_err(y, ref)
+    x32 = None
+    assert e < 5e-6, e
+
+
+def run_conv(ctx, N, Cin, Cout, H, W, pool, engine, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(N, Cin, H, W, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * np.sqrt(2.0 / (9 * Cin))).cuda()
+    b = (torch.randn(Cout, generator=g) * 0.1).cuda()
+    oh, ow = ((H + 1) // 2, (W + 1) // 2) if pool else (H, W)
+    y = torch.full((N, Cout, oh, ow), float("nan"), device="cuda")
+    ctx.check(ctx._lib.dc_conv3x3_relu(ctx.handle, p(x), p(w), p(b), p(y), N, Cin, Cout, H, W, pool, engine, None))
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1).clamp_min(0)
+    if pool:
+        ref = torch.nn.functional.max_pool2d(ref, 2, 2, 0, ceil_mode=True)
+    return y, ref
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W,pool", [(1, 64, 64, 9, 11, 0), (2, 64, 128, 16, 16, 1)])
+def test_simt_conv(ctx, N, Cin, Cout, H, W, pool):
+    y, ref = run_conv(ctx, N, Cin, Cout, H, W, pool, SIMT)
+    assert rel_err(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W,pool", [
+    (1, 64, 64, 8, 16, 0),        # exactly one tile
+    (1, 64, 64, 9, 17, 0),        # ragged tile edges
+    (1, 64, 128, 38, 45, 0),      # conv5-like map
+    (2, 128, 64, 20, 33, 0),      # batch + 2 k-blocks per tap
+    (1, 64, 64, 16, 32, 1),       # separate pool kernel
+    (1, 64, 64, 16, 32, 2),       # fused pool epilogue, even size
+    (1, 64, 128, 75, 90, 2),      # fused ceil-mode pool with odd height (75 -> 38)
+    (2, 256, 256, 19, 23, 2),     # batch, odd both, 4 k-blocks per tap
+])
+def test_tc_conv(ctx, N, Cin, Cout, H, W, pool):
+    y, ref = run_conv(ctx, N, Cin, Cout, H, W, pool, TC, seed=H * W + Cin)
+    assert not torch.isnan(y).any(), "output pixels left unwritten"
+    e = rel_err(y, ref)
+    assert e < 2e-5, "tcgen05 conv rel err %.3e" % e

@@ -1,0 +1,174 @@
+"""GPU parity tests (run with -m gpu on a B200): every leaf operator and the NMS / ROI-pooling
+kernels of libdensecap_b200.so against the CPU oracle on the same inputs, through the C ABI
+(ctypes).  Integer / index outputs and the fp32 box arithmetic must be BIT-EXACT."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import densecap_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_known_answers.json")))
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_bit_equal(a, b, what=""):
+    a = np.asarray(a, np.float32); b = np.asarray(b, np.float32)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    same = (bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))
+    assert same.all(), "%s: %d / %d elements differ, first at %s: %r vs %r" % (
+        what, (~same).sum(), same.size, np.argwhere(~same)[0], a[~same][0], b[~same][0])
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from densecap_b200 import modules, box_utils
+    return modules, box_utils
+
+
+def test_make_anchors_reshape_apply_bit_exact(mods):
+    M, _ = mods
+    rng = np.random.default_rng(0)
+    N, k, H, W = 1, 12, 38, 45
+    anchors = O.DEFAULT_ANCHORS
+    ma = M.MakeAnchors(8.5, 8.5, 16, 16, anchors)
+    x = torch.zeros((N, 4 * k, H, W), device="cuda")
+    a_gpu = ma.forward(x).cpu().numpy()
+    a_ref = O.make_anchors(N, H, W, 8.5, 8.5, 16, 16, anchors)
+    assert_bit_equal(a_gpu, a_ref, "make_anchors")
+    trans = (rng.standard_normal((N, 4 * k, H, W)) * 0.3).astype(np.float32)
+    r = M.ReshapeBoxFeatures(k)
+    t_gpu = r.forward(dev(trans)).cpu().numpy()
+    assert_bit_equal(t_gpu, O.reshape_box_features(trans, k), "reshape")
+    anc = O.reshape_box_features(a_ref, k)
+    b_gpu = M.ApplyBoxTransform().forward([dev(anc), dev(t_gpu)]).cpu().numpy()
+    assert_bit_equal(b_gpu, O.apply_box_transform(anc, t_gpu), "apply_box_transform")
+
+
+def test_known_answers_on_gpu(mods):
+    M, BU = mods
+    c = G["apply_box_transform"]
+    out = M.ApplyBoxTransform().forward([dev(np.array(c["boxes"], np.float32)), dev(np.array(c["trans"], np.float32))])
+    np.testing.assert_allclose(out.cpu().numpy(), np.array(c["expected"], np.float32), atol=c["tol"])
+    c = G["box_to_affine"]
+    th = M.BoxToAffine().setSize(c["H"], c["W"]).forward(dev(np.array(c["boxes"], np.float32)))
+    np.testing.assert_allclose(th.cpu().numpy(), np.array(c["expected"], np.float32), atol=c["tol"])
+    for c in G["nms"]:
+        bs = np.concatenate([np.array(c["boxes"], np.float32), np.array(c["scores"], np.float32)[:, None]], 1)
+        idx = BU.nms(dev(bs), c["thresh"])
+        assert idx.dtype == torch.int64 and idx.cpu().tolist() == c["expected_idx"], c["src"]
+    # make_boxes cases through the hot-path trio
+    for c in G["make_boxes"]:
+        N, k, H, W = c["N"], c["k"], c["H"], c["W"]
+        anchors = np.array(c["anchors"], np.float32)
+        trans = np.zeros((N, 4 * k, H, W), np.float32)
+        for (n, a, h, w, v) in c["inputs"]:
+            trans[n, 4 * a:4 * a + 4, h, w] = v
+        anc = M.ReshapeBoxFeatures(k).forward(M.MakeAnchors(c["x0"], c["y0"], c["sx"], c["sy"], anchors).forward(dev(trans)))
+        boxes = M.ApplyBoxTransform().forward([anc, M.ReshapeBoxFeatures(k).forward(dev(trans))]).cpu().numpy()
+        for (n, h, w, a, v) in c["expected"]:
+            np.testing.assert_allclose(boxes[n, (a * H + h) * W + w], np.array(v, np.float32), atol=c["tol"], err_msg=c["src"])
+
+
+def test_box_conversions_clip_affine_iou_bit_exact(mods):
+    M, BU = mods
+    rng = np.random.default_rng(1)
+    n = 5000
+    boxes = np.concatenate([rng.uniform(-100, 900, (n, 2)), rng.uniform(0.5, 700, (n, 2))], 1).astype(np.float32)
+    assert_bit_equal(BU.xcycwh_to_x1y1x2y2(dev(boxes)).cpu().numpy(), O.xcycwh_to_x1y1x2y2(boxes), "xcycwh_to_x1y1x2y2")
+    c = O.xcycwh_to_x1y1x2y2(boxes)
+    assert_bit_equal(BU.x1y1x2y2_to_xcycwh(dev(c)).cpu().numpy(), O.x1y1x2y2_to_xcycwh(c), "x1y1x2y2_to_xcycwh")
+    bounds = {"x_min": 1, "y_min": 1, "x_max": 720, "y_max": 600}
+    cg, vg = BU.clip_boxes(dev(boxes[None]), bounds, "xcycwh")
+    cr, vr = O.clip_boxes(boxes[None], 1, 1, 720, 600, "xcycwh")
+    assert_bit_equal(cg.cpu().numpy(), cr, "clip_boxes")
+    assert np.array_equal(vg.cpu().numpy(), vr)
+    th = M.BoxToAffine().setSize(600, 720).forward(dev(boxes)).cpu().numpy()
+    assert_bit_equal(th, O.box_to_affine(boxes, 600, 720), "box_to_affine")
+    b1 = boxes[:300][None]; b2 = boxes[300:350][None]
+    iou = M.BoxIoU().forward([dev(b1), dev(b2)]).cpu().numpy()
+    assert_bit_equal(iou, O.box_iou(b1, b2), "box_iou")
+    # documented divergence from the stale reference test: HEAD semantics
+    d = G["documented_divergence"]["box_iou"]
+    v = M.BoxIoU().forward([dev(np.array([[d["box1"]]], np.float32)), dev(np.array([[d["box2"]]], np.float32))]).item()
+    assert abs(v - d["head_gives"]) < 1e-6
+    # invert o apply round trip (test/InvertBoxTransform_test.lua)
+    anchors = boxes[:1000]; targets = boxes[1000:2000]
+    tr = M.InvertBoxTransform().forward([dev(anchors), dev(targets)])
+    assert_bit_equal(tr.cpu().numpy(), O.invert_box_transform(anchors, targets), "invert_box_transform")
+    back = M.ApplyBoxTransform().forward([dev(anchors), tr]).cpu().numpy()
+    np.testing.assert_allclose(back, targets, rtol=1e-4, atol=1e-3)
+
+
+def _random_boxes_scores(rng, n, size=700, ties=False):
+    xy = rng.uniform(0, size, (n, 2))
+    wh = rng.uniform(5, 300, (n, 2))
+    b = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+    s = rng.uniform(0, 1, (n,)).astype(np.float32)
+    if ties:
+        s = np.round(s * 50) / 50     # many exact score ties -> exercises the tie rule
+    return np.concatenate([b, s[:, None].astype(np.float32)], 1)
+
+
+@pytest.mark.parametrize("n,thresh,maxb,ties", [(1, 0.7, None, False), (63, 0.7, None, False), (64, 0.5, 10, False),
+                                                (65, 0.3, None, True), (1000, 0.3, None, False), (3000, 0.7, 300, True),
+                                                (20520, 0.7, 1000, False)])
+def test_nms_matches_oracle_bit_exact(mods, n, thresh, maxb, ties):
+    _, BU = mods
+    rng = np.random.default_rng(n)
+    bs = _random_boxes_scores(rng, n, ties=ties)
+    ref = O.nms(bs, thresh, maxb)
+    got = BU.nms(dev(bs), thresh, maxb).cpu().numpy()
+    assert got.dtype == np.int64
+    assert np.array_equal(got, ref), "n=%d: first mismatch at %s" % (n, np.argwhere(got[:len(ref)] != ref[:len(got)])[:3])
+
+
+def test_nms_empty_and_dense_overlap(mods):
+    _, BU = mods
+    assert BU.nms(torch.zeros((0, 5), device="cuda"), 0.7).numel() == 0
+    # all boxes identical: only the best survives (the highest index among equal scores)
+    bs = np.tile(np.array([[10, 10, 50, 50, 0.5]], np.float32), (200, 1))
+    assert BU.nms(dev(bs), 0.7).cpu().tolist() == O.nms(bs, 0.7).tolist() == [200]
+
+
+def test_objectness_prob_bit_exact():
+    import ctypes as C
+    from densecap_b200 import _lib
+    rng = np.random.default_rng(5)
+    s = (rng.standard_normal((4096, 2)) * 3).astype(np.float32)
+    sd = dev(s)
+    out = torch.empty((4096,), device="cuda")
+    _lib.check(_lib.load().dc_objectness_prob(C.c_void_p(sd.data_ptr()), C.c_void_p(out.data_ptr()), 4096, None))
+    e = O.exp_f32(s)
+    ref = (np.float32(1) / (e[:, 0] + e[:, 1])) * e[:, 0]
+    assert_bit_equal(out.cpu().numpy(), ref, "objectness")
+
+
+@pytest.mark.parametrize("C_,fh,fw,B,ih,iw", [(64, 6, 8, 5, 96, 128), (512, 38, 45, 64, 600, 720), (128, 50, 38, 33, 800, 600)])
+def test_bilinear_roi_pooling_matches_oracle(mods, C_, fh, fw, B, ih, iw):
+    M, _ = mods
+    rng = np.random.default_rng(C_ + B)
+    feats = rng.standard_normal((C_, fh, fw)).astype(np.float32)
+    boxes = np.concatenate([rng.uniform(-20, iw + 20, (B, 1)), rng.uniform(-20, ih + 20, (B, 1)),
+                            rng.uniform(8, iw, (B, 1)), rng.uniform(8, ih, (B, 1))], 1).astype(np.float32)
+    boxes[0] = [(iw + 1) / 2, (ih + 1) / 2, iw, ih]
+    rp = M.BilinearRoiPooling(7, 7)
+    with pytest.raises(AssertionError):
+        rp.forward([dev(feats), dev(boxes)])           # setImageSize protocol (BilinearRoiPooling.lua:85)
+    out = rp.setImageSize(ih, iw).forward([dev(feats), dev(boxes)]).cpu().numpy()
+    ref = O.bilinear_roi_pooling(feats, boxes, ih, iw, 7, 7)
+    assert out.shape == (B, C_, 7, 7)
+    assert_bit_equal(out, ref, "roi_pool BCHW")
+    out2 = rp.setImageSize(ih, iw).forward([dev(feats), dev(boxes)], layout="BHWC").cpu().numpy()
+    assert_bit_equal(out2, ref.transpose(0, 2, 3, 1), "roi_pool BHWC")
