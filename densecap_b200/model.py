@@ -34,7 +34,7 @@ class LocalizationLayer:
         args = args or {}
         self.test_clip_boxes = args.get("clip_boxes", True)
         self.test_nms_thresh = args.get("nms_thresh", 0.7)
-        self.test_max_proposals = args.get("max_proposals", 300)
+        self.test_max_proposals = min(args.get("max_proposals", 300), self.ctx.max_proposals)   # reference default 300
         self._final_thresh = args.get("final_nms_thresh", 0.3)
         self.ctx.set_test_args(self.test_nms_thresh, self._final_thresh, self.test_max_proposals, self.test_clip_boxes)
 
