@@ -57,6 +57,8 @@ struct dc_ctx {
   float* scratch_f32 = nullptr;      // generic fp32 scratch (HWC features for dc_bilinear_roi_pool, ...)
   size_t scratch_elems = 0;
   void* nms_mem = nullptr;
+  void* roi_taps = nullptr;          // per-(roi,position) bilinear tap records
+  int roi_taps_boxes = 0;
   NmsWorkspace nms;
   PhaseTimer timer;
 };
@@ -237,6 +239,12 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
     TRY(dev_alloc(ctx, &mem, nms_workspace_bytes(nms_cap)));
     ctx->nms_mem = mem;
     nms_workspace_carve(ctx->nms, mem, nms_cap);
+  }
+  {
+    char* mem = nullptr;
+    ctx->roi_taps_boxes = (int)std::max((size_t)P, (size_t)1024);
+    TRY(dev_alloc(ctx, &mem, roi_taps_bytes(ctx->roi_taps_boxes, c.pool_hw * c.pool_hw)));
+    ctx->roi_taps = mem;
   }
   // ---- weights ----
   {
@@ -647,8 +655,8 @@ static int run_localization(dc_ctx* ctx, int N, int fh, int fw, int img_h, int i
     const size_t foff = (size_t)b * cells * C5;
     const size_t roff = (size_t)b * P * hw * C5;
     if ((rc = k_roi_pool(ctx, ctx->feats.base + foff, ctx->feats.base + fplane + foff, nullptr, C5, fh, fw, ctx->roi_boxes + (size_t)b * P * 4,
-                         ctx->rpn_count + b, P, img_h, img_w, c.pool_hw, c.pool_hw, ctx->roi.base + roff, ctx->roi.base + rplane + roff,
-                         nullptr, 1, st)))
+                         ctx->rpn_count + b, P, img_h, img_w, c.pool_hw, c.pool_hw, ctx->roi_taps, ctx->roi.base + roff,
+                         ctx->roi.base + rplane + roff, nullptr, 1, st)))
       return rc;
   }
   return DC_OK;
@@ -687,8 +695,7 @@ static int run_recog(dc_ctx* ctx, int rows, cudaStream_t st) {
     if ((rc = gemm(ctx, ctx->fc6o.base, fplane, fc, *w7, fc, rows, fc, fc, ep, st))) return rc;
   }
   phase_mark(ctx, "recog:heads", st);
-  if ((rc = k_small_heads(ctx, ctx->codes, fc, wo->f32, bo->f32, ctx->obj, rows, fc, 1, st))) return rc;
-  if ((rc = k_small_heads(ctx, ctx->codes, fc, wr->f32, br->f32, ctx->trans, rows, fc, 4, st))) return rc;
+  if ((rc = k_recog_heads(ctx, ctx->codes, fc, wo->f32, bo->f32, wr->f32, br->f32, ctx->obj, ctx->trans, rows, fc, st))) return rc;
   if ((rc = k_apply_box_transform(ctx, ctx->roi_boxes, ctx->trans, ctx->boxes_all, rows, st))) return rc;
   return DC_OK;
 }
@@ -726,7 +733,10 @@ static int run_lm(dc_ctx* ctx, int rows, float* logits, cudaStream_t st) {
     if ((rc = k_lstm_pointwise(ctx, ctx->gates, ctx->cstate, xh_hi, xh_lo, ld, E, rows, H, 1, st))) return rc;
   }
   for (int t = 0; t < T; ++t) {
-    if ((rc = k_lm_gather_x(ctx, ctx->tokens, T, t, V + 1, wl->planes, wl->planes + wl->plane_elems, E, xh_hi, xh_lo, ld, rows, st))) return rc;
+    // finish step t-1 (arg-max -> token), look up the input token of step t, reset the arg-max cells
+    if ((rc = k_lm_token_step(ctx, ctx->packed, ctx->tokens, ctx->seq64, T, t, V + 1, wl->planes, wl->planes + wl->plane_elems, E, xh_hi,
+                              xh_lo, ld, rows, st)))
+      return rc;
     {
       GemmEpilogue ep;
       ep.bias = blstm->f32;
@@ -734,7 +744,6 @@ static int run_lm(dc_ctx* ctx, int rows, float* logits, cudaStream_t st) {
       if ((rc = gemm(ctx, xh_hi, xplane, ld, *wlstm, ld, rows, 4 * H, ld, ep, st))) return rc;
     }
     if ((rc = k_lstm_pointwise(ctx, ctx->gates, ctx->cstate, xh_hi, xh_lo, ld, E, rows, H, 0, st))) return rc;
-    if ((rc = k_argmax_init(ctx, ctx->packed, rows, st))) return rc;
     {
       GemmEpilogue ep;
       ep.bias = bv->f32;
@@ -743,8 +752,10 @@ static int run_lm(dc_ctx* ctx, int rows, float* logits, cudaStream_t st) {
       // A = h half of [x|h]
       if ((rc = gemm(ctx, xh_hi + E, xplane, ld, *wv, H, rows, V + 1, H, ep, st))) return rc;
     }
-    if ((rc = k_argmax_finish(ctx, ctx->packed, ctx->tokens, T, t, ctx->seq64, T, rows, st))) return rc;
   }
+  if ((rc = k_lm_token_step(ctx, ctx->packed, ctx->tokens, ctx->seq64, T, T, V + 1, wl->planes, wl->planes + wl->plane_elems, E, xh_hi, xh_lo,
+                            ld, rows, st)))
+    return rc;
   return DC_OK;
 }
 
@@ -989,8 +1000,14 @@ extern "C" int dc_bilinear_roi_pool(dc_ctx* ctx, const float* feats_chw, int C, 
   // nn.Transpose({1,2},{2,3}) (BilinearRoiPooling.lua:56): CHW -> HWC, done once
   chw_to_hwc_kernel<<<(unsigned)std::min<size_t>(2048, DC_CEIL_DIV(n, (size_t)256)), 256, 0, st>>>(feats_chw, ctx->scratch_f32, C, feat_h * feat_w);
   DC_CHECK_LAUNCH(ctx);
-  return k_roi_pool(ctx, nullptr, nullptr, ctx->scratch_f32, C, feat_h, feat_w, boxes, nullptr, B, image_h, image_w, HH, WW, nullptr, nullptr, out,
-                    out_layout, st);
+  DC_REQUIRE(ctx, HH * WW <= ctx->cfg.pool_hw * ctx->cfg.pool_hw, DC_E_UNSUPPORTED, "dc_bilinear_roi_pool: HH*WW exceeds the ctx pool size");
+  for (int b0 = 0; b0 < B; b0 += ctx->roi_taps_boxes) {
+    const int nb = std::min(ctx->roi_taps_boxes, B - b0);
+    int rc = k_roi_pool(ctx, nullptr, nullptr, ctx->scratch_f32, C, feat_h, feat_w, boxes + (size_t)b0 * 4, nullptr, nb, image_h, image_w, HH, WW,
+                        ctx->roi_taps, nullptr, nullptr, out + (size_t)b0 * C * HH * WW, out_layout, st);
+    if (rc) return rc;
+  }
+  return DC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

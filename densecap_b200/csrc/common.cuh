@@ -102,8 +102,12 @@ int k_rpn_postprocess(dc_ctx*, const float* head, int ld, int H, int W, int k, c
 struct NmsWorkspace {
   uint64_t* keys;        // (cap) sort keys
   int32_t* order;        // (cap) sorted position -> box index
+  int32_t* rank;         // (cap) box index -> sorted position
   float* sorted_boxes;   // (cap,4) x1y1x2y2 in sorted order
-  uint64_t* mask;        // (cap, ceil(cap/64)) suppression bitmask
+  float* kept_boxes;     // (cap,4) boxes kept so far, in pick order
+  uint64_t* mask;        // (1024, 16) suppression bitmask of the current super-chunk
+  uint64_t* mask_prev;   // (cap, 16)  kept-so-far x current super-chunk
+  void* state;           // NmsState
   int cap;               // max boxes
 };
 size_t nms_workspace_bytes(int cap);
@@ -116,9 +120,11 @@ int k_nms(dc_ctx*, const float* boxes, int box_stride, const float* scores, int 
 
 // roi_pool.cu
 // feats: split NHWC planes (hi, lo) of one image (H',W',C) or fp32 HWC (feats_f32 != nullptr).
+// taps_ws: scratch of roi_taps_bytes(max_boxes, HH*WW) bytes.
+size_t roi_taps_bytes(int max_boxes, int npos);
 int k_roi_pool(dc_ctx*, const __half* feat_hi, const __half* feat_lo, const float* feats_f32, int C, int fh, int fw,
                const float* boxes, const int32_t* nboxes_dev, int max_boxes, int img_h, int img_w, int HH, int WW,
-               __half* out_hi, __half* out_lo, float* out_f32, int out_layout, cudaStream_t st);
+               void* taps_ws, __half* out_hi, __half* out_lo, float* out_f32, int out_layout, cudaStream_t st);
 
 // layout_kernels.cu
 int k_nchw_to_split_nhwc(dc_ctx*, const float* in, __half* hi, __half* lo, int N, int C, int H, int W, cudaStream_t st);
@@ -155,8 +161,9 @@ int k_simt_conv3x3(dc_ctx*, const __half* x_hi, const __half* x_lo, const __half
 // conv1_1: NCHW fp32 (N,3,H,W) -> split NHWC (N,H,W,Cout), bias+ReLU fused.  w (Cout,3,3,3) fp32 reference layout.
 int k_conv_first(dc_ctx*, const float* img, const float* w, const float* bias, __half* y_hi, __half* y_lo,
                  int N, int H, int W, int Cout, cudaStream_t st);
-// small heads: y[m][j] = dot(x[m,:], w[j,:]) + b[j], x fp32 (M,K), w (J,K) fp32, J <= 8
-int k_small_heads(dc_ctx*, const float* x, int ldx, const float* w, const float* b, float* y, int M, int K, int J, cudaStream_t st);
+// objectness (1 row) + box regression (4 rows) heads in one pass over the codes: obj (M), trans (M,4)
+int k_recog_heads(dc_ctx*, const float* x, int ldx, const float* w_obj, const float* b_obj, const float* w_box, const float* b_box,
+                  float* obj, float* trans, int M, int K, cudaStream_t st);
 
 // tc_gemm.cu : tcgen05 engine
 int tc_init(dc_ctx*);   // resolves cuTensorMapEncodeTiled, sets smem attributes
@@ -168,13 +175,12 @@ int k_tc_conv3x3(dc_ctx*, const __half* x_planes, size_t x_plane_elems, const __
                  cudaStream_t st);
 
 // lm_kernels.cu
-int k_lm_gather_x(dc_ctx*, const int32_t* tokens, int tok_stride, int t, int start_token, const __half* lut_hi, const __half* lut_lo,
-                  int E, __half* xh_hi, __half* xh_lo, int ld, int M, cudaStream_t st);
+// One launch per decode step t (0..T): finishes step t-1 (arg-max -> token t-1 -> seq) and prepares step t
+// (lookup row of the token -> x half of [x|h], reset of the packed arg-max cells).  t == T only finishes.
+int k_lm_token_step(dc_ctx*, unsigned long long* packed, int32_t* tokens, int64_t* seq64, int T, int t, int start_token,
+                    const __half* lut_hi, const __half* lut_lo, int E, __half* xh_hi, __half* xh_lo, int ld, int M, cudaStream_t st);
 int k_lstm_pointwise(dc_ctx*, const float* gates, float* c, __half* xh_hi, __half* xh_lo, int ld, int col0, int M, int H,
                      int first, cudaStream_t st);
-int k_argmax_init(dc_ctx*, unsigned long long* packed, int M, cudaStream_t st);
-int k_argmax_finish(dc_ctx*, const unsigned long long* packed, int32_t* tokens, int tok_stride, int t, int64_t* seq64, int T, int M,
-                    cudaStream_t st);
 int k_final_gather(dc_ctx*, const int32_t* idx32, const int32_t* count, int P, const float* boxes, const float* scores,
                    const int64_t* seq, int T, float* out_boxes, float* out_scores, int64_t* out_seq, cudaStream_t st);
 int k_gather_rows_f32(dc_ctx*, const float* src, int cols, const int32_t* idx32, const int32_t* count, int max_rows, float* dst,

@@ -2,26 +2,43 @@
 // torch-rnn nn.LSTM step) and the final result gathers (DenseCapModel.lua:272-274).
 #include "common.cuh"
 
-// nn.LookupTable row gather into the x half of the [x | h] operand of the gate GEMM.
-// token for step t: START (= V+1) when t == 0 else the token sampled at t-1 (LanguageModel.lua:318-326).
-__global__ void lm_gather_x_kernel(const int32_t* __restrict__ tokens, int tok_stride, int t, int start_token,
-                                   const __half* __restrict__ lut_hi, const __half* __restrict__ lut_lo, int E,
-                                   __half* __restrict__ xh_hi, __half* __restrict__ xh_lo, int ld, int M) {
+// One launch per decode step t in [0, T]:
+//   t > 0 : finish step t-1 -- torch.max(scores, 2) (LanguageModel.lua:330): first maximal index, 1-based -> seq[:, t-1];
+//   t < T : nn.LookupTable row of the input token (START = V+1 when t == 0, else the token just sampled;
+//           LanguageModel.lua:318-326) -> x half of the [x | h] operand of the gate GEMM, and reset of the
+//           packed arg-max cell for the coming vocabulary projection.
+__global__ void __launch_bounds__(64)
+lm_token_step_kernel(unsigned long long* __restrict__ packed, int32_t* __restrict__ tokens, int64_t* __restrict__ seq64, int T, int t,
+                     int start_token, const __half* __restrict__ lut_hi, const __half* __restrict__ lut_lo, int E,
+                     __half* __restrict__ xh_hi, __half* __restrict__ xh_lo, int ld) {
   const int m = blockIdx.x;
-  if (m >= M) return;
-  const int tok = (t == 0) ? start_token : tokens[(size_t)m * tok_stride + (t - 1)];
-  const size_t src = (size_t)(tok - 1) * E;
+  __shared__ int s_tok;
+  if (threadIdx.x == 0) {
+    int tok = start_token;
+    if (t > 0) {
+      const unsigned long long pk = packed[m];
+      const uint32_t col = 0xFFFFFFFFu - (uint32_t)(pk & 0xFFFFFFFFull);
+      tok = (pk == 0ull) ? 1 : (int)min(col, (uint32_t)start_token - 1u) + 1;   // all-NaN row -> first index, like torch.max
+      tokens[(size_t)m * T + (t - 1)] = tok;
+      seq64[(size_t)m * T + (t - 1)] = tok;
+    }
+    packed[m] = 0ull;
+    s_tok = tok;
+  }
+  __syncthreads();
+  if (t >= T) return;
+  const size_t src = (size_t)(s_tok - 1) * E;
   const size_t dst = (size_t)m * ld;
-  for (int e = threadIdx.x * 8; e < E; e += blockDim.x * 8) {
-    *reinterpret_cast<uint4*>(xh_hi + dst + e) = *reinterpret_cast<const uint4*>(lut_hi + src + e);
-    *reinterpret_cast<uint4*>(xh_lo + dst + e) = *reinterpret_cast<const uint4*>(lut_lo + src + e);
+  for (int e = threadIdx.x * 8; e < E; e += 64 * 8) {
+    *reinterpret_cast<uint4*>(xh_hi + dst + e) = __ldg(reinterpret_cast<const uint4*>(lut_hi + src + e));
+    *reinterpret_cast<uint4*>(xh_lo + dst + e) = __ldg(reinterpret_cast<const uint4*>(lut_lo + src + e));
   }
 }
-int k_lm_gather_x(dc_ctx* ctx, const int32_t* tokens, int tok_stride, int t, int start_token, const __half* lut_hi,
-                  const __half* lut_lo, int E, __half* xh_hi, __half* xh_lo, int ld, int M, cudaStream_t st) {
+int k_lm_token_step(dc_ctx* ctx, unsigned long long* packed, int32_t* tokens, int64_t* seq64, int T, int t, int start_token,
+                    const __half* lut_hi, const __half* lut_lo, int E, __half* xh_hi, __half* xh_lo, int ld, int M, cudaStream_t st) {
   if (M <= 0) return DC_OK;
   DC_REQUIRE(ctx, E % 8 == 0 && ld % 8 == 0, DC_E_UNSUPPORTED, "lm: encoding size must be a multiple of 8");
-  lm_gather_x_kernel<<<M, 64, 0, st>>>(tokens, tok_stride, t, start_token, lut_hi, lut_lo, E, xh_hi, xh_lo, ld, M);
+  lm_token_step_kernel<<<M, 64, 0, st>>>(packed, tokens, seq64, T, t, start_token, lut_hi, lut_lo, E, xh_hi, xh_lo, ld);
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }
@@ -70,28 +87,6 @@ int k_fill_u32(dc_ctx* ctx, uint32_t* p, uint32_t v, size_t n, cudaStream_t st) 
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }
-int k_argmax_init(dc_ctx* ctx, unsigned long long* packed, int M, cudaStream_t st) {
-  return k_fill_u32(ctx, (uint32_t*)packed, 0u, (size_t)M * 2, st);
-}
-
-// torch.max(scores, 2) (LanguageModel.lua:330): first maximal index, 1-based.
-__global__ void argmax_finish_kernel(const unsigned long long* __restrict__ packed, int32_t* __restrict__ tokens, int tok_stride,
-                                     int t, int64_t* __restrict__ seq64, int T, int M) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  const uint32_t col = 0xFFFFFFFFu - (uint32_t)(packed[m] & 0xFFFFFFFFull);
-  const int tok = (int)col + 1;
-  tokens[(size_t)m * tok_stride + t] = tok;
-  if (seq64) seq64[(size_t)m * T + t] = tok;
-}
-int k_argmax_finish(dc_ctx* ctx, const unsigned long long* packed, int32_t* tokens, int tok_stride, int t, int64_t* seq64, int T,
-                    int M, cudaStream_t st) {
-  if (M <= 0) return DC_OK;
-  argmax_finish_kernel<<<DC_CEIL_DIV(M, 256), 256, 0, st>>>(packed, tokens, tok_stride, t, seq64, T, M);
-  DC_CHECK_LAUNCH(ctx);
-  return DC_OK;
-}
-
 // Apply the final-NMS selection to output[4], output[1], output[5] (DenseCapModel.lua:272-274).
 __global__ void final_gather_kernel(const int32_t* __restrict__ idx32, const int32_t* __restrict__ count, int P,
                                     const float4* __restrict__ boxes, const float* __restrict__ scores, const int64_t* __restrict__ seq,

@@ -1,33 +1,57 @@
-// Greedy NMS (box_utils.nms, densecap/box_utils.lua:154-256) as sort + bitmask + scan.
+// Greedy NMS (box_utils.nms, densecap/box_utils.lua:154-256) as rank sort + bitmask + scan.
 //
 // Reference: sort scores ascending on the CPU, repeatedly pop the best remaining box i, drop every
 // remaining j with iou(i,j) > thresh, stop after max_boxes picks.  Equivalent GPU formulation
-// (SURVEY.md App. B5): sort descending; mask[p][q] = !(iou(p,q) <= thresh) for q > p in sorted
-// order as 64-bit words; sequential scan "keep p iff not removed; removed |= mask[p]".
-// The IoU expression reproduces the reference's fp32 operation order exactly (no FMA):
+// (SURVEY.md App. B5): visit boxes in descending score order; keep p iff no previously KEPT box
+// suppresses it.  The IoU expression reproduces the reference's fp32 operation order exactly (no FMA):
 //   area = ((x2-x1)+1)*((y2-y1)+1); w = max((min(x2)-max(x1))+1, 0); inter = w*h;
 //   union = (area + area_i) - inter; iou = inter/union; keep iff iou <= thresh (fp32 compare).
-// Tie rule (the reference's quicksort is unstable; the oracle defines it): equal scores are
-// visited higher-index first, i.e. descending order of the 64-bit key (sortable(score)<<32 | idx).
+// Tie rule (the reference's quicksort is unstable; the oracle defines it): equal scores are visited
+// higher-index first, i.e. descending order of the 64-bit key (sortable(score)<<32 | idx).
+//
+// Work-efficient schedule: the sorted candidates are processed in super-chunks of M = 1024.  For
+// super-chunk s one kernel builds (a) the upper-triangular 64-bit suppression mask of the chunk against
+// itself and (b) the mask of the boxes kept so far against the chunk; the last block to finish then
+// scans the chunk entirely out of shared memory (mask 128 KB) and appends the survivors.  Only rows of
+// KEPT boxes are ever needed, so the n^2/2 mask of the textbook formulation (210 M IoUs at n = 20520)
+// shrinks to M^2/2 + kept*M per super-chunk, and every super-chunk after the one that reaches
+// max_boxes exits immediately (with the reference's trained-model statistics, 1000 picks are reached
+// within the first ~1300 candidates).  All launches are unconditional -> CUDA-graph friendly.
 #include "common.cuh"
 
+constexpr int NMS_M = 1024;              // super-chunk size
+constexpr int NMS_W = NMS_M / 64;        // 16 mask words per row
+constexpr int NMS_THREADS = 256;
+
+struct NmsState {
+  int32_t count;      // boxes kept so far
+  int32_t done;       // no further super-chunk needs to run
+  uint32_t ticket;    // last-block-done counter
+  int32_t pad;
+};
+
 size_t nms_workspace_bytes(int cap) {
-  const size_t words = DC_CEIL_DIV(cap, 64);
   size_t b = 0;
-  b += (size_t)cap * sizeof(uint64_t);        // keys
-  b += (size_t)cap * sizeof(int32_t);         // order
-  b += (size_t)cap * 4 * sizeof(float);       // sorted boxes
-  b += (size_t)cap * words * sizeof(uint64_t);  // mask
+  b += (size_t)cap * sizeof(uint64_t);              // keys
+  b += (size_t)cap * 4 * sizeof(float);             // sorted boxes
+  b += (size_t)cap * 4 * sizeof(float);             // kept boxes
+  b += (size_t)NMS_M * NMS_W * sizeof(uint64_t);    // intra mask
+  b += (size_t)cap * NMS_W * sizeof(uint64_t);      // prev mask (row = kept box)
+  b += (size_t)cap * sizeof(int32_t) * 2;           // order, rank
+  b += sizeof(NmsState);
   return b + 1024;
 }
 void nms_workspace_carve(NmsWorkspace& ws, void* base, int cap) {
   char* p = (char*)base;
-  const size_t words = DC_CEIL_DIV(cap, 64);
   ws.cap = cap;
   ws.keys = (uint64_t*)p;          p += (size_t)cap * sizeof(uint64_t);
   ws.sorted_boxes = (float*)p;     p += (size_t)cap * 4 * sizeof(float);
-  ws.mask = (uint64_t*)p;          p += (size_t)cap * words * sizeof(uint64_t);
-  ws.order = (int32_t*)p;
+  ws.kept_boxes = (float*)p;       p += (size_t)cap * 4 * sizeof(float);
+  ws.mask = (uint64_t*)p;          p += (size_t)NMS_M * NMS_W * sizeof(uint64_t);
+  ws.mask_prev = (uint64_t*)p;     p += (size_t)cap * NMS_W * sizeof(uint64_t);
+  ws.order = (int32_t*)p;          p += (size_t)cap * sizeof(int32_t);
+  ws.rank = (int32_t*)p;           p += (size_t)cap * sizeof(int32_t);
+  ws.state = (void*)p;
 }
 
 __device__ __forceinline__ uint32_t sortable_f32(float f) {
@@ -35,40 +59,64 @@ __device__ __forceinline__ uint32_t sortable_f32(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// keys + reset of rank[] and of the scan state
 __global__ void nms_keys_kernel(const float* __restrict__ scores, int stride, int n_max, const int32_t* __restrict__ n_dev,
-                                uint64_t* __restrict__ keys) {
+                                uint64_t* __restrict__ keys, int32_t* __restrict__ rank, NmsState* __restrict__ state,
+                                int32_t* __restrict__ count_out) {
   const int n = n_dev ? min(*n_dev, n_max) : n_max;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keys[i] = ((uint64_t)sortable_f32(scores[(size_t)i * stride]) << 32) | (uint32_t)i;
+  if (i < n) {
+    keys[i] = ((uint64_t)sortable_f32(scores[(size_t)i * stride]) << 32) | (uint32_t)i;
+    rank[i] = 0;
+  }
+  if (i == 0) {
+    state->count = 0;
+    state->done = (n <= 0) ? 1 : 0;
+    state->ticket = 0;
+    *count_out = 0;
+  }
 }
 
-// Rank sort: position of box i in descending key order = #{j : key_j > key_i}.  Keys are unique
-// (index in the low bits), so ranks are a permutation.  O(n^2) compares, fully parallel; n ~ 2e4.
-constexpr int RANK_TILE = 2048;
-__global__ void nms_rank_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ boxes, int box_stride, int n_max,
-                                const int32_t* __restrict__ n_dev, int32_t* __restrict__ order, float4* __restrict__ sorted_boxes) {
-  __shared__ uint64_t tile[RANK_TILE];
+// Rank sort, 2-D decomposition: block (x = 256 keys i, y = slice of the j range) adds its partial
+// count #{j in slice : key_j > key_i} to rank[i].  Keys are unique (index in the low bits).
+constexpr int RANK_SLICE = 2048;
+__global__ void __launch_bounds__(256)
+nms_rank_kernel(const uint64_t* __restrict__ keys, int n_max, const int32_t* __restrict__ n_dev, int32_t* __restrict__ rank) {
+  __shared__ uint64_t tile[RANK_SLICE];
+  const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  const int i0 = blockIdx.x * 512;
+  const int j0 = blockIdx.y * RANK_SLICE;
+  if (i0 >= n || j0 >= n) return;
+  const int jn = min(RANK_SLICE, n - j0);
+  for (int t = threadIdx.x; t < jn; t += blockDim.x) tile[t] = keys[j0 + t];
+  __syncthreads();
+  const int ia = i0 + threadIdx.x, ib = ia + 256;        // two keys per thread: each tile word is read once for both
+  const uint64_t ka = (ia < n) ? keys[ia] : ~0ull, kb = (ib < n) ? keys[ib] : ~0ull;
+  int ra = 0, rb = 0;
+  int t = 0;
+  for (; t + 2 <= jn; t += 2) {
+    const uint64_t k0 = tile[t], k1 = tile[t + 1];
+    ra += (k0 > ka) + (k1 > ka);
+    rb += (k0 > kb) + (k1 > kb);
+  }
+  for (; t < jn; ++t) {
+    const uint64_t k0 = tile[t];
+    ra += (k0 > ka);
+    rb += (k0 > kb);
+  }
+  if (ia < n && ra) atomicAdd(rank + ia, ra);
+  if (ib < n && rb) atomicAdd(rank + ib, rb);
+}
+
+__global__ void nms_scatter_kernel(const int32_t* __restrict__ rank, const float* __restrict__ boxes, int box_stride, int n_max,
+                                   const int32_t* __restrict__ n_dev, int32_t* __restrict__ order, float4* __restrict__ sorted_boxes) {
   const int n = n_dev ? min(*n_dev, n_max) : n_max;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x * blockDim.x >= n) return;
-  const uint64_t mine = (i < n) ? keys[i] : 0;
-  int rank = 0;
-  for (int j0 = 0; j0 < n; j0 += RANK_TILE) {
-    const int jn = min(RANK_TILE, n - j0);
-    __syncthreads();
-    for (int t = threadIdx.x; t < jn; t += blockDim.x) tile[t] = keys[j0 + t];
-    __syncthreads();
-    int t = 0;
-    for (; t + 4 <= jn; t += 4) {
-      rank += (tile[t] > mine) + (tile[t + 1] > mine) + (tile[t + 2] > mine) + (tile[t + 3] > mine);
-    }
-    for (; t < jn; ++t) rank += (tile[t] > mine);
-  }
-  if (i < n) {
-    order[rank] = i;
-    const float* b = boxes + (size_t)i * box_stride;
-    sorted_boxes[rank] = make_float4(b[0], b[1], b[2], b[3]);
-  }
+  if (i >= n) return;
+  const int r = rank[i];
+  order[r] = i;
+  const float* b = boxes + (size_t)i * box_stride;
+  sorted_boxes[r] = make_float4(b[0], b[1], b[2], b[3]);
 }
 
 __device__ __forceinline__ float nms_area(float4 b) {
@@ -86,58 +134,105 @@ __device__ __forceinline__ bool nms_suppresses(float4 p, float ap, float4 q, flo
   return !(iou <= thresh);
 }
 
-// mask[p][cb] bit t = box (64*cb + t) suppressed by box p; only cb >= p/64 is produced, and only
-// bits with q > p are set.  grid = (col blocks, row blocks), 64 threads.
-__global__ void nms_mask_kernel(const float4* __restrict__ sb, int n_max, const int32_t* __restrict__ n_dev, float thresh,
-                                uint64_t* __restrict__ mask, int words) {
-  const int n = n_dev ? min(*n_dev, n_max) : n_max;
-  const int rb = blockIdx.y, cb = blockIdx.x;
-  if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
+// One super-chunk.  Blocks [0, 64): intra-chunk mask (4 row blocks of 256 x 16 column words);
+// blocks [64, 64 + 16*prev_row_blocks): kept-so-far x chunk mask.  The last block to finish scans.
+__global__ void __launch_bounds__(NMS_THREADS, 1)
+nms_chunk_kernel(int s, const float4* __restrict__ sb, const int32_t* __restrict__ order, int n_max, const int32_t* __restrict__ n_dev,
+                 float thresh, int max_boxes, uint64_t* __restrict__ mask_intra, uint64_t* __restrict__ mask_prev,
+                 float4* __restrict__ kept_boxes, NmsState* __restrict__ state, int64_t* __restrict__ idx_out,
+                 int32_t* __restrict__ idx32_out, int32_t* __restrict__ count_out) {
+  extern __shared__ __align__(16) uint64_t smem_mask[];     // [NMS_M][NMS_W] (used by the scanning block only)
   __shared__ float4 cbox[64];
   __shared__ float carea[64];
-  const int cn = min(64, n - cb * 64);
-  if ((int)threadIdx.x < cn) {
-    const float4 b = sb[cb * 64 + threadIdx.x];
-    cbox[threadIdx.x] = b;
-    carea[threadIdx.x] = nms_area(b);
+  __shared__ uint64_t s_removed[NMS_W];
+  __shared__ int s_last;
+
+  const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  const int base = s * NMS_M;
+  if (state->done || base >= n) return;                     // uniform for the whole grid
+  const int kept0 = state->count;                           // boxes kept by previous super-chunks
+  const int cn_total = min(NMS_M, n - base);                // candidates in this super-chunk
+  const int tid = threadIdx.x;
+
+  {
+    const int b = blockIdx.x;
+    const bool intra = b < 64;
+    const int rb = intra ? (b >> 4) : ((b - 64) >> 4);
+    const int cb = b & 15;
+    const int col0 = cb * 64;
+    const int cn = min(64, cn_total - col0);                // columns present in this 64-wide word (<= 0: none)
+    if (cn > 0) {
+      if (tid < cn) {
+        const float4 q = sb[base + col0 + tid];
+        cbox[tid] = q;
+        carea[tid] = nms_area(q);
+      }
+    }
+    __syncthreads();
+    if (intra) {
+      const int p_local = rb * 256 + tid;
+      if (!(col0 + 63 < rb * 256)) {                        // word entirely below the diagonal: never read
+        uint64_t bits = 0;
+        if (p_local < cn_total && cn > 0) {
+          const float4 pb = sb[base + p_local];
+          const float pa = nms_area(pb);
+          const int t0 = max(0, p_local + 1 - col0);        // only q > p
+          for (int t = t0; t < cn; ++t)
+            if (nms_suppresses(pb, pa, cbox[t], carea[t], thresh)) bits |= (1ull << t);
+        }
+        mask_intra[(size_t)p_local * NMS_W + cb] = bits;
+      }
+    } else {
+      const int r = rb * 256 + tid;                         // row = previously kept box r
+      if (r < kept0) {
+        uint64_t bits = 0;
+        if (cn > 0) {
+          const float4 pb = kept_boxes[r];
+          const float pa = nms_area(pb);
+          for (int t = 0; t < cn; ++t)
+            if (nms_suppresses(pb, pa, cbox[t], carea[t], thresh)) bits |= (1ull << t);
+        }
+        mask_prev[(size_t)r * NMS_W + cb] = bits;
+      }
+    }
+  }
+  // ---- last block done? ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned t = atomicAdd(&state->ticket, 1u);
+    s_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  const int p = rb * 64 + threadIdx.x;
-  if (p >= n) return;
-  const float4 pb = sb[p];
-  const float pa = nms_area(pb);
-  uint64_t bits = 0;
-  const int t0 = (cb == rb) ? threadIdx.x + 1 : 0;
-  for (int t = t0; t < cn; ++t)
-    if (nms_suppresses(pb, pa, cbox[t], carea[t], thresh)) bits |= (1ull << t);
-  mask[(size_t)p * words + cb] = bits;
-}
+  if (!s_last) return;
+  __threadfence();
 
-// Sequential scan over 64-box chunks by one block.  removed[] lives in shared memory.
-constexpr int SCAN_THREADS = 512;
-__global__ void nms_scan_kernel(const uint64_t* __restrict__ mask, int words_ld, const int32_t* __restrict__ order, int n_max,
-                                const int32_t* __restrict__ n_dev, int max_boxes, int64_t* __restrict__ idx_out,
-                                int32_t* __restrict__ idx32_out, int32_t* __restrict__ count_out) {
-  extern __shared__ uint64_t removed[];
-  __shared__ uint64_t s_keep;
-  __shared__ int s_count;
-  const int n = n_dev ? min(*n_dev, n_max) : n_max;
-  const int words = DC_CEIL_DIV(n, 64);
+  // =============================== scan of this super-chunk ===============================
   const int cap = (max_boxes > 0) ? max_boxes : n;
-  for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = 0;
-  if (threadIdx.x == 0) s_count = 0;
+  const int chunk_words = DC_CEIL_DIV(cn_total, 64);
+  // mask of the chunk -> shared memory (rows beyond cn_total were written as zeros by the intra blocks)
+  for (int i = tid; i < cn_total * NMS_W; i += NMS_THREADS) smem_mask[i] = __ldcg(mask_intra + i);
+  // removed bits inherited from the boxes kept by earlier super-chunks
+  if (tid < NMS_W) s_removed[tid] = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  for (int c = 0; c < words; ++c) {
-    if (threadIdx.x < 32) {
-      const int base = c * 64;
-      const int p0 = base + lane, p1 = base + 32 + lane;
-      const uint64_t d0 = (p0 < n) ? mask[(size_t)p0 * words_ld + c] : 0ull;
-      const uint64_t d1 = (p1 < n) ? mask[(size_t)p1 * words_ld + c] : 0ull;
-      uint64_t cur = removed[c];
+  {
+    const int w = tid & (NMS_W - 1);
+    uint64_t acc = 0;
+    for (int r = tid >> 4; r < kept0; r += NMS_THREADS / NMS_W) acc |= __ldcg(mask_prev + (size_t)r * NMS_W + w);
+    if (acc) atomicOr((unsigned long long*)&s_removed[w], (unsigned long long)acc);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int lane = tid;
+    int count = kept0;
+    uint64_t my_removed = (lane < NMS_W) ? s_removed[lane] : 0ull;    // lane w owns removed word w
+    for (int c = 0; c < chunk_words && count < cap; ++c) {
+      const int lim = min(64, cn_total - c * 64);
+      const uint64_t d0 = (lane < lim) ? smem_mask[(size_t)(c * 64 + lane) * NMS_W + c] : 0ull;
+      const uint64_t d1 = (lane + 32 < lim) ? smem_mask[(size_t)(c * 64 + 32 + lane) * NMS_W + c] : 0ull;
+      uint64_t cur = __shfl_sync(0xffffffffu, my_removed, c);
       uint64_t keep = 0;
-      int count = s_count;
-      const int lim = min(64, n - base);
+      const int before = count;
       for (int i = 0; i < lim; ++i) {
         const uint64_t row = __shfl_sync(0xffffffffu, (i < 32) ? d0 : d1, i & 31);
         if (!((cur >> i) & 1ull) && count < cap) {
@@ -146,66 +241,71 @@ __global__ void nms_scan_kernel(const uint64_t* __restrict__ mask, int words_ld,
           ++count;
         }
       }
-      // emit kept indices in scan order (= decreasing score)
-      const int before = s_count;
-      if ((keep >> lane) & 1ull) {
-        const int pos = before + __popcll(keep & ((1ull << lane) - 1ull));
-        const int bi = order[p0];
-        if (idx_out) idx_out[pos] = (int64_t)bi + 1;
-        if (idx32_out) idx32_out[pos] = bi;
+      // emit survivors in scan order (= decreasing score) and remember their boxes for later super-chunks
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int i = lane + 32 * half;
+        if ((keep >> i) & 1ull) {
+          const int pos = before + __popcll(keep & ((1ull << i) - 1ull));
+          const int sp = base + c * 64 + i;
+          const int bi = order[sp];
+          if (idx_out) idx_out[pos] = (int64_t)bi + 1;
+          if (idx32_out) idx32_out[pos] = bi;
+          kept_boxes[pos] = sb[sp];
+        }
       }
-      if ((keep >> (lane + 32)) & 1ull) {
-        const int pos = before + __popcll(keep & ((1ull << (lane + 32)) - 1ull));
-        const int bi = order[p1];
-        if (idx_out) idx_out[pos] = (int64_t)bi + 1;
-        if (idx32_out) idx32_out[pos] = bi;
-      }
-      if (lane == 0) {
-        s_keep = keep;
-        s_count = count;
-      }
-    }
-    __syncthreads();
-    const uint64_t keep = s_keep;
-    const bool done = (s_count >= cap);
-    if (!done && keep) {
-      for (int w = c + 1 + threadIdx.x; w < words; w += blockDim.x) {
-        uint64_t acc = 0;
-        uint64_t k = keep;
+      // propagate the suppression rows of the survivors to the later words of this super-chunk
+      if (lane > c && lane < NMS_W) {
+        uint64_t k = keep, acc = 0;
         while (k) {
           const int i = __ffsll((long long)k) - 1;
           k &= k - 1;
-          acc |= mask[(size_t)(c * 64 + i) * words_ld + w];
+          acc |= smem_mask[(size_t)(c * 64 + i) * NMS_W + lane];
         }
-        removed[w] |= acc;
+        my_removed |= acc;
       }
     }
-    __syncthreads();
-    if (done) break;
+    if (lane == 0) {
+      state->count = count;
+      state->ticket = 0;
+      if (count >= cap || base + NMS_M >= n) state->done = 1;
+      *count_out = count;
+    }
   }
-  if (threadIdx.x == 0) *count_out = s_count;
 }
-
-__global__ void nms_empty_kernel(int32_t* count_out) { *count_out = 0; }
 
 int k_nms(dc_ctx* ctx, const float* boxes, int box_stride, const float* scores, int score_stride, int n_max, const int32_t* n_dev,
           float thresh, int max_boxes, NmsWorkspace ws, int64_t* idx_out, int32_t* idx32_out, int32_t* count_out, cudaStream_t st) {
+  NmsState* state = (NmsState*)ws.state;
   if (n_max <= 0) {
-    nms_empty_kernel<<<1, 1, 0, st>>>(count_out);
+    nms_keys_kernel<<<1, 32, 0, st>>>(scores, score_stride, 0, nullptr, ws.keys, ws.rank, state, count_out);
     DC_CHECK_LAUNCH(ctx);
     return DC_OK;
   }
   DC_REQUIRE(ctx, n_max <= ws.cap, DC_E_INVALID, "nms: %d boxes exceed workspace capacity %d", n_max, ws.cap);
-  const int words = DC_CEIL_DIV(n_max, 64);
-  nms_keys_kernel<<<DC_CEIL_DIV(n_max, 256), 256, 0, st>>>(scores, score_stride, n_max, n_dev, ws.keys);
+  static bool attr_set = false;
+  const size_t smem = (size_t)NMS_M * NMS_W * sizeof(uint64_t);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(nms_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "nms smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  nms_keys_kernel<<<DC_CEIL_DIV(n_max, 256), 256, 0, st>>>(scores, score_stride, n_max, n_dev, ws.keys, ws.rank, state, count_out);
   DC_CHECK_LAUNCH(ctx);
-  nms_rank_kernel<<<DC_CEIL_DIV(n_max, 128), 128, 0, st>>>(ws.keys, boxes, box_stride, n_max, n_dev, ws.order, (float4*)ws.sorted_boxes);
+  dim3 rgrid(DC_CEIL_DIV(n_max, 512), DC_CEIL_DIV(n_max, RANK_SLICE));
+  nms_rank_kernel<<<rgrid, 256, 0, st>>>(ws.keys, n_max, n_dev, ws.rank);
   DC_CHECK_LAUNCH(ctx);
-  dim3 grid(words, words);
-  nms_mask_kernel<<<grid, 64, 0, st>>>((const float4*)ws.sorted_boxes, n_max, n_dev, thresh, ws.mask, words);
+  nms_scatter_kernel<<<DC_CEIL_DIV(n_max, 256), 256, 0, st>>>(ws.rank, boxes, box_stride, n_max, n_dev, ws.order, (float4*)ws.sorted_boxes);
   DC_CHECK_LAUNCH(ctx);
-  nms_scan_kernel<<<1, SCAN_THREADS, words * sizeof(uint64_t), st>>>(ws.mask, words, ws.order, n_max, n_dev, max_boxes, idx_out,
-                                                                      idx32_out, count_out);
-  DC_CHECK_LAUNCH(ctx);
+  // rows of the kept-so-far mask: at most max_boxes boxes can have been kept (or n_max when uncapped)
+  const int max_keep = (max_boxes > 0) ? (max_boxes < n_max ? max_boxes : n_max) : n_max;
+  const int chunks = DC_CEIL_DIV(n_max, NMS_M);
+  for (int s = 0; s < chunks; ++s) {
+    const int prev_rows = (s == 0) ? 0 : (max_keep < s * NMS_M ? max_keep : s * NMS_M);
+    const int blocks = 64 + 16 * DC_CEIL_DIV(prev_rows, 256);
+    nms_chunk_kernel<<<blocks, NMS_THREADS, smem, st>>>(s, (const float4*)ws.sorted_boxes, ws.order, n_max, n_dev, thresh, max_boxes,
+                                                        ws.mask, ws.mask_prev, (float4*)ws.kept_boxes, state, idx_out, idx32_out, count_out);
+    DC_CHECK_LAUNCH(ctx);
+  }
   return DC_OK;
 }

@@ -134,13 +134,14 @@ int k_simt_conv3x3(dc_ctx* ctx, const __half* x_hi, const __half* x_lo, const __
   return DC_OK;
 }
 
-// conv1_1 (VGG layer 1): Cin = 3, K = 27: bandwidth bound on the 64-channel output write, so a direct
-// fp32 kernel: one thread = one pixel x 8 output channels; weights + bias in shared memory.
+// conv1_1 (VGG layer 1): Cin = 3, K = 27 -- no tensor-core shape; the layer is bound by the 110 MB split-fp16
+// output write, so a direct fp32 kernel: one thread = one pixel x 16 output channels, weights + bias in shared
+// memory read as broadcast LDS.128, 2 x 32-byte vector stores per plane.
 // img NCHW fp32 (reference input layout, DenseCapModel.lua:244) -> split NHWC, bias + ReLU fused.
 __global__ void __launch_bounds__(256)
 conv_first_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                   __half* __restrict__ y_hi, __half* __restrict__ y_lo, int N, int H, int W, int Cout) {
-  extern __shared__ float sw[];   // [27][Cout] + bias[Cout]
+  extern __shared__ __align__(16) float sw[];   // [27][Cout] + bias[Cout]
   float* sb = sw + 27 * Cout;
   for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
     const int co = i % Cout, k = i / Cout;       // k = ci*9 + r*3 + s  (reference layout (Cout,3,3,3))
@@ -148,15 +149,15 @@ conv_first_kernel(const float* __restrict__ img, const float* __restrict__ w, co
   }
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  const int groups = Cout / 8;
+  const int groups = Cout / 16;
   const size_t total = (size_t)N * H * W * groups;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const int gq = t % groups;
     const size_t pix = t / groups;
     const int x = pix % W, y = (pix / W) % H, n = pix / ((size_t)W * H);
-    float acc[8];
+    float acc[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sb[gq * 8 + j];
+    for (int j = 0; j < 16; ++j) acc[j] = sb[gq * 16 + j];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
@@ -166,23 +167,36 @@ conv_first_kernel(const float* __restrict__ img, const float* __restrict__ w, co
           const int yy = y + r - 1, xx = x + s - 1;
           float v = 0.f;
           if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(img + (((size_t)n * 3 + ci) * H + yy) * W + xx);
-          const float* wp = sw + (ci * 9 + r * 3 + s) * Cout + gq * 8;
+          const float4* wp = reinterpret_cast<const float4*>(sw + (ci * 9 + r * 3 + s) * Cout + gq * 16);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
+          for (int q = 0; q < 4; ++q) {
+            const float4 wv = wp[q];
+            acc[4 * q + 0] = fmaf(v, wv.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+          }
         }
-    __align__(16) __half h[8];
-    __align__(16) __half l[8];
+    uint32_t hh[8], ll[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) split_f32(fmaxf(acc[j], 0.f), h[j], l[j]);
-    const size_t o = pix * Cout + gq * 8;
-    *reinterpret_cast<uint4*>(y_hi + o) = *reinterpret_cast<const uint4*>(h);
-    *reinterpret_cast<uint4*>(y_lo + o) = *reinterpret_cast<const uint4*>(l);
+    for (int j = 0; j < 8; ++j) {
+      __half h0, l0, h1, l1;
+      split_f32(fmaxf(acc[2 * j], 0.f), h0, l0);
+      split_f32(fmaxf(acc[2 * j + 1], 0.f), h1, l1);
+      hh[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      ll[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    const size_t o = pix * Cout + gq * 16;
+    reinterpret_cast<uint4*>(y_hi + o)[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    reinterpret_cast<uint4*>(y_hi + o)[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+    reinterpret_cast<uint4*>(y_lo + o)[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+    reinterpret_cast<uint4*>(y_lo + o)[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
   }
 }
 int k_conv_first(dc_ctx* ctx, const float* img, const float* w, const float* bias, __half* y_hi, __half* y_lo, int N, int H, int W,
                  int Cout, cudaStream_t st) {
-  DC_REQUIRE(ctx, Cout % 8 == 0, DC_E_UNSUPPORTED, "conv1_1: Cout must be a multiple of 8");
-  const size_t total = (size_t)N * H * W * (Cout / 8);
+  DC_REQUIRE(ctx, Cout % 16 == 0, DC_E_UNSUPPORTED, "conv1_1: Cout must be a multiple of 16");
+  const size_t total = (size_t)N * H * W * (Cout / 16);
   if (total == 0) return DC_OK;
   const size_t smem = (size_t)(27 * Cout + Cout) * sizeof(float);
   unsigned blocks = (unsigned)min((size_t)148 * 8, DC_CEIL_DIV(total, (size_t)256));
@@ -191,23 +205,41 @@ int k_conv_first(dc_ctx* ctx, const float* img, const float* w, const float* bia
   return DC_OK;
 }
 
-// objectness (fc_dim -> 1) and box regression (fc_dim -> 4) heads (DenseCapModel.lua:90-99): one warp per row.
-__global__ void small_heads_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b,
-                                   float* __restrict__ y, int M, int K, int J) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= M) return;
-  const float* xr = x + (size_t)warp * ldx;
-  for (int j = 0; j < J; ++j) {
-    const float* wr = w + (size_t)j * K;
-    float s = 0.f;
-    for (int k = lane; k < K; k += 32) s = fmaf(xr[k], wr[k], s);
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) y[(size_t)warp * J + j] = s + (b ? b[j] : 0.f);
+// objectness (fc_dim -> 1) and box regression (fc_dim -> 4) heads (DenseCapModel.lua:90-99): one 128-thread
+// block per ROI row computes all five dot products in a single pass over the codes.
+__global__ void __launch_bounds__(128)
+recog_heads_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w_obj, const float* __restrict__ b_obj,
+                   const float* __restrict__ w_box, const float* __restrict__ b_box, float* __restrict__ obj,
+                   float* __restrict__ trans, int K) {
+  const int m = blockIdx.x;
+  const float* xr = x + (size_t)m * ldx;
+  float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k = threadIdx.x; k < K; k += 128) {
+    const float v = xr[k];
+    s[0] = fmaf(v, __ldg(w_obj + k), s[0]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[1 + j] = fmaf(v, __ldg(w_box + (size_t)j * K + k), s[1 + j]);
+  }
+  __shared__ float red[4][5];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    float v = s[j];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    const int j = threadIdx.x;
+    const float v = red[0][j] + red[1][j] + red[2][j] + red[3][j];
+    if (j == 0) obj[m] = v + (b_obj ? b_obj[0] : 0.f);
+    else trans[(size_t)m * 4 + j - 1] = v + (b_box ? b_box[j - 1] : 0.f);
   }
 }
-int k_small_heads(dc_ctx* ctx, const float* x, int ldx, const float* w, const float* b, float* y, int M, int K, int J, cudaStream_t st) {
-  if (M <= 0 || J <= 0) return DC_OK;
-  small_heads_kernel<<<DC_CEIL_DIV(M * 32, 256), 256, 0, st>>>(x, ldx, w, b, y, M, K, J);
+int k_recog_heads(dc_ctx* ctx, const float* x, int ldx, const float* w_obj, const float* b_obj, const float* w_box, const float* b_box,
+                  float* obj, float* trans, int M, int K, cudaStream_t st) {
+  if (M <= 0) return DC_OK;
+  recog_heads_kernel<<<M, 128, 0, st>>>(x, ldx, w_obj, b_obj, w_box, b_box, obj, trans, K);
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }

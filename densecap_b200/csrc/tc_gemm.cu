@@ -174,7 +174,7 @@ struct Cfg {
   static constexpr uint32_t STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
   static constexpr int STAGES = (BLOCK_N <= 64) ? 4 : (BLOCK_N <= 128 ? 3 : 2);
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;   // power of two for 64/128/256
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
 };
 
 template <int BLOCK_N, bool CONV, bool POOL>
@@ -194,6 +194,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* bias_smem = reinterpret_cast<float*>(smem_aligned + (size_t)STAGES * C::STAGE_BYTES + 256);   // [2][BLOCK_N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -330,6 +331,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float best_v = -INFINITY;
       int best_c = 0x7fffffff;
 
+      // Stage this tile's bias slice in shared memory (one coalesced load per thread, overlapped with the MMAs of
+      // this tile) -- per-element global loads in the column loop would serialise on L2 latency and make every
+      // short-K tile epilogue-bound.  Double-buffered by accumulator stage, so one named barrier per tile suffices.
+      float* sbias = bias_smem + acc * BLOCK_N;
+      if (ep.bias) {
+        for (int j = threadIdx.x - 64; j < BLOCK_N; j += 128) sbias[j] = (n0 + j < pb.N) ? __ldg(ep.bias + n0 + j) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
@@ -344,8 +354,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(raw[j]);
-          const int n = nc + j;
-          if (ep.bias && n < pb.N) x += __ldg(ep.bias + n);
+          if (ep.bias) x += sbias[c * 32 + j];
           if (ep.relu) x = fmaxf(x, 0.f);
           v[j] = x;
         }
@@ -365,27 +374,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             __half* ph = ep.out_hi + (size_t)out_row * ep.ldo + ep.out_col0 + nc;
             __half* pl = ep.out_lo + (size_t)out_row * ep.ldo + ep.out_col0 + nc;
             if (full) {
-              __align__(16) __half2 hh[16];
-              __align__(16) __half2 ll[16];
+              uint32_t hh[16], ll[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 __half h0, l0, h1, l1;
                 split_f32(v[2 * j], h0, l0);
                 split_f32(v[2 * j + 1], h1, l1);
-                hh[j] = __halves2half2(h0, h1);
-                ll[j] = __halves2half2(l0, l1);
+                hh[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                ll[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
               }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                reinterpret_cast<uint4*>(ph)[j] = reinterpret_cast<const uint4*>(hh)[j];
-                reinterpret_cast<uint4*>(pl)[j] = reinterpret_cast<const uint4*>(ll)[j];
+                reinterpret_cast<uint4*>(ph)[j] = make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
+                reinterpret_cast<uint4*>(pl)[j] = make_uint4(ll[4 * j], ll[4 * j + 1], ll[4 * j + 2], ll[4 * j + 3]);
               }
             } else {
-              for (int j = 0; j < 32 && nc + j < pb.N; ++j) {
-                __half h0, l0;
-                split_f32(v[j], h0, l0);
-                ph[j] = h0;
-                pl[j] = l0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {      // fully unrolled + predicated: v[] must stay in registers
+                if (nc + j < pb.N) {
+                  __half h0, l0;
+                  split_f32(v[j], h0, l0);
+                  ph[j] = h0;
+                  pl[j] = l0;
+                }
               }
             }
           }
@@ -396,7 +407,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int j = 0; j < 8; ++j)
                 reinterpret_cast<float4*>(pf)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             } else {
-              for (int j = 0; j < 32 && nc + j < pb.N; ++j) pf[j] = v[j];
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nc + j < pb.N) pf[j] = v[j];
             }
           }
           if (ep.argmax) {

@@ -131,7 +131,7 @@ class DenseCapModel:
     def setTestArgs(self, kwargs):
         self._rpn_nms = kwargs.get("rpn_nms_thresh", 0.7)
         self.opt["final_nms_thresh"] = kwargs.get("final_nms_thresh", 0.3)
-        self._num_proposals = kwargs.get("num_proposals", 1000)
+        self._num_proposals = min(kwargs.get("num_proposals", 1000), self.ctx.max_proposals)   # reference default 1000
         self.ctx.set_test_args(self._rpn_nms, self.opt["final_nms_thresh"], self._num_proposals, True)
 
     def forward_device(self, input):
