@@ -56,10 +56,15 @@ struct dc_ctx {
   float* anchors_dev = nullptr;
   float* scratch_f32 = nullptr;      // generic fp32 scratch (HWC features for dc_bilinear_roi_pool, ...)
   size_t scratch_elems = 0;
-  void* nms_mem = nullptr;
-  void* roi_taps = nullptr;          // per-(roi,position) bilinear tap records
+  void* roi_taps = nullptr;          // per-(roi,position) bilinear tap records, one block per batch image
+  size_t roi_taps_stride = 0;        // bytes between the per-image blocks
   int roi_taps_boxes = 0;
-  NmsWorkspace nms;
+  std::vector<NmsWorkspace> nms;     // one NMS workspace per batch image (images run on forked streams)
+  // per-image side streams: the latency-bound per-image stages (RPN post-processing, NMS, ROI pooling, final NMS)
+  // of different images of a batch overlap instead of queueing behind each other
+  std::vector<cudaStream_t> side;
+  std::vector<cudaEvent_t> side_done;
+  cudaEvent_t fork_ev = nullptr;
   PhaseTimer timer;
 };
 
@@ -234,17 +239,27 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
   ctx->scratch_elems = std::max(cells * C5, (size_t)1 << 20);
   TRY(dev_alloc(ctx, &ctx->scratch_f32, ctx->scratch_elems));
   const int nms_cap = (int)align_up(std::max(A, P), 64);
-  {
+  ctx->nms.resize(B);
+  for (size_t b = 0; b < B; ++b) {
     char* mem = nullptr;
     TRY(dev_alloc(ctx, &mem, nms_workspace_bytes(nms_cap)));
-    ctx->nms_mem = mem;
-    nms_workspace_carve(ctx->nms, mem, nms_cap);
+    nms_workspace_carve(ctx->nms[b], mem, nms_cap);
   }
   {
     char* mem = nullptr;
     ctx->roi_taps_boxes = (int)std::max((size_t)P, (size_t)1024);
-    TRY(dev_alloc(ctx, &mem, roi_taps_bytes(ctx->roi_taps_boxes, c.pool_hw * c.pool_hw)));
+    ctx->roi_taps_stride = align_up(roi_taps_bytes(ctx->roi_taps_boxes, c.pool_hw * c.pool_hw), 256);
+    TRY(dev_alloc(ctx, &mem, ctx->roi_taps_stride * B));
     ctx->roi_taps = mem;
+  }
+  DC_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+  for (size_t b = 1; b < B; ++b) {
+    cudaStream_t sst;
+    cudaEvent_t ev;
+    DC_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&sst, cudaStreamNonBlocking));
+    DC_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ctx->side.push_back(sst);
+    ctx->side_done.push_back(ev);
   }
   // ---- weights ----
   {
@@ -289,6 +304,9 @@ extern "C" int dc_destroy(dc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (void* p : ctx->allocs) cudaFree(p);
+  for (cudaStream_t sst : ctx->side) cudaStreamDestroy(sst);
+  for (cudaEvent_t ev : ctx->side_done) cudaEventDestroy(ev);
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   for (cudaEvent_t ev : ctx->timer.events) cudaEventDestroy(ev);
   delete ctx;
   return DC_OK;
@@ -415,13 +433,23 @@ extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_
     int rc = stage();
     if (rc) return rc;
     Weight& w = ctx->w[n];
-    rc = k_transpose_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, (int)(E + H), (int)(4 * H), st);
+    // rows of the B operand are gate-interleaved (n = 4*j + gate) so the LSTM cell fuses into the GEMM epilogue
+    rc = k_transpose_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, (int)(E + H), (int)(4 * H), (int)H, st);
     w.loaded = true;
     return finish(rc);
   }
+  if (n == "lm.lstm.bias") {
+    if ((int64_t)numel != 4 * H) return bad_shape();
+    std::vector<float> perm(numel);
+    for (int64_t c = 0; c < 4 * H; ++c) perm[4 * (c % H) + c / H] = data_host[c];
+    Weight& w = ctx->w[n];
+    DC_CHECK_CUDA(ctx, cudaMemcpy(w.f32, perm.data(), numel * sizeof(float), cudaMemcpyHostToDevice));
+    w.loaded = true;
+    return DC_OK;
+  }
   struct F32 { const char* name; int64_t n; };
   const F32 fl[] = {{"fc6.bias", fc}, {"fc7.bias", fc}, {"obj.weight", fc}, {"obj.bias", 1}, {"boxreg.weight", 4 * fc}, {"boxreg.bias", 4},
-                    {"lm.encoder.bias", E}, {"lm.lstm.bias", 4 * H}, {"lm.vocab.bias", V + 1}};
+                    {"lm.encoder.bias", E}, {"lm.vocab.bias", V + 1}};
   for (const F32& f : fl) {
     if (n == f.name) {
       if ((int64_t)numel != f.n) return bad_shape();
@@ -625,7 +653,14 @@ static int run_localization(dc_ctx* ctx, int N, int fh, int fw, int img_h, int i
     if ((rc = gemm(ctx, ctx->rpn_hidden.base, hplane, F, *wh, F, N * cells, 6 * k, F, ep, st))) return rc;
   }
   const int P = ctx->P;
+  const int hw = c.pool_hw * c.pool_hw;
+  const size_t rplane = (size_t)N * P * hw * C5;
+  phase_mark(ctx, "nms+roi_pooling", st);
+  // fork: image 0 stays on the caller's stream, image b > 0 runs on side stream b-1
+  if (N > 1) DC_CHECK_CUDA(ctx, cudaEventRecord(ctx->fork_ev, st));
   for (int b = 0; b < N; ++b) {
+    cudaStream_t sb = (b == 0) ? st : ctx->side[b - 1];
+    if (b > 0) DC_CHECK_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->fork_ev, 0));
     RpnPostOut po;
     po.boxes_xcycwh = ctx->pp_boxes + (size_t)b * ctx->A_max * 4;
     po.boxes_x1y1x2y2 = ctx->pp_x1y1 + (size_t)b * ctx->A_max * 4;
@@ -635,29 +670,25 @@ static int run_localization(dc_ctx* ctx, int N, int fh, int fw, int img_h, int i
     po.block_counts = ctx->pp_blocks + (size_t)b * (ctx->A_max / 256 + 2);
     if ((rc = k_rpn_postprocess(ctx, ctx->rpn_head + (size_t)b * cells * 6 * k, 6 * k, fh, fw, k, ctx->anchors_dev, c.field_centers[0],
                                 c.field_centers[1], c.field_centers[2], c.field_centers[3], (float)img_w, (float)img_h, ctx->clip_boxes,
-                                po, st)))
+                                po, sb)))
       return rc;
-  }
-  phase_mark(ctx, "nms", st);
-  for (int b = 0; b < N; ++b) {
     if ((rc = k_nms(ctx, ctx->pp_x1y1 + (size_t)b * ctx->A_max * 4, 4, ctx->pp_prob + (size_t)b * ctx->A_max, 1, A, ctx->pp_nvalid + b,
-                    ctx->rpn_nms_thresh, ctx->num_proposals, ctx->nms, ctx->rpn_idx64 + (size_t)b * P, ctx->rpn_idx32 + (size_t)b * P,
-                    ctx->rpn_count + b, st)))
+                    ctx->rpn_nms_thresh, ctx->num_proposals, ctx->nms[b], ctx->rpn_idx64 + (size_t)b * P, ctx->rpn_idx32 + (size_t)b * P,
+                    ctx->rpn_count + b, sb)))
       return rc;
     if ((rc = k_gather_rows_f32(ctx, ctx->pp_boxes + (size_t)b * ctx->A_max * 4, 4, ctx->rpn_idx32 + (size_t)b * P, ctx->rpn_count + b, P,
-                                ctx->roi_boxes + (size_t)b * P * 4, st)))
+                                ctx->roi_boxes + (size_t)b * P * 4, sb)))
       return rc;
-  }
-  phase_mark(ctx, "roi_pooling:forward_test", st);
-  const int hw = c.pool_hw * c.pool_hw;
-  const size_t rplane = (size_t)N * P * hw * C5;
-  for (int b = 0; b < N; ++b) {
     const size_t foff = (size_t)b * cells * C5;
     const size_t roff = (size_t)b * P * hw * C5;
     if ((rc = k_roi_pool(ctx, ctx->feats.base + foff, ctx->feats.base + fplane + foff, nullptr, C5, fh, fw, ctx->roi_boxes + (size_t)b * P * 4,
-                         ctx->rpn_count + b, P, img_h, img_w, c.pool_hw, c.pool_hw, ctx->roi_taps, ctx->roi.base + roff,
-                         ctx->roi.base + rplane + roff, nullptr, 1, st)))
+                         ctx->rpn_count + b, P, img_h, img_w, c.pool_hw, c.pool_hw, (char*)ctx->roi_taps + ctx->roi_taps_stride * b,
+                         ctx->roi.base + roff, ctx->roi.base + rplane + roff, nullptr, 1, sb)))
       return rc;
+    if (b > 0) {
+      DC_CHECK_CUDA(ctx, cudaEventRecord(ctx->side_done[b - 1], sb));
+      DC_CHECK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->side_done[b - 1], 0));     // join
+    }
   }
   return DC_OK;
 }
@@ -725,25 +756,28 @@ static int run_lm(dc_ctx* ctx, int rows, float* logits, cudaStream_t st) {
     ep.out_hi = xh_hi; ep.out_lo = xh_lo; ep.ldo = ld; ep.out_col0 = 0;
     if ((rc = gemm(ctx, ctx->fc7o.base, fplane, fc, *we, fc, rows, E, fc, ep, st))) return rc;
   }
-  {  // first LSTM step on the encoded image with h0 = c0 = 0: only the Wx rows contribute (K = E)
+  const bool fused_cell = (c.engine == DC_ENGINE_TC);
+  auto lstm_step = [&](int K, int first) -> int {
     GemmEpilogue ep;
     ep.bias = blstm->f32;
+    if (fused_cell) {
+      ep.lstm_c = ctx->cstate; ep.lstm_H = H; ep.lstm_first = first;
+      ep.out_hi = xh_hi; ep.out_lo = xh_lo; ep.ldo = ld; ep.out_col0 = E;
+      return gemm(ctx, xh_hi, xplane, ld, *wlstm, ld, rows, 4 * H, K, ep, st);
+    }
     ep.out_f32 = ctx->gates; ep.ldf = 4 * H;
-    if ((rc = gemm(ctx, xh_hi, xplane, ld, *wlstm, ld, rows, 4 * H, E, ep, st))) return rc;
-    if ((rc = k_lstm_pointwise(ctx, ctx->gates, ctx->cstate, xh_hi, xh_lo, ld, E, rows, H, 1, st))) return rc;
-  }
+    int r = gemm(ctx, xh_hi, xplane, ld, *wlstm, ld, rows, 4 * H, K, ep, st);
+    if (r) return r;
+    return k_lstm_pointwise(ctx, ctx->gates, ctx->cstate, xh_hi, xh_lo, ld, E, rows, H, first, st);
+  };
+  // first LSTM step on the encoded image with h0 = c0 = 0: only the Wx rows contribute (K = E)
+  if ((rc = lstm_step(E, 1))) return rc;
   for (int t = 0; t < T; ++t) {
     // finish step t-1 (arg-max -> token), look up the input token of step t, reset the arg-max cells
     if ((rc = k_lm_token_step(ctx, ctx->packed, ctx->tokens, ctx->seq64, T, t, V + 1, wl->planes, wl->planes + wl->plane_elems, E, xh_hi,
                               xh_lo, ld, rows, st)))
       return rc;
-    {
-      GemmEpilogue ep;
-      ep.bias = blstm->f32;
-      ep.out_f32 = ctx->gates; ep.ldf = 4 * H;
-      if ((rc = gemm(ctx, xh_hi, xplane, ld, *wlstm, ld, rows, 4 * H, ld, ep, st))) return rc;
-    }
-    if ((rc = k_lstm_pointwise(ctx, ctx->gates, ctx->cstate, xh_hi, xh_lo, ld, E, rows, H, 0, st))) return rc;
+    if ((rc = lstm_step(ld, 0))) return rc;
     {
       GemmEpilogue ep;
       ep.bias = bv->f32;
@@ -765,19 +799,26 @@ static int run_final(dc_ctx* ctx, int N, cudaStream_t st) {
   int rc;
   phase_mark(ctx, "final_nms", st);
   if ((rc = k_xcycwh_to_x1y1x2y2(ctx, ctx->boxes_all, ctx->fin_x1y1, N * P, st))) return rc;
+  if (N > 1) DC_CHECK_CUDA(ctx, cudaEventRecord(ctx->fork_ev, st));
   for (int b = 0; b < N; ++b) {
+    cudaStream_t sb = (b == 0) ? st : ctx->side[b - 1];
+    if (b > 0) DC_CHECK_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->fork_ev, 0));
     const size_t o = (size_t)b * P;
     if (ctx->final_nms_thresh > 0.f) {
-      if ((rc = k_nms(ctx, ctx->fin_x1y1 + o * 4, 4, ctx->obj + o, 1, P, ctx->rpn_count + b, ctx->final_nms_thresh, 0, ctx->nms,
-                      ctx->fin_idx64 + o, ctx->fin_idx32 + o, ctx->fin_count + b, st)))
+      if ((rc = k_nms(ctx, ctx->fin_x1y1 + o * 4, 4, ctx->obj + o, 1, P, ctx->rpn_count + b, ctx->final_nms_thresh, 0, ctx->nms[b],
+                      ctx->fin_idx64 + o, ctx->fin_idx32 + o, ctx->fin_count + b, sb)))
         return rc;
     } else {
-      identity_idx_kernel<<<1, 256, 0, st>>>(ctx->rpn_count + b, P, ctx->fin_idx32 + o, ctx->fin_idx64 + o, ctx->fin_count + b);
+      identity_idx_kernel<<<1, 256, 0, sb>>>(ctx->rpn_count + b, P, ctx->fin_idx32 + o, ctx->fin_idx64 + o, ctx->fin_count + b);
       DC_CHECK_LAUNCH(ctx);
     }
     if ((rc = k_final_gather(ctx, ctx->fin_idx32 + o, ctx->fin_count + b, P, ctx->boxes_all + o * 4, ctx->obj + o, ctx->seq64 + o * T, T,
-                             ctx->fin_boxes + o * 4, ctx->fin_scores + o, ctx->fin_seq + o * T, st)))
+                             ctx->fin_boxes + o * 4, ctx->fin_scores + o, ctx->fin_seq + o * T, sb)))
       return rc;
+    if (b > 0) {
+      DC_CHECK_CUDA(ctx, cudaEventRecord(ctx->side_done[b - 1], sb));
+      DC_CHECK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->side_done[b - 1], 0));
+    }
   }
   return DC_OK;
 }
@@ -979,7 +1020,7 @@ extern "C" int dc_box_iou(const float* box1, const float* box2, float* out, int 
 extern "C" int dc_nms(dc_ctx* ctx, const float* boxes_scores, int n, float thresh, int max_boxes, int64_t* idx_out, int32_t* count_out, void* stream) {
   if (!ctx || !count_out || (n > 0 && (!boxes_scores || !idx_out))) return dc_set_error(ctx, DC_E_INVALID, "dc_nms: null argument");
   DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-  return k_nms(ctx, boxes_scores, 5, boxes_scores + 4, 5, n, nullptr, thresh, max_boxes, ctx->nms, idx_out, nullptr, count_out, (cudaStream_t)stream);
+  return k_nms(ctx, boxes_scores, 5, boxes_scores + 4, 5, n, nullptr, thresh, max_boxes, ctx->nms[0], idx_out, nullptr, count_out, (cudaStream_t)stream);
 }
 
 __global__ void chw_to_hwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW) {

@@ -137,7 +137,8 @@ int k_maxpool2x2_split(dc_ctx*, const __half* ihi, const __half* ilo, __half* oh
 // lstm ((D+H),4H) -> [4H][D+H]
 int k_conv_weight_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int Cout, int Cin, cudaStream_t st);
 int k_fc6_weight_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int out, int C, int hw, cudaStream_t st);
-int k_transpose_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int rows, int cols, cudaStream_t st);
+// interleave_h > 0: output row of input column c is 4*(c % H) + c / H (LSTM gate interleave, H = interleave_h)
+int k_transpose_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int rows, int cols, int interleave_h, cudaStream_t st);
 // BCHW (K,C,HH,WW) fp32 -> split rows (K, HH*WW*C) in (y,x,c) order
 int k_bchw_to_split_rows(dc_ctx*, const float* in, __half* hi, __half* lo, int K, int C, int hw, cudaStream_t st);
 int k_bhwc_split_to_bchw(dc_ctx*, const __half* hi, const __half* lo, float* out, int K, int C, int hw, cudaStream_t st);
@@ -153,6 +154,11 @@ struct GemmEpilogue {
   float* out_f32 = nullptr;       // fp32 output (M, ldf) or null
   int ldf = 0;
   unsigned long long* argmax = nullptr;  // (M) packed (sortable(value)<<32 | ~col) atomicMax target or null
+  // Fused torch-rnn LSTM cell (tcgen05 engine): the N columns are the gate pre-activations in INTERLEAVED order
+  // n = 4*j + {i,f,o,g}; the epilogue applies the cell, updates c (M,H) and writes h (split) to out_hi/out_lo.
+  float* lstm_c = nullptr;
+  int lstm_H = 0;
+  int lstm_first = 0;             // 1: c_{t-1} = 0
 };
 int k_simt_gemm(dc_ctx*, const __half* a_hi, const __half* a_lo, int lda, const __half* b_hi, const __half* b_lo, int ldb,
                 int M, int N, int K, GemmEpilogue ep, cudaStream_t st);

@@ -175,7 +175,8 @@ int k_fc6_weight_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, i
 }
 
 // (rows, cols) fp32 -> split (cols, rows)   (torch-rnn LSTM weight ((D+H),4H) -> [4H][D+H])
-__global__ void transpose_to_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int rows, int cols) {
+__global__ void transpose_to_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int rows, int cols,
+                                          int interleave_h) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -188,15 +189,16 @@ __global__ void transpose_to_split_kernel(const float* __restrict__ w, __half* _
     if (c < cols && r < rows) {
       __half h, l;
       split_f32(tile[threadIdx.x][i], h, l);
-      hi[(size_t)c * rows + r] = h;
-      lo[(size_t)c * rows + r] = l;
+      const int oc = interleave_h > 0 ? 4 * (c % interleave_h) + c / interleave_h : c;
+      hi[(size_t)oc * rows + r] = h;
+      lo[(size_t)oc * rows + r] = l;
     }
   }
 }
-int k_transpose_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, int rows, int cols, cudaStream_t st) {
+int k_transpose_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, int rows, int cols, int interleave_h, cudaStream_t st) {
   if ((size_t)rows * cols == 0) return DC_OK;
   dim3 grid(DC_CEIL_DIV(cols, 32), DC_CEIL_DIV(rows, 32)), block(32, 8);
-  transpose_to_split_kernel<<<grid, block, 0, st>>>(w, hi, lo, rows, cols);
+  transpose_to_split_kernel<<<grid, block, 0, st>>>(w, hi, lo, rows, cols, interleave_h);
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }

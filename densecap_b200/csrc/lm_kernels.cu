@@ -45,7 +45,9 @@ int k_lm_token_step(dc_ctx* ctx, unsigned long long* packed, int32_t* tokens, in
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// gates (M,4H) = bias + x Wx + h Wh (bias added by the GEMM epilogue), blocks [i|f|o|g].
+// gates (M,4H) = bias + x Wx + h Wh (bias added by the GEMM epilogue), INTERLEAVED columns 4*j + {i,f,o,g}
+// (the weight rows are permuted at load time so that the tcgen05 engine can fuse this cell into its epilogue;
+// this stand-alone kernel serves the CUDA-core engine).
 // c = f*c + i*g ; h = o*tanh(c).  h is written (split) into columns [col0, col0+H) of the [x|h] operand.
 __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, float* __restrict__ c, __half* __restrict__ xh_hi,
                                       __half* __restrict__ xh_lo, int ld, int col0, int M, int H, int first) {
@@ -54,10 +56,11 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, float* __
     const int j = idx % H;
     const size_t m = idx / H;
     const float* g = gates + m * 4 * (size_t)H;
-    const float ig = sigmoidf_(g[j]);
-    const float fg = sigmoidf_(g[H + j]);
-    const float og = sigmoidf_(g[2 * H + j]);
-    const float gg = tanhf(g[3 * H + j]);
+    const float4 a = *reinterpret_cast<const float4*>(g + 4 * j);
+    const float ig = sigmoidf_(a.x);
+    const float fg = sigmoidf_(a.y);
+    const float og = sigmoidf_(a.z);
+    const float gg = tanhf(a.w);
     const float cp = first ? 0.f : c[idx];
     const float cn = fg * cp + ig * gg;
     c[idx] = cn;

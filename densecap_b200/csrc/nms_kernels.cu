@@ -211,14 +211,40 @@ nms_chunk_kernel(int s, const float4* __restrict__ sb, const int32_t* __restrict
   const int cap = (max_boxes > 0) ? max_boxes : n;
   const int chunk_words = DC_CEIL_DIV(cn_total, 64);
   // mask of the chunk -> shared memory (rows beyond cn_total were written as zeros by the intra blocks)
-  for (int i = tid; i < cn_total * NMS_W; i += NMS_THREADS) smem_mask[i] = __ldcg(mask_intra + i);
+  {
+    // 8 independent loads in flight per thread (a plain copy loop serialises on L2 latency)
+    const int total_words = cn_total * NMS_W;
+    for (int i0 = tid; i0 < total_words; i0 += NMS_THREADS * 8) {
+      uint64_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * NMS_THREADS;
+        v[u] = (i < total_words) ? __ldcg(mask_intra + i) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * NMS_THREADS;
+        if (i < total_words) smem_mask[i] = v[u];
+      }
+    }
+  }
   // removed bits inherited from the boxes kept by earlier super-chunks
   if (tid < NMS_W) s_removed[tid] = 0;
   __syncthreads();
   {
     const int w = tid & (NMS_W - 1);
     uint64_t acc = 0;
-    for (int r = tid >> 4; r < kept0; r += NMS_THREADS / NMS_W) acc |= __ldcg(mask_prev + (size_t)r * NMS_W + w);
+    constexpr int RSTEP = NMS_THREADS / NMS_W;
+    for (int r0 = tid >> 4; r0 < kept0; r0 += RSTEP * 8) {
+      uint64_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + u * RSTEP;
+        v[u] = (r < kept0) ? __ldcg(mask_prev + (size_t)r * NMS_W + w) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc |= v[u];
+    }
     if (acc) atomicOr((unsigned long long*)&s_removed[w], (unsigned long long)acc);
   }
   __syncthreads();

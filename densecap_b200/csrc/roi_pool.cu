@@ -17,7 +17,7 @@
 // contraction (mul/add intrinsics), so fp32 outputs are bit-identical to the oracle.
 #include "common.cuh"
 
-constexpr int ROI_THREADS = 512;
+constexpr int ROI_THREADS = 1024;
 constexpr int ROI_MAX_POS = 64;  // HH*WW <= 64
 
 struct __align__(16) RoiTap {
@@ -117,13 +117,10 @@ roi_pool_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ f
   __syncthreads();
   const int sub = lane / PAIRS;
   const int cp = (lane % PAIRS) * 2;
-  // items (roi*npos + pos) are dealt in contiguous runs of POS_PER_WARP to (blockIdx.y, warp)
+  // items (roi*npos + pos) are dealt in contiguous runs of POS_PER_WARP to (blockIdx.y, warp); two runs per
+  // iteration so that four 16-byte tap loads are in flight per lane before the first gather is issued.
   const int stride = gridDim.y * NWARPS * POS_PER_WARP;
-  for (int it0 = (blockIdx.y * NWARPS + warp) * POS_PER_WARP; it0 < total_items; it0 += stride) {
-    const int it = it0 + sub;
-    if (it >= total_items) continue;
-    const uint4* tp = reinterpret_cast<const uint4*>(taps + it);
-    const uint4 ta = __ldg(tp), tb = __ldg(tp + 1);
+  auto emit = [&](int it, const uint4& ta, const uint4& tb) {
     RoiTap t;
     t.off[0] = (int)ta.x; t.off[1] = (int)ta.y; t.off[2] = (int)ta.z; t.off[3] = (int)ta.w;
     t.w[0] = __uint_as_float(tb.x); t.w[1] = __uint_as_float(tb.y); t.w[2] = __uint_as_float(tb.z); t.w[3] = __uint_as_float(tb.w);
@@ -151,6 +148,15 @@ roi_pool_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ f
         out_f32[((size_t)b * C + c0 + cp + 1) * npos + p] = v1;
       }
     }
+  };
+  for (int it0 = (blockIdx.y * NWARPS + warp) * POS_PER_WARP; it0 < total_items; it0 += 2 * stride) {
+    const int itA = it0 + sub, itB = itA + stride;
+    const bool okA = itA < total_items, okB = itB < total_items;
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+    if (okA) { const uint4* tp = reinterpret_cast<const uint4*>(taps + itA); a0 = __ldg(tp); a1 = __ldg(tp + 1); }
+    if (okB) { const uint4* tp = reinterpret_cast<const uint4*>(taps + itB); b0 = __ldg(tp); b1 = __ldg(tp + 1); }
+    if (okA) emit(itA, a0, a1);
+    if (okB) emit(itB, b0, b1);
   }
 }
 

@@ -368,7 +368,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             v[j] = x;
           }
         }
-        if (out_row >= 0) {
+        if (ep.lstm_c) {
+          // torch-rnn nn.LSTM cell on interleaved gate columns: 8 hidden units per 32-column chunk
+          if (out_row >= 0) {
+            const int j0 = nc >> 2;
+            float* cp = ep.lstm_c + (size_t)out_row * ep.lstm_H + j0;
+            float cprev[8];
+            if (ep.lstm_first) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) cprev[u] = 0.f;
+            } else {
+              const float4 c0 = reinterpret_cast<const float4*>(cp)[0], c1 = reinterpret_cast<const float4*>(cp)[1];
+              cprev[0] = c0.x; cprev[1] = c0.y; cprev[2] = c0.z; cprev[3] = c0.w;
+              cprev[4] = c1.x; cprev[5] = c1.y; cprev[6] = c1.z; cprev[7] = c1.w;
+            }
+            float cn[8];
+            uint32_t hh[4], ll[4];
+            __half hhv[8], hlv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float ig = 1.f / (1.f + expf(-v[4 * u + 0]));
+              const float fg = 1.f / (1.f + expf(-v[4 * u + 1]));
+              const float og = 1.f / (1.f + expf(-v[4 * u + 2]));
+              const float gg = tanhf(v[4 * u + 3]);
+              cn[u] = fg * cprev[u] + ig * gg;
+              split_f32(og * tanhf(cn[u]), hhv[u], hlv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              hh[u] = (uint32_t)__half_as_ushort(hhv[2 * u]) | ((uint32_t)__half_as_ushort(hhv[2 * u + 1]) << 16);
+              ll[u] = (uint32_t)__half_as_ushort(hlv[2 * u]) | ((uint32_t)__half_as_ushort(hlv[2 * u + 1]) << 16);
+            }
+            reinterpret_cast<float4*>(cp)[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            reinterpret_cast<float4*>(cp)[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+            const size_t ho = (size_t)out_row * ep.ldo + ep.out_col0 + j0;
+            *reinterpret_cast<uint4*>(ep.out_hi + ho) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(ep.out_lo + ho) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+          }
+        } else if (out_row >= 0) {
           const bool full = (nc + 32 <= pb.N);
           if (ep.out_hi) {
             __half* ph = ep.out_hi + (size_t)out_row * ep.ldo + ep.out_col0 + nc;
@@ -468,12 +505,21 @@ static int launch(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, con
   return DC_OK;
 }
 
+// Tile width by a bandwidth model: the kernel is bound by the per-SM operand fill rate (~45 B/clk measured), so the
+// cost of a launch is  rounds x bytes-per-k-block  with rounds = ceil(tiles / SMs); wider tiles amortise the A operand.
 static int pick_block_n(int N, int m_tiles) {
-  if (N <= 64) return 64;
-  // prefer the tile width that fills the 148 SMs best
-  const long t128 = (long)m_tiles * DC_CEIL_DIV(N, 128);
-  if (t128 < 148 && N % 64 == 0 && N > 64) return 64;
-  return 128;
+  const int cand[3] = {64, 128, 256};
+  int best = 64;
+  double best_cost = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    if (bn > 64 && N <= bn / 2) continue;                    // mostly-empty tile
+    const long tiles = (long)m_tiles * DC_CEIL_DIV(N, bn);
+    const long rounds = DC_CEIL_DIV(tiles, (long)g_num_sms);
+    const double cost = (double)rounds * (2.0 * A_PLANE_BYTES + 2.0 * bn * BLOCK_K * 2);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
 }
 
 }  // namespace tc
@@ -505,6 +551,7 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
   DC_REQUIRE(ctx, lda % 8 == 0 && ldb % 8 == 0 && a_plane_elems % 8 == 0 && b_plane_elems % 8 == 0, DC_E_UNSUPPORTED,
              "tc_gemm: leading dimensions / plane sizes must be multiples of 8 elements");
   DC_REQUIRE(ctx, !ep.out_hi || (ep.ldo % 8 == 0 && ep.out_col0 % 8 == 0), DC_E_UNSUPPORTED, "tc_gemm: split output alignment");
+  DC_REQUIRE(ctx, !ep.lstm_c || (ep.out_hi && N == 4 * ep.lstm_H && ep.lstm_H % 8 == 0), DC_E_UNSUPPORTED, "tc_gemm: LSTM epilogue shape");
   Problem pb{};
   pb.M = M; pb.N = N; pb.K = K;
   pb.num_k_blocks = K / BLOCK_K;
@@ -528,6 +575,7 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
     if (rc) return rc;
   }
   if (bn == 64) return launch<64, false, false>(ctx, ma, mb, pb, ep, st);
+  if (bn == 256) return launch<256, false, false>(ctx, ma, mb, pb, ep, st);
   return launch<128, false, false>(ctx, ma, mb, pb, ep, st);
 }
 
@@ -575,8 +623,10 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
   }
   if (fuse_pool) {
     if (bn == 64) return launch<64, true, true>(ctx, ma, mb, pb, ep, st);
+    if (bn == 256) return launch<256, true, true>(ctx, ma, mb, pb, ep, st);
     return launch<128, true, true>(ctx, ma, mb, pb, ep, st);
   }
   if (bn == 64) return launch<64, true, false>(ctx, ma, mb, pb, ep, st);
+  if (bn == 256) return launch<256, true, false>(ctx, ma, mb, pb, ep, st);
   return launch<128, true, false>(ctx, ma, mb, pb, ep, st);
 }
