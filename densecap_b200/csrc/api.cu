@@ -10,6 +10,7 @@
 struct Weight {
   __half* planes = nullptr;     // split planes (hi then lo), K-major
   size_t plane_elems = 0;
+  float inv_scale = 1.f;        // planes hold w * 2^s (keeps the lo plane out of fp16 subnormals); accumulators are multiplied by 2^-s
   float* f32 = nullptr;         // fp32 copy (biases, conv1_1, tiny heads)
   size_t n_f32 = 0;
   bool loaded = false;
@@ -325,6 +326,34 @@ static bool shape_is(const int64_t* s, int nd, std::initializer_list<int64_t> wa
   return true;
 }
 
+// Power-of-two pre-scale for a weight tensor.  NN weights are typically |w| < 0.25, for which the fp16 "lo" plane
+// (~ w * 2^-12) would be SUBNORMAL and the split would keep only ~2^-17 relative precision.  Scaling the tensor so
+// that max|w| lands in [2^14, 2^15) keeps hi and lo normal for every element within 2^-17 of the maximum; the exact
+// inverse power of two is applied to the fp32 accumulator in the GEMM epilogue.
+static int weight_scale(dc_ctx* ctx, const float* raw_dev, size_t n, float* scale_out, cudaStream_t st) {
+  float* d = nullptr;
+  DC_CHECK_CUDA(ctx, cudaMalloc((void**)&d, sizeof(float)));
+  cudaMemsetAsync(d, 0, sizeof(float), st);
+  int rc = k_absmax(ctx, raw_dev, n, d, st);
+  float m = 0.f;
+  cudaError_t e = cudaMemcpyAsync(&m, d, sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (rc) return rc;
+  if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "weight_scale: %s", cudaGetErrorString(e));
+  float sc = 1.f;
+  if (m > 0.f && m < 3.0e38f) {
+    int ex = 0;
+    frexpf(m, &ex);                 // m = f * 2^ex, f in [0.5, 1)
+    int shift = 15 - ex;            // max|w| * 2^shift in [2^14, 2^15)
+    if (shift > 40) shift = 40;
+    if (shift < -40) shift = -40;
+    sc = ldexpf(1.f, shift);
+  }
+  *scale_out = sc;
+  return DC_OK;
+}
+
 extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_host, const int64_t* shape, int ndim) {
   if (!ctx || !name || !data_host || !shape) return dc_set_error(ctx, DC_E_INVALID, "dc_load_weights: null argument");
   DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -371,7 +400,10 @@ extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_
         int rc = stage();
         if (rc) return rc;
         Weight& w = ctx->w[n];
-        rc = k_conv_weight_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, cout, cin, st);
+        float sc = 1.f;
+        if ((rc = weight_scale(ctx, raw, numel, &sc, st))) return finish(rc);
+        rc = k_conv_weight_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, cout, cin, st, sc);
+        w.inv_scale = 1.f / sc;
         w.loaded = true;
         return finish(rc);
       }
@@ -387,7 +419,10 @@ extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_
     int rc = stage();
     if (rc) return rc;
     Weight& w = ctx->w[n];
-    rc = k_conv_weight_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, (int)F, (int)C5, st);
+    float sc = 1.f;
+    if ((rc = weight_scale(ctx, raw, numel, &sc, st))) return finish(rc);
+    rc = k_conv_weight_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, (int)F, (int)C5, st, sc);
+    w.inv_scale = 1.f / sc;
     w.loaded = true;
     return finish(rc);
   }
@@ -400,7 +435,10 @@ extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_
     if (rc) return rc;
     Weight& w = ctx->w["rpn.head.weight"];
     const size_t off = box ? 0 : (size_t)4 * k * F;
-    rc = k_rowmajor_to_split(ctx, raw, w.planes + off, w.planes + w.plane_elems + off, numel, st);
+    // box and score rows share one GEMM, hence one (fixed) pre-scale: 2^12 suits the O(0.01..1) RPN head weights
+    const float sc = 4096.f;
+    rc = k_rowmajor_to_split(ctx, raw, w.planes + off, w.planes + w.plane_elems + off, numel, st, sc);
+    w.inv_scale = 1.f / sc;
     w.loaded = true;
     return finish(rc);
   }
@@ -411,7 +449,10 @@ extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_
     int rc = stage();
     if (rc) return rc;
     Weight& w = ctx->w[n];
-    rc = k_fc6_weight_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, (int)fc, (int)C5, (int)hw, st);
+    float sc = 1.f;
+    if ((rc = weight_scale(ctx, raw, numel, &sc, st))) return finish(rc);
+    rc = k_fc6_weight_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, (int)fc, (int)C5, (int)hw, st, sc);
+    w.inv_scale = 1.f / sc;
     w.loaded = true;
     return finish(rc);
   }
@@ -423,7 +464,11 @@ extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_
       int rc = stage();
       if (rc) return rc;
       Weight& w = ctx->w[n];
-      rc = k_rowmajor_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, numel, st);
+      float sc = 1.f;
+      // the lookup table is an ACTIVATION source (rows are copied into the x operand), so it stays unscaled
+      if (n != "lm.lookup.weight" && (rc = weight_scale(ctx, raw, numel, &sc, st))) return finish(rc);
+      rc = k_rowmajor_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, numel, st, sc);
+      w.inv_scale = 1.f / sc;
       w.loaded = true;
       return finish(rc);
     }
@@ -434,7 +479,10 @@ extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_
     if (rc) return rc;
     Weight& w = ctx->w[n];
     // rows of the B operand are gate-interleaved (n = 4*j + gate) so the LSTM cell fuses into the GEMM epilogue
-    rc = k_transpose_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, (int)(E + H), (int)(4 * H), (int)H, st);
+    float sc = 1.f;
+    if ((rc = weight_scale(ctx, raw, numel, &sc, st))) return finish(rc);
+    rc = k_transpose_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, (int)(E + H), (int)(4 * H), (int)H, st, sc);
+    w.inv_scale = 1.f / sc;
     w.loaded = true;
     return finish(rc);
   }
@@ -530,7 +578,9 @@ static int need_weight(dc_ctx* ctx, const char* name, Weight** out) {
 }
 
 static int gemm(dc_ctx* ctx, const __half* a_hi, size_t a_plane, int lda, const Weight& w, int ldb, int M, int N, int K,
-                const GemmEpilogue& ep, cudaStream_t st) {
+                const GemmEpilogue& ep_in, cudaStream_t st) {
+  GemmEpilogue ep = ep_in;
+  ep.acc_scale = w.inv_scale;
   if (ctx->cfg.engine == DC_ENGINE_TC) return k_tc_gemm(ctx, a_hi, a_plane, lda, w.planes, w.plane_elems, ldb, M, N, K, ep, st);
   return k_simt_gemm(ctx, a_hi, a_hi + a_plane, lda, w.planes, w.planes + w.plane_elems, ldb, M, N, K, ep, st);
 }
@@ -544,13 +594,13 @@ static int conv_layer(dc_ctx* ctx, const __half* x, size_t x_plane, __half* y, i
     const bool fuse = pool_after && ctx->cfg.fuse_pool && ceil_mode;
     if (fuse) {
       const size_t yp = (size_t)N * PH * PW * Cout;
-      int rc = k_tc_conv3x3(ctx, x, x_plane, wt.planes, wt.plane_elems, bias.f32, y, y + yp, N, H, W, Cin, Cout, 1, st);
+      int rc = k_tc_conv3x3(ctx, x, x_plane, wt.planes, wt.plane_elems, bias.f32, wt.inv_scale, y, y + yp, N, H, W, Cin, Cout, 1, st);
       *oh = PH; *ow = PW;
       return rc;
     }
     __half* dst = pool_after ? pool_tmp : y;
     const size_t yp = (size_t)N * H * W * Cout;
-    int rc = k_tc_conv3x3(ctx, x, x_plane, wt.planes, wt.plane_elems, bias.f32, dst, dst + yp, N, H, W, Cin, Cout, 0, st);
+    int rc = k_tc_conv3x3(ctx, x, x_plane, wt.planes, wt.plane_elems, bias.f32, wt.inv_scale, dst, dst + yp, N, H, W, Cin, Cout, 0, st);
     if (rc) return rc;
     if (pool_after) {
       const size_t pp = (size_t)N * PH * PW * Cout;
@@ -563,7 +613,7 @@ static int conv_layer(dc_ctx* ctx, const __half* x, size_t x_plane, __half* y, i
   }
   __half* dst = pool_after ? pool_tmp : y;
   const size_t yp = (size_t)N * H * W * Cout;
-  int rc = k_simt_conv3x3(ctx, x, x + x_plane, wt.planes, wt.planes + wt.plane_elems, bias.f32, dst, dst + yp, N, H, W, Cin, Cout, st);
+  int rc = k_simt_conv3x3(ctx, x, x + x_plane, wt.planes, wt.planes + wt.plane_elems, bias.f32, wt.inv_scale, dst, dst + yp, N, H, W, Cin, Cout, st);
   if (rc) return rc;
   if (pool_after) {
     const size_t pp = (size_t)N * PH * PW * Cout;
@@ -1077,8 +1127,11 @@ extern "C" int dc_linear(dc_ctx* ctx, const float* x, const float* w, const floa
   DC_REQUIRE(ctx, a && bw, DC_E_NOMEM, "dc_linear: temporary allocation failed");
   int rc;
   if ((rc = k_rowmajor_to_split(ctx, x, a, a + ap, (size_t)M * K, st))) return rc;
-  if ((rc = k_rowmajor_to_split(ctx, w, bw, bw + bp, (size_t)N * K, st))) return rc;
+  float sc = 1.f;
+  if ((rc = weight_scale(ctx, w, (size_t)N * K, &sc, st))) return rc;
+  if ((rc = k_rowmajor_to_split(ctx, w, bw, bw + bp, (size_t)N * K, st, sc))) return rc;
   GemmEpilogue ep;
+  ep.acc_scale = 1.f / sc;
   ep.bias = b; ep.relu = relu; ep.out_f32 = y; ep.ldf = N;
   if (engine == DC_ENGINE_TC) rc = k_tc_gemm(ctx, a, ap, K, bw, bp, K, M, N, K, ep, st);
   else rc = k_simt_gemm(ctx, a, a + ap, K, bw, bw + bp, K, M, N, K, ep, st);
@@ -1106,16 +1159,19 @@ extern "C" int dc_conv3x3_relu(dc_ctx* ctx, const float* x, const float* w, cons
   int rc;
   const size_t xn = (size_t)N * H * W * Cin, yn = (size_t)N * H * W * Cout, pn = (size_t)N * PH * PW * Cout;
   if ((rc = k_nchw_to_split_nhwc(ctx, x, xs, xs + xn, N, Cin, H, W, st))) return rc;
-  if ((rc = k_conv_weight_to_split(ctx, w, ws, ws + wp, Cout, Cin, st))) return rc;
+  float sc = 1.f;
+  if ((rc = weight_scale(ctx, w, (size_t)Cout * Cin * 9, &sc, st))) return rc;
+  if ((rc = k_conv_weight_to_split(ctx, w, ws, ws + wp, Cout, Cin, st, sc))) return rc;
+  const float isc = 1.f / sc;
   if (engine == DC_ENGINE_TC) {
     if (pool == 2) {        // fused pool epilogue
-      rc = k_tc_conv3x3(ctx, xs, xn, ws, wp, b, ps, ps + pn, N, H, W, Cin, Cout, 1, st);
+      rc = k_tc_conv3x3(ctx, xs, xn, ws, wp, b, isc, ps, ps + pn, N, H, W, Cin, Cout, 1, st);
     } else {
-      rc = k_tc_conv3x3(ctx, xs, xn, ws, wp, b, ys, ys + yn, N, H, W, Cin, Cout, 0, st);
+      rc = k_tc_conv3x3(ctx, xs, xn, ws, wp, b, isc, ys, ys + yn, N, H, W, Cin, Cout, 0, st);
       if (!rc && pool) rc = k_maxpool2x2_split(ctx, ys, ys + yn, ps, ps + pn, N, H, W, Cout, 1, st);
     }
   } else {
-    rc = k_simt_conv3x3(ctx, xs, xs + xn, ws, ws + wp, b, ys, ys + yn, N, H, W, Cin, Cout, st);
+    rc = k_simt_conv3x3(ctx, xs, xs + xn, ws, ws + wp, b, isc, ys, ys + yn, N, H, W, Cin, Cout, st);
     if (!rc && pool) rc = k_maxpool2x2_split(ctx, ys, ys + yn, ps, ps + pn, N, H, W, Cout, 1, st);
   }
   if (!rc) {

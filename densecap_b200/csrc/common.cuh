@@ -129,22 +129,25 @@ int k_roi_pool(dc_ctx*, const __half* feat_hi, const __half* feat_lo, const floa
 // layout_kernels.cu
 int k_nchw_to_split_nhwc(dc_ctx*, const float* in, __half* hi, __half* lo, int N, int C, int H, int W, cudaStream_t st);
 int k_split_nhwc_to_nchw(dc_ctx*, const __half* hi, const __half* lo, float* out, int N, int C, int H, int W, cudaStream_t st);
-int k_rowmajor_to_split(dc_ctx*, const float* in, __half* hi, __half* lo, size_t n, cudaStream_t st);
+// scale: values are multiplied by it (a power of two) before the split -- used for weights, see weight_scale()
+int k_rowmajor_to_split(dc_ctx*, const float* in, __half* hi, __half* lo, size_t n, cudaStream_t st, float scale = 1.f);
+int k_absmax(dc_ctx*, const float* in, size_t n, float* out_dev, cudaStream_t st);   // out_dev must be zeroed
 int k_split_to_rowmajor(dc_ctx*, const __half* hi, const __half* lo, float* out, size_t n, cudaStream_t st);
 int k_maxpool2x2_split(dc_ctx*, const __half* ihi, const __half* ilo, __half* ohi, __half* olo, int N, int H, int W, int C,
                        int ceil_mode, cudaStream_t st);
 // weight re-layout: conv (Cout,Cin,3,3) -> [Cout][(r*3+s)*Cin + ci] split; fc6 (out, C*HH*WW) (c,y,x) -> (y,x,c);
 // lstm ((D+H),4H) -> [4H][D+H]
-int k_conv_weight_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int Cout, int Cin, cudaStream_t st);
-int k_fc6_weight_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int out, int C, int hw, cudaStream_t st);
+int k_conv_weight_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int Cout, int Cin, cudaStream_t st, float scale = 1.f);
+int k_fc6_weight_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int out, int C, int hw, cudaStream_t st, float scale = 1.f);
 // interleave_h > 0: output row of input column c is 4*(c % H) + c / H (LSTM gate interleave, H = interleave_h)
-int k_transpose_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int rows, int cols, int interleave_h, cudaStream_t st);
+int k_transpose_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int rows, int cols, int interleave_h, cudaStream_t st, float scale = 1.f);
 // BCHW (K,C,HH,WW) fp32 -> split rows (K, HH*WW*C) in (y,x,c) order
 int k_bchw_to_split_rows(dc_ctx*, const float* in, __half* hi, __half* lo, int K, int C, int hw, cudaStream_t st);
 int k_bhwc_split_to_bchw(dc_ctx*, const __half* hi, const __half* lo, float* out, int K, int C, int hw, cudaStream_t st);
 
 // simt_kernels.cu : fp32 CUDA-core engine on the same split layout
 struct GemmEpilogue {
+  float acc_scale = 1.f;          // accumulator multiplier (exact power of two undoing the weight pre-scaling)
   const float* bias = nullptr;    // (N) or null
   int relu = 0;
   __half* out_hi = nullptr;       // split output planes (M, ldo) or null
@@ -163,7 +166,7 @@ struct GemmEpilogue {
 int k_simt_gemm(dc_ctx*, const __half* a_hi, const __half* a_lo, int lda, const __half* b_hi, const __half* b_lo, int ldb,
                 int M, int N, int K, GemmEpilogue ep, cudaStream_t st);
 int k_simt_conv3x3(dc_ctx*, const __half* x_hi, const __half* x_lo, const __half* w_hi, const __half* w_lo,
-                   const float* bias, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, cudaStream_t st);
+                   const float* bias, float acc_scale, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, cudaStream_t st);
 // conv1_1: NCHW fp32 (N,3,H,W) -> split NHWC (N,H,W,Cout), bias+ReLU fused.  w (Cout,3,3,3) fp32 reference layout.
 int k_conv_first(dc_ctx*, const float* img, const float* w, const float* bias, __half* y_hi, __half* y_lo,
                  int N, int H, int W, int Cout, cudaStream_t st);
@@ -177,7 +180,7 @@ int k_tc_gemm(dc_ctx*, const __half* a_planes, size_t a_plane_elems, int lda, co
               int M, int N, int K, GemmEpilogue ep, cudaStream_t st);
 // x: split NHWC (N,H,W,Cin) planes; w: split [Cout][9*Cin]; y: split NHWC (N,H,W,Cout) or pooled (N,ceil(H/2),ceil(W/2),Cout)
 int k_tc_conv3x3(dc_ctx*, const __half* x_planes, size_t x_plane_elems, const __half* w_planes, size_t w_plane_elems,
-                 const float* bias, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, int fuse_pool,
+                 const float* bias, float acc_scale, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, int fuse_pool,
                  cudaStream_t st);
 
 // lm_kernels.cu

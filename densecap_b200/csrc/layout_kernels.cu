@@ -66,17 +66,17 @@ int k_split_nhwc_to_nchw(dc_ctx* ctx, const __half* hi, const __half* lo, float*
   return DC_OK;
 }
 
-__global__ void rowmajor_to_split_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, size_t n) {
+__global__ void rowmajor_to_split_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, size_t n, float scale) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     __half h, l;
-    split_f32(in[i], h, l);
+    split_f32(in[i] * scale, h, l);
     hi[i] = h;
     lo[i] = l;
   }
 }
-int k_rowmajor_to_split(dc_ctx* ctx, const float* in, __half* hi, __half* lo, size_t n, cudaStream_t st) {
+int k_rowmajor_to_split(dc_ctx* ctx, const float* in, __half* hi, __half* lo, size_t n, cudaStream_t st, float scale) {
   if (n == 0) return DC_OK;
-  rowmajor_to_split_kernel<<<grid_for(n), 256, 0, st>>>(in, hi, lo, n);
+  rowmajor_to_split_kernel<<<grid_for(n), 256, 0, st>>>(in, hi, lo, n, scale);
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }
@@ -131,29 +131,29 @@ int k_maxpool2x2_split(dc_ctx* ctx, const __half* ihi, const __half* ilo, __half
 }
 
 // conv weight (Cout,Cin,3,3) -> split [Cout][(r*3+s)*Cin + ci]   (K-major B operand of the implicit GEMM)
-__global__ void conv_weight_to_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int Cout, int Cin) {
+__global__ void conv_weight_to_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int Cout, int Cin, float scale) {
   const size_t total = (size_t)Cout * 9 * Cin;
   for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
     const int ci = o % Cin;
     const int tap = (o / Cin) % 9;
     const int co = o / ((size_t)9 * Cin);
     __half h, l;
-    split_f32(w[((size_t)co * Cin + ci) * 9 + tap], h, l);
+    split_f32(w[((size_t)co * Cin + ci) * 9 + tap] * scale, h, l);
     hi[o] = h;
     lo[o] = l;
   }
 }
-int k_conv_weight_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, int Cout, int Cin, cudaStream_t st) {
+int k_conv_weight_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, int Cout, int Cin, cudaStream_t st, float scale) {
   const size_t total = (size_t)Cout * 9 * Cin;
   if (total == 0) return DC_OK;
-  conv_weight_to_split_kernel<<<grid_for(total), 256, 0, st>>>(w, hi, lo, Cout, Cin);
+  conv_weight_to_split_kernel<<<grid_for(total), 256, 0, st>>>(w, hi, lo, Cout, Cin, scale);
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }
 
 // fc6 weight (out, C*hw) with input order (c, pos) -> split (out, hw*C) with input order (pos, c),
 // so that the BHWC output of the ROI pooling feeds fc6 without the reference's nn.Transpose/View.
-__global__ void fc6_weight_to_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int out, int C, int hw) {
+__global__ void fc6_weight_to_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int out, int C, int hw, float scale) {
   const size_t K = (size_t)C * hw;
   const size_t total = (size_t)out * K;
   for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
@@ -161,22 +161,22 @@ __global__ void fc6_weight_to_split_kernel(const float* __restrict__ w, __half* 
     const int pos = (o / C) % hw;
     const size_t row = o / K;
     __half h, l;
-    split_f32(w[row * K + (size_t)c * hw + pos], h, l);
+    split_f32(w[row * K + (size_t)c * hw + pos] * scale, h, l);
     hi[o] = h;
     lo[o] = l;
   }
 }
-int k_fc6_weight_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, int out, int C, int hw, cudaStream_t st) {
+int k_fc6_weight_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, int out, int C, int hw, cudaStream_t st, float scale) {
   const size_t total = (size_t)out * C * hw;
   if (total == 0) return DC_OK;
-  fc6_weight_to_split_kernel<<<grid_for(total, 256, 148 * 64), 256, 0, st>>>(w, hi, lo, out, C, hw);
+  fc6_weight_to_split_kernel<<<grid_for(total, 256, 148 * 64), 256, 0, st>>>(w, hi, lo, out, C, hw, scale);
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }
 
 // (rows, cols) fp32 -> split (cols, rows)   (torch-rnn LSTM weight ((D+H),4H) -> [4H][D+H])
 __global__ void transpose_to_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int rows, int cols,
-                                          int interleave_h) {
+                                          int interleave_h, float scale) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -188,17 +188,17 @@ __global__ void transpose_to_split_kernel(const float* __restrict__ w, __half* _
     const int c = c0 + i, r = r0 + threadIdx.x;
     if (c < cols && r < rows) {
       __half h, l;
-      split_f32(tile[threadIdx.x][i], h, l);
+      split_f32(tile[threadIdx.x][i] * scale, h, l);
       const int oc = interleave_h > 0 ? 4 * (c % interleave_h) + c / interleave_h : c;
       hi[(size_t)oc * rows + r] = h;
       lo[(size_t)oc * rows + r] = l;
     }
   }
 }
-int k_transpose_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, int rows, int cols, int interleave_h, cudaStream_t st) {
+int k_transpose_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, int rows, int cols, int interleave_h, cudaStream_t st, float scale) {
   if ((size_t)rows * cols == 0) return DC_OK;
   dim3 grid(DC_CEIL_DIV(cols, 32), DC_CEIL_DIV(rows, 32)), block(32, 8);
-  transpose_to_split_kernel<<<grid, block, 0, st>>>(w, hi, lo, rows, cols, interleave_h);
+  transpose_to_split_kernel<<<grid, block, 0, st>>>(w, hi, lo, rows, cols, interleave_h, scale);
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }
@@ -237,6 +237,23 @@ int k_bhwc_split_to_bchw(dc_ctx* ctx, const __half* hi, const __half* lo, float*
   const size_t total = (size_t)K * C * hw;
   if (total == 0) return DC_OK;
   bhwc_split_to_bchw_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(hi, lo, out, K, C, hw);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+
+// max |x| of a tensor (used to pick the power-of-two weight pre-scale); out must be zero-initialised
+__global__ void absmax_kernel(const float* __restrict__ in, size_t n, float* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(in[i]);
+    if (v == v) m = fmaxf(m, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));   // valid for non-negative floats
+}
+int k_absmax(dc_ctx* ctx, const float* in, size_t n, float* out_dev, cudaStream_t st) {
+  if (n == 0) return DC_OK;
+  absmax_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(in, n, out_dev);
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }

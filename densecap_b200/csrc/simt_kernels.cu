@@ -11,7 +11,7 @@ __device__ __forceinline__ unsigned long long pack_argmax(float v, int col) {
 
 // Shared epilogue for one output element.
 __device__ __forceinline__ void gemm_epilogue_store(const GemmEpilogue& ep, int m, int n, float acc) {
-  float v = acc;
+  float v = acc * ep.acc_scale;
   if (ep.bias) v += ep.bias[n];
   if (ep.relu) v = fmaxf(v, 0.f);
   if (ep.out_hi) {
@@ -118,11 +118,12 @@ int k_simt_gemm(dc_ctx* ctx, const __half* a_hi, const __half* a_lo, int lda, co
 }
 
 int k_simt_conv3x3(dc_ctx* ctx, const __half* x_hi, const __half* x_lo, const __half* w_hi, const __half* w_lo, const float* bias,
-                   __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, cudaStream_t st) {
+                   float acc_scale, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, cudaStream_t st) {
   const int M = N * H * W, K = 9 * Cin;
   if (M <= 0) return DC_OK;
   GemmEpilogue ep;
   ep.bias = bias;
+  ep.acc_scale = acc_scale;
   ep.relu = 1;
   ep.out_hi = y_hi;
   ep.out_lo = y_lo;
@@ -135,8 +136,10 @@ int k_simt_conv3x3(dc_ctx* ctx, const __half* x_hi, const __half* x_lo, const __
 }
 
 // conv1_1 (VGG layer 1): Cin = 3, K = 27 -- no tensor-core shape; the layer is bound by the 110 MB split-fp16
-// output write, so a direct fp32 kernel: one thread = one pixel x 16 output channels, weights + bias in shared
-// memory read as broadcast LDS.128, 2 x 32-byte vector stores per plane.
+// output write, so a direct fp32 kernel.  A WARP handles 32 consecutive pixels x one group of 16 output channels:
+// the channel group is warp-uniform, so every weight read is a broadcast LDS.128 (one wavefront) -- with the group
+// varying across lanes the kernel was shared-memory-bandwidth bound (8 wavefronts per load, 207 us measured) --
+// image reads are 128-byte coalesced and each lane stores 2 x 32 B per plane.
 // img NCHW fp32 (reference input layout, DenseCapModel.lua:244) -> split NHWC, bias + ReLU fused.
 __global__ void __launch_bounds__(256)
 conv_first_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
@@ -150,10 +153,16 @@ conv_first_kernel(const float* __restrict__ img, const float* __restrict__ w, co
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
   __syncthreads();
   const int groups = Cout / 16;
-  const size_t total = (size_t)N * H * W * groups;
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int gq = t % groups;
-    const size_t pix = t / groups;
+  const size_t npix = (size_t)N * H * W;
+  const size_t pix_blocks = (npix + 31) / 32;
+  const size_t warp_items = pix_blocks * groups;
+  const int lane = threadIdx.x & 31;
+  const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t item = warp_global; item < warp_items; item += nwarps) {
+    const int gq = (int)(item % groups);                  // warp-uniform channel group
+    const size_t pix = (item / groups) * 32 + lane;
+    if (pix >= npix) continue;
     const int x = pix % W, y = (pix / W) % H, n = pix / ((size_t)W * H);
     float acc[16];
 #pragma unroll

@@ -19,6 +19,16 @@
 //   The accumulator is double buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps
 //   the MMAs of tile i+1.
 //
+// CG = 2 variant (cta_group::2): two CTAs of a cluster (an SM pair) compute one 256 x 256 tile.  Each CTA
+// loads its own 128 rows of A and HALF of the B tile (128 of the 256 rows); the leader CTA's single thread
+// issues tcgen05.mma.cta_group::2 (M = 256) which reads A/B from both CTAs' shared memory and writes each
+// CTA's own 128 x 256 accumulator.  Per CTA and K block that is 64 KB of operands for 1536 MMA cycles
+// (42 B/clk) instead of 64 KB per 768 cycles for the 1-CTA 128 x 128 tile -- the kernel is bound by the
+// ~45 B/clk/SM operand fill rate measured with ncu, so halving the bytes per MMA is what raises tensor
+// utilisation.  Barrier protocol (same smem offsets in both CTAs): TMA of both CTAs signals the LEADER's
+// full[] barrier (cta_group::2 TMA + peer-bit mask); tcgen05.commit multicasts to both CTAs' empty[] /
+// tmem_full[]; the epilogue threads of both CTAs arrive on the leader's tmem_empty[] (remote arrive).
+//
 // Implicit GEMM for the 3x3 convolution: activations are NHWC planes; an M tile is an 8x16 pixel patch
 // of one image, so that the A tile of filter tap (r,s) and channel block c0 is exactly the 5-D TMA box
 // {64 ch, 16 w, 8 h, 1 n, 2 planes} at (c0, w0+s-1, h0+r-1, n, 0); the zero padding of the convolution is
@@ -92,6 +102,58 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+// cta_group::2 TMA: data lands in the executing CTA's smem, complete_tx is signalled on the LEADER CTA's barrier
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+// arrive (no tx) on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the leader's MMAs, arriving on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -168,19 +230,26 @@ struct Problem {
   int OH, OW;                  // pooled output size (POOL) or H, W
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG>
 struct Cfg {
-  static constexpr uint32_t B_PLANE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_ROWS = BLOCK_N / CG;                         // rows of the B tile held by one CTA
+  static constexpr uint32_t B_PLANE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr uint32_t STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
-  static constexpr int STAGES = (BLOCK_N <= 64) ? 4 : (BLOCK_N <= 128 ? 3 : 2);
+  static constexpr int STAGES = (STAGE_BYTES <= 49152) ? 4 : (STAGE_BYTES <= 65536 ? 3 : 2);
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;   // power of two for 64/128/256
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
 };
 
-template <int BLOCK_N, bool CONV, bool POOL>
+template <int BLOCK_N, bool CONV, bool POOL, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Problem pb, GemmEpilogue ep) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, CG>;
+  // CG == 2: the two CTAs of a cluster form one 256-row tile; rank 0 (leader) issues the MMAs
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
+  const int worker = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // tile-scheduler slot
+  const int num_workers = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  if (CG == 2) cluster_sync_all();
   constexpr int STAGES = C::STAGES;
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment required by SWIZZLE_128B
@@ -202,18 +271,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), CG);          // one producer arrival per CTA of the pair (leader's barrier is the live one)
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), 128 * CG);  // all epilogue threads of the pair arrive on the leader's barrier
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_holder), C::TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc2(smem_u32(tmem_holder), C::TMEM_COLS);
+    else tmem_alloc(smem_u32(tmem_holder), C::TMEM_COLS);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
@@ -228,43 +300,52 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         int mt, nt;
         tile_coords(tile, mt, nt);
-        const int n0 = nt * BLOCK_N;
+        const int n0 = nt * BLOCK_N + (int)cta_rank * C::B_ROWS;     // this CTA's slice of the B tile
         int img = 0, h0 = 0, w0 = 0;
         if (CONV) {
-          const int per_img = pb.tiles_h * pb.tiles_w;
+          const int per_img = pb.tiles_h * pb.tiles_w;               // CG == 2: tiles_h counts 16-row pair tiles
           img = mt / per_img;
           const int r = mt % per_img;
-          h0 = (r / pb.tiles_w) * TILE_H;
+          h0 = ((r / pb.tiles_w) * CG + (int)cta_rank) * TILE_H;
           w0 = (r % pb.tiles_w) * TILE_W;
         }
+        const int m0 = (mt * CG + (int)cta_rank) * BLOCK_M;
         for (int kb = 0; kb < pb.num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + 2 * A_PLANE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          if (CG == 2) {
+            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);   // both CTAs' bytes land here
+            else mbar_arrive_remote(full_bar(stage), 0);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          }
           if (CONV) {
             const int tap = kb / pb.kb_per_tap;
             const int c0 = (kb % pb.kb_per_tap) * BLOCK_K;
             const int r = tap / 3, s = tap % 3;
-            tma_load_5d(a_dst, &tmap_a, full_bar(stage), c0, w0 + s - 1, h0 + r - 1, img, 0);
+            if (CG == 2) tma2_load_5d(a_dst, &tmap_a, full_bar(stage), c0, w0 + s - 1, h0 + r - 1, img, 0);
+            else tma_load_5d(a_dst, &tmap_a, full_bar(stage), c0, w0 + s - 1, h0 + r - 1, img, 0);
           } else {
-            tma_load_3d(a_dst, &tmap_a, full_bar(stage), kb * BLOCK_K, mt * BLOCK_M, 0);
+            if (CG == 2) tma2_load_3d(a_dst, &tmap_a, full_bar(stage), kb * BLOCK_K, m0, 0);
+            else tma_load_3d(a_dst, &tmap_a, full_bar(stage), kb * BLOCK_K, m0, 0);
           }
-          tma_load_3d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, n0, 0);
+          if (CG == 2) tma2_load_3d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, n0, 0);
+          else tma_load_3d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, n0, 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N);
+    if (lane == 0 && is_leader) {
+      constexpr uint32_t idesc = make_idesc_f16(BLOCK_M * CG, BLOCK_N);
       int stage = 0; uint32_t phase = 0;
       int iter = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -284,12 +365,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff);
             const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff);
             const uint64_t db_lo = make_kmajor_sw128_desc(b_lo + koff);
-            umma_f16(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);   // small terms first
-            umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
-            umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+            if (CG == 2) {
+              umma2_f16(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);
+              umma2_f16(d_tmem, da_hi, db_lo, idesc, 1);
+              umma2_f16(d_tmem, da_hi, db_hi, idesc, 1);
+            } else {
+              umma_f16(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);   // small terms first
+              umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
+              umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+            }
           }
-          umma_commit(empty_bar(stage));                       // smem stage free once these MMAs retire
-          if (kb == pb.num_k_blocks - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+          if (CG == 2) {
+            umma2_commit_mc(empty_bar(stage));                              // frees this stage in BOTH CTAs
+            if (kb == pb.num_k_blocks - 1) umma2_commit_mc(tfull_bar(acc)); // accumulators of both CTAs complete
+          } else {
+            umma_commit(empty_bar(stage));                       // smem stage free once these MMAs retire
+            if (kb == pb.num_k_blocks - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -299,7 +391,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row_in_tile = q * 32 + lane;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
       int mt, nt;
       tile_coords(tile, mt, nt);
       const int n0 = nt * BLOCK_N;
@@ -312,7 +404,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int per_img = pb.tiles_h * pb.tiles_w;
         const int img = mt / per_img;
         const int r = mt % per_img;
-        const int h0 = (r / pb.tiles_w) * TILE_H, w0 = (r % pb.tiles_w) * TILE_W;
+        const int h0 = ((r / pb.tiles_w) * CG + (int)cta_rank) * TILE_H, w0 = (r % pb.tiles_w) * TILE_W;
         const int h = h0 + row_in_tile / TILE_W, w = w0 + row_in_tile % TILE_W;
         in_bounds = (h < pb.H) && (w < pb.W);
         if (!POOL) {
@@ -324,7 +416,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             out_row = ((long long)img * pb.OH + ph) * pb.OW + pw;
         }
       } else {
-        const int m = mt * BLOCK_M + row_in_tile;
+        const int m = (mt * CG + (int)cta_rank) * BLOCK_M + row_in_tile;
         in_bounds = m < pb.M;
         if (in_bounds) out_row = m;
       }
@@ -353,7 +445,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(raw[j]);
+          float x = __uint_as_float(raw[j]) * ep.acc_scale;
           if (ep.bias) x += sbias[c * 32 + j];
           if (ep.relu) x = fmaxf(x, 0.f);
           v[j] = x;
@@ -458,17 +550,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       // TMEM reads of this accumulator are complete: hand it back to the MMA warp
       tcgen05_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      if (CG == 2 && !is_leader) mbar_arrive_remote(tempty_bar(acc), 0);
+      else mbar_arrive(tempty_bar(acc));
       if (ep.argmax && out_row >= 0 && best_c != 0x7fffffff)
         atomicMax(ep.argmax + out_row, pack_argmax_tc(best_v, best_c));
     }
   }
 
+  __syncwarp();     // lanes of the single-thread roles rejoin their warp before the aligned barriers below
   tcgen05_fence_before();
-  __syncthreads();
+  // CG == 2: neither CTA may exit (or free TMEM) while the leader can still read its smem / signal its barriers
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (CG == 2) tmem_dealloc2(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -489,35 +585,67 @@ static int encode_map(dc_ctx* ctx, CUtensorMap* map, const void* base, int rank,
   return DC_OK;
 }
 
-template <int BLOCK_N, bool CONV, bool POOL>
+template <int BLOCK_N, bool CONV, bool POOL, int CG>
 static int launch(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const Problem& pb, const GemmEpilogue& ep, cudaStream_t st) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, CG>;
   static bool attr_set = false;
+  auto kernel = tc_gemm_kernel<BLOCK_N, CONV, POOL, CG>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, CONV, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
     if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "tc_gemm smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int tiles = pb.m_tiles * pb.n_tiles;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  tc_gemm_kernel<BLOCK_N, CONV, POOL><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, pb, ep);
+  const int slots = g_num_sms / CG;                        // CTAs (CG=1) or CTA pairs (CG=2) resident at once
+  const int workers = tiles < slots ? tiles : slots;
+  if (CG == 1) {
+    kernel<<<workers, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, pb, ep);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(workers * 2);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ma, mb, pb, ep);
+    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "tc_gemm cluster launch: %s", cudaGetErrorString(e));
+  }
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }
 
-// Tile width by a bandwidth model: the kernel is bound by the per-SM operand fill rate (~45 B/clk measured), so the
-// cost of a launch is  rounds x bytes-per-k-block  with rounds = ceil(tiles / SMs); wider tiles amortise the A operand.
-static int pick_block_n(int N, int m_tiles) {
-  const int cand[3] = {64, 128, 256};
-  int best = 64;
+// Tile shape by a bandwidth model: the kernel is bound by the per-SM operand fill rate (~45 B/clk measured), so the
+// cost of a launch is  rounds x bytes-per-CTA-per-k-block  with rounds = ceil(tiles / slots); wider tiles amortise
+// the A operand and the 2-CTA (cta_group::2) shape additionally halves the B bytes each CTA has to fetch.
+struct TileCfg { int bn; int cg; };
+static int g_allow_cg2 = -1;
+static TileCfg pick_tile(int N, int m_tiles128, bool lstm) {
+  if (g_allow_cg2 < 0) {
+    const char* e = getenv("DC_TC_CG2");
+    g_allow_cg2 = (e && e[0] == '0') ? 0 : 1;
+  }
+  TileCfg best{64, 1};
   double best_cost = 1e30;
+  const int cand[3] = {64, 128, 256};
   for (int i = 0; i < 3; ++i) {
     const int bn = cand[i];
     if (bn > 64 && N <= bn / 2) continue;                    // mostly-empty tile
-    const long tiles = (long)m_tiles * DC_CEIL_DIV(N, bn);
+    const long tiles = (long)m_tiles128 * DC_CEIL_DIV(N, bn);
     const long rounds = DC_CEIL_DIV(tiles, (long)g_num_sms);
     const double cost = (double)rounds * (2.0 * A_PLANE_BYTES + 2.0 * bn * BLOCK_K * 2);
-    if (cost < best_cost) { best_cost = cost; best = bn; }
+    if (cost < best_cost) { best_cost = cost; best = TileCfg{bn, 1}; }
+  }
+  if (g_allow_cg2 && !lstm && N > 128 && m_tiles128 >= 2) {
+    const long tiles = (long)DC_CEIL_DIV(m_tiles128, 2) * DC_CEIL_DIV(N, 256);
+    const long rounds = DC_CEIL_DIV(tiles, (long)(g_num_sms / 2));
+    const double cost = (double)rounds * (2.0 * A_PLANE_BYTES + 2.0 * 128 * BLOCK_K * 2);
+    if (cost < 0.95 * best_cost) { best_cost = cost; best = TileCfg{256, 2}; }
   }
   return best;
 }
@@ -555,8 +683,10 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
   Problem pb{};
   pb.M = M; pb.N = N; pb.K = K;
   pb.num_k_blocks = K / BLOCK_K;
-  pb.m_tiles = DC_CEIL_DIV(M, BLOCK_M);
-  const int bn = pick_block_n(N, pb.m_tiles);
+  const int m_tiles128 = DC_CEIL_DIV(M, BLOCK_M);
+  const TileCfg tc_ = pick_tile(N, m_tiles128, ep.lstm_c != nullptr);
+  const int bn = tc_.bn, cg = tc_.cg;
+  pb.m_tiles = DC_CEIL_DIV(m_tiles128, cg);
   pb.n_tiles = DC_CEIL_DIV(N, bn);
   pb.m_fastest = pb.m_tiles <= pb.n_tiles;
   CUtensorMap ma, mb;
@@ -570,17 +700,19 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
   {
     const uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, 2};
     const uint64_t str[2] = {(uint64_t)ldb * 2, (uint64_t)b_plane_elems * 2};
-    const uint32_t box[3] = {BLOCK_K, (uint32_t)bn, 2};
+    const uint32_t box[3] = {BLOCK_K, (uint32_t)(bn / cg), 2};
     int rc = encode_map(ctx, &mb, b_planes, 3, dims, str, box);
     if (rc) return rc;
   }
-  if (bn == 64) return launch<64, false, false>(ctx, ma, mb, pb, ep, st);
-  if (bn == 256) return launch<256, false, false>(ctx, ma, mb, pb, ep, st);
-  return launch<128, false, false>(ctx, ma, mb, pb, ep, st);
+  if (cg == 2) return launch<256, false, false, 2>(ctx, ma, mb, pb, ep, st);
+  if (bn == 64) return launch<64, false, false, 1>(ctx, ma, mb, pb, ep, st);
+  if (bn == 256) return launch<256, false, false, 1>(ctx, ma, mb, pb, ep, st);
+  return launch<128, false, false, 1>(ctx, ma, mb, pb, ep, st);
 }
 
 int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, const __half* w_planes, size_t w_plane_elems,
-                 const float* bias, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, int fuse_pool, cudaStream_t st) {
+                 const float* bias, float acc_scale, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, int fuse_pool,
+                 cudaStream_t st) {
   using namespace tc;
   if (N <= 0 || H <= 0 || W <= 0) return DC_OK;
   DC_REQUIRE(ctx, Cin % BLOCK_K == 0, DC_E_UNSUPPORTED, "tc_conv3x3: Cin=%d must be a multiple of 64", Cin);
@@ -591,17 +723,20 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
   pb.K = 9 * Cin;
   pb.num_k_blocks = 9 * pb.kb_per_tap;
   pb.N = Cout;
-  pb.tiles_h = DC_CEIL_DIV(H, TILE_H);
   pb.tiles_w = DC_CEIL_DIV(W, TILE_W);
+  const int m_tiles128 = N * DC_CEIL_DIV(H, TILE_H) * pb.tiles_w;
+  const TileCfg tc_ = pick_tile(Cout, m_tiles128, false);
+  const int bn = tc_.bn, cg = tc_.cg;
+  pb.tiles_h = DC_CEIL_DIV(H, TILE_H * cg);          // cg == 2: a pair tile covers 16 image rows (two stacked 8x16 patches)
   pb.m_tiles = N * pb.tiles_h * pb.tiles_w;
-  pb.M = pb.m_tiles * BLOCK_M;
+  pb.M = pb.m_tiles * BLOCK_M * cg;
   pb.OH = fuse_pool ? (H + 1) / 2 : H;
   pb.OW = fuse_pool ? (W + 1) / 2 : W;
-  const int bn = pick_block_n(Cout, pb.m_tiles);
   pb.n_tiles = DC_CEIL_DIV(Cout, bn);
   pb.m_fastest = 0;   // n fastest: CTAs sharing an activation patch run together, the patch stays in L2
   GemmEpilogue ep;
   ep.bias = bias;
+  ep.acc_scale = acc_scale;
   ep.relu = 1;
   ep.out_hi = y_hi;
   ep.out_lo = y_lo;
@@ -617,16 +752,18 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
   {
     const uint64_t dims[3] = {(uint64_t)pb.K, (uint64_t)Cout, 2};
     const uint64_t str[2] = {(uint64_t)pb.K * 2, (uint64_t)w_plane_elems * 2};
-    const uint32_t box[3] = {BLOCK_K, (uint32_t)bn, 2};
+    const uint32_t box[3] = {BLOCK_K, (uint32_t)(bn / cg), 2};
     int rc = encode_map(ctx, &mb, w_planes, 3, dims, str, box);
     if (rc) return rc;
   }
   if (fuse_pool) {
-    if (bn == 64) return launch<64, true, true>(ctx, ma, mb, pb, ep, st);
-    if (bn == 256) return launch<256, true, true>(ctx, ma, mb, pb, ep, st);
-    return launch<128, true, true>(ctx, ma, mb, pb, ep, st);
+    if (cg == 2) return launch<256, true, true, 2>(ctx, ma, mb, pb, ep, st);
+    if (bn == 64) return launch<64, true, true, 1>(ctx, ma, mb, pb, ep, st);
+    if (bn == 256) return launch<256, true, true, 1>(ctx, ma, mb, pb, ep, st);
+    return launch<128, true, true, 1>(ctx, ma, mb, pb, ep, st);
   }
-  if (bn == 64) return launch<64, true, false>(ctx, ma, mb, pb, ep, st);
-  if (bn == 256) return launch<256, true, false>(ctx, ma, mb, pb, ep, st);
-  return launch<128, true, false>(ctx, ma, mb, pb, ep, st);
+  if (cg == 2) return launch<256, true, false, 2>(ctx, ma, mb, pb, ep, st);
+  if (bn == 64) return launch<64, true, false, 1>(ctx, ma, mb, pb, ep, st);
+  if (bn == 256) return launch<256, true, false, 1>(ctx, ma, mb, pb, ep, st);
+  return launch<128, true, false, 1>(ctx, ma, mb, pb, ep, st);
 }

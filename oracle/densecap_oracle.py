@@ -32,11 +32,31 @@ from __future__ import annotations
 import math
 import numpy as np
 
-f32 = np.float32
+# Working precision.  float32 = the reference's arithmetic (default, what parity is judged against).
+# `with precision(np.float64):` re-runs the SAME restatement in float64 ("gold") so that tests can measure the
+# fp32 summation-order noise floor of the reference path itself and budget tolerances against it.
+_DT = [np.float32]
+
+
+class precision:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        self.prev = _DT[0]
+        _DT[0] = self.dtype
+        return self
+
+    def __exit__(self, *a):
+        _DT[0] = self.prev
+
+
+def f32(v):
+    return _DT[0](v)
 
 
 def _f(x):
-    return np.asarray(x, dtype=np.float32)
+    return np.asarray(x, dtype=_DT[0])
 
 
 # ----------------------------------------------------------------------------------------
@@ -45,7 +65,7 @@ def _f(x):
 # same recipe ((float)exp((double)x)) so both sides agree bit for bit.
 # ----------------------------------------------------------------------------------------
 def exp_f32(x):
-    return np.exp(np.asarray(x, dtype=np.float64)).astype(np.float32)
+    return np.exp(np.asarray(x, dtype=np.float64)).astype(_DT[0])
 
 
 # ----------------------------------------------------------------------------------------
@@ -55,9 +75,9 @@ def make_anchors(N, H, W, x0, y0, sx, sy, anchors):
     """anchors: (2,k) widths/heights.  Returns (N,4k,H,W) fp32, channel 4a+{0:xc,1:yc,2:w,3:h}."""
     anchors = _f(anchors)
     k = anchors.shape[1]
-    xc = np.arange(W, dtype=np.float32) * f32(sx) + f32(x0)      # :mul(sx):add(x0)
-    yc = np.arange(H, dtype=np.float32) * f32(sy) + f32(y0)
-    out = np.empty((N, k, 4, H, W), np.float32)
+    xc = np.arange(W, dtype=_DT[0]) * f32(sx) + f32(x0)      # :mul(sx):add(x0)
+    yc = np.arange(H, dtype=_DT[0]) * f32(sy) + f32(y0)
+    out = np.empty((N, k, 4, H, W), _DT[0])
     out[:, :, 0] = xc[None, None, None, :]
     out[:, :, 1] = yc[None, None, :, None]
     out[:, :, 2] = anchors[0][None, :, None, None]
@@ -118,8 +138,8 @@ def invert_box_transform(anchor_boxes, target_boxes):
     out = np.empty_like(t)
     out[:, 0] = (t[:, 0] - a[:, 0]) / a[:, 2]
     out[:, 1] = (t[:, 1] - a[:, 1]) / a[:, 3]
-    out[:, 2] = np.log((t[:, 2] / a[:, 2]).astype(np.float64)).astype(np.float32)
-    out[:, 3] = np.log((t[:, 3] / a[:, 3]).astype(np.float64)).astype(np.float32)
+    out[:, 2] = np.log((t[:, 2] / a[:, 2]).astype(np.float64)).astype(_DT[0])
+    out[:, 3] = np.log((t[:, 3] / a[:, 3]).astype(np.float64)).astype(_DT[0])
     return out
 
 
@@ -226,7 +246,7 @@ def nms(boxes_scores, overlap, max_boxes=None):
 def box_to_affine(boxes, H, W):
     b = _f(boxes)
     B = b.shape[0]
-    th = np.zeros((B, 2, 3), np.float32)
+    th = np.zeros((B, 2, 3), _DT[0])
     th[:, 1, 2] = (b[:, 0] * f32(2) + f32(-1 - W)) / f32(W - 1)
     th[:, 0, 2] = (b[:, 1] * f32(2) + f32(-1 - H)) / f32(H - 1)
     th[:, 1, 1] = b[:, 2] / f32(W)
@@ -237,7 +257,7 @@ def box_to_affine(boxes, H, W):
 # densecap/modules/BoxToAffine.lua:96-118
 def box_to_affine_backward(grad_theta, H, W):
     g = _f(grad_theta)
-    gi = np.zeros((g.shape[0], 4), np.float32)
+    gi = np.zeros((g.shape[0], 4), _DT[0])
     gi[:, 0] = g[:, 1, 2] * f32(2 / (W - 1))
     gi[:, 1] = g[:, 0, 2] * f32(2 / (H - 1))
     gi[:, 2] = g[:, 1, 1] * f32(1 / W)
@@ -253,12 +273,12 @@ def box_to_affine_backward(grad_theta, H, W):
 # ----------------------------------------------------------------------------------------
 def affine_grid(theta, HH, WW):
     th = _f(theta)
-    ys = np.array([-1 + (i / (HH - 1)) * 2 for i in range(HH)], np.float64).astype(np.float32)
-    xs = np.array([-1 + (j / (WW - 1)) * 2 for j in range(WW)], np.float64).astype(np.float32)
+    ys = np.array([-1 + (i / (HH - 1)) * 2 for i in range(HH)], np.float64).astype(_DT[0])
+    xs = np.array([-1 + (j / (WW - 1)) * 2 for j in range(WW)], np.float64).astype(_DT[0])
     Y = ys[None, :, None]; X = xs[None, None, :]
     gy = (th[:, 0, 0, None, None] * Y + th[:, 0, 1, None, None] * X) + th[:, 0, 2, None, None]
     gx = (th[:, 1, 0, None, None] * Y + th[:, 1, 1, None, None] * X) + th[:, 1, 2, None, None]
-    return np.stack([gy, gx], axis=-1).astype(np.float32)          # (B,HH,WW,2)
+    return np.stack([gy, gx], axis=-1).astype(_DT[0])          # (B,HH,WW,2)
 
 
 # ----------------------------------------------------------------------------------------
@@ -290,7 +310,7 @@ def bilinear_sample(feats_hwc, grids):
     out = out + (omx * wy_) * TR
     out = out + (wx_ * omy) * BL
     out = out + (omx * omy) * BR
-    return out.astype(np.float32)
+    return out.astype(_DT[0])
 
 
 # stnbhwd BilinearSamplerBHWD_updateGradInput (App. B2), summed over the batch as in
@@ -319,7 +339,7 @@ def bilinear_sample_backward(feats_hwc, grids, grad_out):
         dots[name] = (v * go64).sum(-1)
     ggrid[..., 0] = (-wx * dots["TL"] + wx * dots["BL"] - (1 - wx) * dots["TR"] + (1 - wx) * dots["BR"]) * (H - 1) / 2
     ggrid[..., 1] = (-wy * dots["TL"] + wy * dots["TR"] - (1 - wy) * dots["BL"] + (1 - wy) * dots["BR"]) * (W - 1) / 2
-    return gfeat.astype(np.float32), ggrid.astype(np.float32)
+    return gfeat.astype(_DT[0]), ggrid.astype(_DT[0])
 
 
 # ----------------------------------------------------------------------------------------
@@ -351,7 +371,7 @@ def box_iou(box1, box2):
     inter = w * h
     with np.errstate(divide="ignore", invalid="ignore"):
         out = (f32(1) / ((a1 - inter) + a2)) * inter          # add(a1,-1,inter):add(a2):pow(-1):cmul(inter)
-    return out.astype(np.float32)
+    return out.astype(_DT[0])
 
 
 # ========================================================================================
@@ -472,7 +492,7 @@ def recog_head(roi_features, roi_boxes, weights):
 
 
 def sigmoid(x):
-    return (1.0 / (1.0 + np.exp(-x.astype(np.float64)))).astype(np.float32)
+    return (1.0 / (1.0 + np.exp(-x.astype(np.float64)))).astype(_DT[0])
 
 
 # [3P, parity unpinned] jcjohnson/torch-rnn nn.LSTM step, SURVEY.md App. B3:
@@ -481,9 +501,9 @@ def lstm_step(x, h, c, W, b):
     D = x.shape[1]; H = h.shape[1]
     a = linear(x, W[:D].T, None) + linear(h, W[D:].T, None) + _f(b)[None, :]
     i = sigmoid(a[:, 0:H]); f = sigmoid(a[:, H:2 * H]); o = sigmoid(a[:, 2 * H:3 * H])
-    g = np.tanh(a[:, 3 * H:4 * H].astype(np.float64)).astype(np.float32)
+    g = np.tanh(a[:, 3 * H:4 * H].astype(np.float64)).astype(_DT[0])
     c2 = f * c + i * g
-    h2 = o * np.tanh(c2.astype(np.float64)).astype(np.float32)
+    h2 = o * np.tanh(c2.astype(np.float64)).astype(_DT[0])
     return h2, c2
 
 
@@ -495,7 +515,7 @@ def lm_sample(codes, weights, seq_length, return_logits=False):
     V1 = weights["lm.vocab.weight"].shape[0]            # V+1
     START = V1                                           # START = END = V+1  (:32-33)
     enc = relu(linear(codes, weights["lm.encoder.weight"], weights["lm.encoder.bias"]))
-    h = np.zeros((N, H), np.float32); c = np.zeros((N, H), np.float32)
+    h = np.zeros((N, H), _DT[0]); c = np.zeros((N, H), _DT[0])
     h, c = lstm_step(enc, h, c, Wl, bl)                  # first step: image vector, output ignored (:312-313)
     seq = np.zeros((N, seq_length), np.int64)
     logits_all = []
