@@ -187,7 +187,7 @@ nms_cluster_kernel(const float4* __restrict__ sb, const int32_t* __restrict__ or
   const int worker = (int)rank_in_cluster * (NMS_THREADS / 64) + sub;
 
   for (int base = 0; base < n; base += NMS_M) {
-    const int kept0 = state->count;                          // written by CTA 0 before the previous cluster barrier
+    const int kept0 = __ldcg(&state->count);                 // written by CTA 0 before the previous cluster barrier (read at L2)
     if (kept0 >= cap) break;
     const int cn_total = min(NMS_M, n - base);
     const int cwords = DC_CEIL_DIV(cn_total, 64);
@@ -229,7 +229,9 @@ nms_cluster_kernel(const float4* __restrict__ sb, const int32_t* __restrict__ or
       } else {
         const int r = rb * 64 + lrow;
         if (r < kept0) {
-          const float4 pb = kept_boxes[r];
+          // kept_boxes is appended to by CTA 0 between cluster barriers: read it at L2 (another SM's L1 may hold a
+          // line that was only partly written when it was cached in an earlier super-chunk)
+          const float4 pb = __ldcg(kept_boxes + r);
           const float pa = nms_area(pb);
           for (int t = 0; t < cn; ++t) {
             const float4 q = __ldg(sb + base + col0 + t);

