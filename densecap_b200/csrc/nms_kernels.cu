@@ -96,30 +96,30 @@ nms_rank_kernel(const uint64_t* __restrict__ keys, int n_max, const int32_t* __r
   const uint32_t sa = (ia < n) ? (uint32_t)(keys[ia] >> 32) : 0xFFFFFFFFu;
   const uint32_t sb = (ib < n) ? (uint32_t)(keys[ib] >> 32) : 0xFFFFFFFFu;
   int ra = 0, rb = 0;
-  const int jn4 = (jn + 3) & ~3;
-  if (j0 >= i0 + 512) {                 // every j > every i of this block: ties count
-    for (int t = 0; t < jn4; t += 4) {
-      const uint4 k = *reinterpret_cast<const uint4*>(tile + t);
-      ra += (k.x >= sa) + (k.y >= sa) + (k.z >= sa) + (k.w >= sa);
-      rb += (k.x >= sb) + (k.y >= sb) + (k.z >= sb) + (k.w >= sb);
-    }
-    // padding entries are 0 and can only satisfy 0 >= s when s == 0 (score bits of -NaN): remove them again
-    const int pad = jn4 - jn;
-    if (sa == 0u) ra -= pad;
-    if (sb == 0u) rb -= pad;
-  } else if (j0 + RANK_SLICE <= i0) {   // every j < every i: strict
-    for (int t = 0; t < jn4; t += 4) {
+  // j < i0: strict compare; j in [i0, i0+512): explicit tie-break; j >= i0+512: ties count.
+  const int t_lo = min(max(i0 - j0, 0), jn);              // first t of the overlapping segment
+  const int t_hi = min(max(i0 + 512 - j0, 0), jn);        // first t after it
+  {
+    int t = 0;
+    for (; t + 4 <= (t_lo & ~3); t += 4) {                  // vectorised part of the strict segment
       const uint4 k = *reinterpret_cast<const uint4*>(tile + t);
       ra += (k.x > sa) + (k.y > sa) + (k.z > sa) + (k.w > sa);
       rb += (k.x > sb) + (k.y > sb) + (k.z > sb) + (k.w > sb);
     }
-  } else {                              // overlapping slice: explicit tie-break on the index
-    for (int t = 0; t < jn; ++t) {
+    for (; t < t_lo; ++t) { const uint32_t k = tile[t]; ra += (k > sa); rb += (k > sb); }
+    for (; t < t_hi; ++t) {                                 // overlap: index tie-break
       const uint32_t k = tile[t];
       const int j = j0 + t;
       ra += (k > sa) | ((k == sa) & (j > ia));
       rb += (k > sb) | ((k == sb) & (j > ib));
     }
+    for (; t < jn && (t & 3); ++t) { const uint32_t k = tile[t]; ra += (k >= sa); rb += (k >= sb); }
+    for (; t + 4 <= jn; t += 4) {                           // vectorised part of the >= segment
+      const uint4 k = *reinterpret_cast<const uint4*>(tile + t);
+      ra += (k.x >= sa) + (k.y >= sa) + (k.z >= sa) + (k.w >= sa);
+      rb += (k.x >= sb) + (k.y >= sb) + (k.z >= sb) + (k.w >= sb);
+    }
+    for (; t < jn; ++t) { const uint32_t k = tile[t]; ra += (k >= sa); rb += (k >= sb); }
   }
   if (ia < n && ra) atomicAdd(rank + ia, ra);
   if (ib < n && rb) atomicAdd(rank + ib, rb);
@@ -151,16 +151,17 @@ __device__ __forceinline__ bool nms_suppresses(float4 p, float ap, float4 q, flo
   return !(iou <= thresh);
 }
 
-// Mask + scan over all super-chunks in ONE launch of a single thread-block cluster (NMS_CTAS CTAs, co-scheduled by
-// the hardware, synchronised with barrier.cluster): per super-chunk
-//   phase A (all CTAs) : 64x64 mask tiles -- upper-triangular tiles of the chunk against itself, and tiles of the
-//                        boxes kept so far against the chunk -- written to global memory;
-//   phase B (CTA 0)    : chunk mask -> shared memory (128 KB), inherited suppression bits OR-reduced from the
-//                        kept-so-far rows, then the sequential scan in 64-box steps by one warp;
-// and the loop ends as soon as max_boxes survivors exist or the candidates are exhausted.  A cluster (rather than
-// a grid-wide cooperative launch) keeps the footprint at NMS_CTAS SMs, so the NMS of one image overlaps the GEMMs
-// and the NMS of other images running on other streams.
+// ---------------------------------------------------------------------------------------------------------
+// Super-chunk machinery.  Phase A = 64x64 suppression tiles (upper-triangular tiles of the chunk against itself +
+// tiles of the boxes kept so far against the chunk), phase B = scan of the chunk out of shared memory.
+// Launch schedule (k_nms): the first NMS_WIDE_CHUNKS super-chunks run phase A as a WIDE grid (one 64-thread block
+// per tile, all SMs) followed by a one-block scan kernel; both exit immediately once max_boxes survivors exist, so in
+// the common case (1000 picks within the first ~1300 candidates) the whole NMS is a handful of short launches.
+// Candidates beyond those super-chunks (rare: NMS that really has to walk the whole list) are handled by ONE launch
+// of a single thread-block cluster that loops phase A / phase B with barrier.cluster in between.
+// ---------------------------------------------------------------------------------------------------------
 constexpr int NMS_CTAS = 8;
+constexpr int NMS_WIDE_CHUNKS = 2;
 
 __device__ __forceinline__ void nms_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -171,170 +172,223 @@ __device__ __forceinline__ uint32_t nms_cluster_ctarank() {
   return r;
 }
 
+// One 64x64 tile by 64 threads (lrow = row inside the tile).
+__device__ __forceinline__ void nms_mask_tile(int tile, int lrow, const float4* __restrict__ sb, int base, int cn_total, int cwords,
+                                              int kept0, float thresh, uint64_t* __restrict__ mask_intra,
+                                              uint64_t* __restrict__ mask_prev, const float4* __restrict__ kept_boxes) {
+  const int intra_tiles = cwords * (cwords + 1) / 2;       // (rb, cb) with cb >= rb, row-major
+  int rb, cb;
+  const bool intra = tile < intra_tiles;
+  if (intra) {
+    int t = tile;
+    rb = 0;
+    while (t >= cwords - rb) { t -= cwords - rb; ++rb; }
+    cb = rb + t;
+  } else {
+    const int t = tile - intra_tiles;
+    rb = t / cwords;
+    cb = t % cwords;
+  }
+  const int col0 = cb * 64;
+  const int cn = min(64, cn_total - col0);
+  uint64_t bits = 0;
+  if (intra) {
+    const int p_local = rb * 64 + lrow;
+    if (p_local < cn_total) {
+      const float4 pb = sb[base + p_local];
+      const float pa = nms_area(pb);
+      const int t0 = max(0, p_local + 1 - col0);         // only q > p
+      for (int t = t0; t < cn; ++t) {
+        const float4 q = __ldg(sb + base + col0 + t);    // same address for the 64 threads of the tile: broadcast
+        if (nms_suppresses(pb, pa, q, nms_area(q), thresh)) bits |= (1ull << t);
+      }
+    }
+    mask_intra[(size_t)p_local * NMS_W + cb] = bits;
+  } else {
+    const int r = rb * 64 + lrow;
+    if (r < kept0) {
+      // kept_boxes is appended to between launches / cluster barriers: read it at L2 (another SM's L1 may hold a line
+      // that was only partly written when it was cached for an earlier super-chunk)
+      const float4 pb = __ldcg(kept_boxes + r);
+      const float pa = nms_area(pb);
+      for (int t = 0; t < cn; ++t) {
+        const float4 q = __ldg(sb + base + col0 + t);
+        if (nms_suppresses(pb, pa, q, nms_area(q), thresh)) bits |= (1ull << t);
+      }
+      mask_prev[(size_t)r * NMS_W + cb] = bits;
+    }
+  }
+}
+
+// Scan of one super-chunk by one CTA of NMS_THREADS threads.  smem_mask: [NMS_M][NMS_W] words.
+__device__ __forceinline__ void nms_scan_chunk(uint64_t* smem_mask, uint64_t* s_removed, int* s_pos, int* s_cnt, const float4* __restrict__ sb,
+                                               const int32_t* __restrict__ order, int base, int cn_total, int cwords, int kept0, int cap,
+                                               const uint64_t* __restrict__ mask_intra, const uint64_t* __restrict__ mask_prev,
+                                               float4* __restrict__ kept_boxes, NmsState* __restrict__ state, int64_t* __restrict__ idx_out,
+                                               int32_t* __restrict__ idx32_out, int32_t* __restrict__ count_out) {
+  const int tid = threadIdx.x;
+  {
+    // chunk mask -> shared memory, 8 independent loads in flight per thread (a plain copy loop serialises on L2 latency)
+    const int total_words = cn_total * NMS_W;
+    for (int i0 = tid; i0 < total_words; i0 += NMS_THREADS * 8) {
+      uint64_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * NMS_THREADS;
+        v[u] = (i < total_words) ? __ldcg(mask_intra + i) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * NMS_THREADS;
+        if (i < total_words) smem_mask[i] = v[u];
+      }
+    }
+  }
+  if (tid < NMS_W) s_removed[tid] = 0;
+  __syncthreads();
+  {
+    // suppression bits inherited from the boxes kept by earlier super-chunks
+    const int w = tid & (NMS_W - 1);
+    uint64_t acc = 0;
+    constexpr int RSTEP = NMS_THREADS / NMS_W;
+    if (w < cwords) {
+      for (int r0 = tid >> 4; r0 < kept0; r0 += RSTEP * 8) {
+        uint64_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = r0 + u * RSTEP;
+          v[u] = (r < kept0) ? __ldcg(mask_prev + (size_t)r * NMS_W + w) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc |= v[u];
+      }
+    }
+    if (acc) atomicOr((unsigned long long*)&s_removed[w], (unsigned long long)acc);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int lane = tid;
+    int count = kept0;
+    uint64_t my_removed = (lane < NMS_W) ? s_removed[lane] : 0ull;    // lane w owns removed word w
+    for (int c = 0; c < cwords && count < cap; ++c) {
+      const int lim = min(64, cn_total - c * 64);
+      const uint64_t d0 = (lane < lim) ? smem_mask[(size_t)(c * 64 + lane) * NMS_W + c] : 0ull;
+      const uint64_t d1 = (lane + 32 < lim) ? smem_mask[(size_t)(c * 64 + 32 + lane) * NMS_W + c] : 0ull;
+      const uint64_t cur = __shfl_sync(0xffffffffu, my_removed, c);
+      uint64_t keep = 0;
+      const int before = count;
+      // visit only candidates that are still alive; each survivor kills the later ones it suppresses
+      uint64_t alive = ~cur & ((lim == 64) ? ~0ull : ((1ull << lim) - 1ull));
+      while (alive && count < cap) {
+        const int i = __ffsll((long long)alive) - 1;
+        const uint64_t row = __shfl_sync(0xffffffffu, (i < 32) ? d0 : d1, i & 31);
+        keep |= (1ull << i);
+        ++count;
+        alive &= ~row;
+        alive &= ~(1ull << i);
+      }
+      // remember the sorted positions of the survivors (index translation + box copy happen after the loop, in parallel)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int i = lane + 32 * half;
+        if ((keep >> i) & 1ull) s_pos[before - kept0 + __popcll(keep & ((1ull << i) - 1ull))] = base + c * 64 + i;
+      }
+      // propagate the suppression rows of the survivors to the later words of this super-chunk
+      if (lane > c && lane < cwords) {
+        uint64_t k = keep, acc = 0;
+        while (k) {
+          const int i = __ffsll((long long)k) - 1;
+          k &= k - 1;
+          acc |= smem_mask[(size_t)(c * 64 + i) * NMS_W + lane];
+        }
+        my_removed |= acc;
+      }
+    }
+    if (lane == 0) *s_cnt = count;
+  }
+  __syncthreads();
+  const int count = *s_cnt;
+  // emit survivors in scan order (= decreasing score) and keep their boxes for later super-chunks
+  for (int e = tid; e < count - kept0; e += NMS_THREADS) {
+    const int sp = s_pos[e];
+    const int bi = order[sp];
+    const int pos = kept0 + e;
+    if (idx_out) idx_out[pos] = (int64_t)bi + 1;
+    if (idx32_out) idx32_out[pos] = bi;
+    kept_boxes[pos] = sb[sp];
+  }
+  if (tid == 0) {
+    state->count = count;
+    *count_out = count;
+  }
+  __threadfence();
+}
+
+// wide phase A of super-chunk s: one 64-thread block per tile
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(int s, const float4* __restrict__ sb, int n_max, const int32_t* __restrict__ n_dev, float thresh, int max_boxes,
+                uint64_t* __restrict__ mask_intra, uint64_t* __restrict__ mask_prev, const float4* __restrict__ kept_boxes,
+                const NmsState* __restrict__ state) {
+  const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  const int cap = (max_boxes > 0) ? max_boxes : n;
+  const int base = s * NMS_M;
+  const int kept0 = state->count;
+  if (base >= n || kept0 >= cap) return;
+  const int cn_total = min(NMS_M, n - base);
+  const int cwords = DC_CEIL_DIV(cn_total, 64);
+  const int total_tiles = cwords * (cwords + 1) / 2 + DC_CEIL_DIV(kept0, 64) * cwords;
+  if ((int)blockIdx.x >= total_tiles) return;
+  nms_mask_tile(blockIdx.x, threadIdx.x, sb, base, cn_total, cwords, kept0, thresh, mask_intra, mask_prev, kept_boxes);
+}
+
+// phase B of super-chunk s by one block
 __global__ void __launch_bounds__(NMS_THREADS, 1)
-nms_cluster_kernel(const float4* __restrict__ sb, const int32_t* __restrict__ order, int n_max, const int32_t* __restrict__ n_dev,
-                   float thresh, int max_boxes, uint64_t* __restrict__ mask_intra, uint64_t* __restrict__ mask_prev,
-                   float4* __restrict__ kept_boxes, NmsState* __restrict__ state, int64_t* __restrict__ idx_out,
-                   int32_t* __restrict__ idx32_out, int32_t* __restrict__ count_out) {
-  extern __shared__ __align__(16) uint64_t smem_mask[];     // [NMS_M][NMS_W] (used by CTA 0 only)
+nms_scan_kernel(int s, const float4* __restrict__ sb, const int32_t* __restrict__ order, int n_max, const int32_t* __restrict__ n_dev,
+                int max_boxes, const uint64_t* __restrict__ mask_intra, const uint64_t* __restrict__ mask_prev, float4* __restrict__ kept_boxes,
+                NmsState* __restrict__ state, int64_t* __restrict__ idx_out, int32_t* __restrict__ idx32_out, int32_t* __restrict__ count_out) {
+  extern __shared__ __align__(16) uint64_t smem_mask[];     // [NMS_M][NMS_W] then s_pos[NMS_M]
   __shared__ uint64_t s_removed[NMS_W];
+  __shared__ int s_cnt;
+  int* s_pos = reinterpret_cast<int*>(smem_mask + (size_t)NMS_M * NMS_W);
+  const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  const int cap = (max_boxes > 0) ? max_boxes : n;
+  const int base = s * NMS_M;
+  const int kept0 = state->count;
+  if (base >= n || kept0 >= cap) return;
+  const int cn_total = min(NMS_M, n - base);
+  nms_scan_chunk(smem_mask, s_removed, s_pos, &s_cnt, sb, order, base, cn_total, DC_CEIL_DIV(cn_total, 64), kept0, cap, mask_intra, mask_prev,
+                 kept_boxes, state, idx_out, idx32_out, count_out);
+}
+
+// tail: all remaining super-chunks in one launch of a single cluster
+__global__ void __launch_bounds__(NMS_THREADS, 1)
+nms_cluster_kernel(int first_chunk, const float4* __restrict__ sb, const int32_t* __restrict__ order, int n_max,
+                   const int32_t* __restrict__ n_dev, float thresh, int max_boxes, uint64_t* __restrict__ mask_intra,
+                   uint64_t* __restrict__ mask_prev, float4* __restrict__ kept_boxes, NmsState* __restrict__ state,
+                   int64_t* __restrict__ idx_out, int32_t* __restrict__ idx32_out, int32_t* __restrict__ count_out) {
+  extern __shared__ __align__(16) uint64_t smem_mask[];
+  __shared__ uint64_t s_removed[NMS_W];
+  __shared__ int s_cnt;
+  int* s_pos = reinterpret_cast<int*>(smem_mask + (size_t)NMS_M * NMS_W);
   const int n = n_dev ? min(*n_dev, n_max) : n_max;
   const int cap = (max_boxes > 0) ? max_boxes : n;
   const int tid = threadIdx.x;
   const uint32_t rank_in_cluster = nms_cluster_ctarank();
-  const int sub = tid >> 6, lrow = tid & 63;                 // 4 tile workers of 64 threads per CTA
   const int num_workers = NMS_CTAS * (NMS_THREADS / 64);
-  const int worker = (int)rank_in_cluster * (NMS_THREADS / 64) + sub;
-
-  for (int base = 0; base < n; base += NMS_M) {
-    const int kept0 = __ldcg(&state->count);                 // written by CTA 0 before the previous cluster barrier (read at L2)
-    if (kept0 >= cap) break;
+  const int worker = (int)rank_in_cluster * (NMS_THREADS / 64) + (tid >> 6);
+  for (int base = first_chunk * NMS_M; base < n; base += NMS_M) {
+    const int kept0 = __ldcg(&state->count);                 // written by CTA 0 before the previous barrier / launch (read at L2)
+    if (kept0 >= cap) break;                                 // identical in every CTA of the cluster
     const int cn_total = min(NMS_M, n - base);
     const int cwords = DC_CEIL_DIV(cn_total, 64);
-    // ---------------- phase A: mask tiles ----------------
-    const int intra_tiles = cwords * (cwords + 1) / 2;       // (rb, cb) with cb >= rb
-    const int prev_rb = DC_CEIL_DIV(kept0, 64);
-    const int total_tiles = intra_tiles + prev_rb * cwords;
-    for (int tile = worker; tile < total_tiles; tile += num_workers) {
-      int rb, cb;
-      bool intra;
-      if (tile < intra_tiles) {
-        intra = true;
-        // row-major enumeration of the upper triangle: row rb has (cwords - rb) tiles
-        int t = tile;
-        rb = 0;
-        while (t >= cwords - rb) { t -= cwords - rb; ++rb; }
-        cb = rb + t;
-      } else {
-        intra = false;
-        const int t = tile - intra_tiles;
-        rb = t / cwords;
-        cb = t % cwords;
-      }
-      const int col0 = cb * 64;
-      const int cn = min(64, cn_total - col0);
-      uint64_t bits = 0;
-      if (intra) {
-        const int p_local = rb * 64 + lrow;
-        if (p_local < cn_total) {
-          const float4 pb = sb[base + p_local];
-          const float pa = nms_area(pb);
-          const int t0 = max(0, p_local + 1 - col0);         // only q > p
-          for (int t = t0; t < cn; ++t) {
-            const float4 q = __ldg(sb + base + col0 + t);    // same address for the 64 threads of the tile: broadcast
-            if (nms_suppresses(pb, pa, q, nms_area(q), thresh)) bits |= (1ull << t);
-          }
-        }
-        mask_intra[(size_t)p_local * NMS_W + cb] = bits;
-      } else {
-        const int r = rb * 64 + lrow;
-        if (r < kept0) {
-          // kept_boxes is appended to by CTA 0 between cluster barriers: read it at L2 (another SM's L1 may hold a
-          // line that was only partly written when it was cached in an earlier super-chunk)
-          const float4 pb = __ldcg(kept_boxes + r);
-          const float pa = nms_area(pb);
-          for (int t = 0; t < cn; ++t) {
-            const float4 q = __ldg(sb + base + col0 + t);
-            if (nms_suppresses(pb, pa, q, nms_area(q), thresh)) bits |= (1ull << t);
-          }
-          mask_prev[(size_t)r * NMS_W + cb] = bits;
-        }
-      }
-    }
+    const int total_tiles = cwords * (cwords + 1) / 2 + DC_CEIL_DIV(kept0, 64) * cwords;
+    for (int tile = worker; tile < total_tiles; tile += num_workers)
+      nms_mask_tile(tile, tid & 63, sb, base, cn_total, cwords, kept0, thresh, mask_intra, mask_prev, kept_boxes);
     __threadfence();
     nms_cluster_sync();
-    // ---------------- phase B: scan (CTA 0) ----------------
-    if (rank_in_cluster == 0) {
-      {
-        // chunk mask -> shared memory, 8 independent loads in flight per thread
-        const int total_words = cn_total * NMS_W;
-        for (int i0 = tid; i0 < total_words; i0 += NMS_THREADS * 8) {
-          uint64_t v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * NMS_THREADS;
-            v[u] = (i < total_words) ? __ldcg(mask_intra + i) : 0ull;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * NMS_THREADS;
-            if (i < total_words) smem_mask[i] = v[u];
-          }
-        }
-      }
-      if (tid < NMS_W) s_removed[tid] = 0;
-      __syncthreads();
-      {
-        const int w = tid & (NMS_W - 1);
-        uint64_t acc = 0;
-        constexpr int RSTEP = NMS_THREADS / NMS_W;
-        if (w < cwords) {
-          for (int r0 = tid >> 4; r0 < kept0; r0 += RSTEP * 8) {
-            uint64_t v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int r = r0 + u * RSTEP;
-              v[u] = (r < kept0) ? __ldcg(mask_prev + (size_t)r * NMS_W + w) : 0ull;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) acc |= v[u];
-          }
-        }
-        if (acc) atomicOr((unsigned long long*)&s_removed[w], (unsigned long long)acc);
-      }
-      __syncthreads();
-      if (tid < 32) {
-        const int lane = tid;
-        int count = kept0;
-        uint64_t my_removed = (lane < NMS_W) ? s_removed[lane] : 0ull;    // lane w owns removed word w
-        for (int c = 0; c < cwords && count < cap; ++c) {
-          const int lim = min(64, cn_total - c * 64);
-          const uint64_t d0 = (lane < lim) ? smem_mask[(size_t)(c * 64 + lane) * NMS_W + c] : 0ull;
-          const uint64_t d1 = (lane + 32 < lim) ? smem_mask[(size_t)(c * 64 + 32 + lane) * NMS_W + c] : 0ull;
-          uint64_t cur = __shfl_sync(0xffffffffu, my_removed, c);
-          uint64_t keep = 0;
-          const int before = count;
-          // candidates of this step that are still alive; visit only those (each visit may kill later ones)
-          uint64_t alive = ~cur & ((lim == 64) ? ~0ull : ((1ull << lim) - 1ull));
-          while (alive && count < cap) {
-            const int i = __ffsll((long long)alive) - 1;
-            const uint64_t row = __shfl_sync(0xffffffffu, (i < 32) ? d0 : d1, i & 31);
-            keep |= (1ull << i);
-            ++count;
-            alive &= ~row;
-            alive &= ~(1ull << i);
-          }
-          // emit survivors in scan order (= decreasing score) and remember their boxes for later super-chunks
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int i = lane + 32 * half;
-            if ((keep >> i) & 1ull) {
-              const int pos = before + __popcll(keep & ((1ull << i) - 1ull));
-              const int sp = base + c * 64 + i;
-              const int bi = order[sp];
-              if (idx_out) idx_out[pos] = (int64_t)bi + 1;
-              if (idx32_out) idx32_out[pos] = bi;
-              kept_boxes[pos] = sb[sp];
-            }
-          }
-          // propagate the suppression rows of the survivors to the later words of this super-chunk
-          if (lane > c && lane < cwords) {
-            uint64_t k = keep, acc = 0;
-            while (k) {
-              const int i = __ffsll((long long)k) - 1;
-              k &= k - 1;
-              acc |= smem_mask[(size_t)(c * 64 + i) * NMS_W + lane];
-            }
-            my_removed |= acc;
-          }
-        }
-        if (lane == 0) {
-          state->count = count;
-          *count_out = count;
-        }
-      }
-      __threadfence();
-    }
+    if (rank_in_cluster == 0)
+      nms_scan_chunk(smem_mask, s_removed, s_pos, &s_cnt, sb, order, base, cn_total, cwords, kept0, cap, mask_intra, mask_prev, kept_boxes, state,
+                     idx_out, idx32_out, count_out);
     nms_cluster_sync();
   }
 }
@@ -349,9 +403,10 @@ int k_nms(dc_ctx* ctx, const float* boxes, int box_stride, const float* scores, 
   }
   DC_REQUIRE(ctx, n_max <= ws.cap, DC_E_INVALID, "nms: %d boxes exceed workspace capacity %d", n_max, ws.cap);
   static bool attr_set = false;
-  const size_t smem = (size_t)NMS_M * NMS_W * sizeof(uint64_t);
+  const size_t smem = (size_t)NMS_M * NMS_W * sizeof(uint64_t) + (size_t)NMS_M * sizeof(int);
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "nms smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -362,7 +417,20 @@ int k_nms(dc_ctx* ctx, const float* boxes, int box_stride, const float* scores, 
   DC_CHECK_LAUNCH(ctx);
   nms_scatter_kernel<<<DC_CEIL_DIV(n_max, 256), 256, 0, st>>>(ws.rank, boxes, box_stride, n_max, n_dev, ws.order, (float4*)ws.sorted_boxes);
   DC_CHECK_LAUNCH(ctx);
-  {
+  const int chunks = DC_CEIL_DIV(n_max, NMS_M);
+  const int max_keep = (max_boxes > 0) ? (max_boxes < n_max ? max_boxes : n_max) : n_max;
+  const int wide = chunks < NMS_WIDE_CHUNKS ? chunks : NMS_WIDE_CHUNKS;
+  for (int s = 0; s < wide; ++s) {
+    const int prev_rows = (s == 0) ? 0 : (max_keep < s * NMS_M ? max_keep : s * NMS_M);
+    const int tiles = NMS_W * (NMS_W + 1) / 2 + DC_CEIL_DIV(prev_rows, 64) * NMS_W;
+    nms_mask_kernel<<<tiles, 64, 0, st>>>(s, (const float4*)ws.sorted_boxes, n_max, n_dev, thresh, max_boxes, ws.mask, ws.mask_prev,
+                                          (const float4*)ws.kept_boxes, state);
+    DC_CHECK_LAUNCH(ctx);
+    nms_scan_kernel<<<1, NMS_THREADS, smem, st>>>(s, (const float4*)ws.sorted_boxes, ws.order, n_max, n_dev, max_boxes, ws.mask, ws.mask_prev,
+                                                  (float4*)ws.kept_boxes, state, idx_out, idx32_out, count_out);
+    DC_CHECK_LAUNCH(ctx);
+  }
+  if (chunks > wide) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(NMS_CTAS);
     cfg.blockDim = dim3(NMS_THREADS);
@@ -375,8 +443,8 @@ int k_nms(dc_ctx* ctx, const float* boxes, int box_stride, const float* scores, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, nms_cluster_kernel, (const float4*)ws.sorted_boxes, (const int32_t*)ws.order, n_max, n_dev, thresh,
-                                       max_boxes, ws.mask, ws.mask_prev, (float4*)ws.kept_boxes, state, idx_out, idx32_out, count_out);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, nms_cluster_kernel, wide, (const float4*)ws.sorted_boxes, (const int32_t*)ws.order, n_max, n_dev,
+                                       thresh, max_boxes, ws.mask, ws.mask_prev, (float4*)ws.kept_boxes, state, idx_out, idx32_out, count_out);
     if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "nms cluster launch: %s", cudaGetErrorString(e));
     DC_CHECK_LAUNCH(ctx);
   }

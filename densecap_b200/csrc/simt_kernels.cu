@@ -136,7 +136,7 @@ int k_simt_conv3x3(dc_ctx* ctx, const __half* x_hi, const __half* x_lo, const __
 }
 
 // conv1_1 (VGG layer 1): Cin = 3, K = 27 -- no tensor-core shape; the layer is bound by the 110 MB split-fp16
-// output write, so a direct fp32 kernel.  A WARP handles 32 consecutive pixels x one group of 16 output channels:
+// output write, so a direct fp32 kernel.  A WARP handles 64 consecutive pixels (2 per lane) x one group of 16 output channels:
 // the channel group is warp-uniform, so every weight read is a broadcast LDS.128 (one wavefront) -- with the group
 // varying across lanes the kernel was shared-memory-bandwidth bound (8 wavefronts per load, 207 us measured) --
 // image reads are 128-byte coalesced and each lane stores 2 x 32 B per plane.
@@ -154,52 +154,70 @@ conv_first_kernel(const float* __restrict__ img, const float* __restrict__ w, co
   __syncthreads();
   const int groups = Cout / 16;
   const size_t npix = (size_t)N * H * W;
-  const size_t pix_blocks = (npix + 31) / 32;
+  const size_t pix_blocks = (npix + 63) / 64;              // a warp item = 64 consecutive pixels (2 per lane) x one channel group
   const size_t warp_items = pix_blocks * groups;
   const int lane = threadIdx.x & 31;
   const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
   for (size_t item = warp_global; item < warp_items; item += nwarps) {
     const int gq = (int)(item % groups);                  // warp-uniform channel group
-    const size_t pix = (item / groups) * 32 + lane;
-    if (pix >= npix) continue;
-    const int x = pix % W, y = (pix / W) % H, n = pix / ((size_t)W * H);
-    float acc[16];
+    const size_t pix0 = (item / groups) * 64 + lane;      // second pixel: pix0 + 32 (each weight read feeds 2 pixels)
+    float acc[2][16];
+    int px[2], py[2];
+    size_t pn[2];
+    bool ok[2];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = sb[gq * 16 + j];
+    for (int u = 0; u < 2; ++u) {
+      const size_t pix = pix0 + 32 * u;
+      ok[u] = pix < npix;
+      const size_t pc = ok[u] ? pix : 0;
+      px[u] = pc % W; py[u] = (pc / W) % H; pn[u] = pc / ((size_t)W * H);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[u][j] = sb[gq * 16 + j];
+    }
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-          const int yy = y + r - 1, xx = x + s - 1;
-          float v = 0.f;
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(img + (((size_t)n * 3 + ci) * H + yy) * W + xx);
+          float v[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int yy = py[u] + r - 1, xx = px[u] + s - 1;
+            v[u] = (ok[u] && yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + ((pn[u] * 3 + ci) * H + yy) * W + xx) : 0.f;
+          }
           const float4* wp = reinterpret_cast<const float4*>(sw + (ci * 9 + r * 3 + s) * Cout + gq * 16);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 wv = wp[q];
-            acc[4 * q + 0] = fmaf(v, wv.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              acc[u][4 * q + 0] = fmaf(v[u], wv.x, acc[u][4 * q + 0]);
+              acc[u][4 * q + 1] = fmaf(v[u], wv.y, acc[u][4 * q + 1]);
+              acc[u][4 * q + 2] = fmaf(v[u], wv.z, acc[u][4 * q + 2]);
+              acc[u][4 * q + 3] = fmaf(v[u], wv.w, acc[u][4 * q + 3]);
+            }
           }
         }
-    uint32_t hh[8], ll[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      __half h0, l0, h1, l1;
-      split_f32(fmaxf(acc[2 * j], 0.f), h0, l0);
-      split_f32(fmaxf(acc[2 * j + 1], 0.f), h1, l1);
-      hh[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-      ll[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      uint32_t hh[8], ll[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __half h0, l0, h1, l1;
+        split_f32(fmaxf(acc[u][2 * j], 0.f), h0, l0);
+        split_f32(fmaxf(acc[u][2 * j + 1], 0.f), h1, l1);
+        hh[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        ll[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      }
+      const size_t o = (pix0 + 32 * u) * Cout + gq * 16;
+      reinterpret_cast<uint4*>(y_hi + o)[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+      reinterpret_cast<uint4*>(y_hi + o)[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+      reinterpret_cast<uint4*>(y_lo + o)[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+      reinterpret_cast<uint4*>(y_lo + o)[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
     }
-    const size_t o = pix * Cout + gq * 16;
-    reinterpret_cast<uint4*>(y_hi + o)[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-    reinterpret_cast<uint4*>(y_hi + o)[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
-    reinterpret_cast<uint4*>(y_lo + o)[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-    reinterpret_cast<uint4*>(y_lo + o)[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
   }
 }
 int k_conv_first(dc_ctx* ctx, const float* img, const float* w, const float* bias, __half* y_hi, __half* y_lo, int N, int H, int W,

@@ -160,6 +160,26 @@ def test_batched_forward_equals_single(small):
     m.ctx.close()
 
 
+def test_mixed_image_sizes_on_one_context(small):
+    """BASELINE config 3 in miniature: images of different sizes through ONE context (arena sized for the largest),
+    each compared with the oracle run at its own size (ceil-mode pooling gives odd feature-map sizes)."""
+    from densecap_b200.model import DenseCapModel
+    dims, weights, _, cfg, _ = small
+    sizes = [(96, 128), (80, 144), (104, 88), (96, 128)]
+    m = DenseCapModel({"dims": dims, "max_proposals": 64}, weights=weights, max_image_hw=(112, 144), engine=TC)
+    m.setTestArgs({"num_proposals": NPROP})
+    for i, (h, w) in enumerate(sizes):
+        im = make_image(h, w, seed=20 + i)
+        ref = O.densecap_forward_test(im, weights, cfg, return_intermediates=True)
+        r = m.forward_device(dev(im))
+        K = int(r["num_proposals"][0])
+        assert K == ref["ll"]["boxes"].shape[0], (h, w)
+        assert rel(r["roi_boxes"][:K].cpu().numpy(), ref["roi_boxes"]) < 3e-4, (h, w)
+        assert rel(r["all_boxes"][:K].cpu().numpy(), ref["pre_nms"]["final_boxes"]) < 2e-3, (h, w)
+        assert r["all_seq"][:K].cpu().tolist() == ref["pre_nms"]["seq"].tolist(), (h, w)
+    m.ctx.close()
+
+
 def test_full_size_properties():
     """BASELINE config 2 shape: 720x600, 1000 proposals, 15 tokens, full VGG-16 widths.  The oracle is too
     slow at this size for a unit test, so check properties the domain guarantees."""
