@@ -42,8 +42,9 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: the sampler runs from before the warm-up,
+    every line carries a timestamp, and only lines inside [t0, t1] (host clock around the timed region) are used."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -54,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -62,31 +63,34 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if t0 is not None and not (t0 - 0.02 <= ts <= t1 + 0.05):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def cpu_oracle_images_per_sec(threads, n_images=1, num_proposals=NUM_PROPOSALS, verbose=False):
@@ -141,10 +145,10 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("DC_BENCH_BATCH", "2")), help="images per step per GPU")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("DC_BENCH_BATCH", "4")), help="images per step per GPU")
     ap.add_argument("--engine", default="tc", choices=["tc", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -229,11 +233,13 @@ def main():
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         l0 = ctx.kernel_launches()
+        wall[0] = time.time()
         e0.record(stream)
         for j in range(steps):
             fn(warm + j)
         e1.record(stream)
         barrier()
+        wall[1] = time.time()
         ms = e0.elapsed_time(e1)
         launches = ctx.kernel_launches() - l0
         if world > 1:
@@ -242,11 +248,13 @@ def main():
             ms = float(t.item())
         return ms, launches
 
+    wall = [0.0, 0.0]
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(1.0)          # let nvidia-smi start streaming before the (short) timed region
     ms_dev, launches = timed(step_device, args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(wall[0], wall[1]) if sampler else None
     ms_e2e, _ = timed(step_host, args.steps, 1)
 
     # per-phase device times of one step (events only; separate from the timed region)

@@ -136,98 +136,83 @@ int k_simt_conv3x3(dc_ctx* ctx, const __half* x_hi, const __half* x_lo, const __
 }
 
 // conv1_1 (VGG layer 1): Cin = 3, K = 27 -- no tensor-core shape; the layer is bound by the 110 MB split-fp16
-// output write, so a direct fp32 kernel.  A WARP handles 64 consecutive pixels (2 per lane) x one group of 16 output channels:
-// the channel group is warp-uniform, so every weight read is a broadcast LDS.128 (one wavefront) -- with the group
-// varying across lanes the kernel was shared-memory-bandwidth bound (8 wavefronts per load, 207 us measured) --
-// image reads are 128-byte coalesced and each lane stores 2 x 32 B per plane.
+// output write, so a direct fp32 kernel.  A block owns a 32 x 8 pixel tile: the 3 x 10 x 34 input halo and the
+// (27, Cout) weights sit in shared memory; each thread keeps the 27 taps of ITS pixel in registers and sweeps the
+// output channels in groups of 16, so every weight read is a warp-wide broadcast LDS.128 shared by 16 FMAs, the
+// image is read from global memory exactly once per block, and each lane stores 2 x 32 B per plane per group.
 // img NCHW fp32 (reference input layout, DenseCapModel.lua:244) -> split NHWC, bias + ReLU fused.
-__global__ void __launch_bounds__(256)
+constexpr int CF_TW = 32, CF_TH = 8;
+__global__ void __launch_bounds__(CF_TW * CF_TH)
 conv_first_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                   __half* __restrict__ y_hi, __half* __restrict__ y_lo, int N, int H, int W, int Cout) {
-  extern __shared__ __align__(16) float sw[];   // [27][Cout] + bias[Cout]
+  extern __shared__ __align__(16) float sw[];   // [27][Cout] weights, bias[Cout], halo [3][CF_TH+2][CF_TW+2]
   float* sb = sw + 27 * Cout;
-  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
+  float* halo = sb + Cout;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 27 * Cout; i += blockDim.x) {
     const int co = i % Cout, k = i / Cout;       // k = ci*9 + r*3 + s  (reference layout (Cout,3,3,3))
     sw[i] = w[(size_t)co * 27 + k];
   }
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  for (int i = tid; i < Cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.x * CF_TW, y0 = blockIdx.y * CF_TH;
+  constexpr int HW_ = CF_TW + 2, HH_ = CF_TH + 2;
+  for (int i = tid; i < 3 * HH_ * HW_; i += blockDim.x) {
+    const int hx = i % HW_, hy = (i / HW_) % HH_, ci = i / (HW_ * HH_);
+    const int yy = y0 + hy - 1, xx = x0 + hx - 1;
+    halo[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (((size_t)n * 3 + ci) * H + yy) * W + xx) : 0.f;
+  }
   __syncthreads();
-  const int groups = Cout / 16;
-  const size_t npix = (size_t)N * H * W;
-  const size_t pix_blocks = (npix + 63) / 64;              // a warp item = 64 consecutive pixels (2 per lane) x one channel group
-  const size_t warp_items = pix_blocks * groups;
-  const int lane = threadIdx.x & 31;
-  const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  for (size_t item = warp_global; item < warp_items; item += nwarps) {
-    const int gq = (int)(item % groups);                  // warp-uniform channel group
-    const size_t pix0 = (item / groups) * 64 + lane;      // second pixel: pix0 + 32 (each weight read feeds 2 pixels)
-    float acc[2][16];
-    int px[2], py[2];
-    size_t pn[2];
-    bool ok[2];
+  const int tx = tid % CF_TW, ty = tid / CF_TW;
+  const int x = x0 + tx, y = y0 + ty;
+  if (x >= W || y >= H) return;
+  float v[27];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const size_t pix = pix0 + 32 * u;
-      ok[u] = pix < npix;
-      const size_t pc = ok[u] ? pix : 0;
-      px[u] = pc % W; py[u] = (pc / W) % H; pn[u] = pc / ((size_t)W * H);
+  for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[u][j] = sb[gq * 16 + j];
-    }
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
+      for (int s2 = 0; s2 < 3; ++s2) v[ci * 9 + r * 3 + s2] = halo[(ci * HH_ + ty + r) * HW_ + tx + s2];
+  const size_t pix = ((size_t)n * H + y) * W + x;
+  for (int gq = 0; gq < Cout / 16; ++gq) {
+    float acc[16];
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+    for (int j = 0; j < 16; ++j) acc[j] = sb[gq * 16 + j];
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          float v[2];
+    for (int k = 0; k < 27; ++k) {
+      const float4* wp = reinterpret_cast<const float4*>(sw + k * Cout + gq * 16);
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int yy = py[u] + r - 1, xx = px[u] + s - 1;
-            v[u] = (ok[u] && yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + ((pn[u] * 3 + ci) * H + yy) * W + xx) : 0.f;
-          }
-          const float4* wp = reinterpret_cast<const float4*>(sw + (ci * 9 + r * 3 + s) * Cout + gq * 16);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 wv = wp[q];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              acc[u][4 * q + 0] = fmaf(v[u], wv.x, acc[u][4 * q + 0]);
-              acc[u][4 * q + 1] = fmaf(v[u], wv.y, acc[u][4 * q + 1]);
-              acc[u][4 * q + 2] = fmaf(v[u], wv.z, acc[u][4 * q + 2]);
-              acc[u][4 * q + 3] = fmaf(v[u], wv.w, acc[u][4 * q + 3]);
-            }
-          }
-        }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (!ok[u]) continue;
-      uint32_t hh[8], ll[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        __half h0, l0, h1, l1;
-        split_f32(fmaxf(acc[u][2 * j], 0.f), h0, l0);
-        split_f32(fmaxf(acc[u][2 * j + 1], 0.f), h1, l1);
-        hh[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-        ll[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      for (int q = 0; q < 4; ++q) {
+        const float4 wv = wp[q];
+        acc[4 * q + 0] = fmaf(v[k], wv.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(v[k], wv.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(v[k], wv.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(v[k], wv.w, acc[4 * q + 3]);
       }
-      const size_t o = (pix0 + 32 * u) * Cout + gq * 16;
-      reinterpret_cast<uint4*>(y_hi + o)[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-      reinterpret_cast<uint4*>(y_hi + o)[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
-      reinterpret_cast<uint4*>(y_lo + o)[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-      reinterpret_cast<uint4*>(y_lo + o)[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
     }
+    uint32_t hh[8], ll[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __half h0, l0, h1, l1;
+      split_f32(fmaxf(acc[2 * j], 0.f), h0, l0);
+      split_f32(fmaxf(acc[2 * j + 1], 0.f), h1, l1);
+      hh[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      ll[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    const size_t o = pix * Cout + gq * 16;
+    reinterpret_cast<uint4*>(y_hi + o)[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    reinterpret_cast<uint4*>(y_hi + o)[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+    reinterpret_cast<uint4*>(y_lo + o)[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+    reinterpret_cast<uint4*>(y_lo + o)[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
   }
 }
 int k_conv_first(dc_ctx* ctx, const float* img, const float* w, const float* bias, __half* y_hi, __half* y_lo, int N, int H, int W,
                  int Cout, cudaStream_t st) {
   DC_REQUIRE(ctx, Cout % 16 == 0, DC_E_UNSUPPORTED, "conv1_1: Cout must be a multiple of 16");
-  const size_t total = (size_t)N * H * W * (Cout / 16);
-  if (total == 0) return DC_OK;
-  const size_t smem = (size_t)(27 * Cout + Cout) * sizeof(float);
-  unsigned blocks = (unsigned)min((size_t)148 * 8, DC_CEIL_DIV(total, (size_t)256));
-  conv_first_kernel<<<blocks, 256, smem, st>>>(img, w, bias, y_hi, y_lo, N, H, W, Cout);
+  if ((size_t)N * H * W == 0) return DC_OK;
+  const size_t smem = (size_t)(27 * Cout + Cout + 3 * (CF_TH + 2) * (CF_TW + 2)) * sizeof(float);
+  dim3 grid(DC_CEIL_DIV(W, CF_TW), DC_CEIL_DIV(H, CF_TH), N);
+  conv_first_kernel<<<grid, CF_TW * CF_TH, smem, st>>>(img, w, bias, y_hi, y_lo, N, H, W, Cout);
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }
