@@ -28,6 +28,8 @@ struct PhaseTimer {
   std::vector<cudaEvent_t> events;   // events[i] marks the START of phase i; last = end
   bool enabled = false;
   size_t used = 0;
+  cudaEvent_t roi0 = nullptr, roi1 = nullptr;   // bracket the ROI-pooling kernel of image 0 (HBM roofline of that kernel)
+  bool roi_valid = false;
 };
 
 struct dc_ctx {
@@ -309,6 +311,7 @@ extern "C" int dc_destroy(dc_ctx* ctx) {
   for (cudaEvent_t ev : ctx->side_done) cudaEventDestroy(ev);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   for (cudaEvent_t ev : ctx->timer.events) cudaEventDestroy(ev);
+  if (ctx->timer.roi0) { cudaEventDestroy(ctx->timer.roi0); cudaEventDestroy(ctx->timer.roi1); }
   delete ctx;
   return DC_OK;
 }
@@ -562,6 +565,14 @@ extern "C" int dc_get_times(dc_ctx* ctx, const char** names_out, float* ms_out, 
       if (ms_out) ms_out[n] = ms;
     }
   }
+  if (t.roi_valid && n < capacity) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(t.roi1) == cudaSuccess && cudaEventElapsedTime(&ms, t.roi0, t.roi1) == cudaSuccess) {
+      if (names_out) names_out[n] = "kernel:roi_taps+roi_pool(image0)";
+      if (ms_out) ms_out[n] = ms;
+      ++n;
+    }
+  }
   *count_out = n;
   return DC_OK;
 }
@@ -731,10 +742,15 @@ static int run_localization(dc_ctx* ctx, int N, int fh, int fw, int img_h, int i
       return rc;
     const size_t foff = (size_t)b * cells * C5;
     const size_t roff = (size_t)b * P * hw * C5;
+    if (b == 0 && ctx->timer.enabled) {
+      if (!ctx->timer.roi0) { cudaEventCreate(&ctx->timer.roi0); cudaEventCreate(&ctx->timer.roi1); }
+      cudaEventRecord(ctx->timer.roi0, sb);
+    }
     if ((rc = k_roi_pool(ctx, ctx->feats.base + foff, ctx->feats.base + fplane + foff, nullptr, C5, fh, fw, ctx->roi_boxes + (size_t)b * P * 4,
                          ctx->rpn_count + b, P, img_h, img_w, c.pool_hw, c.pool_hw, (char*)ctx->roi_taps + ctx->roi_taps_stride * b,
                          ctx->roi.base + roff, ctx->roi.base + rplane + roff, nullptr, 1, sb)))
       return rc;
+    if (b == 0 && ctx->timer.enabled) { cudaEventRecord(ctx->timer.roi1, sb); ctx->timer.roi_valid = true; }
     if (b > 0) {
       DC_CHECK_CUDA(ctx, cudaEventRecord(ctx->side_done[b - 1], sb));
       DC_CHECK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->side_done[b - 1], 0));     // join

@@ -27,11 +27,15 @@ struct SplitTensor {
   size_t plane_elems = 0;
 };
 
+// cvt.rn.satfinite saturates to +-65504 in the conversion itself (no inf planes, no extra min/max instructions)
+__device__ __forceinline__ __half f32_to_f16_sat(float a) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(a));
+  return __ushort_as_half(r);
+}
 __device__ __forceinline__ void split_f32(float a, __half& hi, __half& lo) {
-  const float c = fminf(fmaxf(a, -65504.f), 65504.f);
-  hi = __float2half_rn(c);
-  const float r = a - __half2float(hi);
-  lo = __float2half_rn(fminf(fmaxf(r, -65504.f), 65504.f));
+  hi = f32_to_f16_sat(a);
+  lo = f32_to_f16_sat(a - __half2float(hi));
 }
 __device__ __forceinline__ float join_f32(__half hi, __half lo) {
   return __half2float(hi) + __half2float(lo);

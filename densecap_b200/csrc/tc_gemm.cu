@@ -212,6 +212,11 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+__device__ __forceinline__ float lstm_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float lstm_tanh(float x) {
+  const float xc = fminf(fmaxf(x, -15.f), 15.f);          // tanh saturates to +-1 in fp32 beyond |x| ~ 9
+  return 1.f - __fdividef(2.f, __expf(2.f * xc) + 1.f);
+}
 __device__ __forceinline__ unsigned long long pack_argmax_tc(float v, int col) {
   uint32_t u = __float_as_uint(v);
   u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -479,12 +484,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             __half hhv[8], hlv[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              const float ig = 1.f / (1.f + expf(-v[4 * u + 0]));
-              const float fg = 1.f / (1.f + expf(-v[4 * u + 1]));
-              const float og = 1.f / (1.f + expf(-v[4 * u + 2]));
-              const float gg = tanhf(v[4 * u + 3]);
+              // sigmoid / tanh through ex2-based __expf (a few ulp for |x| <= 15, far inside the 1e-4 logit budget):
+              // the accurate expf/tanhf sequences made this epilogue the critical path of the 16-k-block gate GEMM
+              const float ig = lstm_sigmoid(v[4 * u + 0]);
+              const float fg = lstm_sigmoid(v[4 * u + 1]);
+              const float og = lstm_sigmoid(v[4 * u + 2]);
+              const float gg = lstm_tanh(v[4 * u + 3]);
               cn[u] = fg * cprev[u] + ig * gg;
-              split_f32(og * tanhf(cn[u]), hhv[u], hlv[u]);
+              split_f32(og * lstm_tanh(cn[u]), hhv[u], hlv[u]);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {

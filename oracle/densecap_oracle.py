@@ -568,3 +568,121 @@ def densecap_forward_test(img, weights, cfg, return_intermediates=False):
         out["feats"] = feats; out["ll"] = ll; out["codes"] = codes
         out["pre_nms"] = {"final_boxes": final_boxes, "obj": obj, "seq": seq}
     return out
+
+
+# ========================================================================================
+# Training-time forward of the LocalizationLayer (BASELINE config 5)
+# ========================================================================================
+
+# densecap/modules/BoxSampler.lua:64-167.  Sampling: torch.multinomial is irreproducible, so -- exactly like the
+# reference's own debug hook (debug_pos_sample_idx / debug_neg_sample_idx, BoxSampler.lua:154-159) -- indices INTO the
+# positive / negative candidate lists are injected; the default injection is "the first P / first M candidates".
+def box_sampler(input_boxes, target_boxes, low_thresh=0.5, high_thresh=0.7, batch_size=256, bounds=None,
+                pos_sample_idx=None, neg_sample_idx=None):
+    """input_boxes (1,B1,4), target_boxes (1,B2,4) xcycwh.  Returns 1-based (pos_input_idx, pos_target_idx, neg_input_idx)
+    plus the masks (for tests)."""
+    ious = box_iou(input_boxes, target_boxes)[0]                      # (B1,B2)
+    B1 = ious.shape[0]
+    input_max_iou = ious.max(axis=1)
+    input_idx = ious.argmax(axis=1)                                   # first maximal target per input (torch.max)
+    target_idx = ious.argmax(axis=0)                                  # best input per target
+    pos_mask = input_max_iou > f32(high_thresh)
+    neg_mask = input_max_iou < f32(low_thresh)
+    if bounds is not None:                                            # BoxSampler.lua:82-98
+        c = xcycwh_to_x1y1x2y2(input_boxes)[0]
+        oob = (c[:, 0] < f32(bounds["x_min"])) | (c[:, 1] < f32(bounds["y_min"])) | \
+              (c[:, 2] > f32(bounds["x_max"])) | (c[:, 3] > f32(bounds["y_max"]))
+        pos_mask = pos_mask & ~oob
+        neg_mask = neg_mask & ~oob
+    pos_mask = pos_mask.copy(); neg_mask = neg_mask.copy()
+    pos_mask[target_idx] = True                                       # :104-105 force the best match of every GT box
+    neg_mask[target_idx] = False
+    if neg_mask.sum() == 0:                                           # :111-128
+        neg_mask = ~pos_mask
+    pos_nz = np.nonzero(pos_mask)[0]
+    neg_nz = np.nonzero(neg_mask)[0]
+    num_pos = int(min(batch_size // 2, pos_nz.size))
+    num_neg = int(batch_size - num_pos)
+    if pos_sample_idx is None:
+        pos_sample_idx = np.arange(num_pos)
+    if neg_sample_idx is None:
+        neg_sample_idx = np.arange(num_neg) % max(neg_nz.size, 1)     # with replacement when there are too few
+    pos_input_idx = pos_nz[np.asarray(pos_sample_idx, np.int64)]
+    neg_input_idx = neg_nz[np.asarray(neg_sample_idx, np.int64)]
+    pos_target_idx = input_idx[pos_input_idx]
+    return pos_input_idx + 1, pos_target_idx + 1, neg_input_idx + 1, pos_mask, neg_mask
+
+
+# densecap/modules/BoxSamplerHelper.lua:68-129 (gather) / :142-182 (scatter of gradients, indexCopy semantics)
+def box_sampler_helper_forward(input_data, target_data, pos_input_idx, pos_target_idx, neg_input_idx):
+    pos = [d[0][pos_input_idx - 1] for d in input_data]
+    tgt = [d[0][pos_target_idx - 1] for d in target_data]
+    neg = [d[0][neg_input_idx - 1] for d in input_data]
+    return pos, tgt, neg
+
+
+def box_sampler_helper_backward(input_shapes, pos_input_idx, neg_input_idx, grad_pos, grad_neg):
+    out = []
+    for i, shp in enumerate(input_shapes):
+        g = np.zeros(shp, _DT[0])
+        if grad_pos[i] is not None:
+            g[0][pos_input_idx - 1] = grad_pos[i]          # indexCopy: later duplicates overwrite
+        if grad_neg[i] is not None:
+            g[0][neg_input_idx - 1] = grad_neg[i]
+        out.append(g)
+    return out
+
+
+# nn.LogSoftMax + nn.ClassNLLCriterion (sizeAverage) = densecap/modules/OurCrossEntropyCriterion.lua:15-32 ; target 1-based
+def cross_entropy(scores, target):
+    s = _f(scores).astype(np.float64)
+    m = s.max(axis=1, keepdims=True)
+    logp = s - m - np.log(np.exp(s - m).sum(axis=1, keepdims=True))
+    n = s.shape[0]
+    loss = -logp[np.arange(n), np.asarray(target) - 1].sum() / max(n, 1)
+    grad = np.exp(logp)
+    grad[np.arange(n), np.asarray(target) - 1] -= 1.0
+    return f32(loss), (grad / max(n, 1)).astype(_DT[0])
+
+
+# [3P] nn.SmoothL1Criterion (sizeAverage), SURVEY.md App. B4
+def smooth_l1(x, t):
+    d = _f(x).astype(np.float64) - _f(t).astype(np.float64)
+    n = d.size
+    a = np.abs(d)
+    loss = np.where(a < 1, 0.5 * d * d, a - 0.5).sum() / max(n, 1)
+    grad = np.clip(d, -1, 1) / max(n, 1)
+    return f32(loss), grad.astype(_DT[0])
+
+
+# densecap/LocalizationLayer.lua:383-526  _forward_train (losses in stats.losses)
+def localization_layer_forward_train(feats, weights, gt_boxes, image_h, image_w, mid_box_reg_weight=0.05,
+                                     mid_objectness_weight=0.1, box_reg_decay=0.0, sampler_low=0.5, sampler_high=0.7,
+                                     batch_size=256, anchors=DEFAULT_ANCHORS, field_centers=FIELD_CENTERS, HH=7, WW=7):
+    """feats (1,C,H',W'), gt_boxes (1,B1,4).  Deterministic sampling = first P positives / first M negatives."""
+    boxes, anc, trans, scores, _ = rpn_forward(feats, weights, anchors, field_centers)
+    bounds = {"x_min": 1, "y_min": 1, "x_max": image_w, "y_max": image_h}          # :414-422
+    pi, pt, ni, pos_mask, neg_mask = box_sampler(boxes, gt_boxes, sampler_low, sampler_high, batch_size, bounds)
+    pos, tgt, neg = box_sampler_helper_forward([boxes, anc, trans, scores], [gt_boxes], pi, pt, ni)
+    pos_boxes, pos_anchors, pos_trans, pos_scores = pos
+    pos_target_boxes = tgt[0]
+    neg_boxes, neg_scores = neg[0], neg[3]
+    num_pos, num_neg = pos_boxes.shape[0], neg_scores.shape[0]
+    roi_boxes = np.concatenate([pos_boxes, neg_boxes], 0)                            # :444-446
+    roi_features = bilinear_roi_pooling(feats[0], roi_boxes, image_h, image_w, HH, WW)
+    lp, gp = cross_entropy(pos_scores, np.full((num_pos,), 1))                       # :464-467 (1 = positive)
+    ln, gn = cross_entropy(neg_scores, np.full((num_neg,), 2))
+    targets = invert_box_transform(pos_anchors, pos_target_boxes)                    # :474-477
+    pos_trans = pos_trans.copy()
+    big = np.abs(targets).max(axis=1) > 10                                           # :481-489 mask hack
+    pos_trans[big] = 0
+    targets = targets.copy(); targets[big] = 0
+    lb, gb = smooth_l1(pos_trans, targets)
+    decay = f32(0.5 * box_reg_decay * float(np.sum(_f(trans).astype(np.float64) ** 2)))   # RegularizeLayer.lua:11-16
+    losses = {"obj_loss_pos": f32(mid_objectness_weight) * lp, "obj_loss_neg": f32(mid_objectness_weight) * ln,
+              "box_reg_loss": f32(mid_box_reg_weight) * lb, "box_decay_loss": decay}
+    losses["total_loss"] = f32(sum(float(v) for v in losses.values()))
+    return {"roi_features": roi_features, "roi_boxes": roi_boxes, "pos_target_boxes": pos_target_boxes,
+            "pos_input_idx": pi, "pos_target_idx": pt, "neg_input_idx": ni, "num_pos": num_pos, "num_neg": num_neg,
+            "losses": losses, "pos_mask": pos_mask, "neg_mask": neg_mask, "masked": int(big.sum()),
+            "grad_pos_scores": gp, "grad_neg_scores": gn, "grad_pos_trans": gb}

@@ -1,0 +1,76 @@
+"""Oracle of the training-time LocalizationLayer forward (BASELINE config 5) pinned to the reference's tests that
+agree with HEAD: the BoxSamplerHelper gather/scatter protocol (test/BoxSamplerHelper_test.lua:30-104, which injects
+the indices through a fake sampler exactly like this restatement does) and the criterion definitions.  CPU only."""
+import numpy as np
+
+from oracle import densecap_oracle as O
+
+
+def test_box_sampler_helper_gather_scatter_protocol():
+    # same structure as test/BoxSamplerHelper_test.lua:30-104
+    rng = np.random.default_rng(0)
+    B1, B2 = 7, 4
+    input_data = [rng.standard_normal((1, B1, D)).astype(np.float32) for D in (4, 5, 3)]
+    target_data = [rng.standard_normal((1, B2, D)).astype(np.float32) for D in (4, 1)]
+    pi = np.array([7, 2, 3]); pt = np.array([1, 2, 1]); ni = np.array([5, 1])
+    pos, tgt, neg = O.box_sampler_helper_forward(input_data, target_data, pi, pt, ni)
+    for i, D in enumerate((4, 5, 3)):
+        assert pos[i].shape == (3, D) and neg[i].shape == (2, D)
+        for j in range(3):
+            assert np.array_equal(pos[i][j], input_data[i][0, pi[j] - 1])
+        for j in range(2):
+            assert np.array_equal(neg[i][j], input_data[i][0, ni[j] - 1])
+    for i, D in enumerate((4, 1)):
+        assert tgt[i].shape == (3, D)
+        for j in range(3):
+            assert np.array_equal(tgt[i][j], target_data[i][0, pt[j] - 1])
+    gp = [rng.standard_normal(p.shape).astype(np.float32) for p in pos]
+    gn = [rng.standard_normal(n.shape).astype(np.float32) for n in neg]
+    gi = O.box_sampler_helper_backward([d.shape for d in input_data], pi, ni, gp, gn)
+    for i in range(3):
+        assert gi[i].shape == input_data[i].shape
+        for j in range(3):
+            assert np.array_equal(gi[i][0, pi[j] - 1], gp[i][j])
+        for j in range(2):
+            assert np.array_equal(gi[i][0, ni[j] - 1], gn[i][j])
+        untouched = [r for r in range(B1) if r + 1 not in set(pi) | set(ni)]
+        assert np.all(gi[i][0, untouched] == 0)
+
+
+def test_box_sampler_masks_and_forced_positives():
+    # two GT boxes; inputs: an exact copy of GT 1 (IoU<1 by the HEAD (w-1)/2 convention but > 0.7), a far box (neg),
+    # a mediocre overlap (neither), and the best-but-weak match of GT 2 (forced positive, BoxSampler.lua:104-105)
+    gt = np.array([[[50, 50, 40, 40], [150, 60, 30, 30]]], np.float32)
+    inp = np.array([[[50, 50, 40, 40], [300, 300, 20, 20], [58, 50, 40, 40], [160, 66, 30, 30], [400, 40, 10, 10]]], np.float32)
+    pi, pt, ni, pm, nm = O.box_sampler(inp, gt, 0.5, 0.7, batch_size=4)
+    iou = O.box_iou(inp, gt)[0]
+    assert iou[0, 0] > 0.7 and iou[0, 0] < 1.0            # HEAD quirk: IoU(box, box) < 1
+    assert pm.tolist() == [True, False, False, True, False]   # row 3 forced although its IoU < 0.7
+    assert iou[3, 1] < 0.7
+    assert nm.tolist() == [False, True, False, False, True] and 0.5 <= iou[2, 0] <= 0.7
+    assert pi.tolist() == [1, 4] and pt.tolist() == [1, 2]
+    assert ni.tolist() == [2, 5]                          # batch 4 -> P = 2, M = 2, first candidates in index order
+    # bounds exclusion (BoxSampler.lua:82-98): box 5 sticks out of a 380-wide image
+    _, _, ni2, _, nm2 = O.box_sampler(inp, gt, 0.5, 0.7, batch_size=4, bounds={"x_min": 1, "y_min": 1, "x_max": 380, "y_max": 400})
+    assert nm2.tolist() == [False, True, False, False, False]
+    assert ni2.tolist() == [2, 2]                         # too few negatives -> sampled with replacement
+
+
+def test_criterions_match_torch_definitions():
+    import torch
+    rng = np.random.default_rng(1)
+    s = rng.standard_normal((9, 2)).astype(np.float32)
+    t = rng.integers(1, 3, size=9)
+    loss, grad = O.cross_entropy(s, t)
+    ts = torch.tensor(s, requires_grad=True)
+    tl = torch.nn.functional.cross_entropy(ts, torch.tensor(t - 1))
+    tl.backward()
+    assert abs(float(loss) - float(tl)) < 1e-6
+    np.testing.assert_allclose(grad, ts.grad.numpy(), atol=1e-6)
+    x = (rng.standard_normal((6, 4)) * 2).astype(np.float32); y = rng.standard_normal((6, 4)).astype(np.float32)
+    loss, grad = O.smooth_l1(x, y)
+    tx = torch.tensor(x, requires_grad=True)
+    tl = torch.nn.functional.smooth_l1_loss(tx, torch.tensor(y))
+    tl.backward()
+    assert abs(float(loss) - float(tl)) < 1e-6
+    np.testing.assert_allclose(grad, tx.grad.numpy(), atol=1e-6)
