@@ -50,6 +50,9 @@ SIGNATURES = {
     "dc_forward_test_host": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_vp]),
     "dc_vgg_trunk_forward": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp]),
     "dc_localization_forward_test": (c_i, [c_vp, c_vp, c_i, c_i, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dc_set_train_args": (c_i, [c_vp, c_f, c_f, c_f, c_f, c_f, c_i, c_i]),
+    "dc_set_ground_truth": (c_i, [c_vp, c_vp, c_i, c_vp]),
+    "dc_localization_forward_train": (c_i, [c_vp, c_vp, c_i, c_i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dc_recog_forward": (c_i, [c_vp, c_vp, c_vp, c_i, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dc_lm_sample": (c_i, [c_vp, c_vp, c_i, c_vp, c_vp, c_vp]),
     "dc_make_anchors": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_vp, c_vp]),

@@ -69,6 +69,16 @@ struct dc_ctx {
   std::vector<cudaEvent_t> side_done;
   cudaEvent_t fork_ev = nullptr;
   PhaseTimer timer;
+  // training-time forward of the LocalizationLayer (setGroundTruth protocol, sampler / loss options)
+  float mid_box_reg_weight = 0.05f, mid_objectness_weight = 0.1f, box_reg_decay = 0.f;   // LocalizationLayer.lua:48-54
+  float sampler_low = 0.5f, sampler_high = 0.7f;                                         // :79-82
+  int sampler_batch = 256, remove_outbounds = 1;
+  void* train = nullptr;             // TrainBuffers (train_kernels.cu), allocated on the first training call
+  char* train_mem = nullptr;
+  int train_A = 0, train_B2max = 0, train_batch = 0;
+  int gt_count = 0;
+  bool gt_consumed = true;
+  float* train_losses = nullptr;
 };
 
 static char g_err[512] = "";
@@ -310,6 +320,8 @@ extern "C" int dc_destroy(dc_ctx* ctx) {
   for (cudaStream_t sst : ctx->side) cudaStreamDestroy(sst);
   for (cudaEvent_t ev : ctx->side_done) cudaEventDestroy(ev);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  if (ctx->train_mem) cudaFree(ctx->train_mem);
+  free(ctx->train);
   for (cudaEvent_t ev : ctx->timer.events) cudaEventDestroy(ev);
   if (ctx->timer.roi0) { cudaEventDestroy(ctx->timer.roi0); cudaEventDestroy(ctx->timer.roi1); }
   delete ctx;
@@ -530,6 +542,62 @@ extern "C" int dc_set_image_size(dc_ctx* ctx, int image_h, int image_w) {
   return DC_OK;
 }
 
+// LocalizationLayer options used by the training-time forward (LocalizationLayer.lua:79-87; train_opts.lua:18-42)
+extern "C" int dc_set_train_args(dc_ctx* ctx, float mid_box_reg_weight, float mid_objectness_weight, float box_reg_decay,
+                                 float sampler_low_thresh, float sampler_high_thresh, int sampler_batch_size, int train_remove_outbounds_boxes) {
+  if (!ctx) return dc_set_error(nullptr, DC_E_INVALID, "dc_set_train_args: null ctx");
+  DC_REQUIRE(ctx, sampler_batch_size >= 2 && sampler_batch_size <= ctx->P * ctx->B && sampler_batch_size <= 1024, DC_E_INVALID,
+             "sampler_batch_size=%d exceeds the ROI capacity %d", sampler_batch_size, std::min(ctx->P * ctx->B, 1024));
+  ctx->mid_box_reg_weight = mid_box_reg_weight;
+  ctx->mid_objectness_weight = mid_objectness_weight;
+  ctx->box_reg_decay = box_reg_decay;
+  ctx->sampler_low = sampler_low_thresh;
+  ctx->sampler_high = sampler_high_thresh;
+  ctx->sampler_batch = sampler_batch_size;
+  ctx->remove_outbounds = train_remove_outbounds_boxes ? 1 : 0;
+  return DC_OK;
+}
+
+size_t train_buffers_struct_bytes();
+size_t train_buffers_carve(void* tb, char* base, int A, int B2max, int batch_size);
+float* train_buffers_roi_boxes(void* tb);
+float* train_buffers_gt(void* tb);
+float* train_buffers_pos_target_boxes(void* tb);
+int32_t* train_buffers_counts(void* tb);
+int k_loc_train_sampler(dc_ctx* ctx, const float* head, int ld, int H, int W, int k, const float* anchors_dev, float x0, float y0, float sx,
+                        float sy, const float* gt_boxes, int B2, float lo, float hi, int batch_size, int has_bounds, float img_w, float img_h,
+                        void* tb, int64_t* pos_target_idx, int64_t* pos_input_idx, int64_t* neg_input_idx, cudaStream_t st);
+int k_loc_train_losses(dc_ctx* ctx, void* tb, int A, float w_obj, float w_box, float w_decay, float* losses, cudaStream_t st);
+
+static const int kMaxGtBoxes = 512;
+static int ensure_train_buffers(dc_ctx* ctx) {
+  if (ctx->train && ctx->train_batch >= ctx->sampler_batch) return DC_OK;
+  if (ctx->train_mem) cudaFree(ctx->train_mem);
+  if (!ctx->train) ctx->train = calloc(1, train_buffers_struct_bytes());
+  const size_t bytes = train_buffers_carve(nullptr, nullptr, ctx->A_max, kMaxGtBoxes, ctx->sampler_batch);
+  cudaError_t e = cudaMalloc((void**)&ctx->train_mem, bytes);
+  if (e != cudaSuccess) { ctx->train_mem = nullptr; return dc_set_error(ctx, DC_E_NOMEM, "training workspace cudaMalloc(%zu) failed", bytes); }
+  train_buffers_carve(ctx->train, ctx->train_mem, ctx->A_max, kMaxGtBoxes, ctx->sampler_batch);
+  ctx->train_batch = ctx->sampler_batch;
+  if (!ctx->train_losses) { int rc = dev_alloc(ctx, &ctx->train_losses, 8); if (rc) return rc; }
+  return DC_OK;
+}
+
+// LocalizationLayer:setGroundTruth (LocalizationLayer.lua:181-186).  Only the boxes take part in the layer's own
+// computation; gt_labels are gathered by the caller with pos_target_idx (the layer just indexes them, :455-457).
+extern "C" int dc_set_ground_truth(dc_ctx* ctx, const float* gt_boxes, int num_gt, void* stream) {
+  if (!ctx || !gt_boxes) return dc_set_error(ctx, DC_E_INVALID, "dc_set_ground_truth: null argument");
+  DC_REQUIRE(ctx, num_gt >= 1 && num_gt <= kMaxGtBoxes, DC_E_INVALID, "gt_boxes must have shape (1, B1, 4) with 1 <= B1 <= %d", kMaxGtBoxes);
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_train_buffers(ctx);
+  if (rc) return rc;
+  DC_CHECK_CUDA(ctx, cudaMemcpyAsync(train_buffers_gt(ctx->train), gt_boxes, (size_t)num_gt * 4 * sizeof(float), cudaMemcpyDefault,
+                                     (cudaStream_t)stream));
+  ctx->gt_count = num_gt;
+  ctx->gt_consumed = false;
+  return DC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // phase timing (LocalizationLayer:timeit, LocalizationLayer.lua:219-230)
 // ------------------------------------------------------------------------------------------------
@@ -688,31 +756,40 @@ __global__ void identity_idx_kernel(const int32_t* __restrict__ count_in, int P,
 }
 __global__ void set_count_kernel(int32_t* p, int v) { *p = v; }
 
-// RPN + post-processing + NMS + ROI pooling for image b of the batch (LocalizationLayer.lua:250-363)
-static int run_localization(dc_ctx* ctx, int N, int fh, int fw, int img_h, int img_w, cudaStream_t st) {
+// nn.Sequential RPN (LocalizationLayer.lua:76-109): 3x3 conv + ReLU, then the 1x1 box and score heads as ONE GEMM
+// whose 6k output columns are [4k box transforms | 2k scores] per feature cell -> ctx->rpn_head (N*cells, 6k)
+static int run_rpn_head(dc_ctx* ctx, int N, int fh, int fw, cudaStream_t st) {
   const dc_config& c = ctx->cfg;
   const int C5 = c.widths[4], F = c.rpn_filters, k = c.num_anchors;
   const int cells = fh * fw;
-  const int A = k * cells;
-  DC_REQUIRE(ctx, A <= ctx->A_max, DC_E_INVALID, "feature map %dx%d exceeds capacity", fh, fw);
+  DC_REQUIRE(ctx, k * cells <= ctx->A_max, DC_E_INVALID, "feature map %dx%d exceeds capacity", fh, fw);
   Weight *wc, *bc, *wh, *bh;
   int rc;
   if ((rc = need_weight(ctx, "rpn.conv.weight", &wc))) return rc;
   if ((rc = need_weight(ctx, "rpn.conv.bias", &bc))) return rc;
   if ((rc = need_weight(ctx, "rpn.head.weight", &wh))) return rc;
   if ((rc = need_weight(ctx, "rpn.head.bias", &bh))) return rc;
-  phase_mark(ctx, "rpn:forward_test", st);
   int oh, ow;
   const size_t fplane = (size_t)N * cells * C5;
   if ((rc = conv_layer(ctx, ctx->feats.base, fplane, ctx->rpn_hidden.base, N, fh, fw, C5, F, *wc, *bc, 0, nullptr, &oh, &ow, st))) return rc;
-  {
-    GemmEpilogue ep;
-    ep.bias = bh->f32;
-    ep.out_f32 = ctx->rpn_head;
-    ep.ldf = 6 * k;
-    const size_t hplane = (size_t)N * cells * F;
-    if ((rc = gemm(ctx, ctx->rpn_hidden.base, hplane, F, *wh, F, N * cells, 6 * k, F, ep, st))) return rc;
-  }
+  GemmEpilogue ep;
+  ep.bias = bh->f32;
+  ep.out_f32 = ctx->rpn_head;
+  ep.ldf = 6 * k;
+  const size_t hplane = (size_t)N * cells * F;
+  return gemm(ctx, ctx->rpn_hidden.base, hplane, F, *wh, F, N * cells, 6 * k, F, ep, st);
+}
+
+// RPN + post-processing + NMS + ROI pooling for image b of the batch (LocalizationLayer.lua:250-363)
+static int run_localization(dc_ctx* ctx, int N, int fh, int fw, int img_h, int img_w, cudaStream_t st) {
+  const dc_config& c = ctx->cfg;
+  const int C5 = c.widths[4], k = c.num_anchors;
+  const int cells = fh * fw;
+  const int A = k * cells;
+  int rc;
+  phase_mark(ctx, "rpn:forward_test", st);
+  if ((rc = run_rpn_head(ctx, N, fh, fw, st))) return rc;
+  const size_t fplane = (size_t)N * cells * C5;
   const int P = ctx->P;
   const int hw = c.pool_hw * c.pool_hw;
   const size_t rplane = (size_t)N * P * hw * C5;
@@ -994,6 +1071,55 @@ extern "C" int dc_localization_forward_test(dc_ctx* ctx, const float* feats_nchw
   if (roi_boxes) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(roi_boxes, ctx->roi_boxes, (size_t)ctx->num_proposals * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (idx) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(idx, ctx->rpn_idx64, (size_t)ctx->num_proposals * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   if (num_out) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(num_out, ctx->rpn_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return DC_OK;
+}
+
+// nn.LocalizationLayer:_forward_train (LocalizationLayer.lua:383-526)
+extern "C" int dc_localization_forward_train(dc_ctx* ctx, const float* feats_nchw, int feat_h, int feat_w, float* roi_features,
+                                             float* roi_boxes, float* pos_target_boxes, int64_t* pos_target_idx, int64_t* pos_input_idx,
+                                             int64_t* neg_input_idx, int32_t* num_pos_neg, float* losses, void* stream) {
+  if (!ctx || !feats_nchw) return dc_set_error(ctx, DC_E_INVALID, "dc_localization_forward_train: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  // same order as the reference's asserts (:385-393)
+  DC_REQUIRE(ctx, ctx->gt_count > 0 && !ctx->gt_consumed, DC_E_PROTOCOL, "Must call setGroundTruth before training-time forward pass");
+  ctx->gt_consumed = true;
+  DC_REQUIRE(ctx, ctx->image_h > 0 && ctx->image_w > 0 && !ctx->size_consumed, DC_E_PROTOCOL,
+             "Must call setImageSize before each forward pass");
+  ctx->size_consumed = true;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dc_config& c = ctx->cfg;
+  const int C5 = c.widths[4], k = c.num_anchors, hw = c.pool_hw * c.pool_hw;
+  DC_REQUIRE(ctx, (size_t)feat_h * feat_w <= (size_t)ctx->fh_max * ctx->fw_max, DC_E_INVALID, "feature map too large");
+  int rc;
+  if ((rc = ensure_train_buffers(ctx))) return rc;
+  const int cells = feat_h * feat_w, A = k * cells, S = ctx->sampler_batch;
+  const size_t plane = (size_t)cells * C5;
+  ctx->timer.used = 0;
+  if ((rc = k_nchw_to_split_nhwc(ctx, feats_nchw, ctx->feats.base, ctx->feats.base + plane, 1, C5, feat_h, feat_w, st))) return rc;
+  phase_mark(ctx, "rpn:forward", st);
+  if ((rc = run_rpn_head(ctx, 1, feat_h, feat_w, st))) return rc;
+  phase_mark(ctx, "sampler:forward", st);
+  if ((rc = k_loc_train_sampler(ctx, ctx->rpn_head, 6 * k, feat_h, feat_w, k, ctx->anchors_dev, c.field_centers[0], c.field_centers[1],
+                                c.field_centers[2], c.field_centers[3], train_buffers_gt(ctx->train), ctx->gt_count, ctx->sampler_low,
+                                ctx->sampler_high, S, ctx->remove_outbounds, (float)ctx->image_w, (float)ctx->image_h, ctx->train, pos_target_idx, pos_input_idx,
+                                neg_input_idx, st)))
+    return rc;
+  phase_mark(ctx, "roi_pooling:forward", st);
+  const size_t rplane = (size_t)S * hw * C5;
+  if ((rc = k_roi_pool(ctx, ctx->feats.base, ctx->feats.base + plane, nullptr, C5, feat_h, feat_w, train_buffers_roi_boxes(ctx->train), nullptr, S,
+                       ctx->image_h, ctx->image_w, c.pool_hw, c.pool_hw, ctx->roi_taps, ctx->roi.base, ctx->roi.base + rplane, nullptr, 1, st)))
+    return rc;
+  phase_mark(ctx, "losses", st);
+  if ((rc = k_loc_train_losses(ctx, ctx->train, A, ctx->mid_objectness_weight, ctx->mid_box_reg_weight, ctx->box_reg_decay, ctx->train_losses,
+                               st)))
+    return rc;
+  phase_mark(ctx, "end", st);
+  if (roi_features && (rc = k_bhwc_split_to_bchw(ctx, ctx->roi.base, ctx->roi.base + rplane, roi_features, S, C5, hw, st))) return rc;
+  if (roi_boxes) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(roi_boxes, train_buffers_roi_boxes(ctx->train), (size_t)S * 16, cudaMemcpyDeviceToDevice, st));
+  if (pos_target_boxes)
+    DC_CHECK_CUDA(ctx, cudaMemcpyAsync(pos_target_boxes, train_buffers_pos_target_boxes(ctx->train), (size_t)S * 16, cudaMemcpyDeviceToDevice, st));
+  if (num_pos_neg) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(num_pos_neg, train_buffers_counts(ctx->train), 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  if (losses) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(losses, ctx->train_losses, 5 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return DC_OK;
 }
 

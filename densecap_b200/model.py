@@ -15,16 +15,69 @@ from .synth import ModelDims, feature_hw
 
 
 class LocalizationLayer:
-    """nn.LocalizationLayer, test-time forward (LocalizationLayer.lua:250-363).
+    """nn.LocalizationLayer: test-time forward (LocalizationLayer.lua:250-363) and training-time forward (:383-526).
 
-    forward(cnn_features (1,C,H',W')) -> [roi_features (K,C,HH,WW), roi_boxes (K,4), empty, empty]."""
+    forward(cnn_features (1,C,H',W')) -> [roi_features (K,C,HH,WW), roi_boxes (K,4), gt_boxes_sample, gt_labels_sample];
+    the last two are empty at test time.  After a training forward self.stats['losses'] holds the mid-level losses."""
 
-    def __init__(self, ctx: Context):
+    def __init__(self, ctx: Context, opt=None):
         self.ctx = ctx
         self.train = False
         self.image_height = None
         self.image_width = None
+        self.gt_labels = None
+        self.stats = {"losses": {}, "vars": {}}
+        opt = dict(opt or {})
+        # defaults of LocalizationLayer.lua:79-87 (mid_* weights are mandatory there; train_opts.lua:32-35 values here)
+        self.opt = {"sampler_batch_size": min(opt.get("sampler_batch_size", 256), ctx.max_proposals, 1024),
+                    "sampler_high_thresh": opt.get("sampler_high_thresh", 0.7), "sampler_low_thresh": opt.get("sampler_low_thresh", 0.5),
+                    "train_remove_outbounds_boxes": opt.get("train_remove_outbounds_boxes", 1),
+                    "mid_box_reg_weight": opt.get("mid_box_reg_weight", 0.05), "mid_objectness_weight": opt.get("mid_objectness_weight", 0.1),
+                    "box_reg_decay": opt.get("box_reg_decay", 0.0)}
+        self._push_train_args()
         self.setTestArgs()
+
+    def _push_train_args(self):
+        o = self.opt
+        self.ctx.check(self.ctx._lib.dc_set_train_args(self.ctx.handle, o["mid_box_reg_weight"], o["mid_objectness_weight"], o["box_reg_decay"],
+                                                      o["sampler_low_thresh"], o["sampler_high_thresh"], int(o["sampler_batch_size"]),
+                                                      int(o["train_remove_outbounds_boxes"])))
+
+    def setGroundTruth(self, gt_boxes, gt_labels):                      # LocalizationLayer.lua:181-186
+        b = _check_cuda_f32(gt_boxes)
+        assert b.dim() == 3 and b.shape[0] == 1 and b.shape[2] == 4, "gt_boxes must have shape (N, B1, 4)"
+        assert gt_labels.dim() == 3 and gt_labels.shape[0] == 1 and gt_labels.shape[1] == b.shape[1], "gt_labels must have shape (N, B1, L)"
+        self.gt_labels = gt_labels
+        self.ctx.check(self.ctx._lib.dc_set_ground_truth(self.ctx.handle, ptr(b), int(b.shape[1]), stream_ptr()))
+
+    def training(self):
+        self.train = True
+
+    def _forward_train(self, f):
+        dims = self.ctx.dims
+        _, C_, fh, fw = f.shape
+        S = int(self.opt["sampler_batch_size"])
+        dev = f.device
+        roi = torch.empty((S, C_, dims.pool_hw, dims.pool_hw), dtype=torch.float32, device=dev)
+        boxes = torch.empty((S, 4), dtype=torch.float32, device=dev)
+        tgt_boxes = torch.empty((S, 4), dtype=torch.float32, device=dev)
+        pt = torch.zeros((S,), dtype=torch.int64, device=dev)
+        pi = torch.zeros((S,), dtype=torch.int64, device=dev)
+        ni = torch.zeros((S,), dtype=torch.int64, device=dev)
+        counts = torch.zeros((4,), dtype=torch.int32, device=dev)
+        losses = torch.zeros((5,), dtype=torch.float32, device=dev)
+        # raises DenseCapError(DC_E_PROTOCOL, 'Must call setGroundTruth ...' / 'Must call setImageSize ...') like the asserts at :385-393
+        self.ctx.check(self.ctx._lib.dc_localization_forward_train(self.ctx.handle, ptr(f), fh, fw, ptr(roi), ptr(boxes), ptr(tgt_boxes), ptr(pt),
+                                                                  ptr(pi), ptr(ni), ptr(counts), ptr(losses), stream_ptr()))
+        tot_pos, tot_neg, P, M = [int(v) for v in counts.tolist()]
+        lv = losses.tolist()
+        self.stats = {"losses": {"obj_loss_pos": lv[0], "obj_loss_neg": lv[1], "box_reg_loss": lv[2], "box_decay_loss": lv[3],
+                                 "total_loss": lv[4]},
+                      "vars": {"num_pos": P, "num_neg": M, "total_pos": tot_pos, "total_neg": tot_neg}}
+        self.pos_input_idx, self.pos_target_idx, self.neg_input_idx = pi[:P], pt[:P], ni[:M]
+        labels = self.gt_labels[0].to(dev)[self.pos_target_idx - 1] if self.gt_labels is not None else torch.empty((0,), device=dev)
+        self.output = [roi, boxes, tgt_boxes[:P], labels]
+        return self.output
 
     def setImageSize(self, image_height, image_width):                 # LocalizationLayer.lua:167-172
         self.image_height, self.image_width = int(image_height), int(image_width)
@@ -42,10 +95,10 @@ class LocalizationLayer:
         self.train = False
 
     def forward(self, input):
-        if self.train:
-            raise NotImplementedError("training-mode LocalizationLayer is not built yet (SURVEY.md 8a row a18)")
         f = _check_cuda_f32(input)
         assert f.dim() == 4 and f.shape[0] == 1, "must have 1 image per batch"
+        if self.train:
+            return self._forward_train(f)
         dims = self.ctx.dims
         _, C_, fh, fw = f.shape
         K = self.ctx.max_proposals if self.test_max_proposals == -1 else self.test_max_proposals

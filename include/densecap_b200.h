@@ -139,6 +139,35 @@ int dc_localization_forward_test(dc_ctx* ctx, const float* feats_nchw, int feat_
                                  float* roi_features, float* roi_boxes, int64_t* idx,
                                  int32_t* num_out, void* stream);
 
+/* ---- training-time forward of the LocalizationLayer (BASELINE configs[4]; forward only this round)
+ * Options of nn.LocalizationLayer used by _forward_train (LocalizationLayer.lua:79-87; train_opts.lua:18-42).
+ * sampler_batch_size <= min(max_batch*max_proposals, 1024). */
+int dc_set_train_args(dc_ctx* ctx, float mid_box_reg_weight, float mid_objectness_weight,
+                      float box_reg_decay, float sampler_low_thresh, float sampler_high_thresh,
+                      int sampler_batch_size, int train_remove_outbounds_boxes);
+/* LocalizationLayer:setGroundTruth (LocalizationLayer.lua:181-186): gt_boxes (B1,4) xcycwh fp32, host or
+ * device memory; must precede every training-time forward.  gt_labels stay with the caller: the layer
+ * only indexes them with pos_target_idx (:455-457). */
+int dc_set_ground_truth(dc_ctx* ctx, const float* gt_boxes, int num_gt, void* stream);
+/* nn.LocalizationLayer:_forward_train (LocalizationLayer.lua:383-526): RPN on ALL k*H'*W' boxes,
+ * nn.BoxSampler (modules/BoxSampler.lua:64-167) with the out-of-bounds exclusion, BoxSamplerHelper
+ * gathers, ROI pooling of the S = sampler_batch_size sampled boxes (positives first), and the mid-level
+ * losses (objectness cross-entropy, SmoothL1 on InvertBoxTransform targets with the |t|>10 mask hack,
+ * box_reg_decay regulariser).  torch.multinomial is replaced by a deterministic selection -- the first P
+ * positives / first M negatives in index order -- the same injection point as the reference's
+ * debug_pos_sample_idx / debug_neg_sample_idx hooks (BoxSampler.lua:154-159).
+ * Errors: DC_E_PROTOCOL 'Must call setGroundTruth before training-time forward pass' /
+ * 'Must call setImageSize before each forward pass' (same order as the reference's asserts).
+ * Outputs (device, any may be NULL): roi_features (S,C,HH,WW); roi_boxes (S,4); pos_target_boxes (S,4;
+ * first P rows valid); pos_target_idx / pos_input_idx / neg_input_idx 1-based int64 (S each; P / P / M
+ * valid); num_pos_neg int32[4] = {total positives, total negatives, P, M}; losses fp32[5] =
+ * {obj_loss_pos, obj_loss_neg, box_reg_loss, box_decay_loss, total}. */
+int dc_localization_forward_train(dc_ctx* ctx, const float* feats_nchw, int feat_h, int feat_w,
+                                  float* roi_features, float* roi_boxes, float* pos_target_boxes,
+                                  int64_t* pos_target_idx, int64_t* pos_input_idx,
+                                  int64_t* neg_input_idx, int32_t* num_pos_neg, float* losses,
+                                  void* stream);
+
 /* recog_base + objectness + box_reg + ApplyBoxTransform (DenseCapModel.lua:87-100,127-162).
  * roi_features (K,C,HH,WW) fp32 BCHW, roi_boxes (K,4).  Outputs (K,fc_dim),(K),(K,4),(K,4). */
 int dc_recog_forward(dc_ctx* ctx, const float* roi_features, const float* roi_boxes, int K,
