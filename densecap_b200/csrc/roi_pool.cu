@@ -8,10 +8,14 @@
 // B200 design of the gather: the op is HBM-write bound (K*HH*WW*C*4 B out = 100 MB at K=1000) but every
 // output element reads 4 feature values, i.e. 4x read amplification if served from L2.  Each CTA
 // therefore owns one 32-channel slice of the whole feature map, staged ONCE into shared memory
-// (38*45*32*4 B = 219 KB of the 227 KB), and serves all of its gathers from there.  A half-warp covers
-// (8 lanes cover the 32 channels of one output position with 4 channels per lane: LDS.128 reads, 8-byte
-// split / 16-byte fp32 stores, full 64/128-byte segments per position); the per-position tap record (32 B)
-// arrives through a broadcast global load.  grid = (C/32 slices) x (148/(C/32) ROI groups), 1024 threads.
+// (38*45*32*4 B = 219 KB of the 227 KB, plus one all-zero row that out-of-map corners point at), and serves
+// all of its gathers from there.  Four lanes cover the 32 channels of one output position (8 channels per
+// lane: 2 LDS.128 per corner; odd positions read their two halves in the opposite order so that one LDS
+// instruction of the warp touches every bank exactly 4 times = the 512-byte minimum), so the 32-byte tap
+// record and its address arithmetic are amortised over 8 channels; the hi/lo split is done on packed
+// half2 pairs (cvt.rn.f16x2.f32).  grid = (C/32 slices) x (148/(C/32) ROI groups), 1024 threads.
+// The slice staging does not depend on the taps, so the kernel is launched with programmatic stream
+// serialisation and overlaps roi_taps_kernel; it waits (griddepcontrol.wait) only before the first tap read.
 //
 // The interpolation arithmetic follows the reference CPU kernel's operation order without FMA
 // contraction (mul/add intrinsics), so fp32 outputs are bit-identical to the oracle.
@@ -21,22 +25,25 @@ constexpr int ROI_THREADS = 1024;
 constexpr int ROI_MAX_POS = 64;  // HH*WW <= 64
 
 struct __align__(16) RoiTap {
-  int off[4];     // cell index (y*fw+x) of TL,TR,BL,BR or -1 when outside
+  int off[4];     // float index (cell*ch) of TL,TR,BL,BR inside a ch-channel slice; outside -> the zero row (fh*fw*ch)
   float w[4];     // (wx*wy), ((1-wx)*wy), (wx*(1-wy)), ((1-wx)*(1-wy))
 };
 
 size_t roi_taps_bytes(int max_boxes, int npos) { return (size_t)max_boxes * npos * sizeof(RoiTap) + 256; }
 
 __global__ void roi_taps_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ nboxes_dev, int max_boxes,
-                                float img_h, float img_w, int fh, int fw, int HH, int WW, RoiTap* __restrict__ taps) {
+                                float img_h, float img_w, int fh, int fw, int HH, int WW, int ch, RoiTap* __restrict__ taps) {
+  // let the dependent roi_pool_kernel start staging its feature slice right away (it waits before reading taps)
+  asm volatile("griddepcontrol.launch_dependents;");
   const int npos = HH * WW;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= max_boxes * npos) return;
   const int b = idx / npos, p = idx % npos;
   const int nboxes = nboxes_dev ? min(*nboxes_dev, max_boxes) : max_boxes;
   RoiTap t;
+  const int zero_row = fh * fw * ch;
   if (b >= nboxes) {
-    t.off[0] = t.off[1] = t.off[2] = t.off[3] = -1;
+    t.off[0] = t.off[1] = t.off[2] = t.off[3] = zero_row;
     t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
     taps[idx] = t;
     return;
@@ -71,10 +78,10 @@ __global__ void roi_taps_kernel(const float4* __restrict__ boxes, const int32_t*
   const bool xin0 = xl >= 0 && xl <= fw - 1, xin1 = xl + 1 >= 0 && xl + 1 <= fw - 1;
   const bool yin0 = yt >= 0 && yt <= fh - 1, yin1 = yt + 1 >= 0 && yt + 1 <= fh - 1;
   const bool finite = (xcoord == xcoord) && (ycoord == ycoord);
-  t.off[0] = (finite && xin0 && yin0) ? yt * fw + xl : -1;
-  t.off[1] = (finite && xin1 && yin0) ? yt * fw + xl + 1 : -1;
-  t.off[2] = (finite && xin0 && yin1) ? (yt + 1) * fw + xl : -1;
-  t.off[3] = (finite && xin1 && yin1) ? (yt + 1) * fw + xl + 1 : -1;
+  t.off[0] = (finite && xin0 && yin0) ? (yt * fw + xl) * ch : zero_row;
+  t.off[1] = (finite && xin1 && yin0) ? (yt * fw + xl + 1) * ch : zero_row;
+  t.off[2] = (finite && xin0 && yin1) ? ((yt + 1) * fw + xl) * ch : zero_row;
+  t.off[3] = (finite && xin1 && yin1) ? ((yt + 1) * fw + xl + 1) * ch : zero_row;
   taps[idx] = t;
 }
 
@@ -86,90 +93,113 @@ __device__ __forceinline__ float roi_blend(const RoiTap& t, float tl, float tr, 
   return v;
 }
 
+// two fp32 values -> packed (hi, hi) and (lo, lo) half2 words of the split-fp16 representation (common.cuh split_f32)
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));        // low half <- a
+  const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+  const float ra = __fsub_rn(a, __low2float(h)), rb = __fsub_rn(b, __high2float(h));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
 template <int CH>
 __global__ void __launch_bounds__(ROI_THREADS, 1)
 roi_pool_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ feat_lo, const float* __restrict__ feats_f32,
                 int C, int fh, int fw, const RoiTap* __restrict__ taps, int total_items, int npos,
                 __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_f32, int out_layout) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* slice = reinterpret_cast<float*>(smem_raw);                               // [fh*fw][CH]
-  constexpr int QUADS = CH / 4;                 // lanes per output position (4 channels per lane)
-  constexpr int POS_PER_WARP = 32 / QUADS;      // positions handled concurrently by one warp
+  float* slice = reinterpret_cast<float*>(smem_raw);                               // [fh*fw + 1][CH], last row = zeros
+  constexpr int LPP = CH / 8;                   // lanes per output position (8 channels per lane)
+  constexpr int POS_PER_WARP = 32 / LPP;        // positions handled concurrently by one warp
   const int c0 = blockIdx.x * CH;
   const int cells = fh * fw;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NWARPS = ROI_THREADS / 32;
-  // ---- stage the channel slice (4 channels per lane) ------------------------------------------
-  for (int cell = warp * POS_PER_WARP + lane / QUADS; cell < cells; cell += NWARPS * POS_PER_WARP) {
-    const int cq = (lane % QUADS) * 4;
-    const size_t g = (size_t)cell * C + c0 + cq;
-    float4 v;
-    if (feats_f32) {
-      v = *reinterpret_cast<const float4*>(feats_f32 + g);
-    } else {
-      const uint2 h = *reinterpret_cast<const uint2*>(feat_hi + g);
-      const uint2 l = *reinterpret_cast<const uint2*>(feat_lo + g);
-      const __half2 h01 = *reinterpret_cast<const __half2*>(&h.x), h23 = *reinterpret_cast<const __half2*>(&h.y);
-      const __half2 l01 = *reinterpret_cast<const __half2*>(&l.x), l23 = *reinterpret_cast<const __half2*>(&l.y);
-      v.x = __half2float(__low2half(h01)) + __half2float(__low2half(l01));
-      v.y = __half2float(__high2half(h01)) + __half2float(__high2half(l01));
-      v.z = __half2float(__low2half(h23)) + __half2float(__low2half(l23));
-      v.w = __half2float(__high2half(h23)) + __half2float(__high2half(l23));
+  // ---- stage the channel slice (4 channels per thread and step) ---------------------------------
+  {
+    constexpr int QUADS = CH / 4;
+    for (int e = threadIdx.x; e < cells * QUADS; e += ROI_THREADS) {
+      const int cell = e / QUADS, cq4 = (e % QUADS) * 4;
+      const size_t g = (size_t)cell * C + c0 + cq4;
+      float4 v;
+      if (feats_f32) {
+        v = *reinterpret_cast<const float4*>(feats_f32 + g);
+      } else {
+        const uint2 h = *reinterpret_cast<const uint2*>(feat_hi + g);
+        const uint2 l = *reinterpret_cast<const uint2*>(feat_lo + g);
+        const __half2 h01 = *reinterpret_cast<const __half2*>(&h.x), h23 = *reinterpret_cast<const __half2*>(&h.y);
+        const __half2 l01 = *reinterpret_cast<const __half2*>(&l.x), l23 = *reinterpret_cast<const __half2*>(&l.y);
+        v.x = __low2float(h01) + __low2float(l01);
+        v.y = __high2float(h01) + __high2float(l01);
+        v.z = __low2float(h23) + __low2float(l23);
+        v.w = __high2float(h23) + __high2float(l23);
+      }
+      *reinterpret_cast<float4*>(slice + cell * CH + cq4) = v;
     }
-    *reinterpret_cast<float4*>(slice + cell * CH + cq) = v;
+    if (threadIdx.x < CH) slice[cells * CH + threadIdx.x] = 0.f;
   }
   __syncthreads();
-  const int sub = lane / QUADS;
-  const int cq = (lane % QUADS) * 4;
-  // items (roi*npos + pos) are dealt in contiguous runs of POS_PER_WARP to (blockIdx.y, warp); two runs per
-  // iteration so that four 16-byte tap loads are in flight per lane before the first gather is issued.
+  // the taps come from roi_taps_kernel, the launch just before this one (programmatic dependent launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int sub = lane / LPP;
+  const int half = sub & 1;                               // odd positions read their two 4-channel halves in swapped order
+  const int cA = (lane % LPP) * 8 + 4 * half, cB = (lane % LPP) * 8 + 4 * (half ^ 1);
+  // items (roi*npos + pos) are dealt in contiguous runs of POS_PER_WARP to (blockIdx.y, warp)
   const int stride = gridDim.y * NWARPS * POS_PER_WARP;
+  auto blend4 = [&](const uint4& ta, const uint4& tb, int cc, float (&v)[4]) {
+    const float w0 = __uint_as_float(tb.x), w1 = __uint_as_float(tb.y), w2 = __uint_as_float(tb.z), w3 = __uint_as_float(tb.w);
+    const float4 tl = *reinterpret_cast<const float4*>(slice + ta.x + cc);
+    const float4 tr = *reinterpret_cast<const float4*>(slice + ta.y + cc);
+    const float4 bl = *reinterpret_cast<const float4*>(slice + ta.z + cc);
+    const float4 br = *reinterpret_cast<const float4*>(slice + ta.w + cc);
+    v[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.x), __fmul_rn(w1, tr.x)), __fmul_rn(w2, bl.x)), __fmul_rn(w3, br.x));
+    v[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.y), __fmul_rn(w1, tr.y)), __fmul_rn(w2, bl.y)), __fmul_rn(w3, br.y));
+    v[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.z), __fmul_rn(w1, tr.z)), __fmul_rn(w2, bl.z)), __fmul_rn(w3, br.z));
+    v[3] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.w), __fmul_rn(w1, tr.w)), __fmul_rn(w2, bl.w)), __fmul_rn(w3, br.w));
+  };
+  const int c8 = (lane % LPP) * 8;
   auto emit = [&](int it, const uint4& ta, const uint4& tb) {
-    RoiTap t;
-    t.off[0] = (int)ta.x; t.off[1] = (int)ta.y; t.off[2] = (int)ta.z; t.off[3] = (int)ta.w;
-    t.w[0] = __uint_as_float(tb.x); t.w[1] = __uint_as_float(tb.y); t.w[2] = __uint_as_float(tb.z); t.w[3] = __uint_as_float(tb.w);
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 tl = t.off[0] >= 0 ? *reinterpret_cast<const float4*>(slice + t.off[0] * CH + cq) : z;
-    const float4 tr = t.off[1] >= 0 ? *reinterpret_cast<const float4*>(slice + t.off[1] * CH + cq) : z;
-    const float4 bl = t.off[2] >= 0 ? *reinterpret_cast<const float4*>(slice + t.off[2] * CH + cq) : z;
-    const float4 br = t.off[3] >= 0 ? *reinterpret_cast<const float4*>(slice + t.off[3] * CH + cq) : z;
-    const float v0 = roi_blend(t, tl.x, tr.x, bl.x, br.x);
-    const float v1 = roi_blend(t, tl.y, tr.y, bl.y, br.y);
-    const float v2 = roi_blend(t, tl.z, tr.z, bl.z, br.z);
-    const float v3 = roi_blend(t, tl.w, tr.w, bl.w, br.w);
+    float va[4], vb[4];
+    blend4(ta, tb, cA, va);
+    blend4(ta, tb, cB, vb);
     if (out_hi) {
-      __half h0, l0, h1, l1, h2, l2, h3, l3;
-      split_f32(v0, h0, l0);
-      split_f32(v1, h1, l1);
-      split_f32(v2, h2, l2);
-      split_f32(v3, h3, l3);
-      const size_t o = (size_t)it * C + c0 + cq;
-      uint2 ph, pl;
-      ph.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-      ph.y = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
-      pl.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-      pl.y = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
-      *reinterpret_cast<uint2*>(out_hi + o) = ph;
-      *reinterpret_cast<uint2*>(out_lo + o) = pl;
+      // one 16-byte store per plane: the lane's 8 channels in memory order (va holds the upper half on odd positions)
+      uint32_t ha0, la0, ha1, la1, hb0, lb0, hb1, lb1;
+      split_pair(va[0], va[1], ha0, la0);
+      split_pair(va[2], va[3], ha1, la1);
+      split_pair(vb[0], vb[1], hb0, lb0);
+      split_pair(vb[2], vb[3], hb1, lb1);
+      const uint4 ph = half ? make_uint4(hb0, hb1, ha0, ha1) : make_uint4(ha0, ha1, hb0, hb1);
+      const uint4 pl = half ? make_uint4(lb0, lb1, la0, la1) : make_uint4(la0, la1, lb0, lb1);
+      const size_t o = (size_t)it * C + c0 + c8;
+      *reinterpret_cast<uint4*>(out_hi + o) = ph;
+      *reinterpret_cast<uint4*>(out_lo + o) = pl;
     }
     if (out_f32) {
       if (out_layout == 1) {
-        *reinterpret_cast<float4*>(out_f32 + (size_t)it * C + c0 + cq) = make_float4(v0, v1, v2, v3);
+        *reinterpret_cast<float4*>(out_f32 + (size_t)it * C + c0 + cA) = make_float4(va[0], va[1], va[2], va[3]);
+        *reinterpret_cast<float4*>(out_f32 + (size_t)it * C + c0 + cB) = make_float4(vb[0], vb[1], vb[2], vb[3]);
       } else {
         const int b = it / npos, p = it % npos;
-        float* o = out_f32 + ((size_t)b * C + c0 + cq) * npos + p;
-        o[0] = v0; o[npos] = v1; o[2 * (size_t)npos] = v2; o[3 * (size_t)npos] = v3;
+        float* oa = out_f32 + ((size_t)b * C + c0 + cA) * npos + p;
+        float* ob = out_f32 + ((size_t)b * C + c0 + cB) * npos + p;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { oa[(size_t)j * npos] = va[j]; ob[(size_t)j * npos] = vb[j]; }
       }
     }
   };
-  for (int it0 = (blockIdx.y * NWARPS + warp) * POS_PER_WARP; it0 < total_items; it0 += 2 * stride) {
-    const int itA = it0 + sub, itB = itA + stride;
-    const bool okA = itA < total_items, okB = itB < total_items;
-    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
-    if (okA) { const uint4* tp = reinterpret_cast<const uint4*>(taps + itA); a0 = __ldg(tp); a1 = __ldg(tp + 1); }
-    if (okB) { const uint4* tp = reinterpret_cast<const uint4*>(taps + itB); b0 = __ldg(tp); b1 = __ldg(tp + 1); }
-    if (okA) emit(itA, a0, a1);
-    if (okB) emit(itB, b0, b1);
+  // (plain L2 loads, not __ldg: the taps are written by the still-running previous launch, so the read-only path
+  // contract does not hold and the compiler must not hoist these above griddepcontrol.wait)
+  // software pipeline of depth one: the tap record of the next item is requested before the current item is gathered,
+  // so the L2 latency of the tap load is covered by this warp's own work
+  int it = (blockIdx.y * NWARPS + warp) * POS_PER_WARP + sub;
+  uint4 t0 = make_uint4(0, 0, 0, 0), t1 = t0;
+  if (it < total_items) { const uint4* tp = reinterpret_cast<const uint4*>(taps + it); t0 = __ldcg(tp); t1 = __ldcg(tp + 1); }
+  while (it < total_items) {
+    const int nx = it + stride;
+    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+    if (nx < total_items) { const uint4* tp = reinterpret_cast<const uint4*>(taps + nx); n0 = __ldcg(tp); n1 = __ldcg(tp + 1); }
+    emit(it, t0, t1);
+    t0 = n0; t1 = n1; it = nx;
   }
 }
 
@@ -182,13 +212,13 @@ int k_roi_pool(dc_ctx* ctx, const __half* feat_hi, const __half* feat_lo, const 
   const int npos = HH * WW;
   const int total = max_boxes * npos;
   RoiTap* taps = reinterpret_cast<RoiTap*>(taps_ws);
-  roi_taps_kernel<<<DC_CEIL_DIV(total, 256), 256, 0, st>>>((const float4*)boxes, nboxes_dev, max_boxes, (float)img_h, (float)img_w, fh, fw,
-                                                          HH, WW, taps);
-  DC_CHECK_LAUNCH(ctx);
   const size_t limit = 227 * 1024;
   int ch = 32;
-  while (ch > 8 && ((size_t)fh * fw * ch * 4 > limit || C % ch != 0)) ch >>= 1;
-  const size_t smem = (size_t)fh * fw * ch * 4;
+  while (ch > 8 && ((size_t)(fh * fw + 1) * ch * 4 > limit || C % ch != 0)) ch >>= 1;
+  const size_t smem = (size_t)(fh * fw + 1) * ch * 4;
+  roi_taps_kernel<<<DC_CEIL_DIV(total, 256), 256, 0, st>>>((const float4*)boxes, nboxes_dev, max_boxes, (float)img_h, (float)img_w, fh, fw,
+                                                          HH, WW, ch, taps);
+  DC_CHECK_LAUNCH(ctx);
   DC_REQUIRE(ctx, smem <= limit && C % ch == 0, DC_E_UNSUPPORTED, "roi_pool: feature map %dx%d too large for the shared-memory slice", fh, fw);
   const int slices = C / ch;
   int groups = 148 / slices;
@@ -198,8 +228,15 @@ int k_roi_pool(dc_ctx* ctx, const __half* feat_hi, const __half* feat_lo, const 
   do {                                                                                                               \
     cudaError_t e = cudaFuncSetAttribute(roi_pool_kernel<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "roi_pool smem attribute: %s", cudaGetErrorString(e));    \
-    roi_pool_kernel<CHV><<<grid, ROI_THREADS, smem, st>>>(feat_hi, feat_lo, feats_f32, C, fh, fw, taps, total, npos,   \
-                                                          out_hi, out_lo, out_f32, out_layout);                          \
+    cudaLaunchConfig_t lc = {};                                                                                      \
+    lc.gridDim = grid; lc.blockDim = dim3(ROI_THREADS); lc.dynamicSmemBytes = smem; lc.stream = st;                   \
+    cudaLaunchAttribute at[1];                                                                                       \
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                   \
+    at[0].val.programmaticStreamSerializationAllowed = 1;                                                            \
+    lc.attrs = at; lc.numAttrs = 1;                                                                                  \
+    e = cudaLaunchKernelEx(&lc, roi_pool_kernel<CHV>, feat_hi, feat_lo, feats_f32, C, fh, fw, (const RoiTap*)taps, total, npos, \
+                           out_hi, out_lo, out_f32, out_layout);                                                     \
+    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "roi_pool launch: %s", cudaGetErrorString(e));          \
   } while (0)
   if (ch == 32) ROI_LAUNCH(32);
   else if (ch == 16) ROI_LAUNCH(16);

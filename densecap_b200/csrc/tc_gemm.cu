@@ -155,6 +155,18 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3)
                : "memory");
 }
+// One lane of a fully converged warp.  The single-thread roles (TMA producer, MMA issuer) must be entered through
+// elect.sync: with a plain `lane == 0` test the compiler cannot prove the region single-threaded and wraps every
+// uniform-datapath instruction (UTCHMMA, UTCBAR, UBLKCP) in an ELECT/BRA.U.ANY waterfall loop, ~100 issue cycles per MMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -241,158 +253,28 @@ struct Cfg {
   static constexpr uint32_t B_PLANE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr uint32_t STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
   static constexpr int STAGES = (STAGE_BYTES <= 49152) ? 4 : (STAGE_BYTES <= 65536 ? 3 : 2);
-  static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;   // power of two for 64/128/256
+  // WIDE: one MMA multiplies A_hi with the hi AND lo plane of B at once (the two planes are adjacent in the stage, so they
+  // form one 2*BLOCK_N-row K-major operand) -- see the MMA issuer.  The accumulator is then 2*BLOCK_N columns wide.
+  static constexpr bool WIDE = (CG == 1 && BLOCK_N <= 128);
+  static constexpr int ACC_COLS = WIDE ? 2 * BLOCK_N : BLOCK_N;
+  static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                            // power of two: 256 or 512
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
 };
 
-template <int BLOCK_N, bool CONV, bool POOL, int CG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Problem pb, GemmEpilogue ep) {
-  using C = Cfg<BLOCK_N, CG>;
-  // CG == 2: the two CTAs of a cluster form one 256-row tile; rank 0 (leader) issues the MMAs
-  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
-  const bool is_leader = (cta_rank == 0);
-  const int worker = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // tile-scheduler slot
-  const int num_workers = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  if (CG == 2) cluster_sync_all();
-  constexpr int STAGES = C::STAGES;
-  extern __shared__ unsigned char smem_dyn[];
-  // 1024-byte alignment required by SWIZZLE_128B
-  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_aligned + (size_t)STAGES * C::STAGE_BYTES);
-  // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem base address holder
-  const uint32_t bar_base = smem_base + STAGES * C::STAGE_BYTES;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* bias_smem = reinterpret_cast<float*>(smem_aligned + (size_t)STAGES * C::STAGE_BYTES + 256);   // [2][BLOCK_N]
-
+// Epilogue warps (2-5) of both kernels: drain the finished accumulator of every tile this CTA owns.
+// tfull0 / tempty0: shared addresses of the two tmem_full / tmem_empty barriers (8 bytes apart).
+template <int BLOCK_N, bool CONV, bool POOL, int CG, bool WIDE>
+__device__ __forceinline__ void epilogue_warps(const Problem& pb, const GemmEpilogue& ep, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                               float* bias_smem, int worker, int num_workers, uint32_t cta_rank, bool is_leader) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    prefetch_tmap(&tmap_a);
-    prefetch_tmap(&tmap_b);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), CG);          // one producer arrival per CTA of the pair (leader's barrier is the live one)
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128 * CG);  // all epilogue threads of the pair arrive on the leader's barrier
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    if (CG == 2) tmem_alloc2(smem_u32(tmem_holder), C::TMEM_COLS);
-    else tmem_alloc(smem_u32(tmem_holder), C::TMEM_COLS);
-  }
-  tcgen05_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
-
   const int num_tiles = pb.m_tiles * pb.n_tiles;
-
   auto tile_coords = [&](int tile, int& mt, int& nt) {
     if (pb.m_fastest) { mt = tile % pb.m_tiles; nt = tile / pb.m_tiles; }
     else { nt = tile % pb.n_tiles; mt = tile / pb.n_tiles; }
   };
-
-  if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
-        int mt, nt;
-        tile_coords(tile, mt, nt);
-        const int n0 = nt * BLOCK_N + (int)cta_rank * C::B_ROWS;     // this CTA's slice of the B tile
-        int img = 0, h0 = 0, w0 = 0;
-        if (CONV) {
-          const int per_img = pb.tiles_h * pb.tiles_w;               // CG == 2: tiles_h counts 16-row pair tiles
-          img = mt / per_img;
-          const int r = mt % per_img;
-          h0 = ((r / pb.tiles_w) * CG + (int)cta_rank) * TILE_H;
-          w0 = (r % pb.tiles_w) * TILE_W;
-        }
-        const int m0 = (mt * CG + (int)cta_rank) * BLOCK_M;
-        for (int kb = 0; kb < pb.num_k_blocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t b_dst = a_dst + 2 * A_PLANE_BYTES;
-          if (CG == 2) {
-            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);   // both CTAs' bytes land here
-            else mbar_arrive_remote(full_bar(stage), 0);
-          } else {
-            mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
-          }
-          if (CONV) {
-            const int tap = kb / pb.kb_per_tap;
-            const int c0 = (kb % pb.kb_per_tap) * BLOCK_K;
-            const int r = tap / 3, s = tap % 3;
-            if (CG == 2) tma2_load_5d(a_dst, &tmap_a, full_bar(stage), c0, w0 + s - 1, h0 + r - 1, img, 0);
-            else tma_load_5d(a_dst, &tmap_a, full_bar(stage), c0, w0 + s - 1, h0 + r - 1, img, 0);
-          } else {
-            if (CG == 2) tma2_load_3d(a_dst, &tmap_a, full_bar(stage), kb * BLOCK_K, m0, 0);
-            else tma_load_3d(a_dst, &tmap_a, full_bar(stage), kb * BLOCK_K, m0, 0);
-          }
-          if (CG == 2) tma2_load_3d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, n0, 0);
-          else tma_load_3d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, n0, 0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0 && is_leader) {
-      constexpr uint32_t idesc = make_idesc_f16(BLOCK_M * CG, BLOCK_N);
-      int stage = 0; uint32_t phase = 0;
-      int iter = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
-        const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < pb.num_k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tcgen05_fence_after();
-          const uint32_t a_hi = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t a_lo = a_hi + A_PLANE_BYTES;
-          const uint32_t b_hi = a_hi + 2 * A_PLANE_BYTES;
-          const uint32_t b_lo = b_hi + C::B_PLANE_BYTES;
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint32_t koff = k * UMMA_K * 2;   // bytes along K inside the swizzle atom
-            const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff);
-            const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff);
-            const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff);
-            const uint64_t db_lo = make_kmajor_sw128_desc(b_lo + koff);
-            if (CG == 2) {
-              umma2_f16(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);
-              umma2_f16(d_tmem, da_hi, db_lo, idesc, 1);
-              umma2_f16(d_tmem, da_hi, db_hi, idesc, 1);
-            } else {
-              umma_f16(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);   // small terms first
-              umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
-              umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
-            }
-          }
-          if (CG == 2) {
-            umma2_commit_mc(empty_bar(stage));                              // frees this stage in BOTH CTAs
-            if (kb == pb.num_k_blocks - 1) umma2_commit_mc(tfull_bar(acc)); // accumulators of both CTAs complete
-          } else {
-            umma_commit(empty_bar(stage));                       // smem stage free once these MMAs retire
-            if (kb == pb.num_k_blocks - 1) umma_commit(tfull_bar(acc));   // accumulator complete
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else {
-    // =============================== epilogue warps ===============================
+  auto tfull_bar = [&](int s) { return tfull0 + 8u * s; };
+  auto tempty_bar = [&](int s) { return tempty0 + 8u * s; };
+  {
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row_in_tile = q * 32 + lane;
     int iter = 0;
@@ -439,7 +321,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+      constexpr int ACC_COLS = WIDE ? 2 * BLOCK_N : BLOCK_N;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t raw[32];
@@ -447,6 +330,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tmem_ld_wait();
         const int nc = n0 + c * 32;
         if (nc >= pb.N) continue;           // whole chunk outside N (uniform across the CTA)
+        if (WIDE) {
+          // columns [BLOCK_N, 2*BLOCK_N) hold the A_hi . B_lo partial sums of the same outputs
+          uint32_t raw2[32];
+          tmem_ld_32x32(t_row + BLOCK_N + c * 32, raw2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+        }
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -563,10 +454,373 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         atomicMax(ep.argmax + out_row, pack_argmax_tc(best_v, best_c));
     }
   }
+}
+
+template <int BLOCK_N, bool CONV, bool POOL, int CG>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Problem pb, GemmEpilogue ep) {
+  using C = Cfg<BLOCK_N, CG>;
+  // CG == 2: the two CTAs of a cluster form one 256-row tile; rank 0 (leader) issues the MMAs
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
+  const int worker = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // tile-scheduler slot
+  const int num_workers = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  if (CG == 2) cluster_sync_all();
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ unsigned char smem_dyn[];
+  // 1024-byte alignment required by SWIZZLE_128B
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_aligned + (size_t)STAGES * C::STAGE_BYTES);
+  // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem base address holder
+  const uint32_t bar_base = smem_base + STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* bias_smem = reinterpret_cast<float*>(smem_aligned + (size_t)STAGES * C::STAGE_BYTES + 256);   // [2][BLOCK_N]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), CG);          // one producer arrival per CTA of the pair (leader's barrier is the live one)
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 128 * CG);  // all epilogue threads of the pair arrive on the leader's barrier
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc2(smem_u32(tmem_holder), C::TMEM_COLS);
+    else tmem_alloc(smem_u32(tmem_holder), C::TMEM_COLS);
+  }
+  tcgen05_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int num_tiles = pb.m_tiles * pb.n_tiles;
+
+  auto tile_coords = [&](int tile, int& mt, int& nt) {
+    if (pb.m_fastest) { mt = tile % pb.m_tiles; nt = tile / pb.m_tiles; }
+    else { nt = tile % pb.n_tiles; mt = tile / pb.n_tiles; }
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        int mt, nt;
+        tile_coords(tile, mt, nt);
+        const int n0 = nt * BLOCK_N + (int)cta_rank * C::B_ROWS;     // this CTA's slice of the B tile
+        int img = 0, h0 = 0, w0 = 0;
+        if (CONV) {
+          const int per_img = pb.tiles_h * pb.tiles_w;               // CG == 2: tiles_h counts 16-row pair tiles
+          img = mt / per_img;
+          const int r = mt % per_img;
+          h0 = ((r / pb.tiles_w) * CG + (int)cta_rank) * TILE_H;
+          w0 = (r % pb.tiles_w) * TILE_W;
+        }
+        const int m0 = (mt * CG + (int)cta_rank) * BLOCK_M;
+        for (int kb = 0; kb < pb.num_k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + 2 * A_PLANE_BYTES;
+          if (CG == 2) {
+            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);   // both CTAs' bytes land here
+            else mbar_arrive_remote(full_bar(stage), 0);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          }
+          if (CONV) {
+            const int tap = kb / pb.kb_per_tap;
+            const int c0 = (kb % pb.kb_per_tap) * BLOCK_K;
+            const int r = tap / 3, s = tap % 3;
+            if (CG == 2) tma2_load_5d(a_dst, &tmap_a, full_bar(stage), c0, w0 + s - 1, h0 + r - 1, img, 0);
+            else tma_load_5d(a_dst, &tmap_a, full_bar(stage), c0, w0 + s - 1, h0 + r - 1, img, 0);
+          } else {
+            if (CG == 2) tma2_load_3d(a_dst, &tmap_a, full_bar(stage), kb * BLOCK_K, m0, 0);
+            else tma_load_3d(a_dst, &tmap_a, full_bar(stage), kb * BLOCK_K, m0, 0);
+          }
+          if (CG == 2) tma2_load_3d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, n0, 0);
+          else tma_load_3d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, n0, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (is_leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(BLOCK_M * CG, BLOCK_N);
+      constexpr uint32_t idesc_wide = make_idesc_f16(BLOCK_M, C::WIDE ? 2 * BLOCK_N : BLOCK_N);
+      int stage = 0; uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
+        for (int kb = 0; kb < pb.num_k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t a_hi = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t a_lo = a_hi + A_PLANE_BYTES;
+          const uint32_t b_hi = a_hi + 2 * A_PLANE_BYTES;
+          const uint32_t b_lo = b_hi + C::B_PLANE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 2;   // bytes along K inside the swizzle atom
+            const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff);
+            const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff);
+            const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff);
+            const uint64_t db_lo = make_kmajor_sw128_desc(b_lo + koff);
+            if (C::WIDE) {
+              // D[:, 0:BN] += A_hi.B_hi and D[:, BN:2BN] += A_hi.B_lo in ONE N = 2*BN instruction (B planes are adjacent), then
+              // D[:, 0:BN] += A_lo.B_hi.  Every MMA reads its 128 x 32 B A slice from shared memory (~90 clk, measured); two
+              // instructions instead of three per K step is what lifts the narrow tiles.
+              umma_f16(d_tmem, da_hi, db_hi, idesc_wide, (kb | k) != 0);
+              umma_f16(d_tmem, da_lo, db_hi, idesc, 1);
+            } else if (CG == 2) {
+              umma2_f16(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);
+              umma2_f16(d_tmem, da_hi, db_lo, idesc, 1);
+              umma2_f16(d_tmem, da_hi, db_hi, idesc, 1);
+            } else {
+              umma_f16(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);   // small terms first
+              umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
+              umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+            }
+          }
+          if (CG == 2) {
+            umma2_commit_mc(empty_bar(stage));                              // frees this stage in BOTH CTAs
+            if (kb == pb.num_k_blocks - 1) umma2_commit_mc(tfull_bar(acc)); // accumulators of both CTAs complete
+          } else {
+            umma_commit(empty_bar(stage));                       // smem stage free once these MMAs retire
+            if (kb == pb.num_k_blocks - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    epilogue_warps<BLOCK_N, CONV, POOL, CG, C::WIDE>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, worker, num_workers, cta_rank, is_leader);
+  }
 
   __syncwarp();     // lanes of the single-thread roles rejoin their warp before the aligned barriers below
   tcgen05_fence_before();
   // CG == 2: neither CTA may exit (or free TMEM) while the leader can still read its smem / signal its barriers
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    if (CG == 2) tmem_dealloc2(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 convolution with vertical tap sharing ("halo" kernel).
+//
+// The plain implicit GEMM above re-fetches the activation patch for each of the 9 filter taps (9 x 32 KB per
+// 64-channel block), and ncu shows the kernel bound by the per-SM operand fill rate.  Here the producer
+// loads ONE {64 ch, 16 w, 10 h} halo box per (horizontal tap s, channel block): its rows are ordered (h, w), so
+// the M = 128 rows of vertical tap r are simply the 128 rows starting 16*r rows (2048 B, a multiple of the
+// 1024-byte swizzle atom) into the box -- three taps read the same shared-memory tile through descriptors
+// that differ only in their start address.  A bytes per tile drop 2.4x (3 x 40 KB instead of 9 x 32 KB).
+// A and B therefore run in two independent mbarrier rings: A ring = 2 stages x 40 KB (one fill per (s, cb)
+// group), B ring = SB stages of one tap's weights each.  When a layer's whole filter bank fits the B ring
+// (Cin = Cout = 64: 9 taps x 16 KB, conv1_2) it is loaded once per CTA and stays resident.
+// ------------------------------------------------------------------------------------------------
+constexpr int HALO_H = TILE_H + 2;
+constexpr uint32_t AH_PLANE_BYTES = HALO_H * TILE_W * BLOCK_K * 2;      // 20480
+constexpr uint32_t AH_STAGE_BYTES = 2 * AH_PLANE_BYTES;                 // 40960
+constexpr int AH_STAGES = 2;
+
+template <int BLOCK_N, int CG>
+struct HaloCfg {
+  static constexpr int B_ROWS = BLOCK_N / CG;
+  static constexpr uint32_t B_PLANE_BYTES = B_ROWS * BLOCK_K * 2;
+  static constexpr uint32_t B_STAGE_BYTES = 2 * B_PLANE_BYTES;
+  static constexpr int SB = (B_STAGE_BYTES <= 16384) ? 9 : (B_STAGE_BYTES <= 32768 ? 4 : 2);
+  static constexpr bool WIDE = (CG == 1 && BLOCK_N <= 128);
+  static constexpr int ACC_COLS = WIDE ? 2 * BLOCK_N : BLOCK_N;
+  static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+  static constexpr uint32_t RING_BYTES = AH_STAGES * AH_STAGE_BYTES + SB * B_STAGE_BYTES;
+  static constexpr size_t SMEM_BYTES = (size_t)RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
+};
+
+template <int BLOCK_N, bool POOL, int CG>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Problem pb, GemmEpilogue ep) {
+  using C = HaloCfg<BLOCK_N, CG>;
+  constexpr int SB = C::SB;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
+  const int worker = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  if (CG == 2) cluster_sync_all();
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  const uint32_t a_ring = smem_base;
+  const uint32_t b_ring = smem_base + AH_STAGES * AH_STAGE_BYTES;
+  // bars: a_full[2], a_empty[2], b_full[SB], b_empty[SB], tmem_full[2], tmem_empty[2], tmem base holder
+  const uint32_t bar_base = smem_base + C::RING_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_aligned + C::RING_BYTES);
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (AH_STAGES + s); };
+  auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * AH_STAGES + s); };
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (2 * AH_STAGES + SB + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * AH_STAGES + 2 * SB + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * AH_STAGES + 2 * SB + 2 + s); };
+  static_assert((2 * AH_STAGES + 2 * SB + 4) * 8 + 8 <= 256, "barrier block overflow");
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * AH_STAGES + 2 * SB + 4);
+  float* bias_smem = reinterpret_cast<float*>(smem_aligned + C::RING_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < AH_STAGES; ++s) { mbar_init(afull_bar(s), CG); mbar_init(aempty_bar(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(bfull_bar(s), CG); mbar_init(bempty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128 * CG); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc2(smem_u32(tmem_holder), C::TMEM_COLS);
+    else tmem_alloc(smem_u32(tmem_holder), C::TMEM_COLS);
+  }
+  tcgen05_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int num_tiles = pb.m_tiles * pb.n_tiles;
+  const int groups = 3 * pb.kb_per_tap;                                 // (s, channel block) groups per tile
+  // whole filter bank of the (single) N tile fits the B ring: load it once, keep it
+  const bool b_resident = (pb.n_tiles == 1) && (pb.num_k_blocks == SB);
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (elect_one()) {
+      int sa = 0; uint32_t pa = 0;
+      int sb = 0; uint32_t pbp = 0;
+      bool first = true;
+      for (int tile = worker; tile < num_tiles; tile += num_workers, first = false) {
+        const int nt = tile % pb.n_tiles, mt = tile / pb.n_tiles;
+        const int n0 = nt * BLOCK_N + (int)cta_rank * C::B_ROWS;
+        const int per_img = pb.tiles_h * pb.tiles_w;
+        const int img = mt / per_img;
+        const int rr = mt % per_img;
+        const int h0 = ((rr / pb.tiles_w) * CG + (int)cta_rank) * TILE_H;
+        const int w0 = (rr % pb.tiles_w) * TILE_W;
+        for (int g = 0; g < groups; ++g) {
+          const int s = g / pb.kb_per_tap, cb = g % pb.kb_per_tap;
+          mbar_wait(aempty_bar(sa), pa ^ 1);
+          const uint32_t a_dst = a_ring + sa * AH_STAGE_BYTES;
+          if (CG == 2) {
+            if (is_leader) mbar_arrive_expect_tx(afull_bar(sa), 2 * AH_STAGE_BYTES);
+            else mbar_arrive_remote(afull_bar(sa), 0);
+            tma2_load_5d(a_dst, &tmap_a, afull_bar(sa), cb * BLOCK_K, w0 + s - 1, h0 - 1, img, 0);
+          } else {
+            mbar_arrive_expect_tx(afull_bar(sa), AH_STAGE_BYTES);
+            tma_load_5d(a_dst, &tmap_a, afull_bar(sa), cb * BLOCK_K, w0 + s - 1, h0 - 1, img, 0);
+          }
+          if (++sa == AH_STAGES) { sa = 0; pa ^= 1; }
+          if (b_resident && !first) continue;
+          for (int r = 0; r < 3; ++r) {
+            mbar_wait(bempty_bar(sb), pbp ^ 1);
+            const uint32_t b_dst = b_ring + sb * C::B_STAGE_BYTES;
+            const int k0 = ((r * 3 + s) * pb.kb_per_tap + cb) * BLOCK_K;
+            if (CG == 2) {
+              if (is_leader) mbar_arrive_expect_tx(bfull_bar(sb), 2 * C::B_STAGE_BYTES);
+              else mbar_arrive_remote(bfull_bar(sb), 0);
+              tma2_load_3d(b_dst, &tmap_b, bfull_bar(sb), k0, n0, 0);
+            } else {
+              mbar_arrive_expect_tx(bfull_bar(sb), C::B_STAGE_BYTES);
+              tma_load_3d(b_dst, &tmap_b, bfull_bar(sb), k0, n0, 0);
+            }
+            if (++sb == SB) { sb = 0; pbp ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (is_leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(BLOCK_M * CG, BLOCK_N);
+      constexpr uint32_t idesc_wide = make_idesc_f16(BLOCK_M, C::WIDE ? 2 * BLOCK_N : BLOCK_N);
+      int sa = 0; uint32_t pa = 0;
+      int sb = 0; uint32_t pbp = 0;
+      int iter = 0;
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait(afull_bar(sa), pa);
+          const uint32_t a_base = a_ring + sa * AH_STAGE_BYTES;
+#pragma unroll 1
+          for (int r = 0; r < 3; ++r) {
+            if (!(b_resident && iter > 0)) mbar_wait(bfull_bar(sb), pbp);
+            tcgen05_fence_after();
+            const uint32_t a_hi = a_base + r * (TILE_W * BLOCK_K * 2);      // 16 rows = 2048 B down the halo box
+            const uint32_t a_lo = a_hi + AH_PLANE_BYTES;
+            const uint32_t b_hi = b_ring + sb * C::B_STAGE_BYTES;
+            const uint32_t b_lo = b_hi + C::B_PLANE_BYTES;
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint32_t koff = k * UMMA_K * 2;
+              const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff);
+              const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff);
+              const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff);
+              const uint64_t db_lo = make_kmajor_sw128_desc(b_lo + koff);
+              const uint32_t accum = (g | r | k) != 0;
+              if (C::WIDE) {
+                umma_f16(d_tmem, da_hi, db_hi, idesc_wide, accum);
+                umma_f16(d_tmem, da_lo, db_hi, idesc, 1);
+              } else if (CG == 2) {
+                umma2_f16(d_tmem, da_lo, db_hi, idesc, accum);
+                umma2_f16(d_tmem, da_hi, db_lo, idesc, 1);
+                umma2_f16(d_tmem, da_hi, db_hi, idesc, 1);
+              } else {
+                umma_f16(d_tmem, da_lo, db_hi, idesc, accum);
+                umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
+                umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+              }
+            }
+            const bool last = (g == groups - 1) && (r == 2);
+            if (CG == 2) {
+              if (!b_resident) umma2_commit_mc(bempty_bar(sb));
+              if (r == 2) umma2_commit_mc(aempty_bar(sa));
+              if (last) umma2_commit_mc(tfull_bar(acc));
+            } else {
+              if (!b_resident) umma_commit(bempty_bar(sb));
+              if (r == 2) umma_commit(aempty_bar(sa));
+              if (last) umma_commit(tfull_bar(acc));
+            }
+            if (++sb == SB) { sb = 0; pbp ^= 1; }
+          }
+          if (++sa == AH_STAGES) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    epilogue_warps<BLOCK_N, true, POOL, CG, C::WIDE>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, worker, num_workers, cta_rank, is_leader);
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
@@ -592,26 +846,24 @@ static int encode_map(dc_ctx* ctx, CUtensorMap* map, const void* base, int rank,
   return DC_OK;
 }
 
-template <int BLOCK_N, bool CONV, bool POOL, int CG>
-static int launch(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const Problem& pb, const GemmEpilogue& ep, cudaStream_t st) {
-  using C = Cfg<BLOCK_N, CG>;
-  static bool attr_set = false;
-  auto kernel = tc_gemm_kernel<BLOCK_N, CONV, POOL, CG>;
+template <typename Kernel>
+static int launch_kernel(dc_ctx* ctx, Kernel kernel, bool& attr_set, size_t smem_bytes, int cg, const CUtensorMap& ma, const CUtensorMap& mb,
+                         const Problem& pb, const GemmEpilogue& ep, cudaStream_t st) {
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "tc_gemm smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int tiles = pb.m_tiles * pb.n_tiles;
-  const int slots = g_num_sms / CG;                        // CTAs (CG=1) or CTA pairs (CG=2) resident at once
+  const int slots = g_num_sms / cg;                        // CTAs (CG=1) or CTA pairs (CG=2) resident at once
   const int workers = tiles < slots ? tiles : slots;
-  if (CG == 1) {
-    kernel<<<workers, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, pb, ep);
+  if (cg == 1) {
+    kernel<<<workers, NUM_THREADS, smem_bytes, st>>>(ma, mb, pb, ep);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(workers * 2);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -627,11 +879,28 @@ static int launch(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, con
   return DC_OK;
 }
 
-// Tile shape by a bandwidth model: the kernel is bound by the per-SM operand fill rate (~45 B/clk measured), so the
-// cost of a launch is  rounds x bytes-per-CTA-per-k-block  with rounds = ceil(tiles / slots); wider tiles amortise
-// the A operand and the 2-CTA (cta_group::2) shape additionally halves the B bytes each CTA has to fetch.
+template <int BLOCK_N, bool CONV, bool POOL, int CG>
+static int launch(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const Problem& pb, const GemmEpilogue& ep, cudaStream_t st) {
+  static bool attr_set = false;
+  return launch_kernel(ctx, tc_gemm_kernel<BLOCK_N, CONV, POOL, CG>, attr_set, Cfg<BLOCK_N, CG>::SMEM_BYTES, CG, ma, mb, pb, ep, st);
+}
+
+template <int BLOCK_N, bool POOL, int CG>
+static int launch_halo(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const Problem& pb, const GemmEpilogue& ep, cudaStream_t st) {
+  static bool attr_set = false;
+  return launch_kernel(ctx, tc_conv_halo_kernel<BLOCK_N, POOL, CG>, attr_set, HaloCfg<BLOCK_N, CG>::SMEM_BYTES, CG, ma, mb, pb, ep, st);
+}
+
+// Tile shape by an MMA-issue model (ncu, r06): a tcgen05.mma of this kernel cannot retire faster than ~90 clk because it
+// streams its 128 x 32 B A slice from shared memory, and it takes N/2 clk on the tensor pipe (M = 128 per CTA).  Per K = 16
+// step a CTA spends
+//   BLOCK_N =  64 (wide): max(64,90) + max(32,90)  = 180 clk for 128 x  64 outputs
+//   BLOCK_N = 128 (wide): max(128,90) + max(64,90) = 218 clk for 128 x 128 outputs
+//   BLOCK_N = 256       : 3 x 128                  = 384 clk for 128 x 256 outputs   (cta_group::2: same per CTA, half the B fill)
+// and a launch costs rounds x that, rounds = ceil(tiles / resident CTAs).
 struct TileCfg { int bn; int cg; };
 static int g_allow_cg2 = -1;
+static int g_allow_halo = -1;
 static TileCfg pick_tile(int N, int m_tiles128, bool lstm) {
   if (g_allow_cg2 < 0) {
     const char* e = getenv("DC_TC_CG2");
@@ -639,23 +908,21 @@ static TileCfg pick_tile(int N, int m_tiles128, bool lstm) {
   }
   TileCfg best{64, 1};
   double best_cost = 1e30;
-  const int cand[3] = {64, 128, 256};
-  for (int i = 0; i < 3; ++i) {
-    const int bn = cand[i];
-    if (bn > 64 && N <= bn / 2) continue;                    // mostly-empty tile
-    const long tiles = (long)m_tiles128 * DC_CEIL_DIV(N, bn);
-    const long rounds = DC_CEIL_DIV(tiles, (long)g_num_sms);
-    const double cost = (double)rounds * (2.0 * A_PLANE_BYTES + 2.0 * bn * BLOCK_K * 2);
-    if (cost < best_cost) { best_cost = cost; best = TileCfg{bn, 1}; }
-  }
-  if (g_allow_cg2 && !lstm && N > 128 && m_tiles128 >= 2) {
-    const long tiles = (long)DC_CEIL_DIV(m_tiles128, 2) * DC_CEIL_DIV(N, 256);
-    const long rounds = DC_CEIL_DIV(tiles, (long)(g_num_sms / 2));
-    const double cost = (double)rounds * (2.0 * A_PLANE_BYTES + 2.0 * 128 * BLOCK_K * 2);
-    if (cost < 0.95 * best_cost) { best_cost = cost; best = TileCfg{256, 2}; }
-  }
+  auto consider = [&](int bn, int cg, double kcyc) {
+    if (bn > 64 && N <= bn / 2) return;                    // mostly-empty tile
+    if (cg == 2 && (lstm || N <= 128 || m_tiles128 < 2)) return;
+    const long tiles = (long)DC_CEIL_DIV(m_tiles128, cg) * DC_CEIL_DIV(N, bn);
+    const long rounds = DC_CEIL_DIV(tiles, (long)(g_num_sms / cg));
+    const double cost = (double)rounds * kcyc;
+    if (cost < best_cost) { best_cost = cost; best = TileCfg{bn, cg}; }
+  };
+  consider(64, 1, 180.0);
+  consider(128, 1, 218.0);
+  consider(256, 1, 384.0);
+  if (g_allow_cg2) consider(256, 2, 384.0 * 0.97);
   return best;
 }
+static TileCfg pick_tile_halo(int N, int m_tiles128) { return pick_tile(N, m_tiles128, false); }
 
 }  // namespace tc
 
@@ -732,7 +999,13 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
   pb.N = Cout;
   pb.tiles_w = DC_CEIL_DIV(W, TILE_W);
   const int m_tiles128 = N * DC_CEIL_DIV(H, TILE_H) * pb.tiles_w;
-  const TileCfg tc_ = pick_tile(Cout, m_tiles128, false);
+  if (g_allow_halo < 0) {
+    const char* e = getenv("DC_TC_HALO");
+    g_allow_halo = (e && e[0] == '0') ? 0 : 1;
+    pick_tile(64, 1, false);                           // initialises g_allow_cg2
+  }
+  const bool halo = g_allow_halo != 0;
+  const TileCfg tc_ = halo ? pick_tile_halo(Cout, m_tiles128) : pick_tile(Cout, m_tiles128, false);
   const int bn = tc_.bn, cg = tc_.cg;
   pb.tiles_h = DC_CEIL_DIV(H, TILE_H * cg);          // cg == 2: a pair tile covers 16 image rows (two stacked 8x16 patches)
   pb.m_tiles = N * pb.tiles_h * pb.tiles_w;
@@ -752,7 +1025,7 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
   {
     const uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N, 2};
     const uint64_t str[4] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2, (uint64_t)x_plane_elems * 2};
-    const uint32_t box[5] = {BLOCK_K, TILE_W, TILE_H, 1, 2};
+    const uint32_t box[5] = {BLOCK_K, TILE_W, (uint32_t)(halo ? HALO_H : TILE_H), 1, 2};
     int rc = encode_map(ctx, &ma, x_planes, 5, dims, str, box);
     if (rc) return rc;
   }
@@ -762,6 +1035,18 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
     const uint32_t box[3] = {BLOCK_K, (uint32_t)(bn / cg), 2};
     int rc = encode_map(ctx, &mb, w_planes, 3, dims, str, box);
     if (rc) return rc;
+  }
+  if (halo) {
+    if (fuse_pool) {
+      if (cg == 2) return launch_halo<256, true, 2>(ctx, ma, mb, pb, ep, st);
+      if (bn == 64) return launch_halo<64, true, 1>(ctx, ma, mb, pb, ep, st);
+      if (bn == 256) return launch_halo<256, true, 1>(ctx, ma, mb, pb, ep, st);
+      return launch_halo<128, true, 1>(ctx, ma, mb, pb, ep, st);
+    }
+    if (cg == 2) return launch_halo<256, false, 2>(ctx, ma, mb, pb, ep, st);
+    if (bn == 64) return launch_halo<64, false, 1>(ctx, ma, mb, pb, ep, st);
+    if (bn == 256) return launch_halo<256, false, 1>(ctx, ma, mb, pb, ep, st);
+    return launch_halo<128, false, 1>(ctx, ma, mb, pb, ep, st);
   }
   if (fuse_pool) {
     if (cg == 2) return launch<256, true, true, 2>(ctx, ma, mb, pb, ep, st);

@@ -98,6 +98,10 @@ def test_simt_conv(ctx, N, Cin, Cout, H, W, pool):
     (1, 64, 64, 16, 32, 2),       # fused pool epilogue, even size
     (1, 64, 128, 75, 90, 2),      # fused ceil-mode pool with odd height (75 -> 38)
     (2, 256, 256, 19, 23, 2),     # batch, odd both, 4 k-blocks per tap
+    (1, 64, 64, 150, 200, 2),     # 247 tiles on 148 SMs: resident filter bank reused across tiles of one CTA (conv1_2 path)
+    (2, 64, 64, 120, 130, 0),     # same, batch 2, no pool
+    (1, 128, 256, 150, 180, 0),   # cta_group::2 pair tiles, several rounds, 2 k-blocks per tap
+    (1, 512, 512, 38, 45, 0),     # conv5 shape: 8 channel blocks per tap through the 9-stage B ring
 ])
 def test_tc_conv(ctx, N, Cin, Cout, H, W, pool):
     y, ref = run_conv(ctx, N, Cin, Cout, H, W, pool, TC, seed=H * W + Cin)
