@@ -67,6 +67,8 @@ struct dc_ctx {
   // of different images of a batch overlap instead of queueing behind each other
   std::vector<cudaStream_t> side;
   std::vector<cudaEvent_t> side_done;
+  cudaStream_t fin_stream0 = nullptr;   // final NMS of image 0 (runs beside the caption decode, see run_final_nms)
+  cudaEvent_t fin_done0 = nullptr;
   cudaEvent_t fork_ev = nullptr;
   PhaseTimer timer;
   // training-time forward of the LocalizationLayer (setGroundTruth protocol, sampler / loss options)
@@ -266,6 +268,8 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
     ctx->roi_taps = mem;
   }
   DC_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+  DC_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->fin_stream0, cudaStreamNonBlocking));
+  DC_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fin_done0, cudaEventDisableTiming));
   for (size_t b = 1; b < B; ++b) {
     cudaStream_t sst;
     cudaEvent_t ev;
@@ -320,6 +324,8 @@ extern "C" int dc_destroy(dc_ctx* ctx) {
   for (cudaStream_t sst : ctx->side) cudaStreamDestroy(sst);
   for (cudaEvent_t ev : ctx->side_done) cudaEventDestroy(ev);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  if (ctx->fin_stream0) cudaStreamDestroy(ctx->fin_stream0);
+  if (ctx->fin_done0) cudaEventDestroy(ctx->fin_done0);
   if (ctx->train_mem) cudaFree(ctx->train_mem);
   free(ctx->train);
   for (cudaEvent_t ev : ctx->timer.events) cudaEventDestroy(ev);
@@ -937,15 +943,17 @@ static int run_lm(dc_ctx* ctx, int rows, float* logits, cudaStream_t st) {
 }
 
 // final NMS + selection (DenseCapModel.lua:261-275)
-static int run_final(dc_ctx* ctx, int N, cudaStream_t st) {
-  const int P = ctx->P, T = ctx->cfg.seq_length;
+// Final NMS (DenseCapModel.lua:261-271) needs only the final boxes and objectness scores of the recognition head, not the
+// captions: it is forked onto per-image side streams right after the head and runs beside the LSTM decode (its kernels are a
+// few small CTAs that co-reside with the persistent GEMM CTAs); run_final_gather joins and filters the outputs (:272-274).
+static int run_final_nms(dc_ctx* ctx, int N, cudaStream_t st) {
+  const int P = ctx->P;
   int rc;
-  phase_mark(ctx, "final_nms", st);
   if ((rc = k_xcycwh_to_x1y1x2y2(ctx, ctx->boxes_all, ctx->fin_x1y1, N * P, st))) return rc;
-  if (N > 1) DC_CHECK_CUDA(ctx, cudaEventRecord(ctx->fork_ev, st));
+  DC_CHECK_CUDA(ctx, cudaEventRecord(ctx->fork_ev, st));
   for (int b = 0; b < N; ++b) {
-    cudaStream_t sb = (b == 0) ? st : ctx->side[b - 1];
-    if (b > 0) DC_CHECK_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->fork_ev, 0));
+    cudaStream_t sb = (b == 0) ? ctx->fin_stream0 : ctx->side[b - 1];
+    DC_CHECK_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->fork_ev, 0));
     const size_t o = (size_t)b * P;
     if (ctx->final_nms_thresh > 0.f) {
       if ((rc = k_nms(ctx, ctx->fin_x1y1 + o * 4, 4, ctx->obj + o, 1, P, ctx->rpn_count + b, ctx->final_nms_thresh, 0, ctx->nms[b],
@@ -955,13 +963,21 @@ static int run_final(dc_ctx* ctx, int N, cudaStream_t st) {
       identity_idx_kernel<<<1, 256, 0, sb>>>(ctx->rpn_count + b, P, ctx->fin_idx32 + o, ctx->fin_idx64 + o, ctx->fin_count + b);
       DC_CHECK_LAUNCH(ctx);
     }
+    DC_CHECK_CUDA(ctx, cudaEventRecord(b == 0 ? ctx->fin_done0 : ctx->side_done[b - 1], sb));
+  }
+  return DC_OK;
+}
+
+static int run_final_gather(dc_ctx* ctx, int N, cudaStream_t st) {
+  const int P = ctx->P, T = ctx->cfg.seq_length;
+  int rc;
+  phase_mark(ctx, "final_nms", st);
+  for (int b = 0; b < N; ++b) {
+    const size_t o = (size_t)b * P;
+    DC_CHECK_CUDA(ctx, cudaStreamWaitEvent(st, b == 0 ? ctx->fin_done0 : ctx->side_done[b - 1], 0));     // join
     if ((rc = k_final_gather(ctx, ctx->fin_idx32 + o, ctx->fin_count + b, P, ctx->boxes_all + o * 4, ctx->obj + o, ctx->seq64 + o * T, T,
-                             ctx->fin_boxes + o * 4, ctx->fin_scores + o, ctx->fin_seq + o * T, sb)))
+                             ctx->fin_boxes + o * 4, ctx->fin_scores + o, ctx->fin_seq + o * T, st)))
       return rc;
-    if (b > 0) {
-      DC_CHECK_CUDA(ctx, cudaEventRecord(ctx->side_done[b - 1], sb));
-      DC_CHECK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->side_done[b - 1], 0));
-    }
   }
   return DC_OK;
 }
@@ -998,8 +1014,9 @@ extern "C" int dc_forward_test(dc_ctx* ctx, const float* img, int batch, int ima
   if ((rc = run_localization(ctx, batch, fh, fw, image_h, image_w, st))) return rc;
   const int rows = batch * ctx->P;
   if ((rc = run_recog(ctx, rows, st))) return rc;
+  if ((rc = run_final_nms(ctx, batch, st))) return rc;
   if ((rc = run_lm(ctx, rows, nullptr, st))) return rc;
-  if ((rc = run_final(ctx, batch, st))) return rc;
+  if ((rc = run_final_gather(ctx, batch, st))) return rc;
   phase_mark(ctx, "end", st);
   if (out) fill_result(ctx, batch, out);
   return DC_OK;

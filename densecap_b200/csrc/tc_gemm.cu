@@ -504,6 +504,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail
+  // of the previous kernel in the stream; from here on this kernel touches that kernel's outputs, so wait for it to finish.
+  // Our own dependents may start their prologue as soon as SMs free up.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int num_tiles = pb.m_tiles * pb.n_tiles;
 
@@ -701,6 +706,11 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail
+  // of the previous kernel in the stream; from here on this kernel touches that kernel's outputs, so wait for it to finish.
+  // Our own dependents may start their prologue as soon as SMs free up.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int num_tiles = pb.m_tiles * pb.n_tiles;
   const int groups = 3 * pb.kb_per_tap;                                 // (s, channel block) groups per tile
@@ -857,24 +867,27 @@ static int launch_kernel(dc_ctx* ctx, Kernel kernel, bool& attr_set, size_t smem
   const int tiles = pb.m_tiles * pb.n_tiles;
   const int slots = g_num_sms / cg;                        // CTAs (CG=1) or CTA pairs (CG=2) resident at once
   const int workers = tiles < slots ? tiles : slots;
-  if (cg == 1) {
-    kernel<<<workers, NUM_THREADS, smem_bytes, st>>>(ma, mb, pb, ep);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(workers * 2);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ma, mb, pb, ep);
-    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "tc_gemm cluster launch: %s", cudaGetErrorString(e));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(workers * cg);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see griddepcontrol.wait in the kernels
+  attr[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
+  if (cg == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ma, mb, pb, ep);
+  if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "tc_gemm launch: %s", cudaGetErrorString(e));
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }
