@@ -221,7 +221,7 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
   TRY(split_alloc(ctx, ctx->roi, B * P * hw * C5));
   TRY(split_alloc(ctx, ctx->fc6o, B * P * fc));
   TRY(split_alloc(ctx, ctx->fc7o, B * P * fc));
-  TRY(split_alloc(ctx, ctx->xh, B * P * (E + H)));
+  TRY(split_alloc(ctx, ctx->xh, 2 * B * P * (E + H)));      // two ping-pong [x|h] operands, see run_lm
   TRY(dev_alloc(ctx, &ctx->codes, B * P * fc));
   TRY(dev_alloc(ctx, &ctx->obj, B * P));
   TRY(dev_alloc(ctx, &ctx->trans, B * P * 4));
@@ -895,49 +895,56 @@ static int run_lm(dc_ctx* ctx, int rows, float* logits, cudaStream_t st) {
   if ((rc = need_weight(ctx, "lm.vocab.bias", &bv))) return rc;
   phase_mark(ctx, "lm:sample", st);
   const int ld = E + H;
-  const size_t xplane = (size_t)rows * ld;
+  // [x | h] operand of the gate GEMM, split planes, TWO buffers used alternately: the gate GEMM of a step reads
+  // [x_t | h_{t-1}] from one buffer while its fused cell epilogue writes h_t into the OTHER one.  (Tiles of one launch
+  // finish at different times; an in-place h would be overwritten while later tiles of the same rows still read it.)
+  const size_t bufelems = (size_t)rows * ld;                  // elements of one plane of one buffer
+  const size_t xplane = 2 * bufelems;                         // plane stride: [hi: buf0, buf1][lo: buf0, buf1]
   const size_t fplane = (size_t)rows * fc;
-  __half* xh_hi = ctx->xh.base;
-  __half* xh_lo = ctx->xh.base + xplane;
-  {  // image_encoder: Linear + ReLU (LanguageModel.lua:27-29) -> x half of [x|h]
+  auto xh_hi = [&](int i) { return ctx->xh.base + (size_t)i * bufelems; };
+  auto xh_lo = [&](int i) { return ctx->xh.base + xplane + (size_t)i * bufelems; };
+  {  // image_encoder: Linear + ReLU (LanguageModel.lua:27-29) -> x half of buffer 0
     GemmEpilogue ep;
     ep.bias = be->f32; ep.relu = 1;
-    ep.out_hi = xh_hi; ep.out_lo = xh_lo; ep.ldo = ld; ep.out_col0 = 0;
+    ep.out_hi = xh_hi(0); ep.out_lo = xh_lo(0); ep.ldo = ld; ep.out_col0 = 0;
     if ((rc = gemm(ctx, ctx->fc7o.base, fplane, fc, *we, fc, rows, E, fc, ep, st))) return rc;
   }
   const bool fused_cell = (c.engine == DC_ENGINE_TC);
-  auto lstm_step = [&](int K, int first) -> int {
+  // reads [x|h] from buffer `src`, writes h into buffer `dst`
+  auto lstm_step = [&](int K, int first, int src, int dst) -> int {
     GemmEpilogue ep;
     ep.bias = blstm->f32;
     if (fused_cell) {
       ep.lstm_c = ctx->cstate; ep.lstm_H = H; ep.lstm_first = first;
-      ep.out_hi = xh_hi; ep.out_lo = xh_lo; ep.ldo = ld; ep.out_col0 = E;
-      return gemm(ctx, xh_hi, xplane, ld, *wlstm, ld, rows, 4 * H, K, ep, st);
+      ep.out_hi = xh_hi(dst); ep.out_lo = xh_lo(dst); ep.ldo = ld; ep.out_col0 = E;
+      return gemm(ctx, xh_hi(src), xplane, ld, *wlstm, ld, rows, 4 * H, K, ep, st);
     }
     ep.out_f32 = ctx->gates; ep.ldf = 4 * H;
-    int r = gemm(ctx, xh_hi, xplane, ld, *wlstm, ld, rows, 4 * H, K, ep, st);
+    int r = gemm(ctx, xh_hi(src), xplane, ld, *wlstm, ld, rows, 4 * H, K, ep, st);
     if (r) return r;
-    return k_lstm_pointwise(ctx, ctx->gates, ctx->cstate, xh_hi, xh_lo, ld, E, rows, H, first, st);
+    return k_lstm_pointwise(ctx, ctx->gates, ctx->cstate, xh_hi(dst), xh_lo(dst), ld, E, rows, H, first, st);
   };
   // first LSTM step on the encoded image with h0 = c0 = 0: only the Wx rows contribute (K = E)
-  if ((rc = lstm_step(E, 1))) return rc;
+  if ((rc = lstm_step(E, 1, 0, 1))) return rc;
+  int cur = 1;                                                // buffer holding h_{t-1}
   for (int t = 0; t < T; ++t) {
-    // finish step t-1 (arg-max -> token), look up the input token of step t, reset the arg-max cells
-    if ((rc = k_lm_token_step(ctx, ctx->packed, ctx->tokens, ctx->seq64, T, t, V + 1, wl->planes, wl->planes + wl->plane_elems, E, xh_hi,
-                              xh_lo, ld, rows, st)))
+    // finish step t-1 (arg-max -> token), look up the input token of step t into the x half of `cur`, reset the arg-max cells
+    if ((rc = k_lm_token_step(ctx, ctx->packed, ctx->tokens, ctx->seq64, T, t, V + 1, wl->planes, wl->planes + wl->plane_elems, E,
+                              xh_hi(cur), xh_lo(cur), ld, rows, st)))
       return rc;
-    if ((rc = lstm_step(ld, 0))) return rc;
+    if ((rc = lstm_step(ld, 0, cur, cur ^ 1))) return rc;
+    cur ^= 1;
     {
       GemmEpilogue ep;
       ep.bias = bv->f32;
       ep.argmax = ctx->packed;
       if (logits) { ep.out_f32 = logits + (size_t)t * (V + 1); ep.ldf = T * (V + 1); }
-      // A = h half of [x|h]
-      if ((rc = gemm(ctx, xh_hi + E, xplane, ld, *wv, H, rows, V + 1, H, ep, st))) return rc;
+      // A = h half of the buffer the cell just wrote
+      if ((rc = gemm(ctx, xh_hi(cur) + E, xplane, ld, *wv, H, rows, V + 1, H, ep, st))) return rc;
     }
   }
-  if ((rc = k_lm_token_step(ctx, ctx->packed, ctx->tokens, ctx->seq64, T, T, V + 1, wl->planes, wl->planes + wl->plane_elems, E, xh_hi, xh_lo,
-                            ld, rows, st)))
+  if ((rc = k_lm_token_step(ctx, ctx->packed, ctx->tokens, ctx->seq64, T, T, V + 1, wl->planes, wl->planes + wl->plane_elems, E, xh_hi(cur),
+                            xh_lo(cur), ld, rows, st)))
     return rc;
   return DC_OK;
 }

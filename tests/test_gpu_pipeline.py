@@ -104,6 +104,39 @@ def test_language_model_sample_logits_and_tokens(model, small):
     assert int(seq.min()) >= 1 and int(seq.max()) <= dims.vocab_size + 1
 
 
+def test_language_model_many_rows_full_width():
+    """Full LM dimensions (E = H = 512, V = 10497) with 1300 rows: 11 x 16 gate tiles > 148 SMs, so the gate GEMM runs in more
+    than one round and every round must still read h_{t-1} (regression test for an in-place [x|h] update), and the 83-tile
+    vocabulary projection exercises the ragged last N tile.  Logits against the oracle for 3 steps."""
+    from densecap_b200.model import LanguageModel
+    from densecap_b200.runtime import Context
+    dims = ModelDims(seq_length=3)
+    rng = np.random.RandomState(11)
+    E, H, V, fc = dims.encoding_size, dims.rnn_size, dims.vocab_size, dims.fc_dim
+    w = {"lm.encoder.weight": (rng.randn(E, fc) * np.sqrt(2.0 / fc)).astype(np.float32), "lm.encoder.bias": np.zeros(E, np.float32),
+         "lm.lookup.weight": (rng.randn(V + 2, E) * 0.5).astype(np.float32),
+         "lm.lstm.weight": (rng.randn(E + H, 4 * H) / np.sqrt(E + H)).astype(np.float32), "lm.lstm.bias": (rng.randn(4 * H) * 0.1).astype(np.float32),
+         "lm.vocab.weight": (rng.randn(V + 1, H) / np.sqrt(H)).astype(np.float32), "lm.vocab.bias": (rng.randn(V + 1) * 0.1).astype(np.float32)}
+    K = 1300
+    codes = np.maximum(rng.randn(K, fc), 0).astype(np.float32)
+    oseq, ologits = O.lm_sample(codes, w, dims.seq_length, return_logits=True)
+    ctx = Context(dims, max_image_hw=(64, 64), max_proposals=K)
+    try:
+        ctx.load_weights(w)
+        lm = LanguageModel(ctx)
+        seq, logits = lm.sample(dev(codes), return_logits=True)
+        got = logits.cpu().numpy()
+        # compare step by step on the rows whose previous tokens agree (a near-tie flip legitimately changes the next input)
+        agree = np.ones(K, bool)
+        for t in range(dims.seq_length):
+            assert agree.mean() > 0.99
+            assert rel(got[agree, t], ologits[agree, t]) < 1e-4, "logits of step %d differ" % t
+            agree &= (seq[:, t].cpu().numpy() == oseq[:, t])
+        assert agree.mean() > 0.99
+    finally:
+        ctx.close()
+
+
 def test_full_forward_matches_oracle(model, small):
     dims, weights, img, cfg, ref = small
     out = model.forward(dev(img))
