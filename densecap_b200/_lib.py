@@ -53,6 +53,9 @@ SIGNATURES = {
     "dc_set_train_args": (c_i, [c_vp, c_f, c_f, c_f, c_f, c_f, c_i, c_i]),
     "dc_set_ground_truth": (c_i, [c_vp, c_vp, c_i, c_vp]),
     "dc_localization_forward_train": (c_i, [c_vp, c_vp, c_i, c_i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dc_localization_backward_train": (c_i, [c_vp, c_vp, c_i, c_i, c_vp, c_vp, c_vp, c_vp]),
+    "dc_zero_grad_parameters": (c_i, [c_vp, c_vp]),
+    "dc_get_grad_parameters": (c_i, [c_vp, C.c_char_p, c_vp, C.c_int64, c_vp]),
     "dc_recog_forward": (c_i, [c_vp, c_vp, c_vp, c_i, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dc_lm_sample": (c_i, [c_vp, c_vp, c_i, c_vp, c_vp, c_vp]),
     "dc_make_anchors": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_vp, c_vp]),

@@ -81,6 +81,16 @@ struct dc_ctx {
   int gt_count = 0;
   bool gt_consumed = true;
   float* train_losses = nullptr;
+  // backward of the training-time forward (LocalizationLayer.lua:529-605)
+  bool gt_bwd_consumed = true, size_bwd_consumed = true, train_fwd_valid = false;
+  int train_fh = 0, train_fw = 0;
+  char* bwd_mem = nullptr;           // workspace, allocated on the first backward call
+  struct Bwd {
+    float *go_bhwc, *gfeat_roi, *ggrid, *gboxes_pool, *g_boxes_all, *g_trans_all, *g_scores_all, *head_grad, *gh, *hid_f32, *feats_f32;
+    __half *head_grad_planes, *gh_planes, *grpn_planes;
+    float *dW_conv, *db_conv, *dW_head, *db_head;      // gradWeight / gradBias accumulators (accGradParameters)
+  } bwd{};
+  int bwd_S = 0;
 };
 
 static char g_err[512] = "";
@@ -136,6 +146,7 @@ static void feat_hw(const dc_config& c, int h, int w, int& fh, int& fw) {
   for (int i = 0; i < 4; ++i) { fh = pooled(fh, c.pool_ceil); fw = pooled(fw, c.pool_ceil); }
 }
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static const size_t kHeadGradLd = 128;     // 6k head-gradient columns padded to a multiple of the GEMM K block
 
 template <typename T>
 static int dev_alloc(dc_ctx* ctx, T** p, size_t n) {
@@ -294,6 +305,10 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
     TRY(weight_alloc_f32(ctx, "rpn.conv.bias", F));
     TRY(weight_alloc_split(ctx, "rpn.head.weight", (size_t)6 * k * F));   // rows [0,4k) box, [4k,6k) score
     TRY(weight_alloc_f32(ctx, "rpn.head.bias", (size_t)6 * k));
+    // layouts for the backward-data passes of the training path: transposed + tap-flipped 3x3 bank, transposed head (K padded to 128)
+    TRY(weight_alloc_split(ctx, "rpn.conv.weight.bwd", C5 * 9 * F));
+    TRY(weight_alloc_split(ctx, "rpn.head.weight.bwd", F * kHeadGradLd));
+    TRY(weight_alloc_f32(ctx, "rpn.head.wT", F * kHeadGradLd));
     TRY(weight_alloc_split(ctx, "fc6.weight", fc * hw * C5));
     TRY(weight_alloc_f32(ctx, "fc6.bias", fc));
     TRY(weight_alloc_split(ctx, "fc7.weight", fc * fc));
@@ -327,6 +342,7 @@ extern "C" int dc_destroy(dc_ctx* ctx) {
   if (ctx->fin_stream0) cudaStreamDestroy(ctx->fin_stream0);
   if (ctx->fin_done0) cudaEventDestroy(ctx->fin_done0);
   if (ctx->train_mem) cudaFree(ctx->train_mem);
+  if (ctx->bwd_mem) cudaFree(ctx->bwd_mem);
   free(ctx->train);
   for (cudaEvent_t ev : ctx->timer.events) cudaEventDestroy(ev);
   if (ctx->timer.roi0) { cudaEventDestroy(ctx->timer.roi0); cudaEventDestroy(ctx->timer.roi1); }
@@ -445,6 +461,18 @@ extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_
     rc = k_conv_weight_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, (int)F, (int)C5, st, sc);
     w.inv_scale = 1.f / sc;
     w.loaded = true;
+    if (rc == DC_OK) {
+      // backward-data bank: W'[c][f][r'][s'] = W[f][c][2-r'][2-s']
+      float* tmp = nullptr;
+      if (cudaMalloc((void**)&tmp, numel * sizeof(float)) != cudaSuccess) return finish(dc_set_error(ctx, DC_E_NOMEM, "rpn.conv.weight: staging"));
+      Weight& wb = ctx->w["rpn.conv.weight.bwd"];
+      rc = k_conv_weight_flip_transpose(ctx, raw, tmp, (int)F, (int)C5, st);
+      if (rc == DC_OK) rc = k_conv_weight_to_split(ctx, tmp, wb.planes, wb.planes + wb.plane_elems, (int)C5, (int)F, st, sc);
+      wb.inv_scale = 1.f / sc;
+      wb.loaded = true;
+      cudaStreamSynchronize(st);
+      cudaFree(tmp);
+    }
     return finish(rc);
   }
   if (n == "rpn.conv.bias") { if (!shape_is(shape, ndim, {F})) return bad_shape(); return copy_f32(n, 0, numel); }
@@ -461,6 +489,14 @@ extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_
     rc = k_rowmajor_to_split(ctx, raw, w.planes + off, w.planes + w.plane_elems + off, numel, st, sc);
     w.inv_scale = 1.f / sc;
     w.loaded = true;
+    if (rc == DC_OK) {
+      Weight& wt = ctx->w["rpn.head.wT"];
+      Weight& wb = ctx->w["rpn.head.weight.bwd"];
+      rc = k_transpose_into(ctx, raw, (int)rows, (int)F, wt.f32, (int)kHeadGradLd, box ? 0 : 4 * (int)k, st);
+      if (rc == DC_OK) rc = k_rowmajor_to_split(ctx, wt.f32, wb.planes, wb.planes + wb.plane_elems, (size_t)F * kHeadGradLd, st, sc);
+      wb.inv_scale = 1.f / sc;
+      wb.loaded = true;
+    }
     return finish(rc);
   }
   if (n == "rpn.box.bias") { if (!shape_is(shape, ndim, {4 * k})) return bad_shape(); return copy_f32("rpn.head.bias", 0, numel); }
@@ -545,6 +581,7 @@ extern "C" int dc_set_image_size(dc_ctx* ctx, int image_h, int image_w) {
   ctx->image_h = image_h;
   ctx->image_w = image_w;
   ctx->size_consumed = false;
+  ctx->size_bwd_consumed = false;
   return DC_OK;
 }
 
@@ -579,6 +616,7 @@ static const int kMaxGtBoxes = 512;
 static int ensure_train_buffers(dc_ctx* ctx) {
   if (ctx->train && ctx->train_batch >= ctx->sampler_batch) return DC_OK;
   if (ctx->train_mem) cudaFree(ctx->train_mem);
+  if (ctx->bwd_mem) cudaFree(ctx->bwd_mem);
   if (!ctx->train) ctx->train = calloc(1, train_buffers_struct_bytes());
   const size_t bytes = train_buffers_carve(nullptr, nullptr, ctx->A_max, kMaxGtBoxes, ctx->sampler_batch);
   cudaError_t e = cudaMalloc((void**)&ctx->train_mem, bytes);
@@ -601,6 +639,7 @@ extern "C" int dc_set_ground_truth(dc_ctx* ctx, const float* gt_boxes, int num_g
                                      (cudaStream_t)stream));
   ctx->gt_count = num_gt;
   ctx->gt_consumed = false;
+  ctx->gt_bwd_consumed = false;
   return DC_OK;
 }
 
@@ -1144,6 +1183,170 @@ extern "C" int dc_localization_forward_train(dc_ctx* ctx, const float* feats_nch
     DC_CHECK_CUDA(ctx, cudaMemcpyAsync(pos_target_boxes, train_buffers_pos_target_boxes(ctx->train), (size_t)S * 16, cudaMemcpyDeviceToDevice, st));
   if (num_pos_neg) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(num_pos_neg, train_buffers_counts(ctx->train), 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   if (losses) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(losses, ctx->train_losses, 5 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ctx->train_fwd_valid = true;
+  ctx->train_fh = feat_h;
+  ctx->train_fw = feat_w;
+  return DC_OK;
+}
+
+// ---- backward of the training-time forward ------------------------------------------------------------------
+int k_loc_bwd_scatter(dc_ctx* ctx, void* tb, int A, int batch_size, const float* grad_roi_boxes_in, const float* grad_boxes_pool, float* g_boxes_all,
+                      float* g_trans_all, float* g_scores_all, cudaStream_t st);
+int k_loc_bwd_head_grad(dc_ctx* ctx, void* tb, int H, int W, int k, const float* g_boxes_all, const float* g_trans_all, const float* g_scores_all,
+                        float w_decay, float* head_grad, int ldh, cudaStream_t st);
+int k_bwd_relu_mask(dc_ctx* ctx, float* gh, const __half* hid_hi, const __half* hid_lo, size_t n, __half* out_hi, __half* out_lo, float* hid_f32,
+                    cudaStream_t st);
+int k_bwd_combine(dc_ctx* ctx, const float* g_roi_hwc, const __half* g_rpn_hi, const __half* g_rpn_lo, int C, int cells, float* out_chw, cudaStream_t st);
+int k_bwd_wgrad(dc_ctx* ctx, const float* A, int Mdim, const float* B, int Ndim, int H, int W, int taps, float* out, const float* bias_src,
+                float* bias_out, cudaStream_t st);
+int k_bchw_to_bhwc_f32(dc_ctx* ctx, const float* in, float* out, int K, int C, int npos, cudaStream_t st);
+
+static int ensure_bwd_buffers(dc_ctx* ctx) {
+  const int S = ctx->sampler_batch;
+  if (ctx->bwd_mem && ctx->bwd_S >= S) return DC_OK;
+  const dc_config& c = ctx->cfg;
+  const size_t C5 = c.widths[4], F = c.rpn_filters, hw = (size_t)c.pool_hw * c.pool_hw, cells = (size_t)ctx->fh_max * ctx->fw_max, A = ctx->A_max;
+  // keep the parameter-gradient accumulators when only the sampler batch grew
+  std::vector<float> keep;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  const size_t o_go = take(S * hw * C5 * 4), o_gfr = take(cells * C5 * 4), o_gg = take(S * hw * 8), o_gbp = take((size_t)S * 16),
+               o_gba = take(A * 16), o_gta = take(A * 16), o_gsa = take(A * 8), o_hg = take(cells * kHeadGradLd * 4), o_gh = take(cells * F * 4),
+               o_hf = take(cells * F * 4), o_ff = take(cells * C5 * 4), o_hgp = take(2 * cells * kHeadGradLd * 2), o_ghp = take(2 * cells * F * 2),
+               o_grp = take(2 * cells * C5 * 2), o_dwc = take(F * C5 * 9 * 4), o_dbc = take(F * 4), o_dwh = take(kHeadGradLd * F * 4),
+               o_dbh = take(kHeadGradLd * 4);
+  char* mem = nullptr;
+  cudaError_t e = cudaMalloc((void**)&mem, off);
+  if (e != cudaSuccess) return dc_set_error(ctx, DC_E_NOMEM, "backward workspace cudaMalloc(%zu) failed", off);
+  cudaMemset(mem, 0, off);
+  if (ctx->bwd_mem) {
+    cudaMemcpy(mem + o_dwc, ctx->bwd.dW_conv, F * C5 * 9 * 4, cudaMemcpyDeviceToDevice);
+    cudaMemcpy(mem + o_dbc, ctx->bwd.db_conv, F * 4, cudaMemcpyDeviceToDevice);
+    cudaMemcpy(mem + o_dwh, ctx->bwd.dW_head, kHeadGradLd * F * 4, cudaMemcpyDeviceToDevice);
+    cudaMemcpy(mem + o_dbh, ctx->bwd.db_head, kHeadGradLd * 4, cudaMemcpyDeviceToDevice);
+    cudaFree(ctx->bwd_mem);
+  }
+  ctx->bwd_mem = mem;
+  ctx->bwd_S = S;
+  dc_ctx::Bwd& b = ctx->bwd;
+  b.go_bhwc = (float*)(mem + o_go); b.gfeat_roi = (float*)(mem + o_gfr); b.ggrid = (float*)(mem + o_gg); b.gboxes_pool = (float*)(mem + o_gbp);
+  b.g_boxes_all = (float*)(mem + o_gba); b.g_trans_all = (float*)(mem + o_gta); b.g_scores_all = (float*)(mem + o_gsa);
+  b.head_grad = (float*)(mem + o_hg); b.gh = (float*)(mem + o_gh); b.hid_f32 = (float*)(mem + o_hf); b.feats_f32 = (float*)(mem + o_ff);
+  b.head_grad_planes = (__half*)(mem + o_hgp); b.gh_planes = (__half*)(mem + o_ghp); b.grpn_planes = (__half*)(mem + o_grp);
+  b.dW_conv = (float*)(mem + o_dwc); b.db_conv = (float*)(mem + o_dbc); b.dW_head = (float*)(mem + o_dwh); b.db_head = (float*)(mem + o_dbh);
+  return DC_OK;
+}
+
+// nn.LocalizationLayer:backward = updateGradInput (LocalizationLayer.lua:529-605) + accGradParameters of the RPN convolutions
+extern "C" int dc_localization_backward_train(dc_ctx* ctx, const float* feats_nchw, int feat_h, int feat_w, const float* grad_roi_features,
+                                              const float* grad_roi_boxes, float* grad_feats_nchw, void* stream) {
+  if (!ctx || !feats_nchw || !grad_roi_features || !grad_roi_boxes || !grad_feats_nchw)
+    return dc_set_error(ctx, DC_E_INVALID, "dc_localization_backward_train: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  // the reference's asserts (:531-537), with its messages
+  DC_REQUIRE(ctx, ctx->gt_count > 0 && !ctx->gt_bwd_consumed, DC_E_PROTOCOL, "Must call setGroundTruth before each forward pass");
+  ctx->gt_bwd_consumed = true;
+  DC_REQUIRE(ctx, ctx->image_h > 0 && ctx->image_w > 0 && !ctx->size_bwd_consumed, DC_E_PROTOCOL, "Must call setImageSize before each forward pass");
+  ctx->size_bwd_consumed = true;
+  DC_REQUIRE(ctx, ctx->train_fwd_valid && ctx->train_fh == feat_h && ctx->train_fw == feat_w, DC_E_PROTOCOL,
+             "backward needs the training-time forward of the same input to have run on this context");
+  ctx->train_fwd_valid = false;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dc_config& c = ctx->cfg;
+  const int C5 = c.widths[4], F = c.rpn_filters, k = c.num_anchors, hw = c.pool_hw * c.pool_hw;
+  const int cells = feat_h * feat_w, A = k * cells, S = ctx->sampler_batch, ldh = (int)kHeadGradLd;
+  DC_REQUIRE(ctx, 6 * k <= ldh, DC_E_UNSUPPORTED, "backward supports at most %d anchors", ldh / 6);
+  int rc;
+  if ((rc = ensure_bwd_buffers(ctx))) return rc;
+  dc_ctx::Bwd& b = ctx->bwd;
+  Weight *wcb, *whb;
+  if ((rc = need_weight(ctx, "rpn.conv.weight.bwd", &wcb))) return rc;
+  if ((rc = need_weight(ctx, "rpn.head.weight.bwd", &whb))) return rc;
+  const size_t plane = (size_t)cells * C5;
+  ctx->timer.used = 0;
+  // the input again (it is the caller's tensor in the reference too): split NHWC planes for the sampler backward, fp32 HWC for gradWeight
+  if ((rc = k_nchw_to_split_nhwc(ctx, feats_nchw, ctx->feats.base, ctx->feats.base + plane, 1, C5, feat_h, feat_w, st))) return rc;
+  if ((rc = k_split_to_rowmajor(ctx, ctx->feats.base, ctx->feats.base + plane, b.feats_f32, plane, st))) return rc;
+  // ---- RoI pooling backward (:573-580)
+  phase_mark(ctx, "roi_pooling:backward", st);
+  if ((rc = k_bchw_to_bhwc_f32(ctx, grad_roi_features, b.go_bhwc, S, C5, hw, st))) return rc;
+  if ((rc = k_roi_pool_backward(ctx, ctx->feats.base, ctx->feats.base + plane, C5, feat_h, feat_w, train_buffers_roi_boxes(ctx->train), S, ctx->image_h,
+                                ctx->image_w, c.pool_hw, c.pool_hw, b.go_bhwc, b.gfeat_roi, b.ggrid, b.gboxes_pool, st)))
+    return rc;
+  // ---- sampler backward (:583-596) and the RPN's box-space modules (:599-602)
+  phase_mark(ctx, "sampler:backward", st);
+  if ((rc = k_loc_bwd_scatter(ctx, ctx->train, A, S, grad_roi_boxes, b.gboxes_pool, b.g_boxes_all, b.g_trans_all, b.g_scores_all, st))) return rc;
+  phase_mark(ctx, "rpn:backward", st);
+  if ((rc = k_loc_bwd_head_grad(ctx, ctx->train, feat_h, feat_w, k, b.g_boxes_all, b.g_trans_all, b.g_scores_all, ctx->box_reg_decay, b.head_grad, ldh,
+                                st)))
+    return rc;
+  // 1x1 heads, backward data: grad_hidden (cells, F) = head_grad (cells, 6k) . W_head (6k, F)
+  const size_t hplane = (size_t)cells * ldh;
+  if ((rc = k_rowmajor_to_split(ctx, b.head_grad, b.head_grad_planes, b.head_grad_planes + hplane, hplane, st))) return rc;
+  {
+    GemmEpilogue ep;
+    ep.out_f32 = b.gh;
+    ep.ldf = F;
+    if ((rc = gemm(ctx, b.head_grad_planes, hplane, ldh, *whb, ldh, cells, F, ldh, ep, st))) return rc;
+  }
+  // ReLU backward + split; the hidden activations of the forward pass are still in ctx->rpn_hidden
+  const size_t gplane = (size_t)cells * F;
+  if ((rc = k_bwd_relu_mask(ctx, b.gh, ctx->rpn_hidden.base, ctx->rpn_hidden.base + gplane, gplane, b.gh_planes, b.gh_planes + gplane, b.hid_f32, st)))
+    return rc;
+  // 3x3 conv, backward data = 3x3 conv of grad_hidden with the flipped / transposed bank (no bias, no ReLU)
+  if (c.engine == DC_ENGINE_TC) {
+    rc = k_tc_conv3x3(ctx, b.gh_planes, gplane, wcb->planes, wcb->plane_elems, nullptr, wcb->inv_scale, b.grpn_planes, b.grpn_planes + plane, 1, feat_h,
+                      feat_w, F, C5, 0, st, 0);
+  } else {
+    rc = k_simt_conv3x3(ctx, b.gh_planes, b.gh_planes + gplane, wcb->planes, wcb->planes + wcb->plane_elems, nullptr, wcb->inv_scale, b.grpn_planes,
+                        b.grpn_planes + plane, 1, feat_h, feat_w, F, C5, st, 0);
+  }
+  if (rc) return rc;
+  if ((rc = k_bwd_combine(ctx, b.gfeat_roi, b.grpn_planes, b.grpn_planes + plane, C5, cells, grad_feats_nchw, st))) return rc;
+  // ---- accGradParameters: gradWeight / gradBias of the RPN convolutions accumulate until dc_zero_grad_parameters
+  phase_mark(ctx, "rpn:accGradParameters", st);
+  if ((rc = k_bwd_wgrad(ctx, b.head_grad, ldh, b.hid_f32, F, feat_h, feat_w, 1, b.dW_head, b.head_grad, b.db_head, st))) return rc;
+  if ((rc = k_bwd_wgrad(ctx, b.gh, F, b.feats_f32, C5, feat_h, feat_w, 9, b.dW_conv, b.gh, b.db_conv, st))) return rc;
+  phase_mark(ctx, "end", st);
+  return DC_OK;
+}
+
+// nn.Module:zeroGradParameters for the layer's parameters (the RPN)
+extern "C" int dc_zero_grad_parameters(dc_ctx* ctx, void* stream) {
+  if (!ctx) return dc_set_error(nullptr, DC_E_INVALID, "dc_zero_grad_parameters: null ctx");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_bwd_buffers(ctx);
+  if (rc) return rc;
+  const dc_config& c = ctx->cfg;
+  const size_t C5 = c.widths[4], F = c.rpn_filters;
+  cudaStream_t st = (cudaStream_t)stream;
+  DC_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->bwd.dW_conv, 0, F * C5 * 9 * 4, st));
+  DC_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->bwd.db_conv, 0, F * 4, st));
+  DC_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->bwd.dW_head, 0, kHeadGradLd * F * 4, st));
+  DC_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->bwd.db_head, 0, kHeadGradLd * 4, st));
+  return DC_OK;
+}
+
+// gradWeight / gradBias by the reference's parameter names: rpn.conv.weight (F,C,3,3), rpn.conv.bias (F), rpn.box.weight (4k,F),
+// rpn.box.bias (4k), rpn.score.weight (2k,F), rpn.score.bias (2k).  out: device or host memory with room for numel floats.
+extern "C" int dc_get_grad_parameters(dc_ctx* ctx, const char* name, float* out, int64_t numel, void* stream) {
+  if (!ctx || !name || !out) return dc_set_error(ctx, DC_E_INVALID, "dc_get_grad_parameters: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  DC_REQUIRE(ctx, ctx->bwd_mem != nullptr, DC_E_PROTOCOL, "no gradients yet: run dc_localization_backward_train first");
+  const dc_config& c = ctx->cfg;
+  const int64_t C5 = c.widths[4], F = c.rpn_filters, k = c.num_anchors;
+  const std::string n(name);
+  const float* src = nullptr;
+  int64_t want = 0;
+  if (n == "rpn.conv.weight") { src = ctx->bwd.dW_conv; want = F * C5 * 9; }
+  else if (n == "rpn.conv.bias") { src = ctx->bwd.db_conv; want = F; }
+  else if (n == "rpn.box.weight") { src = ctx->bwd.dW_head; want = 4 * k * F; }
+  else if (n == "rpn.box.bias") { src = ctx->bwd.db_head; want = 4 * k; }
+  else if (n == "rpn.score.weight") { src = ctx->bwd.dW_head + 4 * k * F; want = 2 * k * F; }
+  else if (n == "rpn.score.bias") { src = ctx->bwd.db_head + 4 * k; want = 2 * k; }
+  else return dc_set_error(ctx, DC_E_INVALID, "dc_get_grad_parameters: unknown parameter '%s'", name);
+  DC_REQUIRE(ctx, numel == want, DC_E_INVALID, "dc_get_grad_parameters(%s): expected %lld elements", name, (long long)want);
+  DC_CHECK_CUDA(ctx, cudaMemcpyAsync(out, src, (size_t)want * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
   return DC_OK;
 }
 

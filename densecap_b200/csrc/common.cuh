@@ -170,7 +170,7 @@ struct GemmEpilogue {
 int k_simt_gemm(dc_ctx*, const __half* a_hi, const __half* a_lo, int lda, const __half* b_hi, const __half* b_lo, int ldb,
                 int M, int N, int K, GemmEpilogue ep, cudaStream_t st);
 int k_simt_conv3x3(dc_ctx*, const __half* x_hi, const __half* x_lo, const __half* w_hi, const __half* w_lo,
-                   const float* bias, float acc_scale, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, cudaStream_t st);
+                   const float* bias, float acc_scale, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, cudaStream_t st, int relu = 1);
 // conv1_1: NCHW fp32 (N,3,H,W) -> split NHWC (N,H,W,Cout), bias+ReLU fused.  w (Cout,3,3,3) fp32 reference layout.
 int k_conv_first(dc_ctx*, const float* img, const float* w, const float* bias, __half* y_hi, __half* y_lo,
                  int N, int H, int W, int Cout, cudaStream_t st);
@@ -185,7 +185,7 @@ int k_tc_gemm(dc_ctx*, const __half* a_planes, size_t a_plane_elems, int lda, co
 // x: split NHWC (N,H,W,Cin) planes; w: split [Cout][9*Cin]; y: split NHWC (N,H,W,Cout) or pooled (N,ceil(H/2),ceil(W/2),Cout)
 int k_tc_conv3x3(dc_ctx*, const __half* x_planes, size_t x_plane_elems, const __half* w_planes, size_t w_plane_elems,
                  const float* bias, float acc_scale, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, int fuse_pool,
-                 cudaStream_t st);
+                 cudaStream_t st, int relu = 1);
 
 // lm_kernels.cu
 // One launch per decode step t (0..T): finishes step t-1 (arg-max -> token t-1 -> seq) and prepares step t
@@ -199,3 +199,12 @@ int k_final_gather(dc_ctx*, const int32_t* idx32, const int32_t* count, int P, c
 int k_gather_rows_f32(dc_ctx*, const float* src, int cols, const int32_t* idx32, const int32_t* count, int max_rows, float* dst,
                       cudaStream_t st);
 int k_fill_u32(dc_ctx*, uint32_t* p, uint32_t v, size_t n, cudaStream_t st);
+
+// roi_pool.cu -- backward of BilinearRoiPooling (training path): grad_out BHWC (K, HH*WW, C) fp32 ->
+// grad_feat HWC fp32 (zeroed here, atomically accumulated), grad_boxes (K,4); grad_grid_ws: K*HH*WW float2 scratch
+int k_roi_pool_backward(dc_ctx*, const __half* feat_hi, const __half* feat_lo, int C, int fh, int fw, const float* boxes, int nboxes,
+                        int img_h, int img_w, int HH, int WW, const float* grad_out_bhwc, float* grad_feat_hwc, float* grad_grid_ws,
+                        float* grad_boxes, cudaStream_t st);
+// train_kernels.cu -- weight re-layouts for the backward-data passes
+int k_conv_weight_flip_transpose(dc_ctx*, const float* w, float* out, int F, int C, cudaStream_t st);
+int k_transpose_into(dc_ctx*, const float* w, int R, int F, float* out, int ld, int col0, cudaStream_t st);

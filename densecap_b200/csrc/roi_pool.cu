@@ -245,3 +245,118 @@ int k_roi_pool(dc_ctx* ctx, const __half* feat_hi, const __half* feat_lo, const 
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Backward of nn.BilinearRoiPooling (modules/BilinearRoiPooling.lua:94-104 -> self.net:backward):
+//   roi_pool_bwd_kernel  : stnbhwd BilinearSamplerBHWD_updateGradInput summed over the ROIs as in
+//                          modules/BatchBilinearSamplerBHWD.lua:125-157 -- scatter-add of w * gradOutput into the feature
+//                          gradient (fp32 atomics, HWC) and the gradient w.r.t. the sampling grid of each output position;
+//   roi_grid_bwd_kernel  : AffineGridGeneratorBHWD backward (gradTheta = gradGrid^T . baseGrid, App. B1) followed by
+//                          nn.BoxToAffine backward (modules/BoxToAffine.lua:96-118) -> gradient w.r.t. the boxes.
+// One block per (roi, position); threads sweep the channels.  grad_out is BHWC (K, HH*WW, C) fp32.
+// ---------------------------------------------------------------------------------------------------------
+struct RoiCoord { int xl, yt; float wx, wy; bool ok; };
+__device__ __forceinline__ RoiCoord roi_coord(float4 box, int i, int j, float img_h, float img_w, int fh, int fw, int HH, int WW) {
+  // identical arithmetic to roi_taps_kernel (forward)
+  const float th11 = __fdiv_rn(box.w, img_h);
+  const float th13 = __fdiv_rn(__fadd_rn(__fmul_rn(box.y, 2.f), -1.f - img_h), img_h - 1.f);
+  const float th22 = __fdiv_rn(box.z, img_w);
+  const float th23 = __fdiv_rn(__fadd_rn(__fmul_rn(box.x, 2.f), -1.f - img_w), img_w - 1.f);
+  const float yb = (float)(-1.0 + ((double)i / (double)(HH - 1)) * 2.0);
+  const float xb = (float)(-1.0 + ((double)j / (double)(WW - 1)) * 2.0);
+  const float gy = __fadd_rn(__fadd_rn(__fmul_rn(th11, yb), __fmul_rn(0.f, xb)), th13);
+  const float gx = __fadd_rn(__fadd_rn(__fmul_rn(0.f, yb), __fmul_rn(th22, xb)), th23);
+  const float xcoord = __fdiv_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)(fw - 1)), 2.f);
+  const float ycoord = __fdiv_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)(fh - 1)), 2.f);
+  const float xf = floorf(xcoord), yf = floorf(ycoord);
+  RoiCoord c;
+  c.wx = __fsub_rn(1.f, __fsub_rn(xcoord, xf));
+  c.wy = __fsub_rn(1.f, __fsub_rn(ycoord, yf));
+  c.xl = (int)fminf(fmaxf(xf, -2.f), (float)fw + 1.f);
+  c.yt = (int)fminf(fmaxf(yf, -2.f), (float)fh + 1.f);
+  c.ok = (xcoord == xcoord) && (ycoord == ycoord);
+  return c;
+}
+
+__global__ void __launch_bounds__(128)
+roi_pool_bwd_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ feat_lo, int C, int fh, int fw,
+                    const float4* __restrict__ boxes, int nboxes, float img_h, float img_w, int HH, int WW,
+                    const float* __restrict__ grad_out_bhwc, float* __restrict__ grad_feat_hwc, float2* __restrict__ grad_grid) {
+  const int npos = HH * WW;
+  const int item = blockIdx.x;
+  const int b = item / npos, p = item % npos;
+  if (b >= nboxes) return;
+  const RoiCoord rc = roi_coord(boxes[b], p / WW, p % WW, img_h, img_w, fh, fw, HH, WW);
+  const bool xin0 = rc.xl >= 0 && rc.xl <= fw - 1, xin1 = rc.xl + 1 >= 0 && rc.xl + 1 <= fw - 1;
+  const bool yin0 = rc.yt >= 0 && rc.yt <= fh - 1, yin1 = rc.yt + 1 >= 0 && rc.yt + 1 <= fh - 1;
+  const bool v[4] = {rc.ok && xin0 && yin0, rc.ok && xin1 && yin0, rc.ok && xin0 && yin1, rc.ok && xin1 && yin1};
+  const int cell[4] = {rc.yt * fw + rc.xl, rc.yt * fw + rc.xl + 1, (rc.yt + 1) * fw + rc.xl, (rc.yt + 1) * fw + rc.xl + 1};
+  const float omx = 1.f - rc.wx, omy = 1.f - rc.wy;
+  const float w[4] = {rc.wx * rc.wy, omx * rc.wy, rc.wx * omy, omx * omy};
+  const float* go = grad_out_bhwc + (size_t)item * C;
+  float dot[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = go[c];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (v[t]) {
+        const size_t o = (size_t)cell[t] * C + c;
+        atomicAdd(grad_feat_hwc + o, w[t] * g);
+        dot[t] += (__half2float(feat_hi[o]) + __half2float(feat_lo[o])) * g;
+      }
+    }
+  }
+  __shared__ float red[4][4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float x = dot[t];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) red[t][threadIdx.x >> 5] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float d[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) d[t] = red[t][0] + red[t][1] + red[t][2] + red[t][3];
+    // d out / d ycoord = -wx*TL - (1-wx)*TR + wx*BL + (1-wx)*BR ; d out / d xcoord = -wy*TL + wy*TR - (1-wy)*BL + (1-wy)*BR
+    const float gy = (-rc.wx * d[0] + rc.wx * d[2] - omx * d[1] + omx * d[3]) * (float)(fh - 1) * 0.5f;
+    const float gx = (-rc.wy * d[0] + rc.wy * d[1] - omy * d[2] + omy * d[3]) * (float)(fw - 1) * 0.5f;
+    grad_grid[item] = make_float2(gy, gx);
+  }
+}
+
+__global__ void roi_grid_bwd_kernel(const float2* __restrict__ grad_grid, int nboxes, int HH, int WW, float img_h, float img_w,
+                                    float4* __restrict__ grad_boxes) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= nboxes) return;
+  const int npos = HH * WW;
+  float t00 = 0.f, t02 = 0.f, t11 = 0.f, t12 = 0.f;      // the four entries of gradTheta that BoxToAffine backward reads
+  for (int p = lane; p < npos; p += 32) {
+    const float2 g = grad_grid[(size_t)b * npos + p];
+    const float yb = (float)(-1.0 + ((double)(p / WW) / (double)(HH - 1)) * 2.0);
+    const float xb = (float)(-1.0 + ((double)(p % WW) / (double)(WW - 1)) * 2.0);
+    t00 += g.x * yb; t02 += g.x;
+    t11 += g.y * xb; t12 += g.y;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    t00 += __shfl_xor_sync(0xffffffffu, t00, o); t02 += __shfl_xor_sync(0xffffffffu, t02, o);
+    t11 += __shfl_xor_sync(0xffffffffu, t11, o); t12 += __shfl_xor_sync(0xffffffffu, t12, o);
+  }
+  if (lane == 0) grad_boxes[b] = make_float4(t12 * (2.f / (img_w - 1.f)), t02 * (2.f / (img_h - 1.f)), t11 * (1.f / img_w), t00 * (1.f / img_h));
+}
+
+int k_roi_pool_backward(dc_ctx* ctx, const __half* feat_hi, const __half* feat_lo, int C, int fh, int fw, const float* boxes, int nboxes,
+                        int img_h, int img_w, int HH, int WW, const float* grad_out_bhwc, float* grad_feat_hwc, float* grad_grid_ws,
+                        float* grad_boxes, cudaStream_t st) {
+  if (nboxes <= 0) return DC_OK;
+  DC_REQUIRE(ctx, HH > 1 && WW > 1, DC_E_UNSUPPORTED, "roi_pool_backward: HH, WW must be > 1");
+  DC_CHECK_CUDA(ctx, cudaMemsetAsync(grad_feat_hwc, 0, (size_t)fh * fw * C * sizeof(float), st));
+  roi_pool_bwd_kernel<<<nboxes * HH * WW, 128, 0, st>>>(feat_hi, feat_lo, C, fh, fw, (const float4*)boxes, nboxes, (float)img_h, (float)img_w, HH, WW,
+                                                       grad_out_bhwc, grad_feat_hwc, (float2*)grad_grid_ws);
+  DC_CHECK_LAUNCH(ctx);
+  roi_grid_bwd_kernel<<<DC_CEIL_DIV(nboxes, 4), 128, 0, st>>>((const float2*)grad_grid_ws, nboxes, HH, WW, (float)img_h, (float)img_w,
+                                                              (float4*)grad_boxes);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}

@@ -118,13 +118,13 @@ int k_simt_gemm(dc_ctx* ctx, const __half* a_hi, const __half* a_lo, int lda, co
 }
 
 int k_simt_conv3x3(dc_ctx* ctx, const __half* x_hi, const __half* x_lo, const __half* w_hi, const __half* w_lo, const float* bias,
-                   float acc_scale, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, cudaStream_t st) {
+                   float acc_scale, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, cudaStream_t st, int relu) {
   const int M = N * H * W, K = 9 * Cin;
   if (M <= 0) return DC_OK;
   GemmEpilogue ep;
   ep.bias = bias;
   ep.acc_scale = acc_scale;
-  ep.relu = 1;
+  ep.relu = relu;
   ep.out_hi = y_hi;
   ep.out_lo = y_lo;
   ep.ldo = Cout;

@@ -999,7 +999,7 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
 
 int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, const __half* w_planes, size_t w_plane_elems,
                  const float* bias, float acc_scale, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, int fuse_pool,
-                 cudaStream_t st) {
+                 cudaStream_t st, int relu) {
   using namespace tc;
   if (N <= 0 || H <= 0 || W <= 0) return DC_OK;
   DC_REQUIRE(ctx, Cin % BLOCK_K == 0, DC_E_UNSUPPORTED, "tc_conv3x3: Cin=%d must be a multiple of 64", Cin);
@@ -1030,7 +1030,7 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
   GemmEpilogue ep;
   ep.bias = bias;
   ep.acc_scale = acc_scale;
-  ep.relu = 1;
+  ep.relu = relu;
   ep.out_hi = y_hi;
   ep.out_lo = y_lo;
   ep.ldo = Cout;

@@ -8,6 +8,7 @@
 // (debug_pos_sample_idx / debug_neg_sample_idx, BoxSampler.lua:154-159) the selection is injected, and the
 // injection implemented here is deterministic: the first P positives / first M negatives in index order.
 #include "common.cuh"
+#include <algorithm>
 
 __device__ __forceinline__ float4 t_xcycwh_to_x1y1x2y2(float4 b) {   // box_utils.lua:270-298 (same op order as box_kernels.cu)
   const float hw = __fdiv_rn(__fadd_rn(b.z, -1.f), 2.f);
@@ -199,17 +200,23 @@ __global__ void __launch_bounds__(1024)
 loc_losses_kernel(const int32_t* __restrict__ counts, const float2* __restrict__ pos_scores, const float2* __restrict__ neg_scores,
                   const float4* __restrict__ pos_anchors, const float4* __restrict__ pos_target_boxes, float4* __restrict__ pos_trans,
                   const float4* __restrict__ all_trans, int A, float w_obj, float w_box, float w_decay, float* __restrict__ losses,
-                  float4* __restrict__ pos_trans_targets, int32_t* __restrict__ masked_out) {
+                  float4* __restrict__ pos_trans_targets, int32_t* __restrict__ masked_out, float4* __restrict__ g_pos_trans,
+                  float2* __restrict__ g_pos_scores, float2* __restrict__ g_neg_scores) {
   const int P = counts[2], M = counts[3];
   // OurCrossEntropyCriterion = LogSoftMax + ClassNLL (size-averaged); target 1 for positives, 2 for negatives
   double lp = 0.0, ln = 0.0;
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
     const double a = pos_scores[i].x, b = pos_scores[i].y, m = fmax(a, b);
-    lp += -(a - m - log(exp(a - m) + exp(b - m)));
+    const double lse = log(exp(a - m) + exp(b - m));
+    lp += -(a - m - lse);
+    // gradient of the size-averaged NLL: (softmax - onehot(class 1)) / P, then scaled by the loss weight in fp32
+    g_pos_scores[i] = make_float2((float)((exp(a - m - lse) - 1.0) / P) * w_obj, (float)(exp(b - m - lse) / P) * w_obj);
   }
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
     const double a = neg_scores[i].x, b = neg_scores[i].y, m = fmax(a, b);
-    ln += -(b - m - log(exp(a - m) + exp(b - m)));
+    const double lse = log(exp(a - m) + exp(b - m));
+    ln += -(b - m - lse);
+    g_neg_scores[i] = make_float2((float)(exp(a - m - lse) / M) * w_obj, (float)((exp(b - m - lse) - 1.0) / M) * w_obj);
   }
   // InvertBoxTransform targets, |t| > 10 mask hack (zeroes prediction AND target in place), SmoothL1 (size-averaged over P*4)
   double lb = 0.0;
@@ -231,11 +238,14 @@ loc_losses_kernel(const int32_t* __restrict__ counts, const float2* __restrict__
     }
     if (pos_trans_targets) pos_trans_targets[i] = t;
     const double d[4] = {(double)p.x - t.x, (double)p.y - t.y, (double)p.z - t.z, (double)p.w - t.w};
+    float gq[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const double a = fabs(d[c]);
       lb += (a < 1.0) ? 0.5 * d[c] * d[c] : a - 0.5;
+      gq[c] = (float)(fmin(fmax(d[c], -1.0), 1.0) / (4.0 * P)) * w_box;        // SmoothL1 gradient (size-averaged), weighted
     }
+    g_pos_trans[i] = make_float4(gq[0], gq[1], gq[2], gq[3]);
   }
   double dec = 0.0;
   if (w_decay != 0.f) {
@@ -260,6 +270,8 @@ loc_losses_kernel(const int32_t* __restrict__ counts, const float2* __restrict__
 struct TrainBuffers {
   float4 *boxes, *anc, *trans, *gt, *roi_boxes, *pos_anchors, *pos_trans, *pos_target_boxes, *pos_trans_targets;
   float2 *scores, *pos_scores, *neg_scores;
+  float4* g_pos_trans;                     // criterion gradients, already scaled by the loss weights (LocalizationLayer.lua:553-570)
+  float2 *g_pos_scores, *g_neg_scores;
   float* iou;
   int32_t *argmax, *target_idx, *pos_idx, *neg_idx, *counts, *masked;
   uint8_t *pos, *neg;
@@ -294,7 +306,7 @@ int k_loc_train_sampler(dc_ctx* ctx, const float* head, int ld, int H, int W, in
 int k_loc_train_losses(dc_ctx* ctx, void* tb_, int A, float w_obj, float w_box, float w_decay, float* losses, cudaStream_t st) {
   TrainBuffers& tb = *reinterpret_cast<TrainBuffers*>(tb_);
   loc_losses_kernel<<<1, 1024, 0, st>>>(tb.counts, tb.pos_scores, tb.neg_scores, tb.pos_anchors, tb.pos_target_boxes, tb.pos_trans, tb.trans, A, w_obj,
-                                        w_box, w_decay, losses, tb.pos_trans_targets, tb.masked);
+                                        w_box, w_decay, losses, tb.pos_trans_targets, tb.masked, tb.g_pos_trans, tb.g_pos_scores, tb.g_neg_scores);
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }
@@ -318,9 +330,252 @@ size_t train_buffers_carve(void* tb_, char* base, int A, int B2max, int batch_si
   tb.pos_trans = (float4*)take((size_t)batch_size * 16); tb.pos_target_boxes = (float4*)take((size_t)batch_size * 16);
   tb.pos_trans_targets = (float4*)take((size_t)batch_size * 16);
   tb.pos_scores = (float2*)take((size_t)batch_size * 8); tb.neg_scores = (float2*)take((size_t)batch_size * 8);
+  tb.g_pos_trans = (float4*)take((size_t)batch_size * 16);
+  tb.g_pos_scores = (float2*)take((size_t)batch_size * 8); tb.g_neg_scores = (float2*)take((size_t)batch_size * 8);
   return off;
 }
 float* train_buffers_roi_boxes(void* tb_) { return (float*)reinterpret_cast<TrainBuffers*>(tb_)->roi_boxes; }
 float* train_buffers_gt(void* tb_) { return (float*)reinterpret_cast<TrainBuffers*>(tb_)->gt; }
 float* train_buffers_pos_target_boxes(void* tb_) { return (float*)reinterpret_cast<TrainBuffers*>(tb_)->pos_target_boxes; }
 int32_t* train_buffers_counts(void* tb_) { return reinterpret_cast<TrainBuffers*>(tb_)->counts; }
+
+// =========================================================================================================
+// Backward of the training-time LocalizationLayer (LocalizationLayer.lua:529-605)
+// =========================================================================================================
+// BoxSamplerHelper backward (modules/BoxSamplerHelper.lua:142-182): indexCopy of the sampled gradients into zeroed (A, .) tensors.
+// Negatives drawn with replacement repeat an index; indexCopy keeps the LAST copy, so only the last occurrence writes.
+// grad_roi_boxes_in: caller's gradOutput[2] (S,4); grad_boxes_pool: RoI-pooling gradient w.r.t. the boxes (S,4) -- summed (:577).
+__global__ void bwd_scatter_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ pos_idx, const int32_t* __restrict__ neg_idx,
+                                   const float4* __restrict__ grad_roi_boxes_in, const float4* __restrict__ grad_boxes_pool,
+                                   const float4* __restrict__ g_pos_trans, const float2* __restrict__ g_pos_scores,
+                                   const float2* __restrict__ g_neg_scores, int batch_size, float4* __restrict__ g_boxes_all,
+                                   float4* __restrict__ g_trans_all, float2* __restrict__ g_scores_all) {
+  const int P = counts[2], M = counts[3];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch_size) return;
+  auto total = [&](int row) {
+    const float4 a = grad_roi_boxes_in[row], b = grad_boxes_pool[row];
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  };
+  if (i < P) {
+    const int r = pos_idx[i];
+    g_boxes_all[r] = total(i);
+    g_trans_all[r] = g_pos_trans[i];
+    g_scores_all[r] = g_pos_scores[i];
+  } else if (i - P < M) {
+    const int j = i - P, r = neg_idx[j];
+    for (int j2 = j + 1; j2 < M; ++j2)
+      if (neg_idx[j2] == r) return;
+    g_boxes_all[r] = total(i);
+    g_scores_all[r] = g_neg_scores[j];
+  }
+}
+
+// Gradient w.r.t. the RPN head outputs, one row (anchor a, cell y,x) per thread:
+//   ApplyBoxTransform backward (modules/ApplyBoxTransform.lua:93-128) + the Identity branch of the ConcatTable,
+//   RegularizeLayer backward (modules/RegularizeLayer.lua:18-22: w * input + gradOutput),
+//   ReshapeBoxFeatures backward (modules/ReshapeBoxFeatures.lua:36-44) = channel 4a+d / 4k+2a+d of cell (y,x).
+// head_grad: (cells, ldh) fp32, columns [0,4k) box transform, [4k,6k) scores, rest (padding up to ldh) pre-zeroed.
+__global__ void bwd_head_grad_kernel(int A, int H, int W, int k, const float4* __restrict__ anc, const float4* __restrict__ trans,
+                                     const float4* __restrict__ boxes, const float4* __restrict__ g_boxes_all,
+                                     const float4* __restrict__ g_trans_all, const float2* __restrict__ g_scores_all, float w_decay,
+                                     float* __restrict__ head_grad, int ldh) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= A) return;
+  const int x = r % W, y = (r / W) % H, a = r / (W * H);
+  const float4 an = anc[r], t = trans[r], o = boxes[r], g = g_boxes_all[r], gt0 = g_trans_all[r];
+  float4 gt;
+  gt.x = __fadd_rn(gt0.x, __fmul_rn(g.x, an.z));
+  gt.y = __fadd_rn(gt0.y, __fmul_rn(g.y, an.w));
+  gt.z = __fadd_rn(gt0.z, __fmul_rn(o.z, g.z));
+  gt.w = __fadd_rn(gt0.w, __fmul_rn(o.w, g.w));
+  gt.x = __fadd_rn(__fmul_rn(t.x, w_decay), gt.x);
+  gt.y = __fadd_rn(__fmul_rn(t.y, w_decay), gt.y);
+  gt.z = __fadd_rn(__fmul_rn(t.z, w_decay), gt.z);
+  gt.w = __fadd_rn(__fmul_rn(t.w, w_decay), gt.w);
+  float* row = head_grad + (size_t)(y * W + x) * ldh;
+  row[4 * a + 0] = gt.x; row[4 * a + 1] = gt.y; row[4 * a + 2] = gt.z; row[4 * a + 3] = gt.w;
+  const float2 gs = g_scores_all[r];
+  row[4 * k + 2 * a + 0] = gs.x; row[4 * k + 2 * a + 1] = gs.y;
+}
+
+// ReLU backward of the RPN hidden layer + re-split for the 3x3 backward-data convolution: gh = gh * (hidden > 0)
+__global__ void bwd_relu_mask_kernel(float* __restrict__ gh, const __half* __restrict__ hid_hi, const __half* __restrict__ hid_lo, size_t n,
+                                     __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ hid_f32) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float h = __half2float(hid_hi[i]) + __half2float(hid_lo[i]);
+    const float g = h > 0.f ? gh[i] : 0.f;
+    gh[i] = g;
+    if (hid_f32) hid_f32[i] = h;
+    __half a, b;
+    split_f32(g, a, b);
+    out_hi[i] = a; out_lo[i] = b;
+  }
+}
+
+// grad_cnn_features (1,C,H,W) = RoI-pooling gradient (HWC fp32) + RPN gradient (split NHWC planes)   (:578, :601)
+__global__ void bwd_combine_kernel(const float* __restrict__ g_roi_hwc, const __half* __restrict__ g_rpn_hi, const __half* __restrict__ g_rpn_lo,
+                                   int C, int cells, float* __restrict__ out_chw) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (p < cells && c < C) {
+      const size_t o = (size_t)p * C + c;
+      v = g_roi_hwc[o] + (__half2float(g_rpn_hi[o]) + __half2float(g_rpn_lo[o]));
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, p = p0 + threadIdx.x;
+    if (p < cells && c < C) out_chw[(size_t)c * cells + p] = tile[threadIdx.x][j];
+  }
+}
+
+// (K, C, npos) -> (K, npos, C)
+__global__ void bchw_to_bhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int npos) {
+  const float* src = in + (size_t)blockIdx.x * C * npos;
+  float* dst = out + (size_t)blockIdx.x * C * npos;
+  for (int i = threadIdx.x; i < C * npos; i += blockDim.x) {
+    const int p = i / C, c = i % C;
+    dst[i] = src[(size_t)c * npos + p];
+  }
+}
+
+// accGradParameters of the RPN convolutions: C[m][n] (+)= sum over cells of A[cell][m] * B[shift_tap(cell)][n]
+//   A (cells, Mdim) and B (cells, Ndim) fp32 row-major over the H x W map; tap = blockIdx.z shifts B by (r-1, s-1) with zero
+//   padding (taps == 1: no shift).  Output element (m, n, tap) at out[(m*Ndim + n)*taps + tap]  (= (Cout, Cin, 3, 3) layout).
+constexpr int WG_T = 64, WG_K = 16;
+__global__ void __launch_bounds__(256)
+bwd_wgrad_kernel(const float* __restrict__ A, int Mdim, const float* __restrict__ B, int Ndim, int H, int W, int taps, float* __restrict__ out) {
+  __shared__ float sa[WG_K][WG_T + 1], sb[WG_K][WG_T + 1];
+  const int m0 = blockIdx.y * WG_T, n0 = blockIdx.x * WG_T, tap = blockIdx.z;
+  const int dr = taps == 9 ? tap / 3 - 1 : 0, ds = taps == 9 ? tap % 3 - 1 : 0;
+  const int cells = H * W;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;           // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < cells; k0 += WG_K) {
+    for (int e = threadIdx.x; e < WG_K * WG_T; e += 256) {
+      const int kk = e / WG_T, j = e % WG_T, cell = k0 + kk;
+      float va = 0.f, vb = 0.f;
+      if (cell < cells) {
+        if (m0 + j < Mdim) va = A[(size_t)cell * Mdim + m0 + j];
+        const int y = cell / W + dr, x = cell % W + ds;
+        if (n0 + j < Ndim && y >= 0 && y < H && x >= 0 && x < W) vb = B[(size_t)(y * W + x) * Ndim + n0 + j];
+      }
+      sa[kk][j] = va; sb[kk][j] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < WG_K; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sa[kk][ty * 4 + i]; b[i] = sb[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < Mdim && n < Ndim) out[((size_t)m * Ndim + n) * taps + tap] += acc[i][j];
+    }
+}
+// gradBias[m] += sum over cells of A[cell][m]
+__global__ void bwd_colsum_kernel(const float* __restrict__ A, int Mdim, int cells, float* __restrict__ out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mdim) return;
+  double s = 0.0;
+  for (int c = 0; c < cells; ++c) s += A[(size_t)c * Mdim + m];
+  out[m] += (float)s;
+}
+
+// weight re-layouts for the backward-data passes
+// (F, C, 3, 3) -> (C, F, 3, 3) with both taps flipped: full-correlation kernel of the transposed convolution
+__global__ void conv_weight_flip_transpose_kernel(const float* __restrict__ w, float* __restrict__ out, int F, int C) {
+  const size_t n = (size_t)F * C * 9;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int tap = i % 9;
+    const int f = (i / 9) % F;
+    const int c = i / ((size_t)9 * F);
+    out[i] = w[((size_t)f * C + c) * 9 + (8 - tap)];
+  }
+}
+// rows (R, F) row-major -> columns [col0, col0+R) of (F, ld) row-major
+__global__ void transpose_into_kernel(const float* __restrict__ w, int R, int F, float* __restrict__ out, int ld, int col0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * F) return;
+  const int r = i / F, f = i % F;
+  out[(size_t)f * ld + col0 + r] = w[i];
+}
+
+int k_conv_weight_flip_transpose(dc_ctx* ctx, const float* w, float* out, int F, int C, cudaStream_t st) {
+  conv_weight_flip_transpose_kernel<<<256, 256, 0, st>>>(w, out, F, C);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+int k_transpose_into(dc_ctx* ctx, const float* w, int R, int F, float* out, int ld, int col0, cudaStream_t st) {
+  transpose_into_kernel<<<DC_CEIL_DIV(R * F, 256), 256, 0, st>>>(w, R, F, out, ld, col0);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+int k_bchw_to_bhwc_f32(dc_ctx* ctx, const float* in, float* out, int K, int C, int npos, cudaStream_t st) {
+  if (K <= 0) return DC_OK;
+  bchw_to_bhwc_kernel<<<K, 256, 0, st>>>(in, out, C, npos);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+
+int k_loc_bwd_scatter(dc_ctx* ctx, void* tb_, int A, int batch_size, const float* grad_roi_boxes_in, const float* grad_boxes_pool,
+                      float* g_boxes_all, float* g_trans_all, float* g_scores_all, cudaStream_t st) {
+  TrainBuffers& tb = *reinterpret_cast<TrainBuffers*>(tb_);
+  DC_CHECK_CUDA(ctx, cudaMemsetAsync(g_boxes_all, 0, (size_t)A * 16, st));
+  DC_CHECK_CUDA(ctx, cudaMemsetAsync(g_trans_all, 0, (size_t)A * 16, st));
+  DC_CHECK_CUDA(ctx, cudaMemsetAsync(g_scores_all, 0, (size_t)A * 8, st));
+  bwd_scatter_kernel<<<DC_CEIL_DIV(batch_size, 128), 128, 0, st>>>(tb.counts, tb.pos_idx, tb.neg_idx, (const float4*)grad_roi_boxes_in,
+                                                                 (const float4*)grad_boxes_pool, tb.g_pos_trans, tb.g_pos_scores, tb.g_neg_scores,
+                                                                 batch_size, (float4*)g_boxes_all, (float4*)g_trans_all, (float2*)g_scores_all);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+int k_loc_bwd_head_grad(dc_ctx* ctx, void* tb_, int H, int W, int k, const float* g_boxes_all, const float* g_trans_all, const float* g_scores_all,
+                        float w_decay, float* head_grad, int ldh, cudaStream_t st) {
+  TrainBuffers& tb = *reinterpret_cast<TrainBuffers*>(tb_);
+  const int A = k * H * W;
+  DC_CHECK_CUDA(ctx, cudaMemsetAsync(head_grad, 0, (size_t)H * W * ldh * sizeof(float), st));
+  bwd_head_grad_kernel<<<DC_CEIL_DIV(A, 256), 256, 0, st>>>(A, H, W, k, tb.anc, tb.trans, tb.boxes, (const float4*)g_boxes_all,
+                                                          (const float4*)g_trans_all, (const float2*)g_scores_all, w_decay, head_grad, ldh);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+int k_bwd_relu_mask(dc_ctx* ctx, float* gh, const __half* hid_hi, const __half* hid_lo, size_t n, __half* out_hi, __half* out_lo, float* hid_f32,
+                    cudaStream_t st) {
+  bwd_relu_mask_kernel<<<(unsigned)std::min<size_t>(148 * 8, DC_CEIL_DIV(n, (size_t)256)), 256, 0, st>>>(gh, hid_hi, hid_lo, n, out_hi, out_lo, hid_f32);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+int k_bwd_combine(dc_ctx* ctx, const float* g_roi_hwc, const __half* g_rpn_hi, const __half* g_rpn_lo, int C, int cells, float* out_chw,
+                  cudaStream_t st) {
+  dim3 grid(DC_CEIL_DIV(C, 32), DC_CEIL_DIV(cells, 32));
+  bwd_combine_kernel<<<grid, dim3(32, 8), 0, st>>>(g_roi_hwc, g_rpn_hi, g_rpn_lo, C, cells, out_chw);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+int k_bwd_wgrad(dc_ctx* ctx, const float* A, int Mdim, const float* B, int Ndim, int H, int W, int taps, float* out, const float* bias_src,
+                float* bias_out, cudaStream_t st) {
+  dim3 grid(DC_CEIL_DIV(Ndim, WG_T), DC_CEIL_DIV(Mdim, WG_T), taps);
+  bwd_wgrad_kernel<<<grid, 256, 0, st>>>(A, Mdim, B, Ndim, H, W, taps, out);
+  DC_CHECK_LAUNCH(ctx);
+  if (bias_out) {
+    bwd_colsum_kernel<<<DC_CEIL_DIV(Mdim, 128), 128, 0, st>>>(bias_src, Mdim, H * W, bias_out);
+    DC_CHECK_LAUNCH(ctx);
+  }
+  return DC_OK;
+}

@@ -53,6 +53,37 @@ class LocalizationLayer:
     def training(self):
         self.train = True
 
+    def zeroGradParameters(self):
+        self.ctx.check(self.ctx._lib.dc_zero_grad_parameters(self.ctx.handle, stream_ptr()))
+
+    def backward(self, input, gradOutput):
+        """nn.Module:backward at training time (LocalizationLayer.lua:529-605 + accGradParameters of the RPN):
+        gradOutput = [grad_roi_features (S,C,HH,WW), grad_roi_boxes (S,4), ...]; returns gradInput (1,C,H',W')."""
+        assert self.train, "can only call updateGradInput in training mode"
+        f = _check_cuda_f32(input)
+        g_feat = _check_cuda_f32(gradOutput[0])
+        g_box = _check_cuda_f32(gradOutput[1])
+        _, C_, fh, fw = f.shape
+        S = int(self.opt["sampler_batch_size"])
+        assert tuple(g_feat.shape) == (S, C_, self.ctx.dims.pool_hw, self.ctx.dims.pool_hw) and tuple(g_box.shape) == (S, 4)
+        self.gradInput = torch.empty_like(f)
+        self.ctx.check(self.ctx._lib.dc_localization_backward_train(self.ctx.handle, ptr(f), fh, fw, ptr(g_feat), ptr(g_box), ptr(self.gradInput),
+                                                                   stream_ptr()))
+        return self.gradInput
+
+    def gradParameters(self):
+        """dict name -> gradWeight / gradBias tensor (reference shapes) accumulated since zeroGradParameters."""
+        d = self.ctx.dims
+        k, F, C5 = d.num_anchors, d.rpn_filters, d.widths[4]
+        shapes = {"rpn.conv.weight": (F, C5, 3, 3), "rpn.conv.bias": (F,), "rpn.box.weight": (4 * k, F, 1, 1), "rpn.box.bias": (4 * k,),
+                  "rpn.score.weight": (2 * k, F, 1, 1), "rpn.score.bias": (2 * k,)}
+        out = {}
+        for name, shp in shapes.items():
+            t = torch.empty(shp, dtype=torch.float32, device="cuda")
+            self.ctx.check(self.ctx._lib.dc_get_grad_parameters(self.ctx.handle, name.encode(), ptr(t), t.numel(), stream_ptr()))
+            out[name] = t
+        return out
+
     def _forward_train(self, f):
         dims = self.ctx.dims
         _, C_, fh, fw = f.shape

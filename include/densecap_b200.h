@@ -139,7 +139,7 @@ int dc_localization_forward_test(dc_ctx* ctx, const float* feats_nchw, int feat_
                                  float* roi_features, float* roi_boxes, int64_t* idx,
                                  int32_t* num_out, void* stream);
 
-/* ---- training-time forward of the LocalizationLayer (BASELINE configs[4]; forward only this round)
+/* ---- training step of the LocalizationLayer (BASELINE configs[4]): forward + backward
  * Options of nn.LocalizationLayer used by _forward_train (LocalizationLayer.lua:79-87; train_opts.lua:18-42).
  * sampler_batch_size <= min(max_batch*max_proposals, 1024). */
 int dc_set_train_args(dc_ctx* ctx, float mid_box_reg_weight, float mid_objectness_weight,
@@ -167,6 +167,24 @@ int dc_localization_forward_train(dc_ctx* ctx, const float* feats_nchw, int feat
                                   int64_t* pos_target_idx, int64_t* pos_input_idx,
                                   int64_t* neg_input_idx, int32_t* num_pos_neg, float* losses,
                                   void* stream);
+
+/* nn.LocalizationLayer:backward for the training path = updateGradInput (LocalizationLayer.lua:529-605: criterion
+ * gradients scaled by the loss weights, BilinearRoiPooling backward [stnbhwd sampler / affine-grid backward +
+ * BoxToAffine.lua:96-118], BoxSamplerHelper scatter [indexCopy, modules/BoxSamplerHelper.lua:142-182], ApplyBoxTransform
+ * backward [:93-128], RegularizeLayer backward, ReshapeBoxFeatures backward, RPN convolutions backward) plus
+ * accGradParameters of the RPN convolutions.  Must follow dc_localization_forward_train of the same input on this
+ * context; dc_set_image_size / dc_set_ground_truth arm one forward AND one backward call each, like the reference's
+ * _called_backward_size / _called_backward_gt flags (DC_E_PROTOCOL with the reference's assert messages otherwise).
+ * grad_roi_features (S,C,HH,WW), grad_roi_boxes (S,4) = gradOutput[1], gradOutput[2];
+ * grad_feats_nchw (1,C,H',W') = gradInput.  All device pointers. */
+int dc_localization_backward_train(dc_ctx* ctx, const float* feats_nchw, int feat_h, int feat_w,
+                                   const float* grad_roi_features, const float* grad_roi_boxes,
+                                   float* grad_feats_nchw, void* stream);
+/* nn.Module:zeroGradParameters / read-out of gradWeight, gradBias by the reference's parameter names
+ * ("rpn.conv.weight" (F,C,3,3), "rpn.conv.bias", "rpn.box.weight" (4k,F), "rpn.box.bias", "rpn.score.weight"
+ * (2k,F), "rpn.score.bias").  Gradients accumulate over backward calls until zeroed.  out: host or device. */
+int dc_zero_grad_parameters(dc_ctx* ctx, void* stream);
+int dc_get_grad_parameters(dc_ctx* ctx, const char* name, float* out, int64_t numel, void* stream);
 
 /* recog_base + objectness + box_reg + ApplyBoxTransform (DenseCapModel.lua:87-100,127-162).
  * roi_features (K,C,HH,WW) fp32 BCHW, roi_boxes (K,4).  Outputs (K,fc_dim),(K),(K,4),(K,4). */

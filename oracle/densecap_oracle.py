@@ -686,3 +686,69 @@ def localization_layer_forward_train(feats, weights, gt_boxes, image_h, image_w,
             "pos_input_idx": pi, "pos_target_idx": pt, "neg_input_idx": ni, "num_pos": num_pos, "num_neg": num_neg,
             "losses": losses, "pos_mask": pos_mask, "neg_mask": neg_mask, "masked": int(big.sum()),
             "grad_pos_scores": gp, "grad_neg_scores": gn, "grad_pos_trans": gb}
+
+
+# densecap/modules/BilinearRoiPooling.lua:94-104 -> self.net:backward: sampler backward (w.r.t. features and grid),
+# stnbhwd AffineGridGeneratorBHWD backward (gradTheta[b] = gradGrid[b]^T . baseGrid, App. B1), BoxToAffine backward.
+def bilinear_roi_pooling_backward(feats_chw, boxes, image_h, image_w, grad_out_bchw, HH=7, WW=7):
+    feats_hwc = np.ascontiguousarray(_f(feats_chw).transpose(1, 2, 0))
+    theta = box_to_affine(boxes, image_h, image_w)
+    grids = affine_grid(theta, HH, WW)
+    go = np.ascontiguousarray(_f(grad_out_bchw).transpose(0, 2, 3, 1))           # BCHW -> BHWC
+    gfeat_hwc, ggrid = bilinear_sample_backward(feats_hwc, grids, go)
+    ys = np.array([-1 + (i / (HH - 1)) * 2 for i in range(HH)], np.float64).astype(_DT[0])
+    xs = np.array([-1 + (j / (WW - 1)) * 2 for j in range(WW)], np.float64).astype(_DT[0])
+    base = np.stack([np.broadcast_to(ys[:, None], (HH, WW)), np.broadcast_to(xs[None, :], (HH, WW)),
+                     np.ones((HH, WW), _DT[0])], axis=-1).astype(np.float64)       # (HH,WW,3) = (y, x, 1)
+    gtheta = np.einsum("bijd,ijk->bdk", ggrid.astype(np.float64), base).astype(_DT[0])   # (B,2,3)
+    gboxes = box_to_affine_backward(gtheta, image_h, image_w)
+    return np.ascontiguousarray(gfeat_hwc.transpose(2, 0, 1)), gboxes
+
+
+# densecap/LocalizationLayer.lua:529-605  updateGradInput (+ accGradParameters of the RPN convolutions through
+# nn.Module:backward).  `fwd` is the dict returned by localization_layer_forward_train for the same inputs.
+# Dense parts (conv backward) use torch autograd on the plain fp32 torch definition of the RPN (App. B4).
+def localization_layer_backward_train(feats, weights, gt_boxes, image_h, image_w, fwd, grad_roi_features, grad_roi_boxes,
+                                      mid_box_reg_weight=0.05, mid_objectness_weight=0.1, box_reg_decay=0.0,
+                                      anchors=DEFAULT_ANCHORS, field_centers=FIELD_CENTERS, HH=7, WW=7):
+    torch = _torch()
+    k = anchors.shape[1]
+    N, C, H, W = feats.shape
+    A = k * H * W
+    P, M = fwd["num_pos"], fwd["num_neg"]
+    pi, ni = fwd["pos_input_idx"], fwd["neg_input_idx"]
+    # criterion gradients, scaled in place by the loss weights (:553-570)
+    grad_pos_trans = fwd["grad_pos_trans"] * f32(mid_box_reg_weight)
+    grad_pos_scores = fwd["grad_pos_scores"] * f32(mid_objectness_weight)
+    grad_neg_scores = fwd["grad_neg_scores"] * f32(mid_objectness_weight)
+    # RoI pooling backward (:573-580)
+    gfeat_roi, gboxes_roi = bilinear_roi_pooling_backward(feats[0], fwd["roi_boxes"], image_h, image_w, grad_roi_features, HH, WW)
+    grad_roi_boxes = _f(grad_roi_boxes) + gboxes_roi
+    # sampler backward (:583-596): indexCopy scatter; anchors receive no gradient
+    g_boxes, g_anc, g_trans, g_scores = box_sampler_helper_backward(
+        [(1, A, 4), (1, A, 4), (1, A, 4), (1, A, 2)], pi, ni,
+        [grad_roi_boxes[:P], None, grad_pos_trans, grad_pos_scores], [grad_roi_boxes[P:P + M], None, None, grad_neg_scores])
+    # RPN backward (:599-602): ApplyBoxTransform backward + Identity branch, ReshapeBoxFeatures backward, RegularizeLayer backward
+    boxes, anc, trans, scores, hid = rpn_forward(feats, weights, anchors, field_centers)
+    _, gt_from_apply = apply_box_transform_backward(anc, trans, boxes, g_boxes)
+    g_trans_total = g_trans + gt_from_apply
+    g_box_out = reshape_box_features_backward(g_trans_total, k, H, W)
+    box_out = reshape_box_features_backward(trans, k, H, W)                   # the box conv output itself
+    g_box_out = (box_out * f32(box_reg_decay) + g_box_out).astype(_DT[0])     # RegularizeLayer.lua:18-22 (gradMul = 1)
+    g_score_out = reshape_box_features_backward(g_scores, k, H, W)
+    tf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).requires_grad_(True)
+    x = tf(feats); wc = tf(weights["rpn.conv.weight"]); bc = tf(weights["rpn.conv.bias"])
+    wb = tf(weights["rpn.box.weight"]); bb = tf(weights["rpn.box.bias"])
+    ws = tf(weights["rpn.score.weight"]); bs = tf(weights["rpn.score.bias"])
+    F = torch.nn.functional
+    h = F.relu(F.conv2d(x, wc, bc, padding=1))
+    bo = F.conv2d(h, wb, bb); so = F.conv2d(h, ws, bs)
+    grads = torch.autograd.grad([bo, so], [x, wc, bc, wb, bb, ws, bs],
+                                [torch.from_numpy(np.ascontiguousarray(g_box_out, dtype=np.float32)),
+                                 torch.from_numpy(np.ascontiguousarray(g_score_out, dtype=np.float32))])
+    gx = grads[0].numpy()
+    grad_feats = (gx + gfeat_roi[None]).astype(_DT[0])
+    names = ["rpn.conv.weight", "rpn.conv.bias", "rpn.box.weight", "rpn.box.bias", "rpn.score.weight", "rpn.score.bias"]
+    return {"grad_feats": grad_feats, "grad_feats_roi": gfeat_roi, "grad_feats_rpn": gx, "grad_roi_boxes_pool": gboxes_roi,
+            "grad_box_out": g_box_out, "grad_score_out": g_score_out,
+            "grad_params": {n: g.numpy() for n, g in zip(names, grads[1:])}}

@@ -172,3 +172,84 @@ def test_train_forward_full_size():
         check_case(ll, out, labels, ref)
     finally:
         ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# backward (LocalizationLayer.lua:529-605 + accGradParameters of the RPN)
+# ---------------------------------------------------------------------------------------------------------
+def run_backward_case(ll, dims, weights, feats, gt, img_h, img_w, S, kw, seed):
+    rng = np.random.RandomState(seed)
+    C5 = dims.widths[4]
+    g1 = (rng.randn(S, C5, 7, 7) * 0.05).astype(np.float32)
+    g2 = (rng.randn(S, 4) * 0.05).astype(np.float32)
+    fwd = O.localization_layer_forward_train(feats, weights, gt, img_h, img_w, batch_size=S, **kw)
+    ref = O.localization_layer_backward_train(feats, weights, gt, img_h, img_w, fwd, g1, g2, mid_box_reg_weight=kw["mid_box_reg_weight"],
+                                              mid_objectness_weight=kw["mid_objectness_weight"], box_reg_decay=kw["box_reg_decay"])
+    out, labels = run_case(ll, feats, gt, img_h, img_w)
+    check_case(ll, out, labels, fwd)
+    ll.zeroGradParameters()
+    gin = ll.backward(dev(feats), [dev(g1), dev(g2)])
+    torch.cuda.synchronize()
+    return gin, ll.gradParameters(), ref
+
+
+def check_backward(gin, gparams, ref, tol=1e-4):
+    assert rel(gin.cpu().numpy(), ref["grad_feats"]) < tol
+    for name, want in ref["grad_params"].items():
+        got = gparams[name].cpu().numpy()
+        assert got.shape == want.shape
+        assert rel(got, want) < tol, name
+
+
+@pytest.mark.parametrize("seed,num_gt", [(0, 6), (4, 3)])
+def test_train_backward_matches_oracle(layer, small, seed, num_gt):
+    dims, weights = small
+    feats, gt = make_case(dims, weights, IMG_H, IMG_W, num_gt, seed)
+    kw = dict(mid_box_reg_weight=0.05, mid_objectness_weight=0.1, box_reg_decay=5e-5)
+    gin, gparams, ref = run_backward_case(layer, dims, weights, feats, gt, IMG_H, IMG_W, 32, kw, seed)
+    check_backward(gin, gparams, ref)
+    layer.train = False
+
+
+def test_train_backward_protocol_and_accumulation(layer, small):
+    from densecap_b200._lib import DenseCapError
+    dims, weights = small
+    feats, gt = make_case(dims, weights, IMG_H, IMG_W, 5, 9)
+    kw = dict(mid_box_reg_weight=0.05, mid_objectness_weight=0.1, box_reg_decay=5e-5)
+    gin, gparams, ref = run_backward_case(layer, dims, weights, feats, gt, IMG_H, IMG_W, 32, kw, 9)
+    g1 = dev(np.zeros((32, dims.widths[4], 7, 7), np.float32)); g2 = dev(np.zeros((32, 4), np.float32))
+    # a second backward without re-arming setGroundTruth / setImageSize fails like the reference asserts (:531-537)
+    with pytest.raises(DenseCapError, match="Must call setGroundTruth before each forward pass"):
+        layer.backward(dev(feats), [g1, g2])
+    # gradients accumulate across backward calls until zeroGradParameters (accGradParameters semantics)
+    out, labels = run_case(layer, feats, gt, IMG_H, IMG_W)
+    rng = np.random.RandomState(9)
+    g1 = (rng.randn(32, dims.widths[4], 7, 7) * 0.05).astype(np.float32); g2 = (rng.randn(32, 4) * 0.05).astype(np.float32)
+    layer.backward(dev(feats), [dev(g1), dev(g2)])
+    twice = layer.gradParameters()
+    for name, want in ref["grad_params"].items():
+        assert rel(twice[name].cpu().numpy(), 2 * want) < 1e-4, name
+    layer.train = False
+
+
+def test_train_backward_full_size():
+    """BASELINE configs[4]: 720x600, 50 GT boxes, 256 sampled ROIs, fwd + bwd against the oracle."""
+    from densecap_b200.model import LocalizationLayer
+    from densecap_b200.runtime import Context
+    dims = ModelDims()
+    rng = np.random.RandomState(5)
+    k, F, C5 = dims.num_anchors, dims.rpn_filters, dims.widths[4]
+    weights = {"rpn.conv.weight": (rng.randn(F, C5, 3, 3) * 0.01).astype(np.float32), "rpn.conv.bias": np.zeros(F, np.float32),
+               "rpn.box.weight": (rng.randn(4 * k, F, 1, 1) * 0.01).astype(np.float32), "rpn.box.bias": np.zeros(4 * k, np.float32),
+               "rpn.score.weight": (rng.randn(2 * k, F, 1, 1) * 0.01).astype(np.float32), "rpn.score.bias": np.zeros(2 * k, np.float32)}
+    H, W = 600, 720
+    feats, gt = make_case(dims, weights, H, W, 50, 11)
+    kw = dict(mid_box_reg_weight=0.05, mid_objectness_weight=0.1, box_reg_decay=5e-5, sampler_low=0.3)
+    ctx = Context(dims, max_image_hw=(H, W), max_proposals=256)
+    try:
+        ctx.load_weights(weights)
+        ll = LocalizationLayer(ctx, {"sampler_batch_size": 256, "sampler_low_thresh": 0.3, "box_reg_decay": 5e-5})
+        gin, gparams, ref = run_backward_case(ll, dims, weights, feats, gt, H, W, 256, kw, 3)
+        check_backward(gin, gparams, ref)
+    finally:
+        ctx.close()
