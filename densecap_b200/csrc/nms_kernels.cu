@@ -197,10 +197,12 @@ __device__ __forceinline__ void nms_mask_tile(int tile, int lrow, const float4* 
     if (p_local < cn_total) {
       const float4 pb = sb[base + p_local];
       const float pa = nms_area(pb);
-      const int t0 = max(0, p_local + 1 - col0);         // only q > p
-      for (int t = t0; t < cn; ++t) {
+      // off-diagonal tiles: every q of the tile is later than p.  Diagonal tile: the FULL row (all q != p) -- the IoU test is
+      // symmetric bit for bit, and the scan resolves a 64-box block through the bits of the EARLIER boxes of each row.
+      const int self = p_local - col0;
+      for (int t = 0; t < cn; ++t) {
         const float4 q = __ldg(sb + base + col0 + t);    // same address for the 64 threads of the tile: broadcast
-        if (nms_suppresses(pb, pa, q, nms_area(q), thresh)) bits |= (1ull << t);
+        if (t != self && nms_suppresses(pb, pa, q, nms_area(q), thresh)) bits |= (1ull << t);
       }
     }
     mask_intra[(size_t)p_local * NMS_W + cb] = bits;
@@ -275,18 +277,29 @@ __device__ __forceinline__ void nms_scan_chunk(uint64_t* smem_mask, uint64_t* s_
       const uint64_t d0 = (lane < lim) ? smem_mask[(size_t)(c * 64 + lane) * NMS_W + c] : 0ull;
       const uint64_t d1 = (lane + 32 < lim) ? smem_mask[(size_t)(c * 64 + 32 + lane) * NMS_W + c] : 0ull;
       const uint64_t cur = __shfl_sync(0xffffffffu, my_removed, c);
-      uint64_t keep = 0;
       const int before = count;
-      // visit only candidates that are still alive; each survivor kills the later ones it suppresses
-      uint64_t alive = ~cur & ((lim == 64) ? ~0ull : ((1ull << lim) - 1ull));
-      while (alive && count < cap) {
-        const int i = __ffsll((long long)alive) - 1;
-        const uint64_t row = __shfl_sync(0xffffffffu, (i < 32) ? d0 : d1, i & 31);
-        keep |= (1ull << i);
-        ++count;
-        alive &= ~row;
-        alive &= ~(1ull << i);
+      // Greedy NMS inside the 64-box block as a fixpoint instead of a serial walk: box i survives iff it is alive and no
+      // SURVIVING earlier box of the block suppresses it, K_i = alive_i & !(row_i & below_i & K).  The solution is unique
+      // (induction on i) and iterating from K = alive fixes at least one more leading box per round; real chains are a few
+      // boxes deep, so a block costs a handful of ballot rounds instead of one shuffle-latency per survivor.
+      const uint64_t alive0 = ~cur & ((lim == 64) ? ~0ull : ((1ull << lim) - 1ull));
+      const bool a0 = (alive0 >> lane) & 1ull, a1 = (alive0 >> (lane + 32)) & 1ull;
+      const uint64_t m0 = d0 & ((1ull << lane) - 1ull), m1 = d1 & ((1ull << (lane + 32)) - 1ull);
+      uint64_t keep = alive0;
+      for (;;) {
+        const bool k0 = a0 && (m0 & keep) == 0ull, k1 = a1 && (m1 & keep) == 0ull;
+        const uint64_t next = (uint64_t)__ballot_sync(0xffffffffu, k0) | ((uint64_t)__ballot_sync(0xffffffffu, k1) << 32);
+        if (next == keep) break;
+        keep = next;
       }
+      int nk = __popcll(keep);
+      if (count + nk > cap) {                      // max_boxes reached inside this block: keep the first (cap - count) survivors
+        uint64_t rest = keep;
+        for (int z = cap - count; z > 0; --z) rest &= rest - 1;
+        keep &= ~rest;
+        nk = cap - count;
+      }
+      count += nk;
       // remember the sorted positions of the survivors (index translation + box copy happen after the loop, in parallel)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
