@@ -48,6 +48,8 @@ SIGNATURES = {
     "dc_set_image_size": (c_i, [c_vp, c_i, c_i]),
     "dc_forward_test": (c_i, [c_vp, c_vp, c_i, c_i, c_i, C.POINTER(DcResult), c_vp]),
     "dc_forward_test_host": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_vp]),
+    "dc_preprocess_u8": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp]),
+    "dc_forward_test_host_u8": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_vp]),
     "dc_vgg_trunk_forward": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp]),
     "dc_localization_forward_test": (c_i, [c_vp, c_vp, c_i, c_i, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dc_set_train_args": (c_i, [c_vp, c_f, c_f, c_f, c_f, c_f, c_i, c_i]),

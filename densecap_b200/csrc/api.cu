@@ -1097,6 +1097,46 @@ extern "C" int dc_forward_test_host(dc_ctx* ctx, const float* img_host, int batc
   return DC_OK;
 }
 
+// run_model.lua:66-74 preprocessing (no resize) on the device: uint8 RGB HWC (batch,H,W,3) -> fp32 BGR mean-subtracted NCHW
+extern "C" int dc_preprocess_u8(dc_ctx* ctx, const uint8_t* img_u8, int batch, int image_h, int image_w, float* img_nchw, void* stream) {
+  if (!ctx || !img_u8 || !img_nchw) return dc_set_error(ctx, DC_E_INVALID, "dc_preprocess_u8: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  return k_preprocess_u8(ctx, img_u8, img_nchw, batch, image_h, image_w, (cudaStream_t)stream);
+}
+
+// dc_forward_test_host with the decoded uint8 image at the boundary: 4x fewer host->device bytes, preprocessing on the device
+extern "C" int dc_forward_test_host_u8(dc_ctx* ctx, const uint8_t* img_host_u8, int batch, int image_h, int image_w, int32_t* num_final_host,
+                                       float* final_boxes_host, float* final_scores_host, int64_t* final_seq_host) {
+  if (!ctx || !img_host_u8) return dc_set_error(ctx, DC_E_INVALID, "dc_forward_test_host_u8: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  DC_REQUIRE(ctx, batch >= 1 && batch <= ctx->B, DC_E_INVALID, "batch %d exceeds max_batch %d", batch, ctx->B);
+  const size_t n = (size_t)batch * 3 * image_h * image_w;
+  static thread_local uint8_t* staging_u8 = nullptr;
+  static thread_local float* staging_f32 = nullptr;
+  static thread_local size_t staging_elems = 0;
+  if (staging_elems < n) {
+    if (staging_u8) cudaFree(staging_u8);
+    if (staging_f32) cudaFree(staging_f32);
+    DC_CHECK_CUDA(ctx, cudaMalloc((void**)&staging_u8, n));
+    DC_CHECK_CUDA(ctx, cudaMalloc((void**)&staging_f32, n * sizeof(float)));
+    staging_elems = n;
+  }
+  cudaStream_t st = 0;
+  DC_CHECK_CUDA(ctx, cudaMemcpyAsync(staging_u8, img_host_u8, n, cudaMemcpyHostToDevice, st));
+  int rc = k_preprocess_u8(ctx, staging_u8, staging_f32, batch, image_h, image_w, st);
+  if (rc) return rc;
+  dc_result r;
+  if ((rc = dc_forward_test(ctx, staging_f32, batch, image_h, image_w, &r, st))) return rc;
+  const size_t rows = (size_t)batch * ctx->P;
+  const int T = ctx->cfg.seq_length;
+  if (num_final_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(num_final_host, r.num_final, batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (final_boxes_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(final_boxes_host, r.final_boxes, rows * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (final_scores_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(final_scores_host, r.final_scores, rows * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (final_seq_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(final_seq_host, r.final_seq, rows * T * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  DC_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+  return DC_OK;
+}
+
 extern "C" int dc_vgg_trunk_forward(dc_ctx* ctx, const float* img, int batch, int image_h, int image_w, float* feats_nchw, void* stream) {
   if (!ctx || !img || !feats_nchw) return dc_set_error(ctx, DC_E_INVALID, "dc_vgg_trunk_forward: null argument");
   DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -208,3 +208,4 @@ int k_roi_pool_backward(dc_ctx*, const __half* feat_hi, const __half* feat_lo, i
 // train_kernels.cu -- weight re-layouts for the backward-data passes
 int k_conv_weight_flip_transpose(dc_ctx*, const float* w, float* out, int F, int C, cudaStream_t st);
 int k_transpose_into(dc_ctx*, const float* w, int R, int F, float* out, int ld, int col0, cudaStream_t st);
+int k_preprocess_u8(dc_ctx*, const uint8_t* in_hwc_rgb, float* out_nchw_bgr, int N, int H, int W, cudaStream_t st);

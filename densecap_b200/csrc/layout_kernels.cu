@@ -1,6 +1,7 @@
 // Layout / format conversion kernels between the reference's tensor layouts (fp32 NCHW, (out,in)
 // Linear weights, ...) and the library's internal "split-fp16 planes" NHWC / K-major layouts.
 #include "common.cuh"
+#include <algorithm>
 
 static inline unsigned grid_for(size_t n, int threads = 256, unsigned cap = 148 * 16) {
   size_t b = DC_CEIL_DIV(n, (size_t)threads);
@@ -254,6 +255,29 @@ __global__ void absmax_kernel(const float* __restrict__ in, size_t n, float* __r
 int k_absmax(dc_ctx* ctx, const float* in, size_t n, float* out_dev, cudaStream_t st) {
   if (n == 0) return DC_OK;
   absmax_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(in, n, out_dev);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+
+// Image preprocessing of run_model.lua:66-74 / webcam/daemon.lua:66-78 without the resize: decoded uint8 RGB HWC ->
+// float [0,1] (image.load: byte / 255), RGB -> BGR, * 255, - VGG mean (add(-1, mean): one product, one sum), NCHW.
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int N, int H, int W) {
+  const size_t hw = (size_t)H * W, total = (size_t)N * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / hw, p = i % hw;
+    const uint8_t* px = in + i * 3;
+    const float mean[3] = {103.939f, 116.779f, 123.68f};              // B, G, R
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __fmul_rn(__fdiv_rn((float)px[2 - c], 255.f), 255.f);
+      out[(n * 3 + c) * hw + p] = __fadd_rn(v, __fmul_rn(-1.f, mean[c]));
+    }
+  }
+}
+int k_preprocess_u8(dc_ctx* ctx, const uint8_t* in, float* out, int N, int H, int W, cudaStream_t st) {
+  const size_t total = (size_t)N * H * W;
+  if (total == 0) return DC_OK;
+  preprocess_u8_kernel<<<(unsigned)std::min<size_t>(148 * 8, DC_CEIL_DIV(total, (size_t)256)), 256, 0, st>>>(in, out, N, H, W);
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }

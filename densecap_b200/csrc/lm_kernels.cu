@@ -11,6 +11,10 @@ __global__ void __launch_bounds__(64)
 lm_token_step_kernel(unsigned long long* __restrict__ packed, int32_t* __restrict__ tokens, int64_t* __restrict__ seq64, int T, int t,
                      int start_token, const __half* __restrict__ lut_hi, const __half* __restrict__ lut_lo, int E,
                      __half* __restrict__ xh_hi, __half* __restrict__ xh_lo, int ld) {
+  // launched with programmatic stream serialisation between the vocabulary GEMM and the next gate GEMM: wait for the
+  // arg-max cells of the former, then let the latter start its prologue while the rows are copied
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int m = blockIdx.x;
   __shared__ int s_tok;
   if (threadIdx.x == 0) {
@@ -38,7 +42,17 @@ int k_lm_token_step(dc_ctx* ctx, unsigned long long* packed, int32_t* tokens, in
                     const __half* lut_hi, const __half* lut_lo, int E, __half* xh_hi, __half* xh_lo, int ld, int M, cudaStream_t st) {
   if (M <= 0) return DC_OK;
   DC_REQUIRE(ctx, E % 8 == 0 && ld % 8 == 0, DC_E_UNSUPPORTED, "lm: encoding size must be a multiple of 8");
-  lm_token_step_kernel<<<M, 64, 0, st>>>(packed, tokens, seq64, T, t, start_token, lut_hi, lut_lo, E, xh_hi, xh_lo, ld);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(M);
+  cfg.blockDim = dim3(64);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lm_token_step_kernel, packed, tokens, seq64, T, t, start_token, lut_hi, lut_lo, E, xh_hi, xh_lo, ld);
+  if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "lm_token_step launch: %s", cudaGetErrorString(e));
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }

@@ -249,6 +249,21 @@ class DenseCapModel:
         return out[3], out[0], captions
 
 
+def preprocess_image(ctx, img_u8):
+    """run_model.lua:66-74 without the resize, on the device: uint8 RGB (N,H,W,3) or (H,W,3) CUDA tensor -> (N,3,H,W) fp32
+    BGR, mean-subtracted -- what DenseCapModel:forward_test expects."""
+    if not isinstance(img_u8, torch.Tensor) or not img_u8.is_cuda or img_u8.dtype != torch.uint8:
+        raise TypeError("preprocess_image takes a CUDA uint8 tensor")
+    x = img_u8.contiguous()
+    if x.dim() == 3:
+        x = x[None]
+    N, H, W, C_ = x.shape
+    assert C_ == 3
+    out = torch.empty((N, 3, H, W), dtype=torch.float32, device=x.device)
+    ctx.check(ctx._lib.dc_preprocess_u8(ctx.handle, ptr(x), N, H, W, ptr(out), stream_ptr()))
+    return out
+
+
 def _dev_tensor(addr, shape, dtype, device):
     """Zero-copy torch view of a ctx-owned device buffer through the CUDA array interface."""
     n = int(np.prod(shape))

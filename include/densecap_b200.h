@@ -124,6 +124,17 @@ int dc_forward_test_host(dc_ctx* ctx, const float* img_host, int batch, int imag
                          int32_t* num_final_host, float* final_boxes_host, float* final_scores_host,
                          int64_t* final_seq_host);
 
+/* SURVEY.md 8f rank 1 -- the step immediately before the path: the image preprocessing of run_model.lua:66-74 /
+ * webcam/daemon.lua:66-78 without the resize (image.scale is third-party and stays with the caller): decoded uint8 RGB
+ * HWC (batch,H,W,3) -> float/255 -> BGR -> *255 -> minus the VGG mean (103.939, 116.779, 123.68) -> fp32 NCHW.
+ * dc_preprocess_u8: device pointers.  dc_forward_test_host_u8: dc_forward_test_host with the uint8 image at the
+ * boundary (4x fewer host->device bytes; the preprocessing runs on the device). */
+int dc_preprocess_u8(dc_ctx* ctx, const uint8_t* img_u8, int batch, int image_h, int image_w,
+                     float* img_nchw, void* stream);
+int dc_forward_test_host_u8(dc_ctx* ctx, const uint8_t* img_host_u8, int batch, int image_h, int image_w,
+                            int32_t* num_final_host, float* final_boxes_host, float* final_scores_host,
+                            int64_t* final_seq_host);
+
 /* ---- stages of the path (each mirrors one reference entry point; used for per-stage parity) */
 
 /* conv_net1+conv_net2 (DenseCapModel.lua:61-76).  feats_nchw out: (batch,C5,H',W') fp32. */

@@ -752,3 +752,15 @@ def localization_layer_backward_train(feats, weights, gt_boxes, image_h, image_w
     return {"grad_feats": grad_feats, "grad_feats_roi": gfeat_roi, "grad_feats_rpn": gx, "grad_roi_boxes_pool": gboxes_roi,
             "grad_box_out": g_box_out, "grad_score_out": g_score_out,
             "grad_params": {n: g.numpy() for n, g in zip(names, grads[1:])}}
+
+
+# run_model.lua:66-74 (and webcam/daemon.lua:66-78) without image.scale: image.load gives float RGB CHW in [0,1]
+# (byte / 255); index {3,2,1} -> BGR; mul(255); add(-1, vgg_mean).  Input: uint8 (H,W,3) RGB.  Output (1,3,H,W) fp32.
+VGG_MEAN_BGR = np.array([103.939, 116.779, 123.68], np.float32)
+def preprocess_u8(img_u8_hwc):
+    img = np.asarray(img_u8_hwc, np.uint8)
+    x = img.astype(np.float32) / f32(255)                       # image.load
+    x = np.ascontiguousarray(x.transpose(2, 0, 1)[::-1])        # CHW, BGR
+    x = x * f32(255)
+    x = x + (f32(-1) * VGG_MEAN_BGR)[:, None, None]
+    return x[None].astype(np.float32)

@@ -174,6 +174,31 @@ def test_host_boundary_call_matches_device_call(model, small):
     assert np.array_equal(fb[:Kf], out[3].cpu().numpy()) and np.array_equal(sq[:Kf], out[4].cpu().numpy())
 
 
+def test_device_preprocessing_and_u8_boundary(model, small):
+    """uint8 RGB HWC -> BGR mean-subtracted NCHW on the device is bit-identical to the oracle's restatement
+    of run_model.lua:66-74, and the uint8 host entry point returns exactly what the fp32 host entry point returns."""
+    import ctypes as C
+    from densecap_b200.model import preprocess_image
+    dims, weights, img, cfg, ref = small
+    rng = np.random.RandomState(2)
+    u8 = rng.randint(0, 256, size=(IMG_H, IMG_W, 3), dtype=np.uint8)
+    want = O.preprocess_u8(u8)
+    got = preprocess_image(model.ctx, torch.from_numpy(u8).cuda())
+    assert np.array_equal(got.cpu().numpy(), want)
+    P, T = model.ctx.max_proposals, dims.seq_length
+    lib, h = model.ctx._lib, model.ctx.handle
+    outs = []
+    for fn, src in ((lib.dc_forward_test_host, np.ascontiguousarray(want)), (lib.dc_forward_test_host_u8, np.ascontiguousarray(u8))):
+        n = np.zeros(1, np.int32); b = np.zeros((P, 4), np.float32); sc = np.zeros(P, np.float32); sq = np.zeros((P, T), np.int64)
+        model.ctx.check(fn(h, src.ctypes.data_as(C.c_void_p), 1, IMG_H, IMG_W, n.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                           sc.ctypes.data_as(C.c_void_p), sq.ctypes.data_as(C.c_void_p)))
+        outs.append((int(n[0]), b.copy(), sc.copy(), sq.copy()))
+    assert outs[0][0] == outs[1][0] and outs[0][0] > 0
+    k = outs[0][0]
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert np.array_equal(a[:k], b[:k])
+
+
 def test_batched_forward_equals_single(small):
     from densecap_b200.model import DenseCapModel
     dims, weights, img, cfg, ref = small

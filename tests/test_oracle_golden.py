@@ -133,3 +133,14 @@ def test_roi_pool_full_image_box_matches_corners():
     assert out.shape == (1, C, 7, 7)
     np.testing.assert_allclose(out[0, :, 0, 0], feats[:, 0, 0], atol=1e-5)
     np.testing.assert_allclose(out[0, :, 6, 6], feats[:, -1, -1], atol=1e-5)
+
+
+def test_preprocess_u8_restates_run_model():
+    """run_model.lua:66-74: image.load float/255, BGR, *255, -mean; values stay within half an ulp of (u8 - mean)."""
+    rng = np.random.RandomState(0)
+    u8 = rng.randint(0, 256, size=(5, 7, 3), dtype=np.uint8)
+    x = O.preprocess_u8(u8)
+    assert x.shape == (1, 3, 5, 7) and x.dtype == np.float32
+    ideal = u8[..., ::-1].transpose(2, 0, 1).astype(np.float64) - O.VGG_MEAN_BGR.astype(np.float64)[:, None, None]
+    assert np.abs(x[0] - ideal).max() < 3e-5
+    assert x[0, 0, 2, 3] == np.float32(np.float32(np.float32(u8[2, 3, 2]) / np.float32(255)) * np.float32(255)) + np.float32(-103.939)
