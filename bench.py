@@ -297,6 +297,17 @@ def main():
     phases = ctx.get_times()
     ctx.enable_timing(False)
     final_counts = _wrap_result(res, dims, torch.device("cuda", local_rank))["num_final"].cpu().tolist()
+    # the ROI-pooling kernel pair alone: in a batch > 1 step the per-image side streams overlap it with other images' kernels,
+    # so its HBM figure is taken from a batch-1 forward (image 0 of the pool)
+    roi_alone_ms = None
+    if B > 1:
+        ctx.enable_timing(True)
+        ctx.check(lib.dc_forward_test(ctx.handle, C.c_void_p(dev_batches[0].data_ptr()), 1, IMG_H, IMG_W, C.byref(res), sp))
+        torch.cuda.synchronize()
+        for n_, ms_ in ctx.get_times():
+            if n_.startswith("kernel:roi_taps+roi_pool"):
+                roi_alone_ms = ms_
+        ctx.enable_timing(False)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -308,7 +319,7 @@ def main():
             ph[n] = ph.get(n, 0.0) + ms
         trunk_ms = ph.get("conv_trunk", 0.0)
         fc6_ms = ph.get("recog:fc6", 0.0)
-        roi_ms = ph.get("kernel:roi_taps+roi_pool(image0)", 0.0)
+        roi_ms = roi_alone_ms if roi_alone_ms else ph.get("kernel:roi_taps+roi_pool(image0)", 0.0)
         # Roofline of the dominant kernel (tc_gemm_kernel, the tcgen05 split-fp16 GEMM / implicit-GEMM conv), quoted on its
         # single largest launch, fc6 (2*M*N*K flops), timed live with CUDA events on the launching stream (phase events of
         # dc_get_times).  The conv trunk (12 launches of the same kernel + conv1_1) and the ROI pooling (HBM) are given beside it.
@@ -317,12 +328,11 @@ def main():
         fc6_tflops = (fc6_gflop / 1e3) / (fc6_ms / 1e3) if fc6_ms > 0 else None
         peak = peaks["bf16_sustained"]
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "roofline_traffic_r05.json")
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic_r06.json")
         if os.path.exists(tpath):
             try:
                 tj = json.load(open(tpath))
-                f = tj["tc_gemm"]["fc6"]
-                traffic = {"bytes_per_launch": int((f["dram_read_MB"] + f["dram_write_MB"]) * 1e6), "at": "batch 1 (ncu --set full, profiles/tc_gemm_r05_ncu_summary.md)",
+                traffic = {"bytes_per_launch": int(tj["bytes_per_launch"]), "at": "batch 1 (ncu --set full, profiles/kernels_r06_ncu_summary.md)",
                            "algorithmic_bytes_per_launch": int(2 * 2 * (dims.fc_dim * dims.feat_dim * 49 + P * dims.feat_dim * 49) + 2 * 2 * P * dims.fc_dim)}
             except Exception:
                 traffic = None
@@ -330,11 +340,13 @@ def main():
                     "achieved": fc6_tflops, "peak": peak, "unit": "TFLOP/s", "frac": (fc6_tflops / peak) if fc6_tflops else None,
                     "traffic": traffic, "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
                     "note": "achieved counts ALGORITHMIC fp32 flops; the kernel issues 3 fp16 MMAs per product (split-fp16, fp32-class accuracy), "
-                            "so the tensor pipe does 3x this work: ncu shows 96.5 % tensor-pipe activity on this launch",
+                            "so the tensor pipe does 3x this work: ncu shows 96.5 % tensor-pipe activity on this launch "
+                            "(profiles/kernels_r06_ncu_summary.md); the 12 tcgen05 VGG convolutions are 70.5 % tensor-pipe active, time-weighted "
+                            "(profiles/launches_r06_summary.md)",
                     "hw_flops_factor": 3, "tensor_pipe_frac_3x": (3 * fc6_tflops / peak) if fc6_tflops else None,
                     "conv_trunk": {"ms": trunk_ms, "algorithmic_tflops": trunk_tflops, "frac": (trunk_tflops / peak) if trunk_tflops else None,
                                    "tensor_pipe_frac_3x": (3 * trunk_tflops / peak) if trunk_tflops else None},
-                    "roi_pool": {"bound": "hbm", "ms": roi_ms, "algorithmic_bytes": 103870080,
+                    "roi_pool": {"bound": "hbm", "ms": roi_ms, "timed": "roi_taps + roi_pool kernels of one image, batch-1 forward", "algorithmic_bytes": 103870080,
                                  "achieved_GBps": (103870080 / 1e9) / (roi_ms / 1e3) if roi_ms > 0 else None, "peak_GBps": peaks["hbm"],
                                  "frac": ((103870080 / 1e9) / (roi_ms / 1e3) / peaks["hbm"]) if roi_ms > 0 else None}}
         line = {
