@@ -764,3 +764,44 @@ def preprocess_u8(img_u8_hwc):
     x = x * f32(255)
     x = x + (f32(-1) * VGG_MEAN_BGR)[:, None, None]
     return x[None].astype(np.float32)
+
+
+# densecap/box_utils.lua:311-341  (x, y, w, h) -> (x1, y1, x2, y2) with x2 = x + w - 1
+def xywh_to_x1y1x2y2(boxes):
+    b = _f(boxes)
+    out = np.empty_like(b)
+    out[..., 0] = b[..., 0]
+    out[..., 1] = b[..., 1]
+    out[..., 2] = (b[..., 0] + b[..., 2]) + f32(-1)
+    out[..., 3] = (b[..., 1] + b[..., 3]) + f32(-1)
+    return out
+
+
+# densecap/modules/InvertBoxTransform.lua:63-97
+def invert_box_transform_backward(anchor_boxes, target_boxes, grad_out):
+    a = _f(anchor_boxes); t = _f(target_boxes); g = _f(grad_out)
+    out = invert_box_transform(a, t)
+    ga = np.zeros_like(a); gt = np.zeros_like(t)
+    ga[:, 0] = (g[:, 0] / a[:, 2]) * f32(-1)
+    ga[:, 1] = (g[:, 1] / a[:, 3]) * f32(-1)
+    ga[:, 2] = ((out[:, 0] * g[:, 0] + g[:, 2]) / a[:, 2]) * f32(-1)
+    ga[:, 3] = ((out[:, 1] * g[:, 1] + g[:, 3]) / a[:, 3]) * f32(-1)
+    gt[:, 0] = g[:, 0] / a[:, 2]
+    gt[:, 1] = g[:, 1] / a[:, 3]
+    gt[:, 2] = g[:, 2] / t[:, 2]
+    gt[:, 3] = g[:, 3] / t[:, 3]
+    return ga, gt
+
+
+# densecap/modules/BoxRegressionCriterion.lua:50-79: w * SmoothL1(transforms, InvertBoxTransform(anchors, targets)) with the
+# |t| > 10 mask hack; backward w.r.t. the transforms and (through InvertBoxTransform backward, negated) the anchors.
+def box_regression_criterion(anchor_boxes, transforms, target_boxes, w=1.0):
+    tt = invert_box_transform(anchor_boxes, target_boxes).copy()
+    tr = _f(transforms).copy()
+    big = np.abs(tt).max(axis=1) > 10
+    tr[big] = 0; tt[big] = 0
+    loss, g = smooth_l1(tr, tt)
+    loss = f32(w) * loss
+    grad_trans = (g * f32(w)).astype(_DT[0])
+    din_anchor, _ = invert_box_transform_backward(anchor_boxes, target_boxes, grad_trans)
+    return loss, (din_anchor * f32(-1)).astype(_DT[0]), grad_trans

@@ -172,3 +172,20 @@ def test_bilinear_roi_pooling_matches_oracle(mods, C_, fh, fw, B, ih, iw):
     assert_bit_equal(out, ref, "roi_pool BCHW")
     out2 = rp.setImageSize(ih, iw).forward([dev(feats), dev(boxes)], layout="BHWC").cpu().numpy()
     assert_bit_equal(out2, ref.transpose(0, 2, 3, 1), "roi_pool BHWC")
+
+
+def test_bilinear_roi_pooling_reference_shape_test(mods):
+    """test/BilinearRoiPooling_test.lua:24-51 (shapeTest): C,H,W = 64,28,29, output 8x7, three forward passes with 10, 13 and 7
+    randn boxes (degenerate / negative sizes included) on one module instance; here also value parity with the oracle.
+    The image size passed is (H, W) of the feature map, exactly as the reference test does."""
+    M, _ = mods
+    rng = np.random.default_rng(8)
+    C_, H, W, HH, WW = 64, 28, 29, 8, 7
+    feats = rng.standard_normal((C_, H, W)).astype(np.float32)
+    rp = M.BilinearRoiPooling(HH, WW)
+    for B in (10, 13, 7):
+        boxes = rng.standard_normal((B, 4)).astype(np.float32)
+        out = rp.setImageSize(H, W).forward([dev(feats), dev(boxes)]).cpu().numpy()
+        assert out.shape == (B, C_, HH, WW)
+        ref = O.bilinear_roi_pooling(feats, boxes, H, W, HH, WW)
+        assert_bit_equal(out, ref, "roi_pool 8x7, B=%d" % B)

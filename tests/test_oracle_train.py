@@ -74,3 +74,47 @@ def test_criterions_match_torch_definitions():
     tl.backward()
     assert abs(float(loss) - float(tl)) < 1e-6
     np.testing.assert_allclose(grad, tx.grad.numpy(), atol=1e-6)
+
+
+def _numeric_gradient(f, x, h=1e-5):
+    g = np.zeros_like(x)
+    it = np.nditer(x, flags=["multi_index"])
+    for _ in it:
+        i = it.multi_index
+        old = x[i]
+        x[i] = old + h; fp = f(x)
+        x[i] = old - h; fm = f(x)
+        x[i] = old
+        g[i] = (fp - fm) / (2 * h)
+    return g
+
+
+def _relative_error(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(a) + np.abs(b), 1e-12))
+
+
+def test_box_regression_criterion_gradcheck():
+    """test/BoxRegressionCriterion_test.lua: numeric gradients w.r.t. the anchors and the transforms, relative error <= 1e-4
+    (run in the oracle's float64 gold mode, like the reference's DoubleTensor test)."""
+    rng = np.random.RandomState(0)
+    B, w = 10, 2.71
+    trans = rng.randn(B, 4)
+    anchors = rng.randn(B, 4); anchors[:, 2:] = np.abs(anchors[:, 2:]) + 0.1
+    targets = rng.randn(B, 4); targets[:, 2:] = np.abs(targets[:, 2:]) + 0.1
+    with O.precision(np.float64):
+        loss, g_anchor, g_trans = O.box_regression_criterion(anchors, trans, targets, w)
+        f_a = lambda x: float(O.box_regression_criterion(x, trans, targets, w)[0])
+        f_t = lambda x: float(O.box_regression_criterion(anchors, x, targets, w)[0])
+        assert _relative_error(_numeric_gradient(f_a, anchors.copy()), g_anchor) <= 1e-4
+        assert _relative_error(_numeric_gradient(f_t, trans.copy()), g_trans) <= 1e-4
+
+
+def test_box_conversion_round_trip():
+    """test/box_conversion_test.lua: xywh -> x1y1x2y2 -> xywh -> x1y1x2y2 is the identity (1e-6)."""
+    rng = np.random.RandomState(1)
+    xywh = rng.randn(100, 4).astype(np.float32)
+    xywh[:, 2:] = np.abs(xywh[:, 2:])
+    a = O.xywh_to_x1y1x2y2(xywh)
+    b = O.x1y1x2y2_to_xywh(a)
+    c = O.xywh_to_x1y1x2y2(b)
+    assert np.abs(a - c).max() <= 1e-6 and np.abs(xywh - b).max() <= 1e-6
