@@ -1500,9 +1500,14 @@ extern "C" int dc_bilinear_roi_pool(dc_ctx* ctx, const float* feats_chw, int C, 
   // nn.Transpose({1,2},{2,3}) (BilinearRoiPooling.lua:56): CHW -> HWC, done once
   chw_to_hwc_kernel<<<(unsigned)std::min<size_t>(2048, DC_CEIL_DIV(n, (size_t)256)), 256, 0, st>>>(feats_chw, ctx->scratch_f32, C, feat_h * feat_w);
   DC_CHECK_LAUNCH(ctx);
-  DC_REQUIRE(ctx, HH * WW <= ctx->cfg.pool_hw * ctx->cfg.pool_hw, DC_E_UNSUPPORTED, "dc_bilinear_roi_pool: HH*WW exceeds the ctx pool size");
-  for (int b0 = 0; b0 < B; b0 += ctx->roi_taps_boxes) {
-    const int nb = std::min(ctx->roi_taps_boxes, B - b0);
+  // the tap workspace holds roi_taps_boxes * pool_hw^2 records; a larger output grid (the reference's own test uses 8 x 7) simply
+  // processes fewer boxes per chunk
+  DC_REQUIRE(ctx, HH >= 1 && WW >= 1, DC_E_INVALID, "dc_bilinear_roi_pool: bad output size %dx%d", HH, WW);
+  const size_t records = (size_t)ctx->roi_taps_boxes * ctx->cfg.pool_hw * ctx->cfg.pool_hw;
+  const int chunk = (int)std::min<size_t>(records / ((size_t)HH * WW), (size_t)ctx->roi_taps_boxes);
+  DC_REQUIRE(ctx, chunk >= 1, DC_E_UNSUPPORTED, "dc_bilinear_roi_pool: output grid %dx%d exceeds the tap workspace", HH, WW);
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
     int rc = k_roi_pool(ctx, nullptr, nullptr, ctx->scratch_f32, C, feat_h, feat_w, boxes + (size_t)b0 * 4, nullptr, nb, image_h, image_w, HH, WW,
                         ctx->roi_taps, nullptr, nullptr, out + (size_t)b0 * C * HH * WW, out_layout, st);
     if (rc) return rc;
