@@ -205,6 +205,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, but carrying the 32 destination registers of an earlier tcgen05.ld as in/out operands: every later use of r[] then
+// depends on the wait, so the compiler cannot schedule it between the (asynchronous) load and the wait.
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 
 // Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B, one 128-byte swizzle atom along K:
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused here)
@@ -323,18 +334,21 @@ __device__ __forceinline__ void epilogue_warps(const Problem& pb, const GemmEpil
       tcgen05_fence_after();
       constexpr int ACC_COLS = WIDE ? 2 * BLOCK_N : BLOCK_N;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(t_row + c * 32, raw);
-        tmem_ld_wait();
+      // The accumulator is drained in 32-column chunks through two register buffers: the tcgen05.ld of chunk c+1 is in flight while
+      // chunk c is converted and stored (ncu r06: with a ld -> wait -> use sequence per chunk the epilogue of the short-K
+      // convolutions, not the MMA, was the critical path -- the issuer spun on tmem_empty).
+      auto issue_chunk = [&](int c, uint32_t (&r1)[32], uint32_t (&r2)[32]) {
+        tmem_ld_32x32(t_row + c * 32, r1);
+        if (WIDE) tmem_ld_32x32(t_row + BLOCK_N + c * 32, r2);      // columns [BLOCK_N, 2*BLOCK_N): the A_hi . B_lo partial sums
+      };
+      auto wait_chunk = [&](uint32_t (&r1)[32], uint32_t (&r2)[32]) {
+        tmem_ld_wait_dep(r1);
+        if (WIDE) tmem_ld_wait_dep(r2);
+      };
+      auto process_chunk = [&](int c, uint32_t (&raw)[32], uint32_t (&raw2)[32]) {
         const int nc = n0 + c * 32;
-        if (nc >= pb.N) continue;           // whole chunk outside N (uniform across the CTA)
+        if (nc >= pb.N) return;             // whole chunk outside N (uniform across the CTA)
         if (WIDE) {
-          // columns [BLOCK_N, 2*BLOCK_N) hold the A_hi . B_lo partial sums of the same outputs
-          uint32_t raw2[32];
-          tmem_ld_32x32(t_row + BLOCK_N + c * 32, raw2);
-          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
         }
@@ -444,6 +458,21 @@ __device__ __forceinline__ void epilogue_warps(const Problem& pb, const GemmEpil
             for (int j = 0; j < 32; ++j)
               if (nc + j < pb.N && v[j] > best_v) { best_v = v[j]; best_c = nc + j; }
           }
+        }
+      };
+      {
+        constexpr int NCH = BLOCK_N / 32;     // 2, 4 or 8
+        uint32_t bufA1[32], bufA2[32], bufB1[32], bufB2[32];
+        issue_chunk(0, bufA1, bufA2);
+        wait_chunk(bufA1, bufA2);
+#pragma unroll 1
+        for (int c = 0; c < NCH; c += 2) {
+          issue_chunk(c + 1, bufB1, bufB2);
+          process_chunk(c, bufA1, bufA2);
+          wait_chunk(bufB1, bufB2);
+          if (c + 2 < NCH) issue_chunk(c + 2, bufA1, bufA2);
+          process_chunk(c + 1, bufB1, bufB2);
+          if (c + 2 < NCH) wait_chunk(bufA1, bufA2);
         }
       }
       // TMEM reads of this accumulator are complete: hand it back to the MMA warp
