@@ -209,6 +209,26 @@ class DenseCapModel:
         if weights is not None:
             self.ctx.load_weights(weights)
 
+    @classmethod
+    def from_checkpoint(cls, path, device=0, max_batch=1, max_image_hw=(600, 720), max_proposals=1000, engine=_lib.DC_ENGINE_TC):
+        """`torch.load(opt.checkpoint).model` (run_model.lua:146-149) for a Torch7 .t7 checkpoint written by train.lua:184:
+        parses the file (densecap_b200/t7.py), maps the module tree onto dc_load_weights names and sizes the context from
+        the tensor shapes.  Returns a ready DenseCapModel with its idx_to_token vocabulary."""
+        from . import t7
+        weights, info = t7.extract_densecap_weights(t7.load(path))
+        widths = (weights["conv1_2.weight"].shape[0], weights["conv2_2.weight"].shape[0], weights["conv3_3.weight"].shape[0],
+                  weights["conv4_3.weight"].shape[0], weights["conv5_3.weight"].shape[0])
+        E = weights["lm.encoder.weight"].shape[0]
+        H = weights["lm.lstm.weight"].shape[1] // 4
+        dims = ModelDims(widths=widths, rpn_filters=weights["rpn.conv.weight"].shape[0], num_anchors=weights["rpn.score.weight"].shape[0] // 2,
+                         fc_dim=weights["fc7.weight"].shape[0], rnn_size=H, encoding_size=E, vocab_size=weights["lm.vocab.weight"].shape[0] - 1,
+                         seq_length=int(info.get("seq_length") or 15))
+        tok = info.get("idx_to_token")
+        if isinstance(tok, dict):
+            tok = {int(k): v for k, v in tok.items()}
+        return cls({"dims": dims, "max_proposals": max_proposals, "idx_to_token": tok}, weights=weights, device=device, max_batch=max_batch,
+                   max_image_hw=max_image_hw, engine=engine)
+
     def evaluate(self):
         self.train = False
 

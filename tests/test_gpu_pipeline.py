@@ -199,6 +199,33 @@ def test_device_preprocessing_and_u8_boundary(model, small):
         assert np.array_equal(a[:k], b[:k])
 
 
+def test_from_checkpoint_equals_direct_weights(small, tmp_path):
+    """a Torch7 .t7 checkpoint with the reference's module tree (train.lua:157-185), read by densecap_b200/t7.py,
+    gives the same model as loading the same tensors directly."""
+    from densecap_b200 import t7
+    from densecap_b200.model import DenseCapModel
+    from test_t7 import fake_checkpoint
+    dims, weights, img, cfg, ref = small
+    w = dict(weights)
+    w["obj.weight"] = np.asarray(w["obj.weight"], np.float32).reshape(1, -1)
+    path = str(tmp_path / "model.t7")
+    t7.save(fake_checkpoint(dims, w), path)
+    m1 = DenseCapModel.from_checkpoint(path, max_image_hw=(IMG_H, IMG_W), max_proposals=64)
+    m2 = DenseCapModel({"dims": dims, "max_proposals": 64}, weights=weights, max_image_hw=(IMG_H, IMG_W))
+    try:
+        assert m1.dims.vocab_size == dims.vocab_size and m1.dims.seq_length == dims.seq_length and m1.dims.rnn_size == dims.rnn_size
+        outs = []
+        for m in (m1, m2):
+            m.setTestArgs({"rpn_nms_thresh": 0.7, "final_nms_thresh": 0.3, "num_proposals": NPROP})
+            boxes, scores, captions = m.forward_test(dev(img))
+            outs.append((boxes.cpu().numpy().copy(), scores.cpu().numpy().copy(), m.output[4].cpu().numpy().copy(), captions))
+        for a, b in zip(outs[0][:3], outs[1][:3]):
+            assert np.array_equal(a, b)
+        assert outs[0][3][0].startswith("w") or outs[0][3][0] == ""          # captions decoded through the checkpoint's idx_to_token
+    finally:
+        m1.ctx.close(); m2.ctx.close()
+
+
 def test_batched_forward_equals_single(small):
     from densecap_b200.model import DenseCapModel
     dims, weights, img, cfg, ref = small

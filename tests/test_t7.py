@@ -1,0 +1,144 @@
+"""Torch7 serialisation reader/writer and the DenseCap checkpoint -> dc_load_weights mapping.
+No Torch7 is available here, so the reader is checked (a) against a hand-assembled byte stream written out from the format
+description of torch7's File.lua, and (b) by round trips through the writer on a checkpoint with the reference's module tree."""
+import struct
+
+import numpy as np
+import pytest
+
+from densecap_b200 import t7
+from densecap_b200.synth import ModelDims, make_weights
+
+
+def i32(v):
+    return struct.pack("<i", v)
+
+
+def i64(v):
+    return struct.pack("<q", v)
+
+
+def s(x):
+    return i32(len(x)) + x.encode()
+
+
+def test_reader_on_hand_assembled_stream():
+    # { ["a"] = 2.5, [1] = true, ["t"] = FloatTensor(2,3) transposed view of a 3x2 storage, ["t2"] = same tensor again (shared) }
+    storage = np.arange(6, dtype=np.float32)
+    tensor = (i32(4) + i32(2) + s("V 1") + s("torch.FloatTensor") + i32(2) + i64(2) + i64(3) + i64(1) + i64(2) + i64(1)
+              + i32(4) + i32(3) + s("V 1") + s("torch.FloatStorage") + i64(6) + storage.tobytes())
+    blob = (i32(3) + i32(1) + i32(4)
+            + i32(2) + s("a") + i32(1) + struct.pack("<d", 2.5)
+            + i32(1) + struct.pack("<d", 1.0) + i32(5) + i32(1)
+            + i32(2) + s("t") + tensor
+            + i32(2) + s("t2") + i32(4) + i32(2))
+    out = t7.loads(blob)
+    assert out["a"] == 2.5 and out[1] is True
+    assert out["t"].dtype == np.float32 and out["t"].tolist() == [[0, 2, 4], [1, 3, 5]]      # sizes (2,3), strides (1,2)
+    assert out["t2"] is out["t"]                                                              # reference sharing by index
+
+
+def test_round_trip_values_and_sharing():
+    shared = {"x": 1, "y": "z"}
+    obj = {"list": [1, 2.5, "three", False, None], "shared_a": shared, "shared_b": shared,
+           "mod": t7.T7Object("nn.Linear", {"weight": np.random.RandomState(0).randn(3, 4).astype(np.float32), "bias": np.zeros(3, np.float32)}),
+           "long": np.arange(5, dtype=np.int64), "dbl": np.linspace(0, 1, 4)}
+    back = t7.loads(t7.dumps(obj))
+    assert back["list"] == {1: 1, 2: 2.5, 3: "three", 4: False, 5: None}
+    assert back["shared_a"] is back["shared_b"] and back["shared_a"] == {"x": 1, "y": "z"}
+    assert back["mod"].classname == "nn.Linear" and np.array_equal(back["mod"]["weight"], obj["mod"]["weight"])
+    assert back["long"].dtype == np.int64 and back["long"].tolist() == [0, 1, 2, 3, 4]
+    assert back["dbl"].dtype == np.float64 and np.array_equal(back["dbl"], obj["dbl"])
+
+
+def seq(*mods):
+    return t7.T7Object("nn.Sequential", {"modules": list(mods)})
+
+
+def conv(w, b, mm=False):
+    cout = w.shape[0]
+    return t7.T7Object("nn.SpatialConvolutionMM" if mm else "nn.SpatialConvolution",
+                       {"weight": w.reshape(cout, -1) if mm else w, "bias": b, "kW": w.shape[3], "kH": w.shape[2]})
+
+
+def lin(w, b):
+    return t7.T7Object("nn.Linear", {"weight": w, "bias": b})
+
+
+def relu():
+    return t7.T7Object("nn.ReLU", {"inplace": True})
+
+
+def fake_checkpoint(dims, w):
+    """The module tree of DenseCapModel.lua:40-125 / LocalizationLayer.lua:609-690 / LanguageModel.lua:26-71, weights from `w`."""
+    names = t7.VGG16_CONV_NAMES
+    vgg = []
+    for i, n in enumerate(names):
+        vgg += [conv(w[n + ".weight"], w[n + ".bias"], mm=(i % 2 == 0)), relu()]
+        if n in ("conv1_2", "conv2_2", "conv3_3", "conv4_3"):
+            vgg.append(t7.T7Object("nn.SpatialMaxPooling", {"kW": 2, "kH": 2, "ceil_mode": True}))
+    conv_net1 = seq(*vgg[:10])
+    conv_net2 = seq(*vgg[10:])
+    box_branch = seq(conv(w["rpn.box.weight"], w["rpn.box.bias"]), t7.T7Object("nn.RegularizeLayer", {"w": 0}),
+                     t7.T7Object("nn.ConcatTable", {"modules": [seq(t7.T7Object("nn.MakeAnchors", {}), t7.T7Object("nn.ReshapeBoxFeatures", {})),
+                                                                t7.T7Object("nn.ReshapeBoxFeatures", {})]}),
+                     t7.T7Object("nn.ConcatTable", {"modules": [t7.T7Object("nn.ApplyBoxTransform", {}), t7.T7Object("nn.Identity", {})]}))
+    rpn_branch = seq(conv(w["rpn.score.weight"], w["rpn.score.bias"]), t7.T7Object("nn.ReshapeBoxFeatures", {}))
+    rpn = seq(conv(w["rpn.conv.weight"], w["rpn.conv.bias"]), relu(), t7.T7Object("nn.ConcatTable", {"modules": [box_branch, rpn_branch]}),
+              t7.T7Object("nn.FlattenTable", {}))
+    loc = t7.T7Object("nn.LocalizationLayer", {"nets": {"rpn": rpn, "roi_pooling": t7.T7Object("nn.BilinearRoiPooling", {})}, "opt": {"std": 0.01}})
+    recog = seq(t7.T7Object("nn.View", {}), lin(w["fc6.weight"], w["fc6.bias"]), relu(), t7.T7Object("nn.Dropout", {"p": 0.5}),
+                lin(w["fc7.weight"], w["fc7.bias"]), relu(), t7.T7Object("nn.Dropout", {"p": 0.5}))
+    lookup = t7.T7Object("nn.LookupTable", {"weight": w["lm.lookup.weight"]})
+    enc = seq(lin(w["lm.encoder.weight"], w["lm.encoder.bias"]), relu(), t7.T7Object("nn.View", {}))
+    rnn = seq(t7.T7Object("nn.LSTM", {"weight": w["lm.lstm.weight"], "bias": w["lm.lstm.bias"]}), t7.T7Object("nn.View", {}),
+              lin(w["lm.vocab.weight"], w["lm.vocab.bias"]), t7.T7Object("nn.View", {}))
+    lm = t7.T7Object("nn.LanguageModel", {"vocab_size": dims.vocab_size, "seq_length": dims.seq_length, "image_encoder": enc, "lookup_table": lookup,
+                                          "rnn": rnn, "idx_to_token": {i + 1: "w%d" % i for i in range(dims.vocab_size)},
+                                          "net": seq(t7.T7Object("nn.ParallelTable", {"modules": [enc, lookup]}), rnn)})   # shared references
+    model = t7.T7Object("DenseCapModel", {"nets": {"conv_net1": conv_net1, "conv_net2": conv_net2, "localization_layer": loc, "recog_base": recog,
+                                                   "objectness_branch": lin(w["obj.weight"], w["obj.bias"]),
+                                                   "box_reg_branch": lin(w["boxreg.weight"], w["boxreg.bias"]), "language_model": lm},
+                                          "opt": {"cnn_name": "vgg-16", "rpn_num_filters": dims.rpn_filters}})
+    return {"opt": {"checkpoint_path": "x.t7"}, "iter": 1000, "model": model}
+
+
+def test_densecap_checkpoint_round_trip(tmp_path):
+    dims = ModelDims(widths=(8, 16, 16, 16, 16), rpn_filters=8, fc_dim=32, rnn_size=16, encoding_size=16, vocab_size=20, seq_length=4)
+    w = make_weights(dims, seed=1, box_variant="B")
+    if w["obj.weight"].ndim == 1:
+        w = dict(w); w["obj.weight"] = w["obj.weight"].reshape(1, -1)
+    path = tmp_path / "ckpt.t7"
+    t7.save(fake_checkpoint(dims, w), str(path))
+    got, info = t7.extract_densecap_weights(t7.load(str(path)))
+    assert info["vocab_size"] == dims.vocab_size and info["idx_to_token"][3] == "w2"
+    assert set(got) == set(w), sorted(set(got) ^ set(w))
+    for k in w:
+        assert got[k].dtype == np.float32
+        assert np.array_equal(got[k].reshape(-1), np.asarray(w[k], np.float32).reshape(-1)), k
+    assert got["conv1_1.weight"].shape == (8, 3, 3, 3) and got["rpn.box.weight"].shape == (4 * dims.num_anchors, 8, 1, 1)
+
+
+def test_unsupported_and_truncated_streams():
+    with pytest.raises(ValueError):
+        t7.loads(i32(6) + i32(1))              # a serialised Lua function
+    with pytest.raises(Exception):
+        t7.loads(i32(2) + i32(10) + b"abc")    # truncated string
+    with pytest.raises(ValueError):
+        t7.loads(i32(42))
+
+
+def test_results_json_matches_run_model_format(tmp_path):
+    """run_model.lua:79,89-95,182-188: boxes leave as (x, y, w, h) = xcycwh_to_xywh, one entry per detection, wrapped with opt."""
+    import json
+    from densecap_b200 import results as R
+    from oracle import densecap_oracle as O
+    boxes = np.array([[10.5, 20.0, 8.0, 6.0], [300.0, 200.0, 101.0, 51.0]], np.float32)
+    r = R.result_to_json(boxes, np.array([[0.5], [-1.25]], np.float32), ["a cat", "the sky"], img_name="elephant.jpg")
+    assert np.array_equal(np.asarray(r["boxes"], np.float32), O.xcycwh_to_xywh(boxes))
+    assert r["boxes"][0] == [7.0, 17.5, 8.0, 6.0] and r["scores"] == [0.5, -1.25] and r["captions"] == ["a cat", "the sky"]
+    doc = R.write_results([r], {"image_size": 720, "num_proposals": 1000}, str(tmp_path / "results.json"))
+    back = json.load(open(tmp_path / "results.json"))
+    assert back == doc and back["results"][0]["img_name"] == "elephant.jpg" and set(back) == {"results", "opt"}
+    with pytest.raises(ValueError):
+        R.result_to_json(boxes, [0.5], ["x", "y"])
