@@ -67,6 +67,10 @@ struct dc_ctx {
   // of different images of a batch overlap instead of queueing behind each other
   std::vector<cudaStream_t> side;
   std::vector<cudaEvent_t> side_done;
+  // device staging of the host-boundary entry points (dc_forward_test_host / _u8), grown on demand, freed with the context
+  float* host_stage_f32 = nullptr;
+  uint8_t* host_stage_u8 = nullptr;
+  size_t host_stage_f32_elems = 0, host_stage_u8_elems = 0;
   cudaStream_t fin_stream0 = nullptr;   // final NMS of image 0 (runs beside the caption decode, see run_final_nms)
   cudaEvent_t fin_done0 = nullptr;
   cudaEvent_t fork_ev = nullptr;
@@ -341,6 +345,8 @@ extern "C" int dc_destroy(dc_ctx* ctx) {
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   if (ctx->fin_stream0) cudaStreamDestroy(ctx->fin_stream0);
   if (ctx->fin_done0) cudaEventDestroy(ctx->fin_done0);
+  if (ctx->host_stage_f32) cudaFree(ctx->host_stage_f32);
+  if (ctx->host_stage_u8) cudaFree(ctx->host_stage_u8);
   if (ctx->train_mem) cudaFree(ctx->train_mem);
   if (ctx->bwd_mem) cudaFree(ctx->bwd_mem);
   free(ctx->train);
@@ -1068,20 +1074,31 @@ extern "C" int dc_forward_test(dc_ctx* ctx, const float* img, int batch, int ima
   return DC_OK;
 }
 
+static int ensure_host_stage(dc_ctx* ctx, size_t f32_elems, size_t u8_elems) {
+  if (ctx->host_stage_f32_elems < f32_elems) {
+    if (ctx->host_stage_f32) cudaFree(ctx->host_stage_f32);
+    ctx->host_stage_f32 = nullptr; ctx->host_stage_f32_elems = 0;
+    DC_CHECK_CUDA(ctx, cudaMalloc((void**)&ctx->host_stage_f32, f32_elems * sizeof(float)));
+    ctx->host_stage_f32_elems = f32_elems;
+  }
+  if (ctx->host_stage_u8_elems < u8_elems) {
+    if (ctx->host_stage_u8) cudaFree(ctx->host_stage_u8);
+    ctx->host_stage_u8 = nullptr; ctx->host_stage_u8_elems = 0;
+    DC_CHECK_CUDA(ctx, cudaMalloc((void**)&ctx->host_stage_u8, u8_elems));
+    ctx->host_stage_u8_elems = u8_elems;
+  }
+  return DC_OK;
+}
+
 extern "C" int dc_forward_test_host(dc_ctx* ctx, const float* img_host, int batch, int image_h, int image_w, int32_t* num_final_host,
                                     float* final_boxes_host, float* final_scores_host, int64_t* final_seq_host) {
   if (!ctx || !img_host) return dc_set_error(ctx, DC_E_INVALID, "dc_forward_test_host: null argument");
   DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
   DC_REQUIRE(ctx, batch >= 1 && batch <= ctx->B, DC_E_INVALID, "batch %d exceeds max_batch %d", batch, ctx->B);
   const size_t n = (size_t)batch * 3 * image_h * image_w;
-  // dedicated device staging buffer for the host image, sized on first use
-  static thread_local float* staging = nullptr;
-  static thread_local size_t staging_elems = 0;
-  if (staging_elems < n) {
-    if (staging) cudaFree(staging);
-    DC_CHECK_CUDA(ctx, cudaMalloc((void**)&staging, n * sizeof(float)));
-    staging_elems = n;
-  }
+  int rc0 = ensure_host_stage(ctx, n, 0);
+  if (rc0) return rc0;
+  float* staging = ctx->host_stage_f32;
   cudaStream_t st = 0;
   DC_CHECK_CUDA(ctx, cudaMemcpyAsync(staging, img_host, n * sizeof(float), cudaMemcpyHostToDevice, st));
   dc_result r;
@@ -1111,16 +1128,10 @@ extern "C" int dc_forward_test_host_u8(dc_ctx* ctx, const uint8_t* img_host_u8, 
   DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
   DC_REQUIRE(ctx, batch >= 1 && batch <= ctx->B, DC_E_INVALID, "batch %d exceeds max_batch %d", batch, ctx->B);
   const size_t n = (size_t)batch * 3 * image_h * image_w;
-  static thread_local uint8_t* staging_u8 = nullptr;
-  static thread_local float* staging_f32 = nullptr;
-  static thread_local size_t staging_elems = 0;
-  if (staging_elems < n) {
-    if (staging_u8) cudaFree(staging_u8);
-    if (staging_f32) cudaFree(staging_f32);
-    DC_CHECK_CUDA(ctx, cudaMalloc((void**)&staging_u8, n));
-    DC_CHECK_CUDA(ctx, cudaMalloc((void**)&staging_f32, n * sizeof(float)));
-    staging_elems = n;
-  }
+  int rc0 = ensure_host_stage(ctx, n, n);
+  if (rc0) return rc0;
+  uint8_t* staging_u8 = ctx->host_stage_u8;
+  float* staging_f32 = ctx->host_stage_f32;
   cudaStream_t st = 0;
   DC_CHECK_CUDA(ctx, cudaMemcpyAsync(staging_u8, img_host_u8, n, cudaMemcpyHostToDevice, st));
   int rc = k_preprocess_u8(ctx, staging_u8, staging_f32, batch, image_h, image_w, st);

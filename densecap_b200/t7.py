@@ -345,3 +345,61 @@ def extract_densecap_weights(checkpoint):
     info = {"vocab_size": int(lf.get("vocab_size", w["lm.vocab.weight"].shape[0] - 1)), "seq_length": lf.get("seq_length"),
             "idx_to_token": lf.get("idx_to_token"), "opt": opt}
     return w, info
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the inverse direction: weights (dc_load_weights names) -> the object tree train.lua:157-185 saves.  Used by the tests and to
+# export synthetic / converted weights in the reference's container (`save(densecap_checkpoint_tree(dims, w), "model.t7")`).
+# ---------------------------------------------------------------------------------------------------------
+def _seq(*mods):
+    return T7Object("nn.Sequential", {"modules": list(mods)})
+
+
+def _conv(w, b, mm=False):
+    cout = w.shape[0]
+    return T7Object("nn.SpatialConvolutionMM" if mm else "nn.SpatialConvolution",
+                       {"weight": w.reshape(cout, -1) if mm else w, "bias": b, "kW": w.shape[3], "kH": w.shape[2]})
+
+
+def _lin(w, b):
+    return T7Object("nn.Linear", {"weight": w, "bias": b})
+
+
+def _relu():
+    return T7Object("nn.ReLU", {"inplace": True})
+
+
+def densecap_checkpoint_tree(dims, w):
+    """The module tree of DenseCapModel.lua:40-125 / LocalizationLayer.lua:609-690 / LanguageModel.lua:26-71, weights from `w`."""
+    names = VGG16_CONV_NAMES
+    vgg = []
+    for i, n in enumerate(names):
+        vgg += [_conv(w[n + ".weight"], w[n + ".bias"], mm=(i % 2 == 0)), _relu()]
+        if n in ("conv1_2", "conv2_2", "conv3_3", "conv4_3"):
+            vgg.append(T7Object("nn.SpatialMaxPooling", {"kW": 2, "kH": 2, "ceil_mode": True}))
+    conv_net1 = _seq(*vgg[:10])
+    conv_net2 = _seq(*vgg[10:])
+    box_branch = _seq(_conv(w["rpn.box.weight"], w["rpn.box.bias"]), T7Object("nn.RegularizeLayer", {"w": 0}),
+                     T7Object("nn.ConcatTable", {"modules": [_seq(T7Object("nn.MakeAnchors", {}), T7Object("nn.ReshapeBoxFeatures", {})),
+                                                                T7Object("nn.ReshapeBoxFeatures", {})]}),
+                     T7Object("nn.ConcatTable", {"modules": [T7Object("nn.ApplyBoxTransform", {}), T7Object("nn.Identity", {})]}))
+    rpn_branch = _seq(_conv(w["rpn.score.weight"], w["rpn.score.bias"]), T7Object("nn.ReshapeBoxFeatures", {}))
+    rpn = _seq(_conv(w["rpn.conv.weight"], w["rpn.conv.bias"]), _relu(), T7Object("nn.ConcatTable", {"modules": [box_branch, rpn_branch]}),
+              T7Object("nn.FlattenTable", {}))
+    loc = T7Object("nn.LocalizationLayer", {"nets": {"rpn": rpn, "roi_pooling": T7Object("nn.BilinearRoiPooling", {})}, "opt": {"std": 0.01}})
+    recog = _seq(T7Object("nn.View", {}), _lin(w["fc6.weight"], w["fc6.bias"]), _relu(), T7Object("nn.Dropout", {"p": 0.5}),
+                _lin(w["fc7.weight"], w["fc7.bias"]), _relu(), T7Object("nn.Dropout", {"p": 0.5}))
+    lookup = T7Object("nn.LookupTable", {"weight": w["lm.lookup.weight"]})
+    enc = _seq(_lin(w["lm.encoder.weight"], w["lm.encoder.bias"]), _relu(), T7Object("nn.View", {}))
+    rnn = _seq(T7Object("nn.LSTM", {"weight": w["lm.lstm.weight"], "bias": w["lm.lstm.bias"]}), T7Object("nn.View", {}),
+              _lin(w["lm.vocab.weight"], w["lm.vocab.bias"]), T7Object("nn.View", {}))
+    lm = T7Object("nn.LanguageModel", {"vocab_size": dims.vocab_size, "seq_length": dims.seq_length, "image_encoder": enc, "lookup_table": lookup,
+                                          "rnn": rnn, "idx_to_token": {i + 1: "w%d" % i for i in range(dims.vocab_size)},
+                                          "net": _seq(T7Object("nn.ParallelTable", {"modules": [enc, lookup]}), rnn)})   # shared references
+    model = T7Object("DenseCapModel", {"nets": {"conv_net1": conv_net1, "conv_net2": conv_net2, "localization_layer": loc, "recog_base": recog,
+                                                   "objectness_branch": _lin(w["obj.weight"], w["obj.bias"]),
+                                                   "box_reg_branch": _lin(w["boxreg.weight"], w["boxreg.bias"]), "language_model": lm},
+                                          "opt": {"cnn_name": "vgg-16", "rpn_num_filters": dims.rpn_filters}})
+    return {"opt": {"checkpoint_path": "x.t7"}, "iter": 1000, "model": model}
+
+

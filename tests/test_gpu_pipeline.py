@@ -204,7 +204,7 @@ def test_from_checkpoint_equals_direct_weights(small, tmp_path):
     gives the same model as loading the same tensors directly."""
     from densecap_b200 import t7
     from densecap_b200.model import DenseCapModel
-    from test_t7 import fake_checkpoint
+    fake_checkpoint = t7.densecap_checkpoint_tree
     dims, weights, img, cfg, ref = small
     w = dict(weights)
     w["obj.weight"] = np.asarray(w["obj.weight"], np.float32).reshape(1, -1)

@@ -51,56 +51,7 @@ def test_round_trip_values_and_sharing():
     assert back["dbl"].dtype == np.float64 and np.array_equal(back["dbl"], obj["dbl"])
 
 
-def seq(*mods):
-    return t7.T7Object("nn.Sequential", {"modules": list(mods)})
-
-
-def conv(w, b, mm=False):
-    cout = w.shape[0]
-    return t7.T7Object("nn.SpatialConvolutionMM" if mm else "nn.SpatialConvolution",
-                       {"weight": w.reshape(cout, -1) if mm else w, "bias": b, "kW": w.shape[3], "kH": w.shape[2]})
-
-
-def lin(w, b):
-    return t7.T7Object("nn.Linear", {"weight": w, "bias": b})
-
-
-def relu():
-    return t7.T7Object("nn.ReLU", {"inplace": True})
-
-
-def fake_checkpoint(dims, w):
-    """The module tree of DenseCapModel.lua:40-125 / LocalizationLayer.lua:609-690 / LanguageModel.lua:26-71, weights from `w`."""
-    names = t7.VGG16_CONV_NAMES
-    vgg = []
-    for i, n in enumerate(names):
-        vgg += [conv(w[n + ".weight"], w[n + ".bias"], mm=(i % 2 == 0)), relu()]
-        if n in ("conv1_2", "conv2_2", "conv3_3", "conv4_3"):
-            vgg.append(t7.T7Object("nn.SpatialMaxPooling", {"kW": 2, "kH": 2, "ceil_mode": True}))
-    conv_net1 = seq(*vgg[:10])
-    conv_net2 = seq(*vgg[10:])
-    box_branch = seq(conv(w["rpn.box.weight"], w["rpn.box.bias"]), t7.T7Object("nn.RegularizeLayer", {"w": 0}),
-                     t7.T7Object("nn.ConcatTable", {"modules": [seq(t7.T7Object("nn.MakeAnchors", {}), t7.T7Object("nn.ReshapeBoxFeatures", {})),
-                                                                t7.T7Object("nn.ReshapeBoxFeatures", {})]}),
-                     t7.T7Object("nn.ConcatTable", {"modules": [t7.T7Object("nn.ApplyBoxTransform", {}), t7.T7Object("nn.Identity", {})]}))
-    rpn_branch = seq(conv(w["rpn.score.weight"], w["rpn.score.bias"]), t7.T7Object("nn.ReshapeBoxFeatures", {}))
-    rpn = seq(conv(w["rpn.conv.weight"], w["rpn.conv.bias"]), relu(), t7.T7Object("nn.ConcatTable", {"modules": [box_branch, rpn_branch]}),
-              t7.T7Object("nn.FlattenTable", {}))
-    loc = t7.T7Object("nn.LocalizationLayer", {"nets": {"rpn": rpn, "roi_pooling": t7.T7Object("nn.BilinearRoiPooling", {})}, "opt": {"std": 0.01}})
-    recog = seq(t7.T7Object("nn.View", {}), lin(w["fc6.weight"], w["fc6.bias"]), relu(), t7.T7Object("nn.Dropout", {"p": 0.5}),
-                lin(w["fc7.weight"], w["fc7.bias"]), relu(), t7.T7Object("nn.Dropout", {"p": 0.5}))
-    lookup = t7.T7Object("nn.LookupTable", {"weight": w["lm.lookup.weight"]})
-    enc = seq(lin(w["lm.encoder.weight"], w["lm.encoder.bias"]), relu(), t7.T7Object("nn.View", {}))
-    rnn = seq(t7.T7Object("nn.LSTM", {"weight": w["lm.lstm.weight"], "bias": w["lm.lstm.bias"]}), t7.T7Object("nn.View", {}),
-              lin(w["lm.vocab.weight"], w["lm.vocab.bias"]), t7.T7Object("nn.View", {}))
-    lm = t7.T7Object("nn.LanguageModel", {"vocab_size": dims.vocab_size, "seq_length": dims.seq_length, "image_encoder": enc, "lookup_table": lookup,
-                                          "rnn": rnn, "idx_to_token": {i + 1: "w%d" % i for i in range(dims.vocab_size)},
-                                          "net": seq(t7.T7Object("nn.ParallelTable", {"modules": [enc, lookup]}), rnn)})   # shared references
-    model = t7.T7Object("DenseCapModel", {"nets": {"conv_net1": conv_net1, "conv_net2": conv_net2, "localization_layer": loc, "recog_base": recog,
-                                                   "objectness_branch": lin(w["obj.weight"], w["obj.bias"]),
-                                                   "box_reg_branch": lin(w["boxreg.weight"], w["boxreg.bias"]), "language_model": lm},
-                                          "opt": {"cnn_name": "vgg-16", "rpn_num_filters": dims.rpn_filters}})
-    return {"opt": {"checkpoint_path": "x.t7"}, "iter": 1000, "model": model}
+fake_checkpoint = t7.densecap_checkpoint_tree
 
 
 def test_densecap_checkpoint_round_trip(tmp_path):
