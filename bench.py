@@ -338,7 +338,7 @@ def main():
                 traffic = None
         roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel<256,gemm,cg2> fc6: M=%d N=%d K=%d" % (B * P, dims.fc_dim, dims.feat_dim * 49),
                     "achieved": fc6_tflops, "peak": peak, "unit": "TFLOP/s", "frac": (fc6_tflops / peak) if fc6_tflops else None,
-                    "traffic": traffic, "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
+                    "traffic": (traffic["bytes_per_launch"] if traffic else None), "traffic_detail": traffic, "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
                     "note": "achieved counts ALGORITHMIC fp32 flops; the kernel issues 3 fp16 MMAs per product (split-fp16, fp32-class accuracy), "
                             "so the tensor pipe does 3x this work: ncu shows 96.5 % tensor-pipe activity on this launch "
                             "(profiles/kernels_r06_ncu_summary.md); the 12 tcgen05 VGG convolutions are 70.5 % tensor-pipe active, time-weighted "
