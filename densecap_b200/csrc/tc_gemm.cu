@@ -8,12 +8,12 @@
 // which drops only the lo*lo term (<= 2^-22 relative) -- fp32-class accuracy at one third of the
 // dense fp16 tensor rate, instead of the 2^-11 error of a single fp16/tf32 pass.
 //
-// Kernel structure (one persistent CTA per SM, 192 threads, no cluster):
+// Kernel structure (one persistent CTA per SM, 320 threads):
 //   warp 0   : TMA producer -- cp.async.bulk.tensor loads of the A and B stage tiles (both planes in one
 //              box) into 128B-swizzled shared memory, signalled through full[] mbarriers;
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases the smem stage
 //              (empty[]) and publishes the finished accumulator (tmem_full[]);
-//   warps 2-5: epilogue -- tcgen05.ld of the 128xBLOCK_N fp32 accumulator (one TMEM lane quarter per
+//   warps 2-9: epilogue -- tcgen05.ld of the 128xBLOCK_N fp32 accumulator (two warps per TMEM lane quarter, half of the columns each;
 //              warp), bias + ReLU (+ fused 2x2 ceil-mode max-pool through warp shuffles for the VGG
 //              layers that precede a pool), re-split to fp16 planes / fp32 / row arg-max, vectorised stores.
 //   The accumulator is double buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps
@@ -40,7 +40,8 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;     // fp16 elements: 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                       // two epilogue warps per TMEM lane quarter, each draining half of the columns
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;   // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue
 constexpr int TILE_H = 8, TILE_W = 16;   // conv M tile = 8x16 output pixels
 constexpr uint32_t A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 
@@ -205,17 +206,6 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// Same wait, but carrying the 32 destination registers of an earlier tcgen05.ld as in/out operands: every later use of r[] then
-// depends on the wait, so the compiler cannot schedule it between the (asynchronous) load and the wait.
-__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t* r) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
-                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
-                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
-                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-               :
-               : "memory");
-}
 
 // Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B, one 128-byte swizzle atom along K:
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused here)
@@ -287,6 +277,7 @@ __device__ __forceinline__ void epilogue_warps(const Problem& pb, const GemmEpil
   auto tempty_bar = [&](int s) { return tempty0 + 8u * s; };
   {
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int chunk_half = (warp - 2) >> 2; // warps 2-5 drain the first half of the accumulator columns, warps 6-9 the second
     const int row_in_tile = q * 32 + lane;
     int iter = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
@@ -326,29 +317,27 @@ __device__ __forceinline__ void epilogue_warps(const Problem& pb, const GemmEpil
       // short-K tile epilogue-bound.  Double-buffered by accumulator stage, so one named barrier per tile suffices.
       float* sbias = bias_smem + acc * BLOCK_N;
       if (ep.bias) {
-        for (int j = threadIdx.x - 64; j < BLOCK_N; j += 128) sbias[j] = (n0 + j < pb.N) ? __ldg(ep.bias + n0 + j) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int j = threadIdx.x - 64; j < BLOCK_N; j += 32 * EPI_WARPS) sbias[j] = (n0 + j < pb.N) ? __ldg(ep.bias + n0 + j) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
       }
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       constexpr int ACC_COLS = WIDE ? 2 * BLOCK_N : BLOCK_N;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
-      // The accumulator is drained in 32-column chunks through two register buffers: the tcgen05.ld of chunk c+1 is in flight while
-      // chunk c is converted and stored (ncu r06: with a ld -> wait -> use sequence per chunk the epilogue of the short-K
-      // convolutions, not the MMA, was the critical path -- the issuer spun on tmem_empty).
-      auto issue_chunk = [&](int c, uint32_t (&r1)[32], uint32_t (&r2)[32]) {
-        tmem_ld_32x32(t_row + c * 32, r1);
-        if (WIDE) tmem_ld_32x32(t_row + BLOCK_N + c * 32, r2);      // columns [BLOCK_N, 2*BLOCK_N): the A_hi . B_lo partial sums
-      };
-      auto wait_chunk = [&](uint32_t (&r1)[32], uint32_t (&r2)[32]) {
-        tmem_ld_wait_dep(r1);
-        if (WIDE) tmem_ld_wait_dep(r2);
-      };
-      auto process_chunk = [&](int c, uint32_t (&raw)[32], uint32_t (&raw2)[32]) {
+      constexpr int CHUNKS_PER_WARP = (BLOCK_N / 32) / (EPI_WARPS / 4);
+#pragma unroll 1
+      for (int c = chunk_half * CHUNKS_PER_WARP; c < (chunk_half + 1) * CHUNKS_PER_WARP; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32(t_row + c * 32, raw);
+        tmem_ld_wait();
         const int nc = n0 + c * 32;
-        if (nc >= pb.N) return;             // whole chunk outside N (uniform across the CTA)
+        if (nc >= pb.N) continue;           // whole chunk outside N (uniform across the CTA)
         if (WIDE) {
+          // columns [BLOCK_N, 2*BLOCK_N) hold the A_hi . B_lo partial sums of the same outputs
+          uint32_t raw2[32];
+          tmem_ld_32x32(t_row + BLOCK_N + c * 32, raw2);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
         }
@@ -459,21 +448,6 @@ __device__ __forceinline__ void epilogue_warps(const Problem& pb, const GemmEpil
               if (nc + j < pb.N && v[j] > best_v) { best_v = v[j]; best_c = nc + j; }
           }
         }
-      };
-      {
-        constexpr int NCH = BLOCK_N / 32;     // 2, 4 or 8
-        uint32_t bufA1[32], bufA2[32], bufB1[32], bufB2[32];
-        issue_chunk(0, bufA1, bufA2);
-        wait_chunk(bufA1, bufA2);
-#pragma unroll 1
-        for (int c = 0; c < NCH; c += 2) {
-          issue_chunk(c + 1, bufB1, bufB2);
-          process_chunk(c, bufA1, bufA2);
-          wait_chunk(bufB1, bufB2);
-          if (c + 2 < NCH) issue_chunk(c + 2, bufA1, bufA2);
-          process_chunk(c + 1, bufB1, bufB2);
-          if (c + 2 < NCH) wait_chunk(bufA1, bufA2);
-        }
       }
       // TMEM reads of this accumulator are complete: hand it back to the MMA warp
       tcgen05_fence_before();
@@ -521,7 +495,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128 * CG);  // all epilogue threads of the pair arrive on the leader's barrier
+      mbar_init(tempty_bar(s), 32 * EPI_WARPS * CG);  // all epilogue threads of the pair arrive on the leader's barrier
     }
     fence_barrier_init();
   }
@@ -724,7 +698,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < AH_STAGES; ++s) { mbar_init(afull_bar(s), CG); mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(bfull_bar(s), CG); mbar_init(bempty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128 * CG); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 32 * EPI_WARPS * CG); }
     fence_barrier_init();
   }
   if (warp == 1) {
