@@ -805,3 +805,76 @@ def box_regression_criterion(anchor_boxes, transforms, target_boxes, w=1.0):
     grad_trans = (g * f32(w)).astype(_DT[0])
     din_anchor, _ = invert_box_transform_backward(anchor_boxes, target_boxes, grad_trans)
     return loss, (din_anchor * f32(-1)).astype(_DT[0]), grad_trans
+
+
+# densecap/LanguageModel.lua:148-164  getTarget: (N,T) ground-truth tokens (0 = padding) -> (N,T+2) targets: a leading 0 for the
+# image time step, the tokens, the first padding slot replaced by END (= V+1).  Pinned by test/LanguageModel_test.lua:46-70.
+def lm_get_target(gt_sequence, vocab_size):
+    gt = np.asarray(gt_sequence, np.int64)
+    N, T = gt.shape
+    target = np.zeros((N, T + 2), np.int64)
+    target[:, 1:T + 1] = gt
+    for i in range(N):
+        for t in range(1, T + 2):
+            if target[i, t] == 0:
+                target[i, t] = vocab_size + 1
+                break
+    return target
+
+
+def log_softmax(x):
+    x = _f(x)
+    m = x.max(axis=1, keepdims=True)
+    return ((x - m) - np.log(np.exp((x - m).astype(np.float64)).sum(axis=1, keepdims=True)).astype(_DT[0])).astype(_DT[0])
+
+
+def _topk_desc(v, k):
+    """torch.topk(v, k, dim, true): the k largest, descending.  The order among exactly equal values is unspecified in TH;
+    the oracle DEFINES it as lower index first (stable)."""
+    idx = np.argsort(-v, kind="stable")[:k]
+    return v[idx], idx
+
+
+# densecap/LanguageModel.lua:170-290  LM:beamsearch -- each image vector separately, beams in the minibatch dimension.
+# Returns (N,T) int64 tokens (1-based).  SURVEY.md 8f rank 3; the GPU implementation is later work, this is its oracle.
+def lm_beamsearch(codes, weights, seq_length, beam_size=20):
+    codes = _f(codes)
+    N = codes.shape[0]
+    Wl = weights["lm.lstm.weight"]; bl = weights["lm.lstm.bias"]
+    H = Wl.shape[1] // 4
+    V1 = weights["lm.vocab.weight"].shape[0]
+    START = END = V1
+    T = seq_length
+    lookup = _f(weights["lm.lookup.weight"])
+    seq = np.zeros((N, T), np.int64)
+    for i in range(N):
+        enc = relu(linear(codes[i:i + 1], weights["lm.encoder.weight"], weights["lm.encoder.bias"]))
+        h = np.zeros((1, H), _DT[0]); c = np.zeros((1, H), _DT[0])
+        h, c = lstm_step(enc, h, c, Wl, bl)                                            # image time step
+        h, c = lstm_step(lookup[np.array([START]) - 1], h, c, Wl, bl)                  # START token
+        scores = linear(h, weights["lm.vocab.weight"], weights["lm.vocab.bias"])
+        all_logprobs = log_softmax(scores)[0]
+        beam_logprobs, idx = _topk_desc(all_logprobs, beam_size)
+        B = idx.shape[0]                                                               # = beam_size (V+1 >= beam_size assumed, as in the reference)
+        beams = np.ones((B, T), np.int64)
+        beams[:, 0] = idx + 1
+        h = np.repeat(h, B, axis=0); c = np.repeat(c, B, axis=0)                        # duplicate the states for all beams (:221-227)
+        for t in range(1, T):
+            words = beams[:, t - 1]
+            h, c = lstm_step(lookup[words - 1], h, c, Wl, bl)
+            next_logprobs = log_softmax(linear(h, weights["lm.vocab.weight"], weights["lm.vocab.bias"]))
+            # a beam that already holds an END token contributes nothing more (:243-247)
+            end_mask = ((beams == END).sum(axis=1) == 0).astype(_DT[0])
+            next_logprobs = next_logprobs * end_mask[:, None]
+            top_lp = np.empty((B, B), _DT[0]); top_ix = np.empty((B, B), np.int64)
+            for b in range(B):
+                top_lp[b], top_ix[b] = _topk_desc(next_logprobs[b], B)
+            all_next = (top_lp + beam_logprobs[:, None]).reshape(-1)                    # index b*B + k
+            beam_logprobs, sel = _topk_desc(all_next, B)
+            src = sel // B
+            new_beams = beams[src].copy()
+            new_beams[:, t] = top_ix.reshape(-1)[sel] + 1
+            beams = new_beams
+            h = h[src]; c = c[src]
+        seq[i] = beams[int(np.argmax(beam_logprobs))]
+    return seq

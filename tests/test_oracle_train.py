@@ -118,3 +118,27 @@ def test_box_conversion_round_trip():
     b = O.x1y1x2y2_to_xywh(a)
     c = O.xywh_to_x1y1x2y2(b)
     assert np.abs(a - c).max() <= 1e-6 and np.abs(xywh - b).max() <= 1e-6
+
+
+def test_lm_get_target_known_answer():
+    """test/LanguageModel_test.lua:46-70 (V = 100, T = 5): the reference's expected tensor."""
+    gt = np.array([[5, 7, 0, 0, 0], [11, 12, 13, 0, 0], [15, 16, 17, 18, 29], [50, 0, 0, 0, 0]])
+    want = np.array([[0, 5, 7, 101, 0, 0, 0], [0, 11, 12, 13, 101, 0, 0], [0, 15, 16, 17, 18, 29, 101], [0, 50, 101, 0, 0, 0, 0]])
+    assert np.array_equal(O.lm_get_target(gt, 100), want)
+
+
+def test_lm_beamsearch_properties():
+    """LanguageModel.lua:170-290: with one beam the search is the greedy sample (until an END token: greedy keeps decoding, the beam
+    search zeroes the log-probs of a finished beam -- so compare up to the first END); wider beams keep shapes and token range."""
+    from densecap_b200.synth import ModelDims, make_weights
+    dims = ModelDims(widths=(8, 8, 8, 8, 8), rpn_filters=8, fc_dim=32, rnn_size=16, encoding_size=16, vocab_size=12, seq_length=6)
+    w = make_weights(dims, seed=4, box_variant="B")
+    codes = np.maximum(np.random.RandomState(0).randn(5, dims.fc_dim), 0).astype(np.float32)
+    greedy = O.lm_sample(codes, w, dims.seq_length)
+    beam1 = O.lm_beamsearch(codes, w, dims.seq_length, beam_size=1)
+    END = dims.vocab_size + 1
+    for g, b in zip(greedy, beam1):
+        stop = (list(g).index(END) + 1) if END in g else len(g)
+        assert list(g[:stop]) == list(b[:stop])
+    beam4 = O.lm_beamsearch(codes, w, dims.seq_length, beam_size=4)
+    assert beam4.shape == (5, dims.seq_length) and beam4.min() >= 1 and beam4.max() <= END
