@@ -19,7 +19,13 @@ PARITY PINNING:
       composition + row order (test/MakeBoxes_test.lua:47-234 through the equivalence
       stated by test/MakeAnchors_test.lua:17-44), ReshapeBoxFeatures strides
       (test/ReshapeBoxFeatures_test.lua:33-58), Apply/Invert round trip
-      (test/InvertBoxTransform_test.lua:15-58).
+      (test/InvertBoxTransform_test.lua:15-58), decodeSequence and getTarget
+      (test/LanguageModel_test.lua:46-70,135-160), BoxSamplerHelper gather / scatter protocol
+      (test/BoxSamplerHelper_test.lua), BoxRegressionCriterion numeric gradient check
+      (test/BoxRegressionCriterion_test.lua), box conversion round trip (test/box_conversion_test.lua).
+  * self-checked where the reference has no numbers: the training-time backward
+    (localization_layer_backward_train) against central finite differences of this file's own
+    float64 forward (7 digits at 720x600 / 256 ROIs).
   * "parity unpinned" (third-party arithmetic that is NOT under /root/reference and
     has no numeric known-answer test there; restated from the published algorithm):
       stnbhwd AffineGridGeneratorBHWD / BilinearSamplerBHWD  (sampler_* below),
