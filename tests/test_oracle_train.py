@@ -142,3 +142,39 @@ def test_lm_beamsearch_properties():
         assert list(g[:stop]) == list(b[:stop])
     beam4 = O.lm_beamsearch(codes, w, dims.seq_length, beam_size=4)
     assert beam4.shape == (5, dims.seq_length) and beam4.min() >= 1 and beam4.max() <= END
+
+
+def test_backward_train_matches_finite_differences():
+    """The oracle's LocalizationLayer backward (LocalizationLayer.lua:529-605) against central differences of its own float64 forward,
+    on a case without duplicated negatives (with duplicates the reference's indexCopy scatter deliberately keeps only the last copy,
+    so its gradient is not the true one)."""
+    rng = np.random.RandomState(3)
+    C5, F, k, H, W = 8, 8, 12, 6, 8
+    img_h, img_w = 96, 128
+    w = {"rpn.conv.weight": (rng.randn(F, C5, 3, 3) * 0.05).astype(np.float32), "rpn.conv.bias": (rng.randn(F) * 0.01).astype(np.float32),
+         "rpn.box.weight": (rng.randn(4 * k, F, 1, 1) * 0.05).astype(np.float32), "rpn.box.bias": np.zeros(4 * k, np.float32),
+         "rpn.score.weight": (rng.randn(2 * k, F, 1, 1) * 0.05).astype(np.float32), "rpn.score.bias": np.zeros(2 * k, np.float32)}
+    feats = np.maximum(rng.randn(1, C5, H, W), 0).astype(np.float32)
+    gt = np.array([[[30, 30, 40, 50], [90, 60, 50, 40], [64, 48, 30, 30]]], np.float32)
+    kw = dict(mid_box_reg_weight=0.5, mid_objectness_weight=1.0, box_reg_decay=1e-3)
+    S = 8
+    fwd = O.localization_layer_forward_train(feats, w, gt, img_h, img_w, batch_size=S, **kw)
+    assert len(set(fwd["neg_input_idx"].tolist())) == fwd["num_neg"], "test case must not repeat negatives"
+    g1 = (rng.randn(S, C5, 7, 7)).astype(np.float32); g2 = (rng.randn(S, 4) * 0.1).astype(np.float32)
+    bwd = O.localization_layer_backward_train(feats, w, gt, img_h, img_w, fwd, g1, g2, **kw)
+    w64 = {n: v.astype(np.float64) for n, v in w.items()}
+
+    def scalar(f):
+        with O.precision(np.float64):
+            r = O.localization_layer_forward_train(f, w64, gt.astype(np.float64), img_h, img_w, batch_size=S, **kw)
+        return float((r["roi_features"] * g1).sum() + (r["roi_boxes"] * g2).sum() + r["losses"]["total_loss"])
+
+    worst = 0.0
+    for ix in [(0, 1, 2, 3), (0, 5, 4, 6), (0, 7, 0, 0), (0, 3, 5, 7)]:
+        eps = 1e-4
+        fp = feats.astype(np.float64).copy(); fp[ix] += eps
+        fm = feats.astype(np.float64).copy(); fm[ix] -= eps
+        num = (scalar(fp) - scalar(fm)) / (2 * eps)
+        ana = float(bwd["grad_feats"][ix])
+        worst = max(worst, abs(num - ana) / max(abs(num), abs(ana), 1e-3))
+    assert worst < 2e-3, worst
