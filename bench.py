@@ -170,7 +170,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("DC_BENCH_BATCH", "4")), help="images per step per GPU")
-    ap.add_argument("--engine", default="tc", choices=["tc", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -202,8 +201,7 @@ def main():
     B = args.batch
     dims = ModelDims()
     weights = make_weights(dims, seed=0, box_variant="A")      # identical replica on every rank
-    engine = _lib.DC_ENGINE_TC if args.engine == "tc" else _lib.DC_ENGINE_SIMT
-    model = DenseCapModel({"dims": dims}, weights=weights, device=local_rank, max_batch=B, max_image_hw=(IMG_H, IMG_W), engine=engine)
+    model = DenseCapModel({"dims": dims}, weights=weights, device=local_rank, max_batch=B, max_image_hw=(IMG_H, IMG_W))
     model.setTestArgs({"rpn_nms_thresh": 0.7, "final_nms_thresh": 0.3, "num_proposals": NUM_PROPOSALS})
     del weights
     ctx = model.ctx
@@ -356,7 +354,6 @@ def main():
             "config": {"workload": "720x600x3 synthetic images, random-init VGG-16 DenseCap (V=10497), 1000 proposals, 15-token greedy decode, "
                                    "final NMS 0.3 (BASELINE configs[1])",
                        "images_per_step_per_gpu": B, "global_batch": B * world, "parallelism": "image-sharded replicas, dp%d" % world,
-                       "engine": args.engine,
                        "arithmetic": "fp32 semantics: split-fp16 (hi+lo) operands, 3 tcgen05 kind::f16 MMAs per product (2 wide ones on 64/128-column tiles), "
                                      "fp32 accumulate in TMEM",
                        "l2": "no explicit flush: each step streams >1 GB (fc6 weights 411 MB + activations), far beyond the 126 MB L2; "

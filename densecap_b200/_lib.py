@@ -10,8 +10,6 @@ from . import build as _build
 
 _LIB = None
 
-DC_ENGINE_TC = 0
-DC_ENGINE_SIMT = 1
 DC_MAX_ANCHORS = 32
 
 c_f = C.c_float
@@ -25,7 +23,7 @@ class DcConfig(C.Structure):
     _fields_ = [("widths", c_i32 * 5), ("rpn_filters", c_i32), ("num_anchors", c_i32), ("fc_dim", c_i32),
                 ("pool_hw", c_i32), ("rnn_size", c_i32), ("encoding_size", c_i32), ("vocab_size", c_i32),
                 ("seq_length", c_i32), ("pool_ceil", c_i32), ("max_batch", c_i32), ("max_image_h", c_i32),
-                ("max_image_w", c_i32), ("max_proposals", c_i32), ("engine", c_i32), ("fuse_pool", c_i32),
+                ("max_image_w", c_i32), ("max_proposals", c_i32), ("reserved0", c_i32), ("fuse_pool", c_i32),
                 ("anchors", c_f * (2 * DC_MAX_ANCHORS)), ("field_centers", c_f * 4)]
 
 
@@ -33,7 +31,7 @@ class DcResult(C.Structure):
     _fields_ = [("batch", c_i32), ("max_proposals", c_i32), ("num_proposals", c_vp), ("num_final", c_vp),
                 ("final_boxes", c_vp), ("final_scores", c_vp), ("final_seq", c_vp), ("final_idx", c_vp),
                 ("roi_boxes", c_vp), ("box_trans", c_vp), ("all_boxes", c_vp), ("all_scores", c_vp),
-                ("all_seq", c_vp), ("codes", c_vp)]
+                ("all_seq", c_vp), ("codes", c_vp), ("proposal_idx", c_vp)]
 
 
 # name -> (restype, argtypes): exactly the declarations of include/densecap_b200.h
@@ -45,6 +43,7 @@ SIGNATURES = {
     "dc_version": (c_i, []),
     "dc_load_weights": (c_i, [c_vp, C.c_char_p, c_vp, C.POINTER(c_i64), c_i]),
     "dc_set_test_args": (c_i, [c_vp, c_f, c_f, c_i, c_i]),
+    "dc_set_decode_all": (c_i, [c_vp, c_i]),
     "dc_set_image_size": (c_i, [c_vp, c_i, c_i]),
     "dc_forward_test": (c_i, [c_vp, c_vp, c_i, c_i, c_i, C.POINTER(DcResult), c_vp]),
     "dc_forward_test_host": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_vp]),
@@ -52,6 +51,7 @@ SIGNATURES = {
     "dc_forward_test_host_u8": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_vp]),
     "dc_vgg_trunk_forward": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp]),
     "dc_localization_forward_test": (c_i, [c_vp, c_vp, c_i, c_i, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dc_rpn_proposals": (c_i, [c_vp, c_vp, c_vp, c_i, c_i, c_vp, c_vp, c_vp, c_vp]),
     "dc_set_train_args": (c_i, [c_vp, c_f, c_f, c_f, c_f, c_f, c_i, c_i]),
     "dc_set_ground_truth": (c_i, [c_vp, c_vp, c_i, c_vp]),
     "dc_localization_forward_train": (c_i, [c_vp, c_vp, c_i, c_i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -72,8 +72,8 @@ SIGNATURES = {
     "dc_box_to_affine": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp]),
     "dc_bilinear_roi_pool": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_i, c_i, c_i, c_i, c_i, c_vp, c_i, c_vp]),
     "dc_box_iou": (c_i, [c_vp, c_vp, c_vp, c_i, c_i, c_vp]),
-    "dc_linear": (c_i, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i, c_vp]),
-    "dc_conv3x3_relu": (c_i, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
+    "dc_linear": (c_i, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_vp]),
+    "dc_conv3x3_relu": (c_i, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "dc_enable_timing": (c_i, [c_vp, c_i]),
     "dc_get_times": (c_i, [c_vp, C.POINTER(C.c_char_p), C.POINTER(c_f), c_i, C.POINTER(c_i)]),
     "dc_kernel_launches": (c_i64, [c_vp]),

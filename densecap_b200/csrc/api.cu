@@ -37,6 +37,7 @@ struct dc_ctx {
   int device = 0;
   char err[512];
   int64_t launches = 0;
+  LaunchState launch;                // per-context launcher state (tensor-map encoder, SM count, smem attributes)
   // test args (DenseCapModel.lua:185-191, LocalizationLayer.lua:233-238)
   float rpn_nms_thresh = 0.7f, final_nms_thresh = 0.3f;
   int num_proposals = 1000, clip_boxes = 1;
@@ -48,11 +49,15 @@ struct dc_ctx {
   // geometry capacity
   int fh_max = 0, fw_max = 0, A_max = 0, P = 0, B = 0;
   // buffers
-  SplitBuf act[2], feats, rpn_hidden, roi, fc6o, fc7o, xh;
-  float *rpn_head = nullptr, *codes = nullptr, *obj = nullptr, *trans = nullptr, *boxes_all = nullptr, *gates = nullptr, *cstate = nullptr;
+  SplitBuf act[2], feats, rpn_hidden, roi, fc6o, fc7o, xh, enc;
+  float *rpn_head = nullptr, *codes = nullptr, *obj = nullptr, *trans = nullptr, *boxes_all = nullptr, *cstate = nullptr;
   float *pp_boxes = nullptr, *pp_x1y1 = nullptr, *pp_prob = nullptr, *roi_boxes = nullptr, *fin_x1y1 = nullptr;
   int32_t *pp_src = nullptr, *pp_nvalid = nullptr, *pp_blocks = nullptr;
-  int32_t *rpn_idx32 = nullptr, *rpn_count = nullptr, *fin_idx32 = nullptr, *fin_count = nullptr, *tokens = nullptr;
+  int32_t *rpn_idx32 = nullptr, *rpn_count = nullptr, *fin_idx32 = nullptr, *fin_count = nullptr;
+  // caption decoder (lm_decode.cu): dependency counters, row maps, number of rows decoded; decode_all = 1 decodes every proposal
+  uint32_t* dec_counters = nullptr;
+  int32_t *dec_rows = nullptr, *dec_dst_final = nullptr, *dec_dst_all = nullptr, *dec_count1 = nullptr;
+  int decode_all = 0;
   int64_t *rpn_idx64 = nullptr, *fin_idx64 = nullptr, *seq64 = nullptr, *fin_seq = nullptr;
   float *fin_boxes = nullptr, *fin_scores = nullptr;
   unsigned long long* packed = nullptr;
@@ -97,7 +102,7 @@ struct dc_ctx {
   int bwd_S = 0;
 };
 
-static char g_err[512] = "";
+static thread_local char g_err[512] = "";   // message of the last ctx-less failure (dc_create, leaf operators), per thread
 
 int dc_set_error(dc_ctx* ctx, int code, const char* fmt, ...) {
   char* dst = ctx ? ctx->err : g_err;
@@ -108,6 +113,7 @@ int dc_set_error(dc_ctx* ctx, int code, const char* fmt, ...) {
   if (ctx) strncpy(g_err, ctx->err, sizeof(g_err) - 1);
   return code;
 }
+LaunchState* dc_launch_state(dc_ctx* ctx) { return &ctx->launch; }
 void dc_count_launch(dc_ctx* ctx, int n) {
   if (ctx) ctx->launches += n;
 }
@@ -134,7 +140,7 @@ extern "C" int dc_config_default(dc_config* c) {
   c->max_image_h = 600;
   c->max_image_w = 720;
   c->max_proposals = 1000;
-  c->engine = DC_ENGINE_TC;
+  c->reserved0 = 0;
   c->fuse_pool = 1;
   // LocalizationLayer.lua:613-618 (stored (2,k): widths then heights)
   const float aw[12] = {45, 90, 64, 90, 180, 128, 181, 362, 256, 362, 724, 512};
@@ -196,6 +202,7 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
   if (c.num_anchors <= 0 || c.num_anchors > DC_MAX_ANCHORS || c.max_batch <= 0 || c.max_proposals <= 0 || c.pool_hw < 2 ||
       c.pool_hw * c.pool_hw > 64 || c.seq_length <= 0 || c.vocab_size <= 0)
     return dc_set_error(nullptr, DC_E_INVALID, "dc_create: invalid configuration");
+  if (c.reserved0 != 0) return dc_set_error(nullptr, DC_E_UNSUPPORTED, "dc_create: reserved0 must be 0 (there is one dense engine, tcgen05)");
   for (int i = 0; i < 5; ++i)
     if (c.widths[i] <= 0 || c.widths[i] % 64 != 0) return dc_set_error(nullptr, DC_E_UNSUPPORTED, "dc_create: stage widths must be multiples of 64");
   if (c.rpn_filters % 64 || c.fc_dim % 64 || c.rnn_size % 64 || c.encoding_size % 64)
@@ -209,7 +216,7 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
   ctx->num_proposals = c.max_proposals;
   int rc = DC_OK;
 #define TRY(x) do { rc = (x); if (rc != DC_OK) { strncpy(g_err, ctx->err, sizeof(g_err) - 1); dc_destroy(ctx); return rc; } } while (0)
-  if (c.engine == DC_ENGINE_TC) TRY(tc_init(ctx));
+  TRY(tc_init(ctx));
   ctx->B = c.max_batch;
   ctx->P = c.max_proposals;
   feat_hw(c, c.max_image_h, c.max_image_w, ctx->fh_max, ctx->fw_max);
@@ -236,12 +243,17 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
   TRY(split_alloc(ctx, ctx->roi, B * P * hw * C5));
   TRY(split_alloc(ctx, ctx->fc6o, B * P * fc));
   TRY(split_alloc(ctx, ctx->fc7o, B * P * fc));
-  TRY(split_alloc(ctx, ctx->xh, 2 * B * P * (E + H)));      // two ping-pong [x|h] operands, see run_lm
+  TRY(split_alloc(ctx, ctx->xh, 2 * B * P * (E + H)));      // two ping-pong [x|h] operands of the decoder (lm_decode.cu)
+  TRY(split_alloc(ctx, ctx->enc, B * P * E));
+  TRY(dev_alloc(ctx, &ctx->dec_counters, lm_decode_counter_words((int)T, (int)(B * P))));
+  TRY(dev_alloc(ctx, &ctx->dec_rows, 1));
+  TRY(dev_alloc(ctx, &ctx->dec_count1, 1));
+  TRY(dev_alloc(ctx, &ctx->dec_dst_final, B * P));
+  TRY(dev_alloc(ctx, &ctx->dec_dst_all, B * P));
   TRY(dev_alloc(ctx, &ctx->codes, B * P * fc));
   TRY(dev_alloc(ctx, &ctx->obj, B * P));
   TRY(dev_alloc(ctx, &ctx->trans, B * P * 4));
   TRY(dev_alloc(ctx, &ctx->boxes_all, B * P * 4));
-  TRY(dev_alloc(ctx, &ctx->gates, B * P * 4 * H));
   TRY(dev_alloc(ctx, &ctx->cstate, B * P * H));
   const size_t A = ctx->A_max;
   TRY(dev_alloc(ctx, &ctx->pp_boxes, B * A * 4));
@@ -258,7 +270,6 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
   TRY(dev_alloc(ctx, &ctx->fin_idx32, B * P));
   TRY(dev_alloc(ctx, &ctx->fin_idx64, B * P));
   TRY(dev_alloc(ctx, &ctx->fin_count, B));
-  TRY(dev_alloc(ctx, &ctx->tokens, B * P * T));
   TRY(dev_alloc(ctx, &ctx->seq64, B * P * T));
   TRY(dev_alloc(ctx, &ctx->fin_seq, B * P * T));
   TRY(dev_alloc(ctx, &ctx->fin_boxes, B * P * 4));
@@ -581,6 +592,12 @@ extern "C" int dc_set_test_args(dc_ctx* ctx, float rpn_nms_thresh, float final_n
   return DC_OK;
 }
 
+extern "C" int dc_set_decode_all(dc_ctx* ctx, int enable) {
+  if (!ctx) return dc_set_error(nullptr, DC_E_INVALID, "dc_set_decode_all: null ctx");
+  ctx->decode_all = enable ? 1 : 0;
+  return DC_OK;
+}
+
 extern "C" int dc_set_image_size(dc_ctx* ctx, int image_h, int image_w) {
   if (!ctx) return dc_set_error(nullptr, DC_E_INVALID, "dc_set_image_size: null ctx");
   DC_REQUIRE(ctx, image_h > 0 && image_w > 0, DC_E_INVALID, "setImageSize: bad size %dx%d", image_h, image_w);
@@ -697,7 +714,7 @@ extern "C" int dc_get_times(dc_ctx* ctx, const char** names_out, float* ms_out, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// dense-layer helpers (engine dispatch)
+// dense-layer helpers
 // ------------------------------------------------------------------------------------------------
 static int need_weight(dc_ctx* ctx, const char* name, Weight** out) {
   auto it = ctx->w.find(name);
@@ -711,8 +728,7 @@ static int gemm(dc_ctx* ctx, const __half* a_hi, size_t a_plane, int lda, const 
                 const GemmEpilogue& ep_in, cudaStream_t st) {
   GemmEpilogue ep = ep_in;
   ep.acc_scale = w.inv_scale;
-  if (ctx->cfg.engine == DC_ENGINE_TC) return k_tc_gemm(ctx, a_hi, a_plane, lda, w.planes, w.plane_elems, ldb, M, N, K, ep, st);
-  return k_simt_gemm(ctx, a_hi, a_hi + a_plane, lda, w.planes, w.planes + w.plane_elems, ldb, M, N, K, ep, st);
+  return k_tc_gemm(ctx, a_hi, a_plane, lda, w.planes, w.plane_elems, ldb, M, N, K, ep, st);
 }
 
 // y = relu(conv3x3(x)+b) [+pool]; returns the spatial size of y through oh/ow
@@ -720,32 +736,18 @@ static int conv_layer(dc_ctx* ctx, const __half* x, size_t x_plane, __half* y, i
                       const Weight& bias, int pool_after, __half* pool_tmp, int* oh, int* ow, cudaStream_t st) {
   const int ceil_mode = ctx->cfg.pool_ceil;
   const int PH = pooled(H, ceil_mode), PW = pooled(W, ceil_mode);
-  if (ctx->cfg.engine == DC_ENGINE_TC) {
-    const bool fuse = pool_after && ctx->cfg.fuse_pool && ceil_mode;
-    if (fuse) {
-      const size_t yp = (size_t)N * PH * PW * Cout;
-      int rc = k_tc_conv3x3(ctx, x, x_plane, wt.planes, wt.plane_elems, bias.f32, wt.inv_scale, y, y + yp, N, H, W, Cin, Cout, 1, st);
-      *oh = PH; *ow = PW;
-      return rc;
-    }
-    __half* dst = pool_after ? pool_tmp : y;
-    const size_t yp = (size_t)N * H * W * Cout;
-    int rc = k_tc_conv3x3(ctx, x, x_plane, wt.planes, wt.plane_elems, bias.f32, wt.inv_scale, dst, dst + yp, N, H, W, Cin, Cout, 0, st);
-    if (rc) return rc;
-    if (pool_after) {
-      const size_t pp = (size_t)N * PH * PW * Cout;
-      rc = k_maxpool2x2_split(ctx, dst, dst + yp, y, y + pp, N, H, W, Cout, ceil_mode, st);
-      *oh = PH; *ow = PW;
-      return rc;
-    }
-    *oh = H; *ow = W;
-    return DC_OK;
+  const bool fuse = pool_after && ctx->cfg.fuse_pool && ceil_mode;
+  if (fuse) {
+    const size_t yp = (size_t)N * PH * PW * Cout;
+    int rc = k_tc_conv3x3(ctx, x, x_plane, wt.planes, wt.plane_elems, bias.f32, wt.inv_scale, y, y + yp, N, H, W, Cin, Cout, 1, st);
+    *oh = PH; *ow = PW;
+    return rc;
   }
   __half* dst = pool_after ? pool_tmp : y;
   const size_t yp = (size_t)N * H * W * Cout;
-  int rc = k_simt_conv3x3(ctx, x, x + x_plane, wt.planes, wt.planes + wt.plane_elems, bias.f32, wt.inv_scale, dst, dst + yp, N, H, W, Cin, Cout, st);
+  int rc = k_tc_conv3x3(ctx, x, x_plane, wt.planes, wt.plane_elems, bias.f32, wt.inv_scale, dst, dst + yp, N, H, W, Cin, Cout, 0, st);
   if (rc) return rc;
-  if (pool_after) {
+  if (pool_after) {      // floor-mode pooling (pool_ceil = 0) or fuse_pool = 0: stand-alone pooling kernel
     const size_t pp = (size_t)N * PH * PW * Cout;
     rc = k_maxpool2x2_split(ctx, dst, dst + yp, y, y + pp, N, H, W, Cout, ceil_mode, st);
     *oh = PH; *ow = PW;
@@ -787,7 +789,7 @@ static int run_trunk(dc_ctx* ctx, const float* img, int N, int H, int W, int* fh
       // last layer writes straight into the feature buffer (no pool after conv5_3; pool5 is excluded)
       if ((rc = conv_layer(ctx, x, xp, ctx->feats.base, N, h, w, cin, cout, *wt, *bs, 0, nullptr, &oh, &ow, st))) return rc;
     } else {
-      const bool unfused_pool = kPoolAfter[i] && !(c.engine == DC_ENGINE_TC && c.fuse_pool && c.pool_ceil);
+      const bool unfused_pool = kPoolAfter[i] && !(c.fuse_pool && c.pool_ceil);
       // unfused pool: conv x(cur) -> tmp(other), pool tmp(other) -> y(cur): x is dead by then
       __half* y = unfused_pool ? ctx->act[cur].base : ctx->act[cur ^ 1].base;
       __half* tmp = ctx->act[cur ^ 1].base;
@@ -831,12 +833,35 @@ static int run_rpn_head(dc_ctx* ctx, int N, int fh, int fw, cudaStream_t st) {
   return gemm(ctx, ctx->rpn_hidden.base, hplane, F, *wh, F, N * cells, 6 * k, F, ep, st);
 }
 
-// RPN + post-processing + NMS + ROI pooling for image b of the batch (LocalizationLayer.lua:250-363)
+// LocalizationLayer.lua:262-338 for image b of the batch, from the RPN head outputs in ctx->rpn_head: anchors + reshape +
+// ApplyBoxTransform + clip + objectness (fused), NMS, index gathers -> ctx->roi_boxes / rpn_idx / rpn_count rows of image b
+static int run_proposals_image(dc_ctx* ctx, int b, int fh, int fw, int img_h, int img_w, cudaStream_t sb) {
+  const dc_config& c = ctx->cfg;
+  const int k = c.num_anchors, cells = fh * fw, A = k * cells, P = ctx->P;
+  int rc;
+  RpnPostOut po;
+  po.boxes_xcycwh = ctx->pp_boxes + (size_t)b * ctx->A_max * 4;
+  po.boxes_x1y1x2y2 = ctx->pp_x1y1 + (size_t)b * ctx->A_max * 4;
+  po.prob = ctx->pp_prob + (size_t)b * ctx->A_max;
+  po.src_row = ctx->pp_src + (size_t)b * ctx->A_max;
+  po.n_valid = ctx->pp_nvalid + b;
+  po.block_counts = ctx->pp_blocks + (size_t)b * (ctx->A_max / 256 + 2);
+  if ((rc = k_rpn_postprocess(ctx, ctx->rpn_head + (size_t)b * cells * 6 * k, 6 * k, fh, fw, k, ctx->anchors_dev, c.field_centers[0],
+                              c.field_centers[1], c.field_centers[2], c.field_centers[3], (float)img_w, (float)img_h, ctx->clip_boxes, po, sb)))
+    return rc;
+  if ((rc = k_nms(ctx, ctx->pp_x1y1 + (size_t)b * ctx->A_max * 4, 4, ctx->pp_prob + (size_t)b * ctx->A_max, 1, A, ctx->pp_nvalid + b,
+                  ctx->rpn_nms_thresh, ctx->num_proposals, ctx->nms[b], ctx->rpn_idx64 + (size_t)b * P, ctx->rpn_idx32 + (size_t)b * P,
+                  ctx->rpn_count + b, sb)))
+    return rc;
+  return k_gather_rows_f32(ctx, ctx->pp_boxes + (size_t)b * ctx->A_max * 4, 4, ctx->rpn_idx32 + (size_t)b * P, ctx->rpn_count + b, P,
+                           ctx->roi_boxes + (size_t)b * P * 4, sb);
+}
+
+// RPN + post-processing + NMS + ROI pooling for every image of the batch (LocalizationLayer.lua:250-363)
 static int run_localization(dc_ctx* ctx, int N, int fh, int fw, int img_h, int img_w, cudaStream_t st) {
   const dc_config& c = ctx->cfg;
-  const int C5 = c.widths[4], k = c.num_anchors;
+  const int C5 = c.widths[4];
   const int cells = fh * fw;
-  const int A = k * cells;
   int rc;
   phase_mark(ctx, "rpn:forward_test", st);
   if ((rc = run_rpn_head(ctx, N, fh, fw, st))) return rc;
@@ -850,24 +875,7 @@ static int run_localization(dc_ctx* ctx, int N, int fh, int fw, int img_h, int i
   for (int b = 0; b < N; ++b) {
     cudaStream_t sb = (b == 0) ? st : ctx->side[b - 1];
     if (b > 0) DC_CHECK_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->fork_ev, 0));
-    RpnPostOut po;
-    po.boxes_xcycwh = ctx->pp_boxes + (size_t)b * ctx->A_max * 4;
-    po.boxes_x1y1x2y2 = ctx->pp_x1y1 + (size_t)b * ctx->A_max * 4;
-    po.prob = ctx->pp_prob + (size_t)b * ctx->A_max;
-    po.src_row = ctx->pp_src + (size_t)b * ctx->A_max;
-    po.n_valid = ctx->pp_nvalid + b;
-    po.block_counts = ctx->pp_blocks + (size_t)b * (ctx->A_max / 256 + 2);
-    if ((rc = k_rpn_postprocess(ctx, ctx->rpn_head + (size_t)b * cells * 6 * k, 6 * k, fh, fw, k, ctx->anchors_dev, c.field_centers[0],
-                                c.field_centers[1], c.field_centers[2], c.field_centers[3], (float)img_w, (float)img_h, ctx->clip_boxes,
-                                po, sb)))
-      return rc;
-    if ((rc = k_nms(ctx, ctx->pp_x1y1 + (size_t)b * ctx->A_max * 4, 4, ctx->pp_prob + (size_t)b * ctx->A_max, 1, A, ctx->pp_nvalid + b,
-                    ctx->rpn_nms_thresh, ctx->num_proposals, ctx->nms[b], ctx->rpn_idx64 + (size_t)b * P, ctx->rpn_idx32 + (size_t)b * P,
-                    ctx->rpn_count + b, sb)))
-      return rc;
-    if ((rc = k_gather_rows_f32(ctx, ctx->pp_boxes + (size_t)b * ctx->A_max * 4, 4, ctx->rpn_idx32 + (size_t)b * P, ctx->rpn_count + b, P,
-                                ctx->roi_boxes + (size_t)b * P * 4, sb)))
-      return rc;
+    if ((rc = run_proposals_image(ctx, b, fh, fw, img_h, img_w, sb))) return rc;
     const size_t foff = (size_t)b * cells * C5;
     const size_t roff = (size_t)b * P * hw * C5;
     if (b == 0 && ctx->timer.enabled) {
@@ -925,79 +933,56 @@ static int run_recog(dc_ctx* ctx, int rows, cudaStream_t st) {
   return DC_OK;
 }
 
-// LanguageModel:sample on ctx->fc7o (rows), greedy (LanguageModel.lua:293-348)
-static int run_lm(dc_ctx* ctx, int rows, float* logits, cudaStream_t st) {
+// LanguageModel image_encoder (Linear + ReLU, LanguageModel.lua:27-29) on ctx->fc7o (rows) -> ctx->enc (rows, E) split planes.
+// Runs for EVERY proposal: in the full forward it executes on the main stream while the final NMS runs on the side streams,
+// so it costs no wall time, and the decoder then only gathers the rows it keeps.
+static int run_lm_encoder(dc_ctx* ctx, int rows, cudaStream_t st) {
   const dc_config& c = ctx->cfg;
-  const int fc = c.fc_dim, E = c.encoding_size, H = c.rnn_size, V = c.vocab_size, T = c.seq_length;
-  Weight *we, *be, *wl, *wlstm, *blstm, *wv, *bv;
+  const int fc = c.fc_dim, E = c.encoding_size;
+  Weight *we, *be;
   int rc;
   if ((rc = need_weight(ctx, "lm.encoder.weight", &we))) return rc;
   if ((rc = need_weight(ctx, "lm.encoder.bias", &be))) return rc;
+  const size_t fplane = (size_t)rows * fc;
+  GemmEpilogue ep;
+  ep.bias = be->f32; ep.relu = 1;
+  ep.out_hi = ctx->enc.base; ep.out_lo = ctx->enc.base + ctx->enc.cap_elems; ep.ldo = E; ep.out_col0 = 0;
+  return gemm(ctx, ctx->fc7o.base, fplane, fc, *we, fc, rows, E, fc, ep, st);
+}
+
+// LanguageModel:sample, greedy (LanguageModel.lua:293-348), as one compaction launch + ONE persistent decoder launch (lm_decode.cu)
+// over the rows selected by (counts, idx32) of each of the B images (row stride P).
+static int run_lm_decode(dc_ctx* ctx, int B, int P, const int32_t* counts, const int32_t* idx32, int survivors, int64_t* fin_seq, float* logits,
+                         cudaStream_t st) {
+  const dc_config& c = ctx->cfg;
+  Weight *wl, *wlstm, *blstm, *wv, *bv;
+  int rc;
   if ((rc = need_weight(ctx, "lm.lookup.weight", &wl))) return rc;
   if ((rc = need_weight(ctx, "lm.lstm.weight", &wlstm))) return rc;
   if ((rc = need_weight(ctx, "lm.lstm.bias", &blstm))) return rc;
   if ((rc = need_weight(ctx, "lm.vocab.weight", &wv))) return rc;
   if ((rc = need_weight(ctx, "lm.vocab.bias", &bv))) return rc;
-  phase_mark(ctx, "lm:sample", st);
-  const int ld = E + H;
-  // [x | h] operand of the gate GEMM, split planes, TWO buffers used alternately: the gate GEMM of a step reads
-  // [x_t | h_{t-1}] from one buffer while its fused cell epilogue writes h_t into the OTHER one.  (Tiles of one launch
-  // finish at different times; an in-place h would be overwritten while later tiles of the same rows still read it.)
-  const size_t bufelems = (size_t)rows * ld;                  // elements of one plane of one buffer
-  const size_t xplane = 2 * bufelems;                         // plane stride: [hi: buf0, buf1][lo: buf0, buf1]
-  const size_t fplane = (size_t)rows * fc;
-  auto xh_hi = [&](int i) { return ctx->xh.base + (size_t)i * bufelems; };
-  auto xh_lo = [&](int i) { return ctx->xh.base + xplane + (size_t)i * bufelems; };
-  {  // image_encoder: Linear + ReLU (LanguageModel.lua:27-29) -> x half of buffer 0
-    GemmEpilogue ep;
-    ep.bias = be->f32; ep.relu = 1;
-    ep.out_hi = xh_hi(0); ep.out_lo = xh_lo(0); ep.ldo = ld; ep.out_col0 = 0;
-    if ((rc = gemm(ctx, ctx->fc7o.base, fplane, fc, *we, fc, rows, E, fc, ep, st))) return rc;
-  }
-  const bool fused_cell = (c.engine == DC_ENGINE_TC);
-  // reads [x|h] from buffer `src`, writes h into buffer `dst`
-  auto lstm_step = [&](int K, int first, int src, int dst) -> int {
-    GemmEpilogue ep;
-    ep.bias = blstm->f32;
-    if (fused_cell) {
-      ep.lstm_c = ctx->cstate; ep.lstm_H = H; ep.lstm_first = first;
-      ep.out_hi = xh_hi(dst); ep.out_lo = xh_lo(dst); ep.ldo = ld; ep.out_col0 = E;
-      return gemm(ctx, xh_hi(src), xplane, ld, *wlstm, ld, rows, 4 * H, K, ep, st);
-    }
-    ep.out_f32 = ctx->gates; ep.ldf = 4 * H;
-    int r = gemm(ctx, xh_hi(src), xplane, ld, *wlstm, ld, rows, 4 * H, K, ep, st);
-    if (r) return r;
-    return k_lstm_pointwise(ctx, ctx->gates, ctx->cstate, xh_hi(dst), xh_lo(dst), ld, E, rows, H, first, st);
-  };
-  // first LSTM step on the encoded image with h0 = c0 = 0: only the Wx rows contribute (K = E)
-  if ((rc = lstm_step(E, 1, 0, 1))) return rc;
-  int cur = 1;                                                // buffer holding h_{t-1}
-  for (int t = 0; t < T; ++t) {
-    // finish step t-1 (arg-max -> token), look up the input token of step t into the x half of `cur`, reset the arg-max cells
-    if ((rc = k_lm_token_step(ctx, ctx->packed, ctx->tokens, ctx->seq64, T, t, V + 1, wl->planes, wl->planes + wl->plane_elems, E,
-                              xh_hi(cur), xh_lo(cur), ld, rows, st)))
-      return rc;
-    if ((rc = lstm_step(ld, 0, cur, cur ^ 1))) return rc;
-    cur ^= 1;
-    {
-      GemmEpilogue ep;
-      ep.bias = bv->f32;
-      ep.argmax = ctx->packed;
-      if (logits) { ep.out_f32 = logits + (size_t)t * (V + 1); ep.ldf = T * (V + 1); }
-      // A = h half of the buffer the cell just wrote
-      if ((rc = gemm(ctx, xh_hi(cur) + E, xplane, ld, *wv, H, rows, V + 1, H, ep, st))) return rc;
-    }
-  }
-  if ((rc = k_lm_token_step(ctx, ctx->packed, ctx->tokens, ctx->seq64, T, T, V + 1, wl->planes, wl->planes + wl->plane_elems, E, xh_hi(cur),
-                            xh_lo(cur), ld, rows, st)))
-    return rc;
-  return DC_OK;
+  LmDecodeArgs a{};
+  a.B = B; a.P = P; a.E = c.encoding_size; a.H = c.rnn_size; a.V = c.vocab_size; a.T = c.seq_length;
+  a.counts = counts; a.idx32 = idx32; a.survivors = survivors;
+  a.enc_planes = ctx->enc.base; a.enc_plane_elems = ctx->enc.cap_elems;
+  a.xh_planes = ctx->xh.base;
+  a.cstate = ctx->cstate;
+  a.lstm_planes = wlstm->planes; a.lstm_plane_elems = wlstm->plane_elems; a.lstm_bias = blstm->f32; a.lstm_acc_scale = wlstm->inv_scale;
+  a.vocab_planes = wv->planes; a.vocab_plane_elems = wv->plane_elems; a.vocab_bias = bv->f32; a.vocab_acc_scale = wv->inv_scale;
+  a.lut_planes = wl->planes; a.lut_plane_elems = wl->plane_elems;
+  a.packed = ctx->packed;
+  a.counters = ctx->dec_counters;
+  a.m_rows = ctx->dec_rows;
+  a.dst_final = ctx->dec_dst_final; a.dst_all = ctx->dec_dst_all;
+  a.fin_seq = fin_seq; a.all_seq = ctx->seq64;
+  a.logits = logits;
+  return k_lm_decode(ctx, a, st);
 }
 
-// final NMS + selection (DenseCapModel.lua:261-275)
-// Final NMS (DenseCapModel.lua:261-271) needs only the final boxes and objectness scores of the recognition head, not the
-// captions: it is forked onto per-image side streams right after the head and runs beside the LSTM decode (its kernels are a
-// few small CTAs that co-reside with the persistent GEMM CTAs); run_final_gather joins and filters the outputs (:272-274).
+// Final NMS (DenseCapModel.lua:261-271) needs only the final boxes and objectness scores of the recognition head.  It is forked
+// onto per-image side streams right after the head and runs beside the LM image encoder; join_final_nms makes the caller's stream
+// wait for the selection, which decides the rows the caption decoder processes (:272-274 keeps only those rows of the LM output).
 static int run_final_nms(dc_ctx* ctx, int N, cudaStream_t st) {
   const int P = ctx->P;
   int rc;
@@ -1019,16 +1004,20 @@ static int run_final_nms(dc_ctx* ctx, int N, cudaStream_t st) {
   }
   return DC_OK;
 }
+static int join_final_nms(dc_ctx* ctx, int N, cudaStream_t st) {
+  for (int b = 0; b < N; ++b) DC_CHECK_CUDA(ctx, cudaStreamWaitEvent(st, b == 0 ? ctx->fin_done0 : ctx->side_done[b - 1], 0));
+  return DC_OK;
+}
 
-static int run_final_gather(dc_ctx* ctx, int N, cudaStream_t st) {
+// output[4], output[1] (and, when every proposal was decoded, output[5]) filtered by the final-NMS selection (DenseCapModel.lua:272-274)
+static int run_final_gather(dc_ctx* ctx, int N, bool with_seq, cudaStream_t st) {
   const int P = ctx->P, T = ctx->cfg.seq_length;
   int rc;
-  phase_mark(ctx, "final_nms", st);
   for (int b = 0; b < N; ++b) {
     const size_t o = (size_t)b * P;
-    DC_CHECK_CUDA(ctx, cudaStreamWaitEvent(st, b == 0 ? ctx->fin_done0 : ctx->side_done[b - 1], 0));     // join
-    if ((rc = k_final_gather(ctx, ctx->fin_idx32 + o, ctx->fin_count + b, P, ctx->boxes_all + o * 4, ctx->obj + o, ctx->seq64 + o * T, T,
-                             ctx->fin_boxes + o * 4, ctx->fin_scores + o, ctx->fin_seq + o * T, st)))
+    if ((rc = k_final_gather(ctx, ctx->fin_idx32 + o, ctx->fin_count + b, P, ctx->boxes_all + o * 4, ctx->obj + o,
+                             with_seq ? ctx->seq64 + o * T : nullptr, T, ctx->fin_boxes + o * 4, ctx->fin_scores + o,
+                             with_seq ? ctx->fin_seq + o * T : nullptr, st)))
       return rc;
   }
   return DC_OK;
@@ -1049,6 +1038,7 @@ static void fill_result(dc_ctx* ctx, int N, dc_result* out) {
   out->all_scores = ctx->obj;
   out->all_seq = ctx->seq64;
   out->codes = ctx->codes;
+  out->proposal_idx = ctx->rpn_idx64;
 }
 
 extern "C" int dc_forward_test(dc_ctx* ctx, const float* img, int batch, int image_h, int image_w, dc_result* out, void* stream) {
@@ -1066,9 +1056,17 @@ extern "C" int dc_forward_test(dc_ctx* ctx, const float* img, int batch, int ima
   if ((rc = run_localization(ctx, batch, fh, fw, image_h, image_w, st))) return rc;
   const int rows = batch * ctx->P;
   if ((rc = run_recog(ctx, rows, st))) return rc;
-  if ((rc = run_final_nms(ctx, batch, st))) return rc;
-  if ((rc = run_lm(ctx, rows, nullptr, st))) return rc;
-  if ((rc = run_final_gather(ctx, batch, st))) return rc;
+  phase_mark(ctx, "final_nms|lm:encoder", st);
+  if ((rc = run_final_nms(ctx, batch, st))) return rc;            // side streams
+  if ((rc = run_lm_encoder(ctx, rows, st))) return rc;            // main stream, beside the NMS
+  if ((rc = join_final_nms(ctx, batch, st))) return rc;
+  phase_mark(ctx, "lm:sample", st);
+  // decode only what the reference returns (the final-NMS survivors), or every proposal when all_seq was asked for
+  if (ctx->decode_all) rc = run_lm_decode(ctx, batch, ctx->P, ctx->rpn_count, nullptr, 0, nullptr, nullptr, st);
+  else rc = run_lm_decode(ctx, batch, ctx->P, ctx->fin_count, ctx->fin_idx32, 1, ctx->fin_seq, nullptr, st);
+  if (rc) return rc;
+  phase_mark(ctx, "final_gather", st);
+  if ((rc = run_final_gather(ctx, batch, ctx->decode_all != 0, st))) return rc;
   phase_mark(ctx, "end", st);
   if (out) fill_result(ctx, batch, out);
   return DC_OK;
@@ -1184,6 +1182,38 @@ extern "C" int dc_localization_forward_test(dc_ctx* ctx, const float* feats_nchw
   }
   if (roi_boxes) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(roi_boxes, ctx->roi_boxes, (size_t)ctx->num_proposals * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (idx) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(idx, ctx->rpn_idx64, (size_t)ctx->num_proposals * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  if (num_out) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(num_out, ctx->rpn_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return DC_OK;
+}
+
+// (4k | 2k, H', W') NCHW head maps of the reference's RPN -> the (cells, 6k) row-major head matrix of this library
+__global__ void rpn_maps_to_head_kernel(const float* __restrict__ trans, const float* __restrict__ scores, float* __restrict__ head, int k, int cells) {
+  const int ld = 6 * k;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < (size_t)cells * ld; o += (size_t)gridDim.x * blockDim.x) {
+    const int col = o % ld;
+    const size_t cell = o / ld;
+    head[o] = col < 4 * k ? trans[(size_t)col * cells + cell] : scores[(size_t)(col - 4 * k) * cells + cell];
+  }
+}
+
+// LocalizationLayer:_forward_test after self.rpn:forward (LocalizationLayer.lua:262-338), fed with the RPN's raw outputs
+extern "C" int dc_rpn_proposals(dc_ctx* ctx, const float* rpn_trans_nchw, const float* rpn_scores_nchw, int feat_h, int feat_w, float* roi_boxes,
+                                int64_t* idx, int32_t* num_out, void* stream) {
+  if (!ctx || !rpn_trans_nchw || !rpn_scores_nchw) return dc_set_error(ctx, DC_E_INVALID, "dc_rpn_proposals: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  DC_REQUIRE(ctx, ctx->image_h > 0 && ctx->image_w > 0 && !ctx->size_consumed, DC_E_PROTOCOL, "Must call setImageSize before each forward pass");
+  ctx->size_consumed = true;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int k = ctx->cfg.num_anchors, cells = feat_h * feat_w;
+  DC_REQUIRE(ctx, feat_h > 0 && feat_w > 0 && (size_t)cells <= (size_t)ctx->fh_max * ctx->fw_max, DC_E_INVALID, "feature map too large");
+  rpn_maps_to_head_kernel<<<(unsigned)std::min<size_t>(1184, DC_CEIL_DIV((size_t)cells * 6 * k, (size_t)256)), 256, 0, st>>>(
+      rpn_trans_nchw, rpn_scores_nchw, ctx->rpn_head, k, cells);
+  DC_CHECK_LAUNCH(ctx);
+  int rc;
+  if ((rc = run_proposals_image(ctx, 0, feat_h, feat_w, ctx->image_h, ctx->image_w, st))) return rc;
+  const size_t n = (size_t)ctx->num_proposals;
+  if (roi_boxes) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(roi_boxes, ctx->roi_boxes, n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (idx) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(idx, ctx->rpn_idx64, n * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   if (num_out) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(num_out, ctx->rpn_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   return DC_OK;
 }
@@ -1345,13 +1375,8 @@ extern "C" int dc_localization_backward_train(dc_ctx* ctx, const float* feats_nc
   if ((rc = k_bwd_relu_mask(ctx, b.gh, ctx->rpn_hidden.base, ctx->rpn_hidden.base + gplane, gplane, b.gh_planes, b.gh_planes + gplane, b.hid_f32, st)))
     return rc;
   // 3x3 conv, backward data = 3x3 conv of grad_hidden with the flipped / transposed bank (no bias, no ReLU)
-  if (c.engine == DC_ENGINE_TC) {
-    rc = k_tc_conv3x3(ctx, b.gh_planes, gplane, wcb->planes, wcb->plane_elems, nullptr, wcb->inv_scale, b.grpn_planes, b.grpn_planes + plane, 1, feat_h,
-                      feat_w, F, C5, 0, st, 0);
-  } else {
-    rc = k_simt_conv3x3(ctx, b.gh_planes, b.gh_planes + gplane, wcb->planes, wcb->planes + wcb->plane_elems, nullptr, wcb->inv_scale, b.grpn_planes,
-                        b.grpn_planes + plane, 1, feat_h, feat_w, F, C5, st, 0);
-  }
+  rc = k_tc_conv3x3(ctx, b.gh_planes, gplane, wcb->planes, wcb->plane_elems, nullptr, wcb->inv_scale, b.grpn_planes, b.grpn_planes + plane, 1, feat_h,
+                    feat_w, F, C5, 0, st, 0);
   if (rc) return rc;
   if ((rc = k_bwd_combine(ctx, b.gfeat_roi, b.grpn_planes, b.grpn_planes + plane, C5, cells, grad_feats_nchw, st))) return rc;
   // ---- accGradParameters: gradWeight / gradBias of the RPN convolutions accumulate until dc_zero_grad_parameters
@@ -1432,7 +1457,10 @@ extern "C" int dc_lm_sample(dc_ctx* ctx, const float* codes, int K, int64_t* seq
   int rc;
   if ((rc = k_rowmajor_to_split(ctx, codes, ctx->fc7o.base, ctx->fc7o.base + fplane, fplane, st))) return rc;
   ctx->timer.used = 0;
-  if ((rc = run_lm(ctx, K, logits, st))) return rc;
+  if ((rc = run_lm_encoder(ctx, K, st))) return rc;
+  set_count_kernel<<<1, 1, 0, st>>>(ctx->dec_count1, K);
+  DC_CHECK_LAUNCH(ctx);
+  if ((rc = run_lm_decode(ctx, 1, K, ctx->dec_count1, nullptr, 0, nullptr, logits, st))) return rc;
   DC_CHECK_CUDA(ctx, cudaMemcpyAsync(seq, ctx->seq64, (size_t)K * T * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   return DC_OK;
 }
@@ -1540,11 +1568,10 @@ struct TmpBufs {
   }
 };
 
-extern "C" int dc_linear(dc_ctx* ctx, const float* x, const float* w, const float* b, float* y, int M, int N, int K, int relu, int engine, void* stream) {
+extern "C" int dc_linear(dc_ctx* ctx, const float* x, const float* w, const float* b, float* y, int M, int N, int K, int relu, void* stream) {
   if (!ctx || !x || !w || !y) return dc_set_error(ctx, DC_E_INVALID, "dc_linear: null argument");
   DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == DC_ENGINE_TC) { int rc = tc_init(ctx); if (rc) return rc; }
   TmpBufs tmp;
   const size_t ap = align_up((size_t)M * K, 64), bp = align_up((size_t)N * K, 64);
   __half* a = tmp.get<__half>(2 * ap);
@@ -1558,8 +1585,7 @@ extern "C" int dc_linear(dc_ctx* ctx, const float* x, const float* w, const floa
   GemmEpilogue ep;
   ep.acc_scale = 1.f / sc;
   ep.bias = b; ep.relu = relu; ep.out_f32 = y; ep.ldf = N;
-  if (engine == DC_ENGINE_TC) rc = k_tc_gemm(ctx, a, ap, K, bw, bp, K, M, N, K, ep, st);
-  else rc = k_simt_gemm(ctx, a, a + ap, K, bw, bw + bp, K, M, N, K, ep, st);
+  rc = k_tc_gemm(ctx, a, ap, K, bw, bp, K, M, N, K, ep, st);
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc) return rc;
   if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "dc_linear: %s", cudaGetErrorString(e));
@@ -1567,11 +1593,10 @@ extern "C" int dc_linear(dc_ctx* ctx, const float* x, const float* w, const floa
 }
 
 extern "C" int dc_conv3x3_relu(dc_ctx* ctx, const float* x, const float* w, const float* b, float* y, int N, int Cin, int Cout, int H, int W, int pool,
-                               int engine, void* stream) {
+                               void* stream) {
   if (!ctx || !x || !w || !y) return dc_set_error(ctx, DC_E_INVALID, "dc_conv3x3_relu: null argument");
   DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == DC_ENGINE_TC) { int rc = tc_init(ctx); if (rc) return rc; }
   TmpBufs tmp;
   const size_t xp = align_up((size_t)N * H * W * Cin, 64), wp = align_up((size_t)Cout * 9 * Cin, 64), yp = align_up((size_t)N * H * W * Cout, 64);
   const int PH = (H + 1) / 2, PW = (W + 1) / 2;
@@ -1588,15 +1613,10 @@ extern "C" int dc_conv3x3_relu(dc_ctx* ctx, const float* x, const float* w, cons
   if ((rc = weight_scale(ctx, w, (size_t)Cout * Cin * 9, &sc, st))) return rc;
   if ((rc = k_conv_weight_to_split(ctx, w, ws, ws + wp, Cout, Cin, st, sc))) return rc;
   const float isc = 1.f / sc;
-  if (engine == DC_ENGINE_TC) {
-    if (pool == 2) {        // fused pool epilogue
-      rc = k_tc_conv3x3(ctx, xs, xn, ws, wp, b, isc, ps, ps + pn, N, H, W, Cin, Cout, 1, st);
-    } else {
-      rc = k_tc_conv3x3(ctx, xs, xn, ws, wp, b, isc, ys, ys + yn, N, H, W, Cin, Cout, 0, st);
-      if (!rc && pool) rc = k_maxpool2x2_split(ctx, ys, ys + yn, ps, ps + pn, N, H, W, Cout, 1, st);
-    }
+  if (pool == 2) {        // fused pool epilogue
+    rc = k_tc_conv3x3(ctx, xs, xn, ws, wp, b, isc, ps, ps + pn, N, H, W, Cin, Cout, 1, st);
   } else {
-    rc = k_simt_conv3x3(ctx, xs, xs + xn, ws, ws + wp, b, isc, ys, ys + yn, N, H, W, Cin, Cout, st);
+    rc = k_tc_conv3x3(ctx, xs, xn, ws, wp, b, isc, ys, ys + yn, N, H, W, Cin, Cout, 0, st);
     if (!rc && pool) rc = k_maxpool2x2_split(ctx, ys, ys + yn, ps, ps + pn, N, H, W, Cout, 1, st);
   }
   if (!rc) {

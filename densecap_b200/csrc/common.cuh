@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -46,6 +47,26 @@ __device__ __forceinline__ float join_f32(__half hi, __half lo) {
 struct dc_ctx;
 int dc_set_error(dc_ctx* ctx, int code, const char* fmt, ...);
 void dc_count_launch(dc_ctx* ctx, int n = 1);
+
+// Launcher state owned by ONE context (a process may hold several contexts on different GPUs; nothing here is process-global):
+// the driver entry point for tensor-map encoding, the SM count of the context's device, and which kernels already had their
+// dynamic shared-memory limit raised on that device.
+struct LaunchState {
+  void* encode_tiled = nullptr;            // cuTensorMapEncodeTiled (resolved by tc_init)
+  int num_sms = 148;
+  std::set<const void*> smem_attr_done;    // kernel function pointers
+};
+LaunchState* dc_launch_state(dc_ctx* ctx);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (context, kernel)
+template <typename Kernel>
+static inline cudaError_t dc_ensure_smem(dc_ctx* ctx, Kernel kernel, size_t bytes) {
+  LaunchState* ls = dc_launch_state(ctx);
+  const void* key = reinterpret_cast<const void*>(kernel);
+  if (ls->smem_attr_done.count(key)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) ls->smem_attr_done.insert(key);
+  return e;
+}
 
 #define DC_CHECK_CUDA(ctx, expr)                                                            \
   do {                                                                                      \
@@ -149,7 +170,7 @@ int k_transpose_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int ro
 int k_bchw_to_split_rows(dc_ctx*, const float* in, __half* hi, __half* lo, int K, int C, int hw, cudaStream_t st);
 int k_bhwc_split_to_bchw(dc_ctx*, const __half* hi, const __half* lo, float* out, int K, int C, int hw, cudaStream_t st);
 
-// simt_kernels.cu : fp32 CUDA-core engine on the same split layout
+// epilogue description shared by the GEMM launchers
 struct GemmEpilogue {
   float acc_scale = 1.f;          // accumulator multiplier (exact power of two undoing the weight pre-scaling)
   const float* bias = nullptr;    // (N) or null
@@ -167,10 +188,7 @@ struct GemmEpilogue {
   int lstm_H = 0;
   int lstm_first = 0;             // 1: c_{t-1} = 0
 };
-int k_simt_gemm(dc_ctx*, const __half* a_hi, const __half* a_lo, int lda, const __half* b_hi, const __half* b_lo, int ldb,
-                int M, int N, int K, GemmEpilogue ep, cudaStream_t st);
-int k_simt_conv3x3(dc_ctx*, const __half* x_hi, const __half* x_lo, const __half* w_hi, const __half* w_lo,
-                   const float* bias, float acc_scale, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, cudaStream_t st, int relu = 1);
+// small_dense_kernels.cu
 // conv1_1: NCHW fp32 (N,3,H,W) -> split NHWC (N,H,W,Cout), bias+ReLU fused.  w (Cout,3,3,3) fp32 reference layout.
 int k_conv_first(dc_ctx*, const float* img, const float* w, const float* bias, __half* y_hi, __half* y_lo,
                  int N, int H, int W, int Cout, cudaStream_t st);
@@ -187,13 +205,29 @@ int k_tc_conv3x3(dc_ctx*, const __half* x_planes, size_t x_plane_elems, const __
                  const float* bias, float acc_scale, __half* y_hi, __half* y_lo, int N, int H, int W, int Cin, int Cout, int fuse_pool,
                  cudaStream_t st, int relu = 1);
 
+// lm_decode.cu : persistent caption decoder (LanguageModel:sample over the rows to decode of all images of a batch)
+struct LmDecodeArgs {
+  int B, P, E, H, V, T;                     // images, row stride per image, encoding / rnn size, vocabulary, steps
+  const int32_t* counts;                    // (B) device: rows to decode per image
+  const int32_t* idx32;                     // (B*P) device: per-image source row of each row to decode, or null = identity
+  int survivors;                            // 1: rows are final-NMS survivors, tokens go to fin_seq rows b*P+i (and all_seq[src])
+  const __half* enc_planes; size_t enc_plane_elems;       // (B*P, E) split: encoded image vectors of every proposal
+  __half* xh_planes;                        // [hi: buf0, buf1][lo: buf0, buf1], each (B*P, E+H)
+  float* cstate;                            // (B*P, H)
+  const __half* lstm_planes; size_t lstm_plane_elems; const float* lstm_bias; float lstm_acc_scale;
+  const __half* vocab_planes; size_t vocab_plane_elems; const float* vocab_bias; float vocab_acc_scale;
+  const __half* lut_planes; size_t lut_plane_elems;
+  unsigned long long* packed;               // (B*P)
+  uint32_t* counters;                       // lm_decode_counter_words(T, B*P) words
+  int32_t* m_rows;                          // (1) device out: total rows decoded
+  int32_t* dst_final; int32_t* dst_all;     // (B*P) scratch
+  int64_t* fin_seq; int64_t* all_seq;       // (B*P, T) token outputs (all_seq may be null)
+  float* logits;                            // optional (rows, T, V+1)
+};
+size_t lm_decode_counter_words(int T, int rows_cap);
+int k_lm_decode(dc_ctx*, const LmDecodeArgs& a, cudaStream_t st);
+
 // lm_kernels.cu
-// One launch per decode step t (0..T): finishes step t-1 (arg-max -> token t-1 -> seq) and prepares step t
-// (lookup row of the token -> x half of [x|h], reset of the packed arg-max cells).  t == T only finishes.
-int k_lm_token_step(dc_ctx*, unsigned long long* packed, int32_t* tokens, int64_t* seq64, int T, int t, int start_token,
-                    const __half* lut_hi, const __half* lut_lo, int E, __half* xh_hi, __half* xh_lo, int ld, int M, cudaStream_t st);
-int k_lstm_pointwise(dc_ctx*, const float* gates, float* c, __half* xh_hi, __half* xh_lo, int ld, int col0, int M, int H,
-                     int first, cudaStream_t st);
 int k_final_gather(dc_ctx*, const int32_t* idx32, const int32_t* count, int P, const float* boxes, const float* scores,
                    const int64_t* seq, int T, float* out_boxes, float* out_scores, int64_t* out_seq, cudaStream_t st);
 int k_gather_rows_f32(dc_ctx*, const float* src, int cols, const int32_t* idx32, const int32_t* count, int max_rows, float* dst,

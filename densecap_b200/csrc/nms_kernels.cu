@@ -415,13 +415,11 @@ int k_nms(dc_ctx* ctx, const float* boxes, int box_stride, const float* scores, 
     return DC_OK;
   }
   DC_REQUIRE(ctx, n_max <= ws.cap, DC_E_INVALID, "nms: %d boxes exceed workspace capacity %d", n_max, ws.cap);
-  static bool attr_set = false;
   const size_t smem = (size_t)NMS_M * NMS_W * sizeof(uint64_t) + (size_t)NMS_M * sizeof(int);
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = dc_ensure_smem(ctx, nms_cluster_kernel, smem);
+    if (e == cudaSuccess) e = dc_ensure_smem(ctx, nms_scan_kernel, smem);
     if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "nms smem attribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   nms_keys_kernel<<<DC_CEIL_DIV(n_max, 256), 256, 0, st>>>(scores, score_stride, n_max, n_dev, ws.keys, ws.rank, state, count_out);
   DC_CHECK_LAUNCH(ctx);

@@ -221,12 +221,12 @@ int k_roi_pool(dc_ctx* ctx, const __half* feat_hi, const __half* feat_lo, const 
   DC_CHECK_LAUNCH(ctx);
   DC_REQUIRE(ctx, smem <= limit && C % ch == 0, DC_E_UNSUPPORTED, "roi_pool: feature map %dx%d too large for the shared-memory slice", fh, fw);
   const int slices = C / ch;
-  int groups = 148 / slices;
+  int groups = dc_launch_state(ctx)->num_sms / slices;
   if (groups < 1) groups = 1;
   dim3 grid(slices, groups);
 #define ROI_LAUNCH(CHV)                                                                                              \
   do {                                                                                                               \
-    cudaError_t e = cudaFuncSetAttribute(roi_pool_kernel<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaError_t e = dc_ensure_smem(ctx, roi_pool_kernel<CHV>, limit);                                                  \
     if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "roi_pool smem attribute: %s", cudaGetErrorString(e));    \
     cudaLaunchConfig_t lc = {};                                                                                      \
     lc.gridDim = grid; lc.blockDim = dim3(ROI_THREADS); lc.dynamicSmemBytes = smem; lc.stream = st;                   \

@@ -119,8 +119,9 @@ class LocalizationLayer:
         self.test_clip_boxes = args.get("clip_boxes", True)
         self.test_nms_thresh = args.get("nms_thresh", 0.7)
         self.test_max_proposals = min(args.get("max_proposals", 300), self.ctx.max_proposals)   # reference default 300
-        self._final_thresh = args.get("final_nms_thresh", 0.3)
-        self.ctx.set_test_args(self.test_nms_thresh, self._final_thresh, self.test_max_proposals, self.test_clip_boxes)
+        # final_nms_thresh belongs to DenseCapModel (DenseCapModel.lua:185-191); the layer's setTestArgs touches only nms_thresh,
+        # max_proposals and clip_boxes (LocalizationLayer.lua:233-238), so the context's current final threshold is passed through
+        self.ctx.set_test_args(self.test_nms_thresh, None, self.test_max_proposals, self.test_clip_boxes)
 
     def evaluate(self):
         self.train = False
@@ -191,8 +192,7 @@ class LanguageModel:
 class DenseCapModel:
     """DenseCapModel test-time API (DenseCapModel.lua:185-191, 242-282, 319-327)."""
 
-    def __init__(self, opt=None, weights=None, device=0, max_batch=1, max_image_hw=(600, 720), engine=_lib.DC_ENGINE_TC,
-                 fuse_pool=True):
+    def __init__(self, opt=None, weights=None, device=0, max_batch=1, max_image_hw=(600, 720), fuse_pool=True):
         opt = dict(opt or {})
         self.opt = opt
         dims = opt.get("dims") or ModelDims(vocab_size=opt.get("vocab_size", 10497), seq_length=opt.get("seq_length", 15),
@@ -200,7 +200,7 @@ class DenseCapModel:
         self.dims = dims
         self.opt.setdefault("final_nms_thresh", 0.3)
         self.ctx = Context(dims, device=device, max_batch=max_batch, max_image_hw=max_image_hw,
-                           max_proposals=opt.get("max_proposals", 1000), engine=engine, fuse_pool=fuse_pool,
+                           max_proposals=opt.get("max_proposals", 1000), fuse_pool=fuse_pool,
                            pool_ceil=opt.get("pool_ceil", True))
         self.train = False
         self.nets = {"localization_layer": LocalizationLayer(self.ctx),
@@ -210,7 +210,7 @@ class DenseCapModel:
             self.ctx.load_weights(weights)
 
     @classmethod
-    def from_checkpoint(cls, path, device=0, max_batch=1, max_image_hw=(600, 720), max_proposals=1000, engine=_lib.DC_ENGINE_TC):
+    def from_checkpoint(cls, path, device=0, max_batch=1, max_image_hw=(600, 720), max_proposals=1000):
         """`torch.load(opt.checkpoint).model` (run_model.lua:146-149) for a Torch7 .t7 checkpoint written by train.lua:184:
         parses the file (densecap_b200/t7.py), maps the module tree onto dc_load_weights names and sizes the context from
         the tensor shapes.  Returns a ready DenseCapModel with its idx_to_token vocabulary."""
@@ -227,7 +227,7 @@ class DenseCapModel:
         if isinstance(tok, dict):
             tok = {int(k): v for k, v in tok.items()}
         return cls({"dims": dims, "max_proposals": max_proposals, "idx_to_token": tok}, weights=weights, device=device, max_batch=max_batch,
-                   max_image_hw=max_image_hw, engine=engine)
+                   max_image_hw=max_image_hw)
 
     def evaluate(self):
         self.train = False
@@ -313,5 +313,6 @@ def _wrap_result(res, dims, device):
         "all_scores": _dev_tensor(res.all_scores, (rows,), torch.float32, device),
         "all_seq": _dev_tensor(res.all_seq, (rows, T), torch.int64, device),
         "codes": _dev_tensor(res.codes, (rows, dims.fc_dim), torch.float32, device),
+        "proposal_idx": _dev_tensor(res.proposal_idx, (rows,), torch.int64, device),
         "max_proposals": P,
     }

@@ -33,7 +33,7 @@ class Context:
     """Owns one dc_ctx (weights + workspace arena) on one GPU.  One Context per GPU; single-threaded."""
 
     def __init__(self, dims: ModelDims = None, device=0, max_batch=1, max_image_hw=(600, 720), max_proposals=1000,
-                 engine=_lib.DC_ENGINE_TC, fuse_pool=True, pool_ceil=True, anchors=None, field_centers=None):
+                 fuse_pool=True, pool_ceil=True, anchors=None, field_centers=None):
         lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("densecap_b200 needs a CUDA device (B200 / sm_100a); no CPU fallback exists")
@@ -56,7 +56,6 @@ class Context:
         cfg.max_batch = max_batch
         cfg.max_image_h, cfg.max_image_w = max_image_hw
         cfg.max_proposals = max_proposals
-        cfg.engine = engine
         cfg.fuse_pool = 1 if fuse_pool else 0
         if anchors is not None:
             a = np.asarray(anchors, np.float32)
@@ -98,8 +97,16 @@ class Context:
             self.check(self._lib.dc_load_weights(self.handle, name.encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim))
 
     def set_test_args(self, rpn_nms_thresh=0.7, final_nms_thresh=0.3, num_proposals=1000, clip_boxes=True):
+        """final_nms_thresh=None keeps the value of the last call (the LocalizationLayer does not own that option)."""
+        if final_nms_thresh is None:
+            final_nms_thresh = getattr(self, "_final_nms_thresh", 0.3)
+        self._final_nms_thresh = float(final_nms_thresh)
         self.check(self._lib.dc_set_test_args(self.handle, float(rpn_nms_thresh), float(final_nms_thresh), int(num_proposals),
                                               1 if clip_boxes else 0))
+
+    def set_decode_all(self, on=True):
+        """Decode a caption for every proposal (fills `all_seq`) instead of only for the rows kept by the final NMS."""
+        self.check(self._lib.dc_set_decode_all(self.handle, 1 if on else 0))
 
     def enable_timing(self, on=True):
         self.check(self._lib.dc_enable_timing(self.handle, 1 if on else 0))
@@ -126,7 +133,7 @@ def default_context(device=0, min_boxes=0):
         cells = max(2048, (min_boxes + k - 1) // k)
         side = int(np.ceil(np.sqrt(cells)))
         dims = ModelDims(widths=(64, 64, 64, 64, 512), fc_dim=64, vocab_size=64, rnn_size=64, encoding_size=64)
-        ctx = Context(dims, device=device, max_image_hw=(side * 16, side * 16), max_proposals=64, engine=_lib.DC_ENGINE_SIMT)
+        ctx = Context(dims, device=device, max_image_hw=(side * 16, side * 16), max_proposals=64)
         ctx._cap_boxes = k * side * side
         _DEFAULT_CTX[key] = ctx
     return ctx

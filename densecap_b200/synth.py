@@ -60,7 +60,12 @@ def feature_hw(h, w, pool_ceil=True):
 def make_weights(dims: ModelDims, seed=0, box_variant="A"):
     """box_variant 'A': reference default init (RPN box conv and final box_reg zero ->
     proposals are clipped anchors; LocalizationLayer.lua:645-646, DenseCapModel.lua:98-99).
-    'B': small random box heads so that exp()/transform paths are exercised."""
+    'B': small random box heads so that exp()/transform paths are exercised.
+    'C': 'B' with conv1_1 scaled by 1/64, i.e. the input normalised to unit scale.  He-init VGG preserves the variance of its
+         +-128 input, so with 'A'/'B' the conv5_3 features are O(100) where a trained VGG's are O(1): at 720x600 the RPN score
+         differences then have std ~20 and ~20 % of the 20,520 objectness probabilities round to exactly 1.0f (mass ties whose
+         membership flips on last-bit noise), and 'B' box deltas reach exp(40).  'C' keeps every stage in the numeric range of a
+         trained model (scores spread over (0,1), |tw| < 1): the well-conditioned full-size parity workload."""
     rng = np.random.default_rng(np.random.PCG64(seed))
     w = {}
 
@@ -70,9 +75,14 @@ def make_weights(dims: ModelDims, seed=0, box_variant="A"):
     def uniform(shape, a):
         return rng.uniform(-a, a, size=shape).astype(np.float32)
 
+    calibrated = (box_variant == "C")
+    if calibrated:
+        box_variant = "B"
     for name, cout, cin in dims.conv_shapes():
         w[name + ".weight"] = normal((cout, cin, 3, 3), np.sqrt(2.0 / (9 * cin)))
         w[name + ".bias"] = np.zeros((cout,), np.float32)
+    if calibrated:
+        w["conv1_1.weight"] = (w["conv1_1.weight"] * np.float32(1.0 / 64.0)).astype(np.float32)
     C = dims.feat_dim
     k = dims.num_anchors
     F = dims.rpn_filters

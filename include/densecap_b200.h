@@ -38,12 +38,6 @@ extern "C" {
 
 #define DC_MAX_ANCHORS 32
 
-/* GEMM/conv engine.  TC = tcgen05 tensor cores on error-compensated split-fp16 operands
- * (fp32-class accuracy, fp32 accumulate in TMEM).  SIMT = plain fp32 CUDA-core kernels
- * (bring-up / on-device cross-check path; same data layout). */
-#define DC_ENGINE_TC   0
-#define DC_ENGINE_SIMT 1
-
 typedef struct dc_ctx dc_ctx;
 
 /* Effective defaults = the reference's (DenseCapModel.lua:22-43,61-67;
@@ -62,8 +56,8 @@ typedef struct dc_config {
   int32_t max_batch;        /* images per dc_forward_test call (reference: 1)                */
   int32_t max_image_h, max_image_w;
   int32_t max_proposals;    /* capacity for num_proposals (default 1000)                     */
-  int32_t engine;           /* DC_ENGINE_*                                                   */
-  int32_t fuse_pool;        /* 1 = 2x2 max-pool fused into the conv epilogue (TC engine)     */
+  int32_t reserved0;        /* must be 0 (was: engine selector; the library has ONE dense engine, tcgen05) */
+  int32_t fuse_pool;        /* 1 = 2x2 ceil-mode max-pool fused into the conv epilogue        */
   float   anchors[2 * DC_MAX_ANCHORS]; /* (2,k) row-major: widths then heights               */
   float   field_centers[4]; /* x0, y0, sx, sy; default 8.5, 8.5, 16, 16                      */
 } dc_config;
@@ -85,8 +79,11 @@ typedef struct dc_result {
   const float*   box_trans;      /* (batch*P,4) final box transforms, unfiltered    output[3]    */
   const float*   all_boxes;      /* (batch*P,4) final boxes before the final NMS                 */
   const float*   all_scores;     /* (batch*P)                                                    */
-  const int64_t* all_seq;        /* (batch*P,T)                                                  */
+  const int64_t* all_seq;        /* (batch*P,T) tokens by proposal row; rows dropped by the final NMS are 0
+                                    unless dc_set_decode_all(ctx, 1)                               */
   const float*   codes;          /* (batch*P,fc_dim) fc7 codes (recog_base output)               */
+  const int64_t* proposal_idx;   /* (batch*P)   1-based row, among the clipped-valid RPN boxes, of each proposal
+                                    (`idx` of LocalizationLayer.lua:322-338; dump_vars 'rpn_idx')    */
 } dc_result;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -108,6 +105,11 @@ int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_host,
 /* DenseCapModel:setTestArgs (DenseCapModel.lua:185-191) + LocalizationLayer:setTestArgs (:233-238) */
 int dc_set_test_args(dc_ctx* ctx, float rpn_nms_thresh, float final_nms_thresh,
                      int num_proposals, int clip_boxes);
+/* The reference decodes a caption for every proposal and then keeps only the rows selected by the final NMS
+ * (DenseCapModel.lua:261-275).  By default this library runs the final NMS first and decodes only the surviving rows (rows are
+ * independent, so output[5] is identical).  enable = 1 decodes every proposal, which fills dc_result.all_seq completely
+ * (debugging / parity of the unfiltered LM output). */
+int dc_set_decode_all(dc_ctx* ctx, int enable);
 /* LocalizationLayer:setImageSize (LocalizationLayer.lua:167-172): must precede each forward. */
 int dc_set_image_size(dc_ctx* ctx, int image_h, int image_w);
 
@@ -149,6 +151,15 @@ int dc_vgg_trunk_forward(dc_ctx* ctx, const float* img, int batch, int image_h, 
 int dc_localization_forward_test(dc_ctx* ctx, const float* feats_nchw, int feat_h, int feat_w,
                                  float* roi_features, float* roi_boxes, int64_t* idx,
                                  int32_t* num_out, void* stream);
+
+/* The second half of LocalizationLayer:_forward_test (LocalizationLayer.lua:262-338) on the RPN's raw outputs as the
+ * reference's nn.Sequential RPN returns them: rpn_trans (1,4k,H',W') and rpn_scores (1,2k,H',W') fp32 NCHW (channel 4a+d /
+ * 2a+d).  MakeAnchors + ReshapeBoxFeatures + ApplyBoxTransform + clip_boxes + objectness + box_utils.nms + the index gathers.
+ * Every step is exact fp32 arithmetic in the reference's operation order, so idx is bit-exact for identical inputs.
+ * Requires dc_set_image_size (consumed).  Outputs (any may be NULL): roi_boxes (K,4) xcycwh; idx (K) 1-based int64 rows
+ * among the clipped-valid boxes, in pick order; num_out (1) int32 = K.  Capacity num_proposals rows. */
+int dc_rpn_proposals(dc_ctx* ctx, const float* rpn_trans_nchw, const float* rpn_scores_nchw, int feat_h, int feat_w,
+                     float* roi_boxes, int64_t* idx, int32_t* num_out, void* stream);
 
 /* ---- training step of the LocalizationLayer (BASELINE configs[4]): forward + backward
  * Options of nn.LocalizationLayer used by _forward_train (LocalizationLayer.lua:79-87; train_opts.lua:18-42).
@@ -245,13 +256,14 @@ int dc_box_iou(const float* box1, const float* box2, float* out, int B1, int B2,
 
 /* ---- dense kernels exposed for parity tests / micro-benchmarks --------------------------
  * y = act(x W^T + b), x (M,K) fp32, W (N,K) fp32 (nn.Linear layout), y (M,N) fp32.
- * engine: DC_ENGINE_TC or DC_ENGINE_SIMT.  relu: 0/1.  K must be a multiple of 64. */
+ * relu: 0/1.  K must be a multiple of 64. */
 int dc_linear(dc_ctx* ctx, const float* x, const float* w, const float* b, float* y,
-              int M, int N, int K, int relu, int engine, void* stream);
+              int M, int N, int K, int relu, void* stream);
 /* y = relu(conv3x3(x) + b) [+ optional 2x2 ceil max-pool], x (N,Cin,H,W) fp32 NCHW,
- * w (Cout,Cin,3,3), y (N,Cout,H,W) or pooled.  Cin must be a multiple of 64 for DC_ENGINE_TC. */
+ * w (Cout,Cin,3,3), y (N,Cout,H,W) or pooled (pool 1: stand-alone pooling kernel, 2: fused epilogue).
+ * Cin must be a multiple of 64. */
 int dc_conv3x3_relu(dc_ctx* ctx, const float* x, const float* w, const float* b, float* y,
-                    int N, int Cin, int Cout, int H, int W, int pool, int engine, void* stream);
+                    int N, int Cin, int Cout, int H, int W, int pool, void* stream);
 
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Per-phase device times of the last dc_forward_test (milliseconds, cudaEvent based), in the

@@ -1,4 +1,4 @@
-"""GPU parity of the dense kernels (tcgen05 split-fp16 engine and the fp32 CUDA-core engine)
+"""GPU parity of the dense tcgen05 split-fp16 kernels
 against an fp64 torch reference of the same op: y = act(x W^T + b) and 3x3 conv + bias + ReLU
 (+ 2x2 ceil max-pool).  Tolerance: 1e-4 relative to the output scale (BASELINE north_star);
 the split-fp16 scheme is expected to land around 1e-6."""
@@ -10,15 +10,13 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-TC, SIMT = 0, 1
-
 
 @pytest.fixture(scope="module")
 def ctx():
     from densecap_b200.runtime import Context
     from densecap_b200.synth import ModelDims
     d = ModelDims(widths=(64, 64, 64, 64, 64), fc_dim=64, vocab_size=64, rnn_size=64, encoding_size=64, seq_length=2)
-    c = Context(d, max_image_hw=(64, 64), max_proposals=64, engine=SIMT)
+    c = Context(d, max_image_hw=(64, 64), max_proposals=64)
     yield c
     c.close()
 
@@ -32,13 +30,13 @@ def rel_err(got, ref):
     return ((got.double() - ref).abs().max().item()) / scale
 
 
-def run_linear(ctx, M, N, K, relu, engine, seed=0, bias=True):
+def run_linear(ctx, M, N, K, relu, seed=0, bias=True):
     g = torch.Generator(device="cpu").manual_seed(seed)
     x = torch.randn(M, K, generator=g).cuda()
     w = (torch.randn(N, K, generator=g) / np.sqrt(K)).cuda()
     b = torch.randn(N, generator=g).cuda() if bias else None
     y = torch.full((M, N), float("nan"), device="cuda")
-    ctx.check(ctx._lib.dc_linear(ctx.handle, p(x), p(w), p(b), p(y), M, N, K, relu, engine, None))
+    ctx.check(ctx._lib.dc_linear(ctx.handle, p(x), p(w), p(b), p(y), M, N, K, relu, None))
     ref = x.double() @ w.double().t()
     if bias:
         ref = ref + b.double()
@@ -47,16 +45,10 @@ def run_linear(ctx, M, N, K, relu, engine, seed=0, bias=True):
     return y, ref
 
 
-@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (130, 72, 128), (257, 100, 192)])
-def test_simt_linear(ctx, M, N, K):
-    y, ref = run_linear(ctx, M, N, K, 1, SIMT)
-    assert rel_err(y, ref) < 1e-5
-
-
 @pytest.mark.parametrize("M,N,K,relu", [(128, 64, 64, 0), (128, 128, 64, 0), (128, 128, 256, 1), (1, 64, 64, 0),
                                         (300, 200, 512, 1), (1000, 72, 256, 0), (257, 1030, 1024, 0), (1000, 4096, 4096, 1)])
 def test_tc_linear(ctx, M, N, K, relu):
-    y, ref = run_linear(ctx, M, N, K, relu, TC, seed=M + N + K)
+    y, ref = run_linear(ctx, M, N, K, relu, seed=M + N + K)
     assert not torch.isnan(y).any(), "output rows left unwritten"
     e = rel_err(y, ref)
     assert e < 2e-5, "tcgen05 linear M=%d N=%d K=%d rel err %.3e" % (M, N, K, e)
@@ -64,29 +56,23 @@ def test_tc_linear(ctx, M, N, K, relu):
 
 def test_tc_linear_is_fp32_class_accurate(ctx):
     # the split scheme must beat a single fp16 pass by orders of magnitude
-    y, ref = run_linear(ctx, 256, 256, 2048, 0, TC, seed=7, bias=False)
+    y, ref = run_linear(ctx, 256, 256, 2048, 0, seed=7, bias=False)
     e = rel_err(y, ref)
     assert e < 2e-5, e   # fp32-accumulate class (a single fp16 pass would be ~5e-4)
 
 
-def run_conv(ctx, N, Cin, Cout, H, W, pool, engine, seed=0):
+def run_conv(ctx, N, Cin, Cout, H, W, pool, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     x = torch.randn(N, Cin, H, W, generator=g).cuda()
     w = (torch.randn(Cout, Cin, 3, 3, generator=g) * np.sqrt(2.0 / (9 * Cin))).cuda()
     b = (torch.randn(Cout, generator=g) * 0.1).cuda()
     oh, ow = ((H + 1) // 2, (W + 1) // 2) if pool else (H, W)
     y = torch.full((N, Cout, oh, ow), float("nan"), device="cuda")
-    ctx.check(ctx._lib.dc_conv3x3_relu(ctx.handle, p(x), p(w), p(b), p(y), N, Cin, Cout, H, W, pool, engine, None))
+    ctx.check(ctx._lib.dc_conv3x3_relu(ctx.handle, p(x), p(w), p(b), p(y), N, Cin, Cout, H, W, pool, None))
     ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1).clamp_min(0)
     if pool:
         ref = torch.nn.functional.max_pool2d(ref, 2, 2, 0, ceil_mode=True)
     return y, ref
-
-
-@pytest.mark.parametrize("N,Cin,Cout,H,W,pool", [(1, 64, 64, 9, 11, 0), (2, 64, 128, 16, 16, 1)])
-def test_simt_conv(ctx, N, Cin, Cout, H, W, pool):
-    y, ref = run_conv(ctx, N, Cin, Cout, H, W, pool, SIMT)
-    assert rel_err(y, ref) < 1e-5
 
 
 @pytest.mark.parametrize("N,Cin,Cout,H,W,pool", [
@@ -104,7 +90,7 @@ def test_simt_conv(ctx, N, Cin, Cout, H, W, pool):
     (1, 512, 512, 38, 45, 0),     # conv5 shape: 8 channel blocks per tap through the 9-stage B ring
 ])
 def test_tc_conv(ctx, N, Cin, Cout, H, W, pool):
-    y, ref = run_conv(ctx, N, Cin, Cout, H, W, pool, TC, seed=H * W + Cin)
+    y, ref = run_conv(ctx, N, Cin, Cout, H, W, pool, seed=H * W + Cin)
     assert not torch.isnan(y).any(), "output pixels left unwritten"
     e = rel_err(y, ref)
     assert e < 2e-5, "tcgen05 conv rel err %.3e" % e

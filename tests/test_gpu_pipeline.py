@@ -1,5 +1,5 @@
 """GPU parity of the composed stages and of the whole test-time forward against the CPU oracle,
-on a small random-init model (sizes the oracle finishes in seconds), for both engines; plus
+on a small random-init model (sizes the oracle finishes in seconds); plus
 size-independent property checks at the BASELINE size (720x600, 1000 proposals, 15 tokens)."""
 import numpy as np
 import pytest
@@ -10,7 +10,6 @@ from densecap_b200.synth import ModelDims, make_weights, make_image, feature_hw
 
 pytestmark = pytest.mark.gpu
 
-TC, SIMT = 0, 1
 SMALL = dict(widths=(64, 64, 64, 64, 64), rpn_filters=64, fc_dim=128, rnn_size=64, encoding_size=64, vocab_size=200, seq_length=5)
 IMG_H, IMG_W = 96, 128
 NPROP = 50
@@ -35,11 +34,26 @@ def small():
     return dims, weights, img, cfg, ref
 
 
-@pytest.fixture(scope="module", params=[SIMT, TC], ids=["simt", "tc"])
-def model(request, small):
+def gold_of(img, weights, cfg):
+    """The same restatement re-run in float64: |oracle_fp32 - gold| is the fp32 noise floor of the reference path itself on this
+    input, the yardstick for every chained (end-to-end) tolerance below."""
+    with O.precision(np.float64):
+        return O.densecap_forward_test(img, weights, cfg, return_intermediates=True)
+
+
+def assert_within_fp32_noise(got, ref32, gold, what, factor=2.0):
+    """|got - gold| <= factor * |oracle_fp32 - gold| (max-norm, relative to the tensor scale) -- the GPU result may not be
+    further from the fp64 truth than `factor` times the fp32 oracle is."""
+    e = rel(got, gold); floor = rel(ref32, gold)
+    assert e <= factor * floor + 1e-6, "%s: |gpu - fp64| = %.3g exceeds %.1f x the oracle's own fp32 noise %.3g" % (what, e, factor, floor)
+    return e, floor
+
+
+@pytest.fixture(scope="module")
+def model(small):
     from densecap_b200.model import DenseCapModel
     dims, weights, img, cfg, ref = small
-    m = DenseCapModel({"dims": dims, "max_proposals": 64}, weights=weights, max_image_hw=(IMG_H, IMG_W), engine=request.param)
+    m = DenseCapModel({"dims": dims, "max_proposals": 64}, weights=weights, max_image_hw=(IMG_H, IMG_W))
     m.setTestArgs({"rpn_nms_thresh": 0.7, "final_nms_thresh": 0.3, "num_proposals": NPROP})
     yield m
     m.ctx.close()
@@ -143,20 +157,42 @@ def test_full_forward_matches_oracle(model, small):
     r = model._last
     K = int(r["num_proposals"][0])
     assert K == ref["ll"]["boxes"].shape[0]
-    # proposals through the GPU's own trunk: per-stage parity is 1e-4 (tests above); the chain trunk -> RPN -> exp()
-    # measured 1.1e-4 on this deliberately harsh variant-B model (|activations| ~ 1e3, |tw| up to 2)
-    assert rel(out[1].cpu().numpy(), ref["roi_boxes"]) < 3e-4
-    # End to end the error of the proposals moves the ROI sampling grid, which perturbs the fc codes, which are then
-    # exponentiated again by the (random, variant-B) final box head: two chained exp() amplifications of fp32 noise.
-    # Per-stage parity (tests above, each stage fed the oracle's inputs) holds 1e-4; end to end we allow 2e-3 here.
-    assert rel(r["all_boxes"][:K].cpu().numpy(), ref["pre_nms"]["final_boxes"]) < 2e-3
-    assert rel(r["all_scores"][:K].cpu().numpy(), ref["pre_nms"]["obj"][:, 0]) < 2e-3
+    # Chained end to end (GPU trunk -> RPN -> exp() -> pooling -> heads -> exp()) fp32 rounding noise is amplified by this
+    # deliberately harsh variant-B model (|activations| ~ 1e3, |tw| up to 2).  The budget is MEASURED, not picked: the same
+    # restatement in float64 gives the fp32 noise of the reference path itself on this input, and the GPU result must lie
+    # within twice that of the fp64 truth.  (Per-stage parity, each stage fed the oracle's inputs, holds 1e-4: tests above.)
+    gold = gold_of(img, weights, cfg)
+    assert gold["ll"]["idx"].tolist() == ref["ll"]["idx"].tolist(), "test premise: fp32 and fp64 oracles pick the same proposals"
+    assert_within_fp32_noise(out[1].cpu().numpy(), ref["roi_boxes"], gold["roi_boxes"], "roi_boxes")
+    assert_within_fp32_noise(r["all_boxes"][:K].cpu().numpy(), ref["pre_nms"]["final_boxes"], gold["pre_nms"]["final_boxes"], "final boxes")
+    assert_within_fp32_noise(r["all_scores"][:K].cpu().numpy(), ref["pre_nms"]["obj"][:, 0], gold["pre_nms"]["obj"][:, 0], "objectness")
     Kf = int(r["num_final"][0])
     assert r["final_idx"][:Kf].cpu().tolist() == ref["final_idx"].tolist()
-    assert rel(out[3].cpu().numpy(), ref["final_boxes"]) < 2e-3
+    assert_within_fp32_noise(out[3].cpu().numpy(), ref["final_boxes"], gold["final_boxes"], "filtered final boxes")
     assert out[4].cpu().tolist() == ref["seq"].tolist()
     boxes, scores, captions = model.forward_test(dev(img))
     assert len(captions) == Kf and boxes.shape == (Kf, 4) and scores.shape == (Kf, 1)
+
+
+def test_survivor_decode_equals_full_decode(model, small):
+    """The reference decodes every proposal and filters afterwards (DenseCapModel.lua:261-275); the library decodes only the rows
+    the final NMS keeps.  Rows are independent: output[5] must be identical either way, and all_seq holds exactly those rows."""
+    dims, weights, img, cfg, ref = small
+    model.ctx.set_decode_all(True)
+    r = model.forward_device(dev(img))
+    Kf = int(r["num_final"][0])
+    full_final = r["final_seq"][:Kf].cpu().numpy().copy(); full_all = r["all_seq"].cpu().numpy().copy()
+    fidx = r["final_idx"][:Kf].cpu().numpy() - 1
+    assert np.array_equal(full_all[fidx], full_final)
+    model.ctx.set_decode_all(False)
+    r = model.forward_device(dev(img))
+    assert int(r["num_final"][0]) == Kf
+    assert np.array_equal(r["final_seq"][:Kf].cpu().numpy(), full_final)
+    surv_all = r["all_seq"].cpu().numpy()
+    assert np.array_equal(surv_all[fidx], full_final)
+    mask = np.ones(surv_all.shape[0], bool); mask[fidx] = False
+    assert (surv_all[mask] == 0).all(), "rows dropped by the final NMS must not be decoded"
+    assert full_final.tolist() == ref["seq"].tolist()
 
 
 def test_host_boundary_call_matches_device_call(model, small):
@@ -230,7 +266,7 @@ def test_batched_forward_equals_single(small):
     from densecap_b200.model import DenseCapModel
     dims, weights, img, cfg, ref = small
     img2 = make_image(IMG_H, IMG_W, seed=2)
-    m = DenseCapModel({"dims": dims, "max_proposals": 64}, weights=weights, max_batch=2, max_image_hw=(IMG_H, IMG_W), engine=TC)
+    m = DenseCapModel({"dims": dims, "max_proposals": 64}, weights=weights, max_batch=2, max_image_hw=(IMG_H, IMG_W))
     m.setTestArgs({"num_proposals": NPROP})
     both = m.forward_device(dev(np.concatenate([img, img2], 0)))
     nf = both["num_final"].cpu().numpy().copy()
@@ -251,28 +287,32 @@ def test_mixed_image_sizes_on_one_context(small):
     from densecap_b200.model import DenseCapModel
     dims, weights, _, cfg, _ = small
     sizes = [(96, 128), (80, 144), (104, 88), (96, 128)]
-    m = DenseCapModel({"dims": dims, "max_proposals": 64}, weights=weights, max_image_hw=(112, 144), engine=TC)
+    m = DenseCapModel({"dims": dims, "max_proposals": 64}, weights=weights, max_image_hw=(112, 144))
     m.setTestArgs({"num_proposals": NPROP})
+    m.ctx.set_decode_all(True)            # all_seq of every proposal is compared below
     for i, (h, w) in enumerate(sizes):
         im = make_image(h, w, seed=20 + i)
         ref = O.densecap_forward_test(im, weights, cfg, return_intermediates=True)
         r = m.forward_device(dev(im))
         K = int(r["num_proposals"][0])
         assert K == ref["ll"]["boxes"].shape[0], (h, w)
-        assert rel(r["roi_boxes"][:K].cpu().numpy(), ref["roi_boxes"]) < 3e-4, (h, w)
-        assert rel(r["all_boxes"][:K].cpu().numpy(), ref["pre_nms"]["final_boxes"]) < 2e-3, (h, w)
+        gold = gold_of(im, weights, cfg)
+        assert gold["ll"]["idx"].tolist() == ref["ll"]["idx"].tolist()
+        assert_within_fp32_noise(r["roi_boxes"][:K].cpu().numpy(), ref["roi_boxes"], gold["roi_boxes"], "roi_boxes %dx%d" % (h, w))
+        assert_within_fp32_noise(r["all_boxes"][:K].cpu().numpy(), ref["pre_nms"]["final_boxes"], gold["pre_nms"]["final_boxes"],
+                                 "final boxes %dx%d" % (h, w))
         assert r["all_seq"][:K].cpu().tolist() == ref["pre_nms"]["seq"].tolist(), (h, w)
     m.ctx.close()
 
 
 def test_full_size_properties():
-    """BASELINE config 2 shape: 720x600, 1000 proposals, 15 tokens, full VGG-16 widths.  The oracle is too
-    slow at this size for a unit test, so check properties the domain guarantees."""
+    """BASELINE config 2 shape: 720x600, 1000 proposals, 15 tokens, full VGG-16 widths: size-independent properties the domain
+    guarantees (the value-level parity against the oracle at this size lives in tests/test_gpu_fullsize.py)."""
     from densecap_b200.model import DenseCapModel
     dims = ModelDims()
     weights = make_weights(dims, seed=0, box_variant="B")
     img = make_image(600, 720, seed=0)
-    m = DenseCapModel({"dims": dims}, weights=weights, engine=TC)
+    m = DenseCapModel({"dims": dims}, weights=weights)
     m.setTestArgs({"num_proposals": 1000})
     r = m.forward_device(dev(img))
     torch.cuda.synchronize()

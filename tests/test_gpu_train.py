@@ -11,7 +11,6 @@ from densecap_b200.synth import ModelDims, make_weights, feature_hw
 
 pytestmark = pytest.mark.gpu
 
-TC, SIMT = 0, 1
 SMALL = dict(widths=(64, 64, 64, 64, 64), rpn_filters=64, fc_dim=128, rnn_size=64, encoding_size=64, vocab_size=200, seq_length=5)
 IMG_H, IMG_W = 96, 128
 
@@ -85,12 +84,12 @@ def small():
     return dims, make_weights(dims, seed=3, box_variant="B")
 
 
-@pytest.fixture(scope="module", params=[SIMT, TC], ids=["simt", "tc"])
-def layer(request, small):
+@pytest.fixture(scope="module")
+def layer(small):
     from densecap_b200.model import LocalizationLayer
     from densecap_b200.runtime import Context
     dims, weights = small
-    ctx = Context(dims, max_image_hw=(IMG_H, IMG_W), max_proposals=64, engine=request.param)
+    ctx = Context(dims, max_image_hw=(IMG_H, IMG_W), max_proposals=64)
     ctx.load_weights({k: v for k, v in weights.items() if k.startswith("rpn.")})
     ll = LocalizationLayer(ctx, {"sampler_batch_size": 32, "mid_box_reg_weight": 0.05, "mid_objectness_weight": 0.1, "box_reg_decay": 5e-5})
     yield ll
