@@ -49,14 +49,16 @@ struct dc_ctx {
   // geometry capacity
   int fh_max = 0, fw_max = 0, A_max = 0, P = 0, B = 0;
   // buffers
-  SplitBuf act[2], feats, rpn_hidden, roi, fc6o, fc7o, xh, enc;
+  SplitBuf act[2], feats, rpn_hidden, roi, fc6o, fc7o, xh, enc, encx;
   float *rpn_head = nullptr, *codes = nullptr, *obj = nullptr, *trans = nullptr, *boxes_all = nullptr, *cstate = nullptr;
   float *pp_boxes = nullptr, *pp_x1y1 = nullptr, *pp_prob = nullptr, *roi_boxes = nullptr, *fin_x1y1 = nullptr;
   int32_t *pp_src = nullptr, *pp_nvalid = nullptr, *pp_blocks = nullptr;
   int32_t *rpn_idx32 = nullptr, *rpn_count = nullptr, *fin_idx32 = nullptr, *fin_count = nullptr;
   // caption decoder (lm_decode.cu): dependency counters, row maps, number of rows decoded; decode_all = 1 decodes every proposal
   uint32_t* dec_counters = nullptr;
-  int32_t *dec_rows = nullptr, *dec_dst_final = nullptr, *dec_dst_all = nullptr, *dec_count1 = nullptr;
+  int32_t *dec_rows = nullptr, *dec_dst_final = nullptr, *dec_dst_all = nullptr, *dec_count1 = nullptr, *dec_tokens = nullptr;
+  float* lm_gate_table = nullptr;    // (V+2, 4H) fp32: b + lookup . Wx (gate-interleaved), rebuilt when an LM weight is loaded
+  bool lm_gate_table_valid = false;
   int decode_all = 0;
   int64_t *rpn_idx64 = nullptr, *fin_idx64 = nullptr, *seq64 = nullptr, *fin_seq = nullptr;
   float *fin_boxes = nullptr, *fin_scores = nullptr;
@@ -243,8 +245,11 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
   TRY(split_alloc(ctx, ctx->roi, B * P * hw * C5));
   TRY(split_alloc(ctx, ctx->fc6o, B * P * fc));
   TRY(split_alloc(ctx, ctx->fc7o, B * P * fc));
-  TRY(split_alloc(ctx, ctx->xh, 2 * B * P * (E + H)));      // two ping-pong [x|h] operands of the decoder (lm_decode.cu)
+  TRY(split_alloc(ctx, ctx->xh, 2 * B * P * H));            // two ping-pong h_t operands of the decoder (lm_decode.cu)
   TRY(split_alloc(ctx, ctx->enc, B * P * E));
+  TRY(split_alloc(ctx, ctx->encx, B * P * E));
+  TRY(dev_alloc(ctx, &ctx->dec_tokens, B * P));
+  TRY(dev_alloc(ctx, &ctx->lm_gate_table, (size_t)(c.vocab_size + 2) * 4 * H));
   TRY(dev_alloc(ctx, &ctx->dec_counters, lm_decode_counter_words((int)T, (int)(B * P))));
   TRY(dev_alloc(ctx, &ctx->dec_rows, 1));
   TRY(dev_alloc(ctx, &ctx->dec_count1, 1));
@@ -544,6 +549,7 @@ extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_
       rc = k_rowmajor_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, numel, st, sc);
       w.inv_scale = 1.f / sc;
       w.loaded = true;
+      if (n == "lm.lookup.weight") ctx->lm_gate_table_valid = false;
       return finish(rc);
     }
   }
@@ -558,6 +564,7 @@ extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_
     rc = k_transpose_to_split(ctx, raw, w.planes, w.planes + w.plane_elems, (int)(E + H), (int)(4 * H), (int)H, st, sc);
     w.inv_scale = 1.f / sc;
     w.loaded = true;
+    ctx->lm_gate_table_valid = false;
     return finish(rc);
   }
   if (n == "lm.lstm.bias") {
@@ -567,6 +574,7 @@ extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_
     Weight& w = ctx->w[n];
     DC_CHECK_CUDA(ctx, cudaMemcpy(w.f32, perm.data(), numel * sizeof(float), cudaMemcpyHostToDevice));
     w.loaded = true;
+    ctx->lm_gate_table_valid = false;
     return DC_OK;
   }
   struct F32 { const char* name; int64_t n; };
@@ -962,15 +970,28 @@ static int run_lm_decode(dc_ctx* ctx, int B, int P, const int32_t* counts, const
   if ((rc = need_weight(ctx, "lm.lstm.bias", &blstm))) return rc;
   if ((rc = need_weight(ctx, "lm.vocab.weight", &wv))) return rc;
   if ((rc = need_weight(ctx, "lm.vocab.bias", &bv))) return rc;
+  // gate table = b + lookup . Wx for every token (the input half of the LSTM pre-activations), built on first use after a weight load
+  const int E = c.encoding_size, H = c.rnn_size, V = c.vocab_size;
+  if (!ctx->lm_gate_table_valid) {
+    GemmEpilogue ep;
+    ep.bias = blstm->f32;
+    ep.acc_scale = wlstm->inv_scale;
+    ep.out_f32 = ctx->lm_gate_table;
+    ep.ldf = 4 * H;
+    if ((rc = k_tc_gemm(ctx, wl->planes, wl->plane_elems, E, wlstm->planes, wlstm->plane_elems, E + H, V + 2, 4 * H, E, ep, st))) return rc;
+    ctx->lm_gate_table_valid = true;
+  }
   LmDecodeArgs a{};
-  a.B = B; a.P = P; a.E = c.encoding_size; a.H = c.rnn_size; a.V = c.vocab_size; a.T = c.seq_length;
+  a.B = B; a.P = P; a.E = E; a.H = H; a.V = V; a.T = c.seq_length;
   a.counts = counts; a.idx32 = idx32; a.survivors = survivors;
   a.enc_planes = ctx->enc.base; a.enc_plane_elems = ctx->enc.cap_elems;
-  a.xh_planes = ctx->xh.base;
+  a.x_planes = ctx->encx.base; a.x_plane_elems = ctx->encx.cap_elems;
+  a.h_planes = ctx->xh.base;
   a.cstate = ctx->cstate;
+  a.gate_table = ctx->lm_gate_table;
+  a.tokens = ctx->dec_tokens;
   a.lstm_planes = wlstm->planes; a.lstm_plane_elems = wlstm->plane_elems; a.lstm_bias = blstm->f32; a.lstm_acc_scale = wlstm->inv_scale;
   a.vocab_planes = wv->planes; a.vocab_plane_elems = wv->plane_elems; a.vocab_bias = bv->f32; a.vocab_acc_scale = wv->inv_scale;
-  a.lut_planes = wl->planes; a.lut_plane_elems = wl->plane_elems;
   a.packed = ctx->packed;
   a.counters = ctx->dec_counters;
   a.m_rows = ctx->dec_rows;

@@ -126,8 +126,7 @@ int k_rpn_postprocess(dc_ctx*, const float* head, int ld, int H, int W, int k, c
 // nms_kernels.cu
 struct NmsWorkspace {
   uint64_t* keys;        // (cap) sort keys
-  int32_t* order;        // (cap) sorted position -> box index
-  int32_t* rank;         // (cap) box index -> sorted position
+  int32_t* order;        // (cap) sorted position -> box index (valid below NmsState::sorted_n)
   float* sorted_boxes;   // (cap,4) x1y1x2y2 in sorted order
   float* kept_boxes;     // (cap,4) boxes kept so far, in pick order
   uint64_t* mask;        // (1024, 16) suppression bitmask of the current super-chunk
@@ -187,6 +186,11 @@ struct GemmEpilogue {
   float* lstm_c = nullptr;
   int lstm_H = 0;
   int lstm_first = 0;             // 1: c_{t-1} = 0
+  // LSTM epilogue only: instead of `bias`, add row gather_idx[m] (1-based token) of a precomputed fp32 table (gather_ld columns)
+  // = b + lookup[token] . Wx  (the input half of the gate pre-activations, see lm_decode.cu)
+  const float* gather_tab = nullptr;
+  const int32_t* gather_idx = nullptr;
+  int gather_ld = 0;
 };
 // small_dense_kernels.cu
 // conv1_1: NCHW fp32 (N,3,H,W) -> split NHWC (N,H,W,Cout), bias+ReLU fused.  w (Cout,3,3,3) fp32 reference layout.
@@ -212,11 +216,13 @@ struct LmDecodeArgs {
   const int32_t* idx32;                     // (B*P) device: per-image source row of each row to decode, or null = identity
   int survivors;                            // 1: rows are final-NMS survivors, tokens go to fin_seq rows b*P+i (and all_seq[src])
   const __half* enc_planes; size_t enc_plane_elems;       // (B*P, E) split: encoded image vectors of every proposal
-  __half* xh_planes;                        // [hi: buf0, buf1][lo: buf0, buf1], each (B*P, E+H)
+  __half* x_planes; size_t x_plane_elems;   // (B*P, E) split scratch: the compacted encoded vectors (input of the first LSTM step)
+  __half* h_planes;                         // [hi: buf0, buf1][lo: buf0, buf1], each (B*P, H): h_t ping-pong
   float* cstate;                            // (B*P, H)
+  const float* gate_table;                  // (V+2, 4H) fp32: b + lookup . Wx, gate-interleaved columns
+  int32_t* tokens;                          // (B*P) scratch: current input token of each row
   const __half* lstm_planes; size_t lstm_plane_elems; const float* lstm_bias; float lstm_acc_scale;
   const __half* vocab_planes; size_t vocab_plane_elems; const float* vocab_bias; float vocab_acc_scale;
-  const __half* lut_planes; size_t lut_plane_elems;
   unsigned long long* packed;               // (B*P)
   uint32_t* counters;                       // lm_decode_counter_words(T, B*P) words
   int32_t* m_rows;                          // (1) device out: total rows decoded

@@ -1,4 +1,4 @@
-// Greedy NMS (box_utils.nms, densecap/box_utils.lua:154-256) as rank sort + bitmask + scan.
+// Greedy NMS (box_utils.nms, densecap/box_utils.lua:154-256) as partial sort + bitmask + scan.
 //
 // Reference: sort scores ascending on the CPU, repeatedly pop the best remaining box i, drop every
 // remaining j with iou(i,j) > thresh, stop after max_boxes picks.  Equivalent GPU formulation
@@ -8,6 +8,12 @@
 //   union = (area + area_i) - inter; iou = inter/union; keep iff iou <= thresh (fp32 compare).
 // Tie rule (the reference's quicksort is unstable; the oracle defines it): equal scores are visited
 // higher-index first, i.e. descending order of the 64-bit key (sortable(score)<<32 | idx).
+//
+// Front end: the scan stops after max_boxes picks, which lie within the first few thousand candidates, so the boxes are
+// never fully sorted.  nms_select_sort produces the NEXT 2048 positions of the descending key order on demand: a 12-bit-
+// per-level radix select (histogram in shared memory) finds the 2048-th largest key below the last one emitted, the
+// selected keys are compacted and bitonic-sorted in shared memory, and order[] / sorted_boxes[] are extended.  Round 0 is
+// its own 1024-thread launch; later rounds (deep NMS only) run inside the tail kernel.
 //
 // Work-efficient schedule: the sorted candidates are processed in super-chunks of M = 1024.  Per
 // super-chunk the kernel builds (a) the upper-triangular 64-bit suppression mask of the chunk against
@@ -22,11 +28,13 @@ constexpr int NMS_M = 1024;              // super-chunk size
 constexpr int NMS_W = NMS_M / 64;        // 16 mask words per row
 constexpr int NMS_THREADS = 256;
 
+constexpr int NMS_SEL = 2048;            // sorted positions produced per select/sort round
 struct NmsState {
   int32_t count;      // boxes kept so far
   int32_t done;       // no further super-chunk needs to run
-  uint32_t ticket;    // last-block-done counter
+  int32_t sorted_n;   // sorted positions produced so far (order[], sorted_boxes[] valid below it)
   int32_t pad;
+  unsigned long long last_key;   // smallest key emitted so far (exclusive upper bound of the next round)
 };
 
 size_t nms_workspace_bytes(int cap) {
@@ -36,7 +44,7 @@ size_t nms_workspace_bytes(int cap) {
   b += (size_t)cap * 4 * sizeof(float);             // kept boxes
   b += (size_t)NMS_M * NMS_W * sizeof(uint64_t);    // intra mask
   b += (size_t)cap * NMS_W * sizeof(uint64_t);      // prev mask (row = kept box)
-  b += (size_t)cap * sizeof(int32_t) * 2;           // order, rank
+  b += (size_t)cap * sizeof(int32_t);               // order
   b += sizeof(NmsState);
   return b + 1024;
 }
@@ -49,7 +57,6 @@ void nms_workspace_carve(NmsWorkspace& ws, void* base, int cap) {
   ws.mask = (uint64_t*)p;          p += (size_t)NMS_M * NMS_W * sizeof(uint64_t);
   ws.mask_prev = (uint64_t*)p;     p += (size_t)cap * NMS_W * sizeof(uint64_t);
   ws.order = (int32_t*)p;          p += (size_t)cap * sizeof(int32_t);
-  ws.rank = (int32_t*)p;           p += (size_t)cap * sizeof(int32_t);
   ws.state = (void*)p;
 }
 
@@ -58,82 +65,148 @@ __device__ __forceinline__ uint32_t sortable_f32(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// keys + reset of rank[] and of the scan state
+// keys + reset of the scan state
 __global__ void nms_keys_kernel(const float* __restrict__ scores, int stride, int n_max, const int32_t* __restrict__ n_dev,
-                                uint64_t* __restrict__ keys, int32_t* __restrict__ rank, NmsState* __restrict__ state,
-                                int32_t* __restrict__ count_out) {
+                                uint64_t* __restrict__ keys, NmsState* __restrict__ state, int32_t* __restrict__ count_out) {
   const int n = n_dev ? min(*n_dev, n_max) : n_max;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    keys[i] = ((uint64_t)sortable_f32(scores[(size_t)i * stride]) << 32) | (uint32_t)i;
-    rank[i] = 0;
-  }
+  if (i < n) keys[i] = ((uint64_t)sortable_f32(scores[(size_t)i * stride]) << 32) | (uint32_t)i;
   if (i == 0) {
     state->count = 0;
     state->done = (n <= 0) ? 1 : 0;
-    state->ticket = 0;
+    state->sorted_n = 0;
+    state->last_key = ~0ull;
     *count_out = 0;
   }
 }
 
-// Rank sort, 2-D decomposition: block (x = 512 keys i, y = slice of 2048 keys j) adds its partial count
-// #{j in slice : key_j > key_i} to rank[i], where key = (sortable(score), index).  Because the index is the
-// tie-break, a slice lying entirely ABOVE the i block satisfies key_j > key_i <=> score_j >= score_i and a slice
-// entirely BELOW it <=> score_j > score_i: one 32-bit compare per pair; only the slice that overlaps the i block
-// needs the explicit tie term.
-constexpr int RANK_SLICE = 2048;
-__global__ void __launch_bounds__(256)
-nms_rank_kernel(const uint64_t* __restrict__ keys, int n_max, const int32_t* __restrict__ n_dev, int32_t* __restrict__ rank) {
-  __shared__ __align__(16) uint32_t tile[RANK_SLICE];
-  const int n = n_dev ? min(*n_dev, n_max) : n_max;
-  const int i0 = blockIdx.x * 512;
-  const int j0 = blockIdx.y * RANK_SLICE;
-  if (i0 >= n || j0 >= n) return;
-  const int jn = min(RANK_SLICE, n - j0);
-  for (int t = threadIdx.x; t < RANK_SLICE; t += blockDim.x) tile[t] = (t < jn) ? (uint32_t)(keys[j0 + t] >> 32) : 0u;   // 0 < every real key
-  __syncthreads();
-  const int ia = i0 + threadIdx.x, ib = ia + 256;        // two keys per thread
-  const uint32_t sa = (ia < n) ? (uint32_t)(keys[ia] >> 32) : 0xFFFFFFFFu;
-  const uint32_t sb = (ib < n) ? (uint32_t)(keys[ib] >> 32) : 0xFFFFFFFFu;
-  int ra = 0, rb = 0;
-  // j < i0: strict compare; j in [i0, i0+512): explicit tie-break; j >= i0+512: ties count.
-  const int t_lo = min(max(i0 - j0, 0), jn);              // first t of the overlapping segment
-  const int t_hi = min(max(i0 + 512 - j0, 0), jn);        // first t after it
-  {
-    int t = 0;
-    for (; t + 4 <= (t_lo & ~3); t += 4) {                  // vectorised part of the strict segment
-      const uint4 k = *reinterpret_cast<const uint4*>(tile + t);
-      ra += (k.x > sa) + (k.y > sa) + (k.z > sa) + (k.w > sa);
-      rb += (k.x > sb) + (k.y > sb) + (k.z > sb) + (k.w > sb);
+// ---------------------------------------------------------------------------------------------------------
+// nms_select_sort: extend the descending order by the next m = min(NMS_SEL, n - base) positions, base = state->sorted_n.
+// Candidates are the keys strictly below state->last_key (keys are unique 64-bit values, so "position >= base" is
+// exactly "key < key at position base-1").  Radix select, most significant digit first, 12 bits per level:
+//   hist[d] = #candidates matching the digits fixed so far whose next digit is d;  the boundary digit is the largest
+//   d with #(digit > d) < need <= #(digit >= d);  everything above it is selected, the search continues inside it.
+// It stops as soon as the boundary bin is needed entirely (typical: 3 levels = the 32 score bits; exact score ties
+// continue into the index bits, which realises the higher-index-first tie rule).  Then: compaction of the selected
+// keys into shared memory, bitonic sort (descending), gather of the boxes.  One CTA of NT threads; smem: NmsSelSmem.
+// ---------------------------------------------------------------------------------------------------------
+struct NmsSelSmem {
+  uint32_t hist[4096];
+  unsigned long long sel[NMS_SEL];
+  uint32_t warp_sums[32];
+  uint32_t n_sel;
+  uint32_t bnd_digit, bnd_above, found;
+};
+
+template <int NT>
+__device__ void nms_select_sort(NmsSelSmem& sm, const uint64_t* __restrict__ keys, int n, const float* __restrict__ boxes, int box_stride,
+                                NmsState* __restrict__ state, int32_t* __restrict__ order, float4* __restrict__ sorted_boxes) {
+  const int tid = threadIdx.x;
+  const int base = __ldcg(&state->sorted_n);
+  const unsigned long long last_key = __ldcg(&state->last_key);
+  const int remaining = n - base;
+  if (remaining <= 0) return;
+  const int m = min(NMS_SEL, remaining);
+  // ---- radix select of the m-th largest candidate key ----
+  unsigned long long prefix = 0ull, pmask = 0ull;      // digits fixed so far
+  uint32_t need = (uint32_t)m;
+  bool take_all = (remaining <= NMS_SEL);              // everything left is selected: no search needed
+  for (int shift = 52; !take_all; shift -= 12) {
+    const int sh = shift < 0 ? 0 : shift;
+    const uint32_t dmask = shift < 0 ? 0xFu : 0xFFFu;          // last level: the remaining 4 bits
+    for (int i = tid; i < 4096; i += NT) sm.hist[i] = 0u;
+    if (tid == 0) sm.found = 0u;
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) {
+      const unsigned long long k = __ldg(keys + i);
+      if (k < last_key && (k & pmask) == prefix) atomicAdd(&sm.hist[(uint32_t)(k >> sh) & dmask], 1u);
     }
-    for (; t < t_lo; ++t) { const uint32_t k = tile[t]; ra += (k > sa); rb += (k > sb); }
-    for (; t < t_hi; ++t) {                                 // overlap: index tie-break
-      const uint32_t k = tile[t];
-      const int j = j0 + t;
-      ra += (k > sa) | ((k == sa) & (j > ia));
-      rb += (k > sb) | ((k == sb) & (j > ib));
+    __syncthreads();
+    // suffix sums over the 4096 bins: thread t owns bins [t*PB, t*PB + PB)
+    constexpr int PB = 4096 / NT;
+    uint32_t loc[PB];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int j = 0; j < PB; ++j) { loc[j] = sm.hist[tid * PB + j]; tsum += loc[j]; }
+    // inclusive suffix scan of tsum across threads (warp shuffle + warp totals)
+    uint32_t suf = tsum;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += v;
     }
-    for (; t < jn && (t & 3); ++t) { const uint32_t k = tile[t]; ra += (k >= sa); rb += (k >= sb); }
-    for (; t + 4 <= jn; t += 4) {                           // vectorised part of the >= segment
-      const uint4 k = *reinterpret_cast<const uint4*>(tile + t);
-      ra += (k.x >= sa) + (k.y >= sa) + (k.z >= sa) + (k.w >= sa);
-      rb += (k.x >= sb) + (k.y >= sb) + (k.z >= sb) + (k.w >= sb);
+    if (lane == 0) sm.warp_sums[warp] = suf;
+    __syncthreads();
+    uint32_t above_warps = 0;
+    for (int w = warp + 1; w < NT / 32; ++w) above_warps += sm.warp_sums[w];
+    uint32_t above = above_warps + suf - tsum;             // candidates in bins owned by later threads
+    // walk my bins from the top: above = #(digit > current bin)
+#pragma unroll
+    for (int j = PB - 1; j >= 0; --j) {
+      if (above < need && need <= above + loc[j]) { sm.bnd_digit = (uint32_t)(tid * PB + j); sm.bnd_above = above; sm.found = 1u; }
+      above += loc[j];
     }
-    for (; t < jn; ++t) { const uint32_t k = tile[t]; ra += (k >= sa); rb += (k >= sb); }
+    __syncthreads();
+    const uint32_t d = sm.bnd_digit, ab = sm.bnd_above;
+    const uint32_t in_bin = sm.hist[d];
+    need -= ab;
+    prefix |= (unsigned long long)d << sh;
+    pmask |= (unsigned long long)dmask << sh;
+    __syncthreads();
+    if (in_bin == need || shift < 0) break;             // whole boundary bin selected (always true once all 64 bits are fixed)
   }
-  if (ia < n && ra) atomicAdd(rank + ia, ra);
-  if (ib < n && rb) atomicAdd(rank + ib, rb);
+  // selected = candidates with key >= threshold, threshold = prefix with the undecided low bits cleared
+  const unsigned long long thr = take_all ? 0ull : prefix;
+  if (tid == 0) sm.n_sel = 0u;
+  __syncthreads();
+  for (int i = tid; i < n; i += NT) {
+    const unsigned long long k = __ldg(keys + i);
+    if (k < last_key && k >= thr) {
+      const uint32_t pos = atomicAdd(&sm.n_sel, 1u);
+      if (pos < (uint32_t)NMS_SEL) sm.sel[pos] = k;
+    }
+  }
+  __syncthreads();
+  const int cnt = (int)min(sm.n_sel, (uint32_t)NMS_SEL);      // == m by construction
+  for (int i = cnt + tid; i < NMS_SEL; i += NT) sm.sel[i] = 0ull;      // padding sorts to the end (real keys are > 0: sortable(score) != 0)
+  __syncthreads();
+  // ---- bitonic sort, descending ----
+  for (int k2 = 2; k2 <= NMS_SEL; k2 <<= 1) {
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < NMS_SEL; i += NT) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = sm.sel[i], b = sm.sel[l];
+          const bool desc = (i & k2) == 0;
+          if ((a < b) == desc) { sm.sel[i] = b; sm.sel[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < cnt; i += NT) {
+    const int bi = (int)(uint32_t)(sm.sel[i] & 0xFFFFFFFFull);
+    order[base + i] = bi;
+    const float* b = boxes + (size_t)bi * box_stride;
+    sorted_boxes[base + i] = make_float4(b[0], b[1], b[2], b[3]);
+  }
+  __syncthreads();
+  if (tid == 0 && cnt > 0) {
+    state->last_key = sm.sel[cnt - 1];
+    state->sorted_n = base + cnt;
+  }
+  __threadfence();
 }
 
-__global__ void nms_scatter_kernel(const int32_t* __restrict__ rank, const float* __restrict__ boxes, int box_stride, int n_max,
-                                   const int32_t* __restrict__ n_dev, int32_t* __restrict__ order, float4* __restrict__ sorted_boxes) {
+constexpr int NMS_SEL_THREADS = 1024;
+__global__ void __launch_bounds__(NMS_SEL_THREADS, 1)
+nms_select_kernel(const uint64_t* __restrict__ keys, int n_max, const int32_t* __restrict__ n_dev, const float* __restrict__ boxes, int box_stride,
+                  NmsState* __restrict__ state, int32_t* __restrict__ order, float4* __restrict__ sorted_boxes) {
+  extern __shared__ __align__(16) unsigned char sel_smem_raw[];
+  NmsSelSmem& sm = *reinterpret_cast<NmsSelSmem*>(sel_smem_raw);
   const int n = n_dev ? min(*n_dev, n_max) : n_max;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int r = rank[i];
-  order[r] = i;
-  const float* b = boxes + (size_t)i * box_stride;
-  sorted_boxes[r] = make_float4(b[0], b[1], b[2], b[3]);
+  nms_select_sort<NMS_SEL_THREADS>(sm, keys, n, boxes, box_stride, state, order, sorted_boxes);
 }
 
 __device__ __forceinline__ float nms_area(float4 b) {
@@ -162,6 +235,7 @@ __device__ __forceinline__ bool nms_suppresses(float4 p, float ap, float4 q, flo
 // ---------------------------------------------------------------------------------------------------------
 constexpr int NMS_CTAS = 8;
 constexpr int NMS_WIDE_CHUNKS = 2;
+static_assert(NMS_WIDE_CHUNKS * NMS_M == NMS_SEL, "the wide super-chunks cover exactly the first select/sort round");
 
 __device__ __forceinline__ void nms_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -172,10 +246,13 @@ __device__ __forceinline__ uint32_t nms_cluster_ctarank() {
   return r;
 }
 
-// One 64x64 tile by 64 threads (lrow = row inside the tile).
-__device__ __forceinline__ void nms_mask_tile(int tile, int lrow, const float4* __restrict__ sb, int base, int cn_total, int cwords,
+// One 64x64 tile by 256 threads: thread (lrow, qt) evaluates row lrow against the 16 columns of quarter qt; the four partial
+// masks of a row are combined with shuffles (the 4 threads of a row are adjacent lanes) and written by qt == 0.
+constexpr int NMS_TILE_THREADS = 256;
+__device__ __forceinline__ void nms_mask_tile(int tile, int tt, const float4* __restrict__ sb, int base, int cn_total, int cwords,
                                               int kept0, float thresh, uint64_t* __restrict__ mask_intra,
                                               uint64_t* __restrict__ mask_prev, const float4* __restrict__ kept_boxes) {
+  const int lrow = tt >> 2, qt = tt & 3;
   const int intra_tiles = cwords * (cwords + 1) / 2;       // (rb, cb) with cb >= rb, row-major
   int rb, cb;
   const bool intra = tile < intra_tiles;
@@ -191,57 +268,61 @@ __device__ __forceinline__ void nms_mask_tile(int tile, int lrow, const float4* 
   }
   const int col0 = cb * 64;
   const int cn = min(64, cn_total - col0);
+  const int t0 = qt * 16, t1 = min(cn, t0 + 16);
   uint64_t bits = 0;
-  if (intra) {
-    const int p_local = rb * 64 + lrow;
-    if (p_local < cn_total) {
-      const float4 pb = sb[base + p_local];
-      const float pa = nms_area(pb);
-      // off-diagonal tiles: every q of the tile is later than p.  Diagonal tile: the FULL row (all q != p) -- the IoU test is
-      // symmetric bit for bit, and the scan resolves a 64-box block through the bits of the EARLIER boxes of each row.
-      const int self = p_local - col0;
-      for (int t = 0; t < cn; ++t) {
-        const float4 q = __ldg(sb + base + col0 + t);    // same address for the 64 threads of the tile: broadcast
-        if (t != self && nms_suppresses(pb, pa, q, nms_area(q), thresh)) bits |= (1ull << t);
-      }
+  const int r = rb * 64 + lrow;
+  const bool row_ok = intra ? (r < cn_total) : (r < kept0);
+  if (row_ok) {
+    // kept_boxes is appended to between launches / cluster barriers: read it at L2 (another SM's L1 may hold a line
+    // that was only partly written when it was cached for an earlier super-chunk)
+    const float4 pb = intra ? sb[base + r] : __ldcg(kept_boxes + r);
+    const float pa = nms_area(pb);
+    // off-diagonal intra tiles: every q of the tile is later than p.  Diagonal tile: the FULL row (all q != p) -- the IoU test is
+    // symmetric bit for bit, and the scan resolves a 64-box block through the bits of the EARLIER boxes of each row.
+    const int self = intra ? (r - col0) : -1;
+#pragma unroll 4
+    for (int t = t0; t < t1; ++t) {
+      const float4 q = __ldg(sb + base + col0 + t);
+      if (t != self && nms_suppresses(pb, pa, q, nms_area(q), thresh)) bits |= (1ull << t);
     }
-    mask_intra[(size_t)p_local * NMS_W + cb] = bits;
-  } else {
-    const int r = rb * 64 + lrow;
-    if (r < kept0) {
-      // kept_boxes is appended to between launches / cluster barriers: read it at L2 (another SM's L1 may hold a line
-      // that was only partly written when it was cached for an earlier super-chunk)
-      const float4 pb = __ldcg(kept_boxes + r);
-      const float pa = nms_area(pb);
-      for (int t = 0; t < cn; ++t) {
-        const float4 q = __ldg(sb + base + col0 + t);
-        if (nms_suppresses(pb, pa, q, nms_area(q), thresh)) bits |= (1ull << t);
-      }
-      mask_prev[(size_t)r * NMS_W + cb] = bits;
-    }
+  }
+  bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+  bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+  if (qt == 0) {
+    if (intra) mask_intra[(size_t)r * NMS_W + cb] = bits;          // rows >= cn_total of the last block are zero (never read)
+    else if (row_ok) mask_prev[(size_t)r * NMS_W + cb] = bits;
   }
 }
 
-// Scan of one super-chunk by one CTA of NMS_THREADS threads.  smem_mask: [NMS_M][NMS_W] words.
-__device__ __forceinline__ void nms_scan_chunk(uint64_t* smem_mask, uint64_t* s_removed, int* s_pos, int* s_cnt, const float4* __restrict__ sb,
-                                               const int32_t* __restrict__ order, int base, int cn_total, int cwords, int kept0, int cap,
-                                               const uint64_t* __restrict__ mask_intra, const uint64_t* __restrict__ mask_prev,
+// Scan of one super-chunk by one CTA (any multiple of 32 threads >= 64).  smem_mask: [NMS_M][NMS_W] words.
+// Block c of 64 sorted boxes is resolved by warp 0 (fixpoint below) as soon as its "removed" word is final.  The removed word of
+// the NEXT block gets the rows of block c's survivors from warp 0 itself (critical path: two LDS + a warp OR-reduction); the
+// words of all later blocks are accumulated meanwhile by the other warps, one word per warp, so the serial chain per block is
+// fixpoint + reduction + one barrier instead of a dependent shared-memory walk over every survivor.
+__device__ __forceinline__ uint64_t nms_warp_or64(uint64_t v) {
+  const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v), hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
+  return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ void nms_scan_chunk(uint64_t* smem_mask, uint64_t* s_removed, uint64_t* s_keep, int* s_pos, int* s_cnt,
+                                               const float4* __restrict__ sb, const int32_t* __restrict__ order, int base, int cn_total, int cwords,
+                                               int kept0, int cap, const uint64_t* __restrict__ mask_intra, const uint64_t* __restrict__ mask_prev,
                                                float4* __restrict__ kept_boxes, NmsState* __restrict__ state, int64_t* __restrict__ idx_out,
                                                int32_t* __restrict__ idx32_out, int32_t* __restrict__ count_out) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
   {
     // chunk mask -> shared memory, 8 independent loads in flight per thread (a plain copy loop serialises on L2 latency)
     const int total_words = cn_total * NMS_W;
-    for (int i0 = tid; i0 < total_words; i0 += NMS_THREADS * 8) {
+    for (int i0 = tid; i0 < total_words; i0 += nthreads * 8) {
       uint64_t v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * NMS_THREADS;
+        const int i = i0 + u * nthreads;
         v[u] = (i < total_words) ? __ldcg(mask_intra + i) : 0ull;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * NMS_THREADS;
+        const int i = i0 + u * nthreads;
         if (i < total_words) smem_mask[i] = v[u];
       }
     }
@@ -252,13 +333,13 @@ __device__ __forceinline__ void nms_scan_chunk(uint64_t* smem_mask, uint64_t* s_
     // suppression bits inherited from the boxes kept by earlier super-chunks
     const int w = tid & (NMS_W - 1);
     uint64_t acc = 0;
-    constexpr int RSTEP = NMS_THREADS / NMS_W;
+    const int rstep = nthreads / NMS_W;
     if (w < cwords) {
-      for (int r0 = tid >> 4; r0 < kept0; r0 += RSTEP * 8) {
+      for (int r0 = tid >> 4; r0 < kept0; r0 += rstep * 8) {
         uint64_t v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int r = r0 + u * RSTEP;
+          const int r = r0 + u * rstep;
           v[u] = (r < kept0) ? __ldcg(mask_prev + (size_t)r * NMS_W + w) : 0ull;
         }
 #pragma unroll
@@ -267,17 +348,16 @@ __device__ __forceinline__ void nms_scan_chunk(uint64_t* smem_mask, uint64_t* s_
     }
     if (acc) atomicOr((unsigned long long*)&s_removed[w], (unsigned long long)acc);
   }
+  if (tid == 0) *s_cnt = kept0;
   __syncthreads();
-  if (tid < 32) {
-    const int lane = tid;
-    int count = kept0;
-    uint64_t my_removed = (lane < NMS_W) ? s_removed[lane] : 0ull;    // lane w owns removed word w
-    for (int c = 0; c < cwords && count < cap; ++c) {
-      const int lim = min(64, cn_total - c * 64);
+  for (int c = 0; c < cwords; ++c) {
+    if (*s_cnt >= cap) break;                       // uniform: s_cnt is only written before the barrier below
+    const int lim = min(64, cn_total - c * 64);
+    if (warp == 0) {
+      const int before = *s_cnt;
       const uint64_t d0 = (lane < lim) ? smem_mask[(size_t)(c * 64 + lane) * NMS_W + c] : 0ull;
       const uint64_t d1 = (lane + 32 < lim) ? smem_mask[(size_t)(c * 64 + 32 + lane) * NMS_W + c] : 0ull;
-      const uint64_t cur = __shfl_sync(0xffffffffu, my_removed, c);
-      const int before = count;
+      const uint64_t cur = s_removed[c];
       // Greedy NMS inside the 64-box block as a fixpoint instead of a serial walk: box i survives iff it is alive and no
       // SURVIVING earlier box of the block suppresses it, K_i = alive_i & !(row_i & below_i & K).  The solution is unique
       // (induction on i) and iterating from K = alive fixes at least one more leading box per round; real chains are a few
@@ -293,36 +373,45 @@ __device__ __forceinline__ void nms_scan_chunk(uint64_t* smem_mask, uint64_t* s_
         keep = next;
       }
       int nk = __popcll(keep);
-      if (count + nk > cap) {                      // max_boxes reached inside this block: keep the first (cap - count) survivors
+      if (before + nk > cap) {                      // max_boxes reached inside this block: keep the first (cap - count) survivors
         uint64_t rest = keep;
-        for (int z = cap - count; z > 0; --z) rest &= rest - 1;
+        for (int z = cap - before; z > 0; --z) rest &= rest - 1;
         keep &= ~rest;
-        nk = cap - count;
+        nk = cap - before;
       }
-      count += nk;
       // remember the sorted positions of the survivors (index translation + box copy happen after the loop, in parallel)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int i = lane + 32 * half;
         if ((keep >> i) & 1ull) s_pos[before - kept0 + __popcll(keep & ((1ull << i) - 1ull))] = base + c * 64 + i;
       }
-      // propagate the suppression rows of the survivors to the later words of this super-chunk
-      if (lane > c && lane < cwords) {
-        uint64_t k = keep, acc = 0;
-        while (k) {
-          const int i = __ffsll((long long)k) - 1;
-          k &= k - 1;
-          acc |= smem_mask[(size_t)(c * 64 + i) * NMS_W + lane];
-        }
-        my_removed |= acc;
+      // rows of this block's survivors -> removed word of the NEXT block (the only word on the critical path)
+      if (c + 1 < cwords) {
+        uint64_t acc = 0;
+        if ((keep >> lane) & 1ull) acc |= smem_mask[(size_t)(c * 64 + lane) * NMS_W + c + 1];
+        if ((keep >> (lane + 32)) & 1ull) acc |= smem_mask[(size_t)(c * 64 + 32 + lane) * NMS_W + c + 1];
+        acc = nms_warp_or64(acc);
+        if (lane == 0) s_removed[c + 1] |= acc;
+      }
+      if (lane == 0) { s_keep[0] = keep; *s_cnt = before + nk; }
+    }
+    __syncthreads();
+    // the other warps: rows of block c's survivors -> removed words c+2 .. cwords-1, one word per warp (warp 0 joins late)
+    {
+      const uint64_t keep = s_keep[0];
+      for (int w = c + 2 + warp; w < cwords; w += nwarps) {
+        uint64_t acc = 0;
+        if ((keep >> lane) & 1ull) acc |= smem_mask[(size_t)(c * 64 + lane) * NMS_W + w];
+        if ((keep >> (lane + 32)) & 1ull) acc |= smem_mask[(size_t)(c * 64 + 32 + lane) * NMS_W + w];
+        acc = nms_warp_or64(acc);
+        if (lane == 0 && acc) s_removed[w] |= acc;
       }
     }
-    if (lane == 0) *s_cnt = count;
+    __syncthreads();                                // s_keep / s_removed[w] settled before the next block is resolved
   }
-  __syncthreads();
   const int count = *s_cnt;
   // emit survivors in scan order (= decreasing score) and keep their boxes for later super-chunks
-  for (int e = tid; e < count - kept0; e += NMS_THREADS) {
+  for (int e = tid; e < count - kept0; e += nthreads) {
     const int sp = s_pos[e];
     const int bi = order[sp];
     const int pos = kept0 + e;
@@ -337,8 +426,8 @@ __device__ __forceinline__ void nms_scan_chunk(uint64_t* smem_mask, uint64_t* s_
   __threadfence();
 }
 
-// wide phase A of super-chunk s: one 64-thread block per tile
-__global__ void __launch_bounds__(64)
+// wide phase A of super-chunk s: one 256-thread block per 64x64 tile
+__global__ void __launch_bounds__(NMS_TILE_THREADS)
 nms_mask_kernel(int s, const float4* __restrict__ sb, int n_max, const int32_t* __restrict__ n_dev, float thresh, int max_boxes,
                 uint64_t* __restrict__ mask_intra, uint64_t* __restrict__ mask_prev, const float4* __restrict__ kept_boxes,
                 const NmsState* __restrict__ state) {
@@ -355,12 +444,14 @@ nms_mask_kernel(int s, const float4* __restrict__ sb, int n_max, const int32_t* 
 }
 
 // phase B of super-chunk s by one block
-__global__ void __launch_bounds__(NMS_THREADS, 1)
+constexpr int NMS_SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(NMS_SCAN_THREADS, 1)
 nms_scan_kernel(int s, const float4* __restrict__ sb, const int32_t* __restrict__ order, int n_max, const int32_t* __restrict__ n_dev,
                 int max_boxes, const uint64_t* __restrict__ mask_intra, const uint64_t* __restrict__ mask_prev, float4* __restrict__ kept_boxes,
                 NmsState* __restrict__ state, int64_t* __restrict__ idx_out, int32_t* __restrict__ idx32_out, int32_t* __restrict__ count_out) {
   extern __shared__ __align__(16) uint64_t smem_mask[];     // [NMS_M][NMS_W] then s_pos[NMS_M]
   __shared__ uint64_t s_removed[NMS_W];
+  __shared__ uint64_t s_keep[1];
   __shared__ int s_cnt;
   int* s_pos = reinterpret_cast<int*>(smem_mask + (size_t)NMS_M * NMS_W);
   const int n = n_dev ? min(*n_dev, n_max) : n_max;
@@ -369,38 +460,46 @@ nms_scan_kernel(int s, const float4* __restrict__ sb, const int32_t* __restrict_
   const int kept0 = state->count;
   if (base >= n || kept0 >= cap) return;
   const int cn_total = min(NMS_M, n - base);
-  nms_scan_chunk(smem_mask, s_removed, s_pos, &s_cnt, sb, order, base, cn_total, DC_CEIL_DIV(cn_total, 64), kept0, cap, mask_intra, mask_prev,
+  nms_scan_chunk(smem_mask, s_removed, s_keep, s_pos, &s_cnt, sb, order, base, cn_total, DC_CEIL_DIV(cn_total, 64), kept0, cap, mask_intra, mask_prev,
                  kept_boxes, state, idx_out, idx32_out, count_out);
 }
 
-// tail: all remaining super-chunks in one launch of a single cluster
+// tail: all remaining super-chunks in one launch of a single cluster (deep NMS only).  CTA 0 extends the sorted order by
+// another NMS_SEL positions whenever the scan has consumed what is there.
 __global__ void __launch_bounds__(NMS_THREADS, 1)
-nms_cluster_kernel(int first_chunk, const float4* __restrict__ sb, const int32_t* __restrict__ order, int n_max,
-                   const int32_t* __restrict__ n_dev, float thresh, int max_boxes, uint64_t* __restrict__ mask_intra,
-                   uint64_t* __restrict__ mask_prev, float4* __restrict__ kept_boxes, NmsState* __restrict__ state,
+nms_cluster_kernel(int first_chunk, const uint64_t* __restrict__ keys, const float* __restrict__ boxes, int box_stride,
+                   float4* __restrict__ sb, int32_t* __restrict__ order, int n_max, const int32_t* __restrict__ n_dev, float thresh, int max_boxes,
+                   uint64_t* __restrict__ mask_intra, uint64_t* __restrict__ mask_prev, float4* __restrict__ kept_boxes, NmsState* __restrict__ state,
                    int64_t* __restrict__ idx_out, int32_t* __restrict__ idx32_out, int32_t* __restrict__ count_out) {
-  extern __shared__ __align__(16) uint64_t smem_mask[];
+  extern __shared__ __align__(16) uint64_t smem_mask[];     // [NMS_M][NMS_W], s_pos[NMS_M], NmsSelSmem
   __shared__ uint64_t s_removed[NMS_W];
+  __shared__ uint64_t s_keep[1];
   __shared__ int s_cnt;
   int* s_pos = reinterpret_cast<int*>(smem_mask + (size_t)NMS_M * NMS_W);
+  NmsSelSmem& sel = *reinterpret_cast<NmsSelSmem*>(s_pos + NMS_M);
   const int n = n_dev ? min(*n_dev, n_max) : n_max;
   const int cap = (max_boxes > 0) ? max_boxes : n;
   const int tid = threadIdx.x;
   const uint32_t rank_in_cluster = nms_cluster_ctarank();
-  const int num_workers = NMS_CTAS * (NMS_THREADS / 64);
-  const int worker = (int)rank_in_cluster * (NMS_THREADS / 64) + (tid >> 6);
+  const int num_workers = NMS_CTAS * (NMS_THREADS / NMS_TILE_THREADS);
+  const int worker = (int)rank_in_cluster * (NMS_THREADS / NMS_TILE_THREADS) + (tid / NMS_TILE_THREADS);
   for (int base = first_chunk * NMS_M; base < n; base += NMS_M) {
     const int kept0 = __ldcg(&state->count);                 // written by CTA 0 before the previous barrier / launch (read at L2)
     if (kept0 >= cap) break;                                 // identical in every CTA of the cluster
+    if (__ldcg(&state->sorted_n) <= base) {                  // identical in every CTA: the order must be extended first
+      if (rank_in_cluster == 0) nms_select_sort<NMS_THREADS>(sel, keys, n, boxes, box_stride, state, order, sb);
+      __threadfence();
+      nms_cluster_sync();
+    }
     const int cn_total = min(NMS_M, n - base);
     const int cwords = DC_CEIL_DIV(cn_total, 64);
     const int total_tiles = cwords * (cwords + 1) / 2 + DC_CEIL_DIV(kept0, 64) * cwords;
     for (int tile = worker; tile < total_tiles; tile += num_workers)
-      nms_mask_tile(tile, tid & 63, sb, base, cn_total, cwords, kept0, thresh, mask_intra, mask_prev, kept_boxes);
+      nms_mask_tile(tile, tid % NMS_TILE_THREADS, sb, base, cn_total, cwords, kept0, thresh, mask_intra, mask_prev, kept_boxes);
     __threadfence();
     nms_cluster_sync();
     if (rank_in_cluster == 0)
-      nms_scan_chunk(smem_mask, s_removed, s_pos, &s_cnt, sb, order, base, cn_total, cwords, kept0, cap, mask_intra, mask_prev, kept_boxes, state,
+      nms_scan_chunk(smem_mask, s_removed, s_keep, s_pos, &s_cnt, sb, order, base, cn_total, cwords, kept0, cap, mask_intra, mask_prev, kept_boxes, state,
                      idx_out, idx32_out, count_out);
     nms_cluster_sync();
   }
@@ -410,23 +509,24 @@ int k_nms(dc_ctx* ctx, const float* boxes, int box_stride, const float* scores, 
           float thresh, int max_boxes, NmsWorkspace ws, int64_t* idx_out, int32_t* idx32_out, int32_t* count_out, cudaStream_t st) {
   NmsState* state = (NmsState*)ws.state;
   if (n_max <= 0) {
-    nms_keys_kernel<<<1, 32, 0, st>>>(scores, score_stride, 0, nullptr, ws.keys, ws.rank, state, count_out);
+    nms_keys_kernel<<<1, 32, 0, st>>>(scores, score_stride, 0, nullptr, ws.keys, state, count_out);
     DC_CHECK_LAUNCH(ctx);
     return DC_OK;
   }
   DC_REQUIRE(ctx, n_max <= ws.cap, DC_E_INVALID, "nms: %d boxes exceed workspace capacity %d", n_max, ws.cap);
-  const size_t smem = (size_t)NMS_M * NMS_W * sizeof(uint64_t) + (size_t)NMS_M * sizeof(int);
+  const size_t smem_scan = (size_t)NMS_M * NMS_W * sizeof(uint64_t) + (size_t)NMS_M * sizeof(int);
+  const size_t smem_cluster = smem_scan + sizeof(NmsSelSmem);
+  const size_t smem_sel = sizeof(NmsSelSmem);
   {
-    cudaError_t e = dc_ensure_smem(ctx, nms_cluster_kernel, smem);
-    if (e == cudaSuccess) e = dc_ensure_smem(ctx, nms_scan_kernel, smem);
+    cudaError_t e = dc_ensure_smem(ctx, nms_cluster_kernel, smem_cluster);
+    if (e == cudaSuccess) e = dc_ensure_smem(ctx, nms_scan_kernel, smem_scan);
+    if (e == cudaSuccess) e = dc_ensure_smem(ctx, nms_select_kernel, smem_sel);
     if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "nms smem attribute: %s", cudaGetErrorString(e));
   }
-  nms_keys_kernel<<<DC_CEIL_DIV(n_max, 256), 256, 0, st>>>(scores, score_stride, n_max, n_dev, ws.keys, ws.rank, state, count_out);
+  nms_keys_kernel<<<DC_CEIL_DIV(n_max, 256), 256, 0, st>>>(scores, score_stride, n_max, n_dev, ws.keys, state, count_out);
   DC_CHECK_LAUNCH(ctx);
-  dim3 rgrid(DC_CEIL_DIV(n_max, 512), DC_CEIL_DIV(n_max, RANK_SLICE));
-  nms_rank_kernel<<<rgrid, 256, 0, st>>>(ws.keys, n_max, n_dev, ws.rank);
-  DC_CHECK_LAUNCH(ctx);
-  nms_scatter_kernel<<<DC_CEIL_DIV(n_max, 256), 256, 0, st>>>(ws.rank, boxes, box_stride, n_max, n_dev, ws.order, (float4*)ws.sorted_boxes);
+  // sorted positions [0, NMS_SEL) = the first NMS_WIDE_CHUNKS super-chunks
+  nms_select_kernel<<<1, NMS_SEL_THREADS, smem_sel, st>>>(ws.keys, n_max, n_dev, boxes, box_stride, state, ws.order, (float4*)ws.sorted_boxes);
   DC_CHECK_LAUNCH(ctx);
   const int chunks = DC_CEIL_DIV(n_max, NMS_M);
   const int max_keep = (max_boxes > 0) ? (max_boxes < n_max ? max_boxes : n_max) : n_max;
@@ -434,18 +534,18 @@ int k_nms(dc_ctx* ctx, const float* boxes, int box_stride, const float* scores, 
   for (int s = 0; s < wide; ++s) {
     const int prev_rows = (s == 0) ? 0 : (max_keep < s * NMS_M ? max_keep : s * NMS_M);
     const int tiles = NMS_W * (NMS_W + 1) / 2 + DC_CEIL_DIV(prev_rows, 64) * NMS_W;
-    nms_mask_kernel<<<tiles, 64, 0, st>>>(s, (const float4*)ws.sorted_boxes, n_max, n_dev, thresh, max_boxes, ws.mask, ws.mask_prev,
-                                          (const float4*)ws.kept_boxes, state);
+    nms_mask_kernel<<<tiles, NMS_TILE_THREADS, 0, st>>>(s, (const float4*)ws.sorted_boxes, n_max, n_dev, thresh, max_boxes, ws.mask, ws.mask_prev,
+                                                        (const float4*)ws.kept_boxes, state);
     DC_CHECK_LAUNCH(ctx);
-    nms_scan_kernel<<<1, NMS_THREADS, smem, st>>>(s, (const float4*)ws.sorted_boxes, ws.order, n_max, n_dev, max_boxes, ws.mask, ws.mask_prev,
-                                                  (float4*)ws.kept_boxes, state, idx_out, idx32_out, count_out);
+    nms_scan_kernel<<<1, NMS_SCAN_THREADS, smem_scan, st>>>(s, (const float4*)ws.sorted_boxes, ws.order, n_max, n_dev, max_boxes, ws.mask, ws.mask_prev,
+                                                            (float4*)ws.kept_boxes, state, idx_out, idx32_out, count_out);
     DC_CHECK_LAUNCH(ctx);
   }
   if (chunks > wide) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(NMS_CTAS);
     cfg.blockDim = dim3(NMS_THREADS);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = smem_cluster;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -454,8 +554,8 @@ int k_nms(dc_ctx* ctx, const float* boxes, int box_stride, const float* scores, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, nms_cluster_kernel, wide, (const float4*)ws.sorted_boxes, (const int32_t*)ws.order, n_max, n_dev,
-                                       thresh, max_boxes, ws.mask, ws.mask_prev, (float4*)ws.kept_boxes, state, idx_out, idx32_out, count_out);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, nms_cluster_kernel, wide, (const uint64_t*)ws.keys, boxes, box_stride, (float4*)ws.sorted_boxes, ws.order,
+                                       n_max, n_dev, thresh, max_boxes, ws.mask, ws.mask_prev, (float4*)ws.kept_boxes, state, idx_out, idx32_out, count_out);
     if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "nms cluster launch: %s", cudaGetErrorString(e));
     DC_CHECK_LAUNCH(ctx);
   }

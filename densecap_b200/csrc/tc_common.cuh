@@ -9,7 +9,16 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;     // fp16 elements: 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;                       // two epilogue warps per TMEM lane quarter, each draining half of the columns
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;   // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue
+constexpr int EPI_WARP0 = 4;                       // first epilogue warp
+constexpr int EPI_THREAD0 = 32 * EPI_WARP0;
+// Warp roles by WARPGROUP (setmaxnreg works on groups of 4 warps): warpgroup 0 = {warp 0: TMA producer, warp 1: MMA issuer + TMEM
+// allocator, warps 2-3: idle}, warpgroups 1-2 = the 8 epilogue warps.  The kernels are compiled for 384 threads (168 registers); at
+// start warpgroup 0 shrinks to 40 registers and the epilogue warpgroups grow to 232, which is what lets an epilogue thread keep the
+// 128 running sums of a 256-column tile (hierarchical accumulation, see epilogue_tile) in registers.
+constexpr int NUM_THREADS = EPI_THREAD0 + 32 * EPI_WARPS;
+constexpr int REGS_CONTROL = 80, REGS_EPILOGUE = 216;
+__device__ __forceinline__ void regs_shrink_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL)); }
+__device__ __forceinline__ void regs_grow_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE)); }
 constexpr int TILE_H = 8, TILE_W = 16;   // conv M tile = 8x16 output pixels
 constexpr uint32_t A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 
@@ -206,6 +215,7 @@ __device__ __forceinline__ unsigned long long pack_argmax_tc(float v, int col) {
 struct Problem {
   int M, N, K;                 // GEMM view (conv: M = tiles*128 is implicit, N = Cout, K = 9*Cin)
   int num_k_blocks;
+  int kb_per_group;            // k-blocks accumulated in TMEM before the partial sum is taken over by the epilogue (>= 1)
   int m_tiles, n_tiles;
   int m_fastest;               // tile order
   // conv geometry
@@ -228,19 +238,77 @@ struct Cfg {
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
 };
 
-// Epilogue of ONE finished accumulator tile (mt, nt) by the 8 epilogue warps (threads 64..319) of a CTA: tcgen05.ld, bias / ReLU /
-// pool / LSTM cell / arg-max, stores, and the hand-back of the TMEM stage to the MMA warp.  acc = accumulator stage (0/1),
-// acc_phase = parity of its tmem_full barrier.  tfull0 / tempty0: shared addresses of the two tmem_full / tmem_empty barriers.
+// Epilogue of ONE output tile (mt, nt) by the 8 epilogue warps (threads 128..383) of a CTA.
+//
+// Hierarchical accumulation.  The tensor core adds every MMA result into the fp32 TMEM accumulator with TRUNCATION (round toward
+// zero), so a tile accumulated in one go drifts by ~0.5 ulp per MMA: measured 1.2e-4 relative on fc6 (K = 25088, 4704 MMAs per
+// output) -- two orders of magnitude worse than an fp32 sgemm.  The MMA warp therefore closes an accumulator every
+// pb.kb_per_group k-blocks (8-12 MMAs), alternating between the two TMEM stages, and the epilogue warps add the finished
+// partial sums into registers with round-to-nearest (run[][] below) while the next group is being multiplied.  The drift is
+// then bounded by the MMAs of ONE group (<= 4e-7), i.e. fp32-sgemm class, at the cost of one tcgen05.ld sweep per group.
+// gi = running count of accumulator groups of this CTA (selects the TMEM stage and its barrier parity); advanced here.
+// tfull0 / tempty0: shared addresses of the two tmem_full / tmem_empty barriers.
 template <int BLOCK_N, bool CONV, bool POOL, int CG, bool WIDE>
 __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilogue& ep, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
-                                              float* bias_smem, int mt, int nt, int acc, uint32_t acc_phase, uint32_t cta_rank, bool is_leader) {
+                                              float* bias_smem, int mt, int nt, int num_groups, int& gi, int tile_parity, uint32_t cta_rank, bool is_leader) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto tfull_bar = [&](int s) { return tfull0 + 8u * s; };
   auto tempty_bar = [&](int s) { return tempty0 + 8u * s; };
   const int q = warp & 3;                 // TMEM lane quarter this warp may access
-  const int chunk_half = (warp - 2) >> 2; // warps 2-5 drain the first half of the accumulator columns, warps 6-9 the second
+  const int chunk_half = (warp - EPI_WARP0) >> 2; // epilogue warps 0-3 drain the first half of the accumulator columns, 4-7 the second
   const int row_in_tile = q * 32 + lane;
   const int n0 = nt * BLOCK_N;
+  constexpr int ACC_COLS = WIDE ? 2 * BLOCK_N : BLOCK_N;
+  constexpr int CHUNKS_PER_WARP = (BLOCK_N / 32) / (EPI_WARPS / 4);
+  const int c_first = chunk_half * CHUNKS_PER_WARP;
+
+  // ---- partial sums of every accumulator group of this tile -> registers (RN adds) ----
+  float run[CHUNKS_PER_WARP][32];
+  // decoder gate tiles: the input half of the pre-activations comes from a table row per output row (token); it is requested
+  // when the first group arrives (the token is final by then) and added after the last one
+  float4 gath[CHUNKS_PER_WARP][8];
+  const bool use_gather = !CONV && ep.gather_tab != nullptr;
+#pragma unroll 1
+  for (int g = 0; g < num_groups; ++g, ++gi) {
+    const int acc = gi & 1;
+    mbar_wait(tfull_bar(acc), (uint32_t)((gi >> 1) & 1));
+    tcgen05_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
+#pragma unroll
+    for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
+      const int c = c_first + cc;
+      uint32_t raw[32];
+      tmem_ld_32x32(t_row + c * 32, raw);
+      tmem_ld_wait();
+      if (WIDE) {
+        // columns [BLOCK_N, 2*BLOCK_N) hold the A_hi . B_lo partial sums of the same outputs
+        uint32_t raw2[32];
+        tmem_ld_32x32(t_row + BLOCK_N + c * 32, raw2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+      }
+      if (g == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) run[cc][j] = __uint_as_float(raw[j]);
+        if (use_gather) {
+          const int m = (mt * CG + (int)cta_rank) * BLOCK_M + row_in_tile;
+          const int tok = (m < pb.M) ? __ldcg(ep.gather_idx + m) : 1;           // written by another SM during this kernel: read at L2
+          const float4* gp = reinterpret_cast<const float4*>(ep.gather_tab + (size_t)(tok - 1) * ep.gather_ld + n0 + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gath[cc][j] = __ldg(gp + j);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) run[cc][j] += __uint_as_float(raw[j]);
+      }
+    }
+    // TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
+    tcgen05_fence_before();
+    if (CG == 2 && !is_leader) mbar_arrive_remote(tempty_bar(acc), 0);
+    else mbar_arrive(tempty_bar(acc));
+  }
+
   // ---- which output row does this thread own? ----
   long long out_row = -1;     // row index into the (rows, ld) output matrices, -1 = masked
   bool in_bounds = false;     // accumulator row corresponds to a real element
@@ -267,40 +335,27 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
   float best_v = -INFINITY;
   int best_c = 0x7fffffff;
 
-  // Stage this tile's bias slice in shared memory (one coalesced load per thread, overlapped with the MMAs of
-  // this tile) -- per-element global loads in the column loop would serialise on L2 latency and make every
-  // short-K tile epilogue-bound.  Double-buffered by accumulator stage, so one named barrier per tile suffices.
-  float* sbias = bias_smem + acc * BLOCK_N;
-  if (ep.bias) {
-    for (int j = threadIdx.x - 64; j < BLOCK_N; j += 32 * EPI_WARPS) sbias[j] = (n0 + j < pb.N) ? __ldg(ep.bias + n0 + j) : 0.f;
+  // Stage this tile's bias slice in shared memory (one coalesced load per thread) -- per-element global loads in the column
+  // loop would serialise on L2 latency.  Two buffers used alternately by consecutive tiles, so one named barrier per tile suffices.
+  float* sbias = bias_smem + (tile_parity & 1) * BLOCK_N;
+  if (ep.bias && !use_gather) {
+    for (int j = threadIdx.x - EPI_THREAD0; j < BLOCK_N; j += 32 * EPI_WARPS) sbias[j] = (n0 + j < pb.N) ? __ldg(ep.bias + n0 + j) : 0.f;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
   }
 
-  mbar_wait(tfull_bar(acc), acc_phase);
-  tcgen05_fence_after();
-  constexpr int ACC_COLS = WIDE ? 2 * BLOCK_N : BLOCK_N;
-  const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
-  constexpr int CHUNKS_PER_WARP = (BLOCK_N / 32) / (EPI_WARPS / 4);
-  #pragma unroll 1
-  for (int c = chunk_half * CHUNKS_PER_WARP; c < (chunk_half + 1) * CHUNKS_PER_WARP; ++c) {
-    uint32_t raw[32];
-    tmem_ld_32x32(t_row + c * 32, raw);
-    tmem_ld_wait();
+#pragma unroll
+  for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
+    const int c = c_first + cc;
     const int nc = n0 + c * 32;
     if (nc >= pb.N) continue;           // whole chunk outside N (uniform across the CTA)
-    if (WIDE) {
-      // columns [BLOCK_N, 2*BLOCK_N) hold the A_hi . B_lo partial sums of the same outputs
-      uint32_t raw2[32];
-      tmem_ld_32x32(t_row + BLOCK_N + c * 32, raw2);
-      tmem_ld_wait();
-  #pragma unroll
-      for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
-    }
     float v[32];
   #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      float x = __uint_as_float(raw[j]) * ep.acc_scale;
-      if (ep.bias) x += sbias[c * 32 + j];
+      float x = run[cc][j] * ep.acc_scale;
+      if (use_gather) {
+        const float4 gq = gath[cc][j >> 2];
+        x += (j & 3) == 0 ? gq.x : ((j & 3) == 1 ? gq.y : ((j & 3) == 2 ? gq.z : gq.w));
+      } else if (ep.bias) x += sbias[c * 32 + j];
       if (ep.relu) x = fmaxf(x, 0.f);
       v[j] = x;
     }
@@ -405,26 +460,22 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
       }
     }
   }
-  // TMEM reads of this accumulator are complete: hand it back to the MMA warp
-  tcgen05_fence_before();
-  if (CG == 2 && !is_leader) mbar_arrive_remote(tempty_bar(acc), 0);
-  else mbar_arrive(tempty_bar(acc));
   if (ep.argmax && out_row >= 0 && best_c != 0x7fffffff)
     atomicMax(ep.argmax + out_row, pack_argmax_tc(best_v, best_c));
 }
 
-// Epilogue warps of the GEMM / convolution kernels: drain the finished accumulator of every tile this CTA owns.
+// Epilogue warps of the GEMM / convolution kernels: drain the accumulator groups of every tile this CTA owns.
 template <int BLOCK_N, bool CONV, bool POOL, int CG, bool WIDE>
 __device__ __forceinline__ void epilogue_warps(const Problem& pb, const GemmEpilogue& ep, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                                float* bias_smem, int worker, int num_workers, uint32_t cta_rank, bool is_leader) {
   const int num_tiles = pb.m_tiles * pb.n_tiles;
-  int iter = 0;
+  const int num_groups = (pb.num_k_blocks + pb.kb_per_group - 1) / pb.kb_per_group;
+  int gi = 0, iter = 0;
   for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
     int mt, nt;
     if (pb.m_fastest) { mt = tile % pb.m_tiles; nt = tile / pb.m_tiles; }
     else { nt = tile % pb.n_tiles; mt = tile / pb.n_tiles; }
-    epilogue_tile<BLOCK_N, CONV, POOL, CG, WIDE>(pb, ep, tmem_base, tfull0, tempty0, bias_smem, mt, nt, iter & 1, (uint32_t)((iter >> 1) & 1), cta_rank,
-                                                 is_leader);
+    epilogue_tile<BLOCK_N, CONV, POOL, CG, WIDE>(pb, ep, tmem_base, tfull0, tempty0, bias_smem, mt, nt, num_groups, gi, iter, cta_rank, is_leader);
   }
 }
 

@@ -8,12 +8,12 @@
 // which drops only the lo*lo term (<= 2^-22 relative) -- fp32-class accuracy at one third of the
 // dense fp16 tensor rate, instead of the 2^-11 error of a single fp16/tf32 pass.
 //
-// Kernel structure (one persistent CTA per SM, 320 threads):
+// Kernel structure (one persistent CTA per SM, 384 threads = 3 warpgroups, see tc_common.cuh):
 //   warp 0   : TMA producer -- cp.async.bulk.tensor loads of the A and B stage tiles (both planes in one
 //              box) into 128B-swizzled shared memory, signalled through full[] mbarriers;
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases the smem stage
 //              (empty[]) and publishes the finished accumulator (tmem_full[]);
-//   warps 2-9: epilogue -- tcgen05.ld of the 128xBLOCK_N fp32 accumulator (two warps per TMEM lane quarter, half of the columns each;
+//   warps 4-11: epilogue -- tcgen05.ld of the 128xBLOCK_N fp32 accumulator (two warps per TMEM lane quarter, half of the columns each;
 //              warp), bias + ReLU (+ fused 2x2 ceil-mode max-pool through warp shuffles for the VGG
 //              layers that precede a pool), re-split to fp16 planes / fp32 / row arg-max, vectorised stores.
 //   The accumulator is double buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps
@@ -98,6 +98,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     else { nt = tile % pb.n_tiles; mt = tile / pb.n_tiles; }
   };
 
+  if (warp < EPI_WARP0) {
+    regs_shrink_control();
+  }
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (elect_one()) {
@@ -147,14 +150,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       constexpr uint32_t idesc = make_idesc_f16(BLOCK_M * CG, BLOCK_N);
       constexpr uint32_t idesc_wide = make_idesc_f16(BLOCK_M, C::WIDE ? 2 * BLOCK_N : BLOCK_N);
       int stage = 0; uint32_t phase = 0;
-      int iter = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
-        const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
+      int gi = 0;                                     // accumulator groups issued so far (TMEM stage = gi & 1)
+      const int G = pb.kb_per_group;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        uint32_t d_tmem = 0;
+        int acc = 0;
         for (int kb = 0; kb < pb.num_k_blocks; ++kb) {
+          const bool group_start = (kb % G) == 0;
+          if (group_start) {
+            // a fresh accumulator every G k-blocks: the epilogue warps sum the groups in registers (see epilogue_tile)
+            acc = gi & 1;
+            mbar_wait(tempty_bar(acc), (uint32_t)(((gi >> 1) & 1) ^ 1));
+            tcgen05_fence_after();
+            d_tmem = tmem_base + acc * C::ACC_COLS;
+          }
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t a_hi = smem_base + stage * C::STAGE_BYTES;
@@ -168,35 +177,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff);
             const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff);
             const uint64_t db_lo = make_kmajor_sw128_desc(b_lo + koff);
+            const uint32_t accum = !(group_start && k == 0);
             if (C::WIDE) {
               // D[:, 0:BN] += A_hi.B_hi and D[:, BN:2BN] += A_hi.B_lo in ONE N = 2*BN instruction (B planes are adjacent), then
               // D[:, 0:BN] += A_lo.B_hi.  Every MMA reads its 128 x 32 B A slice from shared memory (~90 clk, measured); two
               // instructions instead of three per K step is what lifts the narrow tiles.
-              umma_f16(d_tmem, da_hi, db_hi, idesc_wide, (kb | k) != 0);
+              umma_f16(d_tmem, da_hi, db_hi, idesc_wide, accum);
               umma_f16(d_tmem, da_lo, db_hi, idesc, 1);
             } else if (CG == 2) {
-              umma2_f16(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);
+              umma2_f16(d_tmem, da_lo, db_hi, idesc, accum);
               umma2_f16(d_tmem, da_hi, db_lo, idesc, 1);
               umma2_f16(d_tmem, da_hi, db_hi, idesc, 1);
             } else {
-              umma_f16(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);   // small terms first
+              umma_f16(d_tmem, da_lo, db_hi, idesc, accum);   // small terms first
               umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
               umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
             }
           }
+          const bool group_end = (kb % G) == G - 1 || kb == pb.num_k_blocks - 1;
           if (CG == 2) {
             umma2_commit_mc(empty_bar(stage));                              // frees this stage in BOTH CTAs
-            if (kb == pb.num_k_blocks - 1) umma2_commit_mc(tfull_bar(acc)); // accumulators of both CTAs complete
+            if (group_end) umma2_commit_mc(tfull_bar(acc));                 // partial accumulators of both CTAs complete
           } else {
             umma_commit(empty_bar(stage));                       // smem stage free once these MMAs retire
-            if (kb == pb.num_k_blocks - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+            if (group_end) umma_commit(tfull_bar(acc));          // partial accumulator complete
           }
+          if (group_end) ++gi;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else {
+  } else if (warp >= EPI_WARP0) {
     // =============================== epilogue warps ===============================
+    regs_grow_epilogue();
     epilogue_warps<BLOCK_N, CONV, POOL, CG, C::WIDE>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, worker, num_workers, cta_rank, is_leader);
   }
 
@@ -298,6 +311,9 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // whole filter bank of the (single) N tile fits the B ring: load it once, keep it
   const bool b_resident = (pb.n_tiles == 1) && (pb.num_k_blocks == SB);
 
+  if (warp < EPI_WARP0) {
+    regs_shrink_control();
+  }
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (elect_one()) {
@@ -350,19 +366,25 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       constexpr uint32_t idesc_wide = make_idesc_f16(BLOCK_M, C::WIDE ? 2 * BLOCK_N : BLOCK_N);
       int sa = 0; uint32_t pa = 0;
       int sb = 0; uint32_t pbp = 0;
-      int iter = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
-        const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
+      int gi = 0;                                     // accumulator groups issued so far (TMEM stage = gi & 1)
+      const int G = pb.kb_per_group;
+      bool first_tile = true;
+      for (int tile = worker; tile < num_tiles; tile += num_workers, first_tile = false) {
+        uint32_t d_tmem = 0;
+        int acc = 0;
+        int kb = 0;                                   // (group, vertical tap) counter = k-block index of the tile
         for (int g = 0; g < groups; ++g) {
           mbar_wait(afull_bar(sa), pa);
           const uint32_t a_base = a_ring + sa * AH_STAGE_BYTES;
 #pragma unroll 1
-          for (int r = 0; r < 3; ++r) {
-            if (!(b_resident && iter > 0)) mbar_wait(bfull_bar(sb), pbp);
+          for (int r = 0; r < 3; ++r, ++kb) {
+            const bool group_start = (kb % G) == 0;
+            if (group_start) {
+              acc = gi & 1;
+              mbar_wait(tempty_bar(acc), (uint32_t)(((gi >> 1) & 1) ^ 1));
+              d_tmem = tmem_base + acc * C::ACC_COLS;
+            }
+            if (!(b_resident && !first_tile)) mbar_wait(bfull_bar(sb), pbp);
             tcgen05_fence_after();
             const uint32_t a_hi = a_base + r * (TILE_W * BLOCK_K * 2);      // 16 rows = 2048 B down the halo box
             const uint32_t a_lo = a_hi + AH_PLANE_BYTES;
@@ -375,7 +397,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff);
               const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff);
               const uint64_t db_lo = make_kmajor_sw128_desc(b_lo + koff);
-              const uint32_t accum = (g | r | k) != 0;
+              const uint32_t accum = !(group_start && k == 0);
               if (C::WIDE) {
                 umma_f16(d_tmem, da_hi, db_hi, idesc_wide, accum);
                 umma_f16(d_tmem, da_lo, db_hi, idesc, 1);
@@ -389,24 +411,26 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
               }
             }
-            const bool last = (g == groups - 1) && (r == 2);
+            const bool group_end = (kb % G) == G - 1 || kb == pb.num_k_blocks - 1;
             if (CG == 2) {
               if (!b_resident) umma2_commit_mc(bempty_bar(sb));
               if (r == 2) umma2_commit_mc(aempty_bar(sa));
-              if (last) umma2_commit_mc(tfull_bar(acc));
+              if (group_end) umma2_commit_mc(tfull_bar(acc));
             } else {
               if (!b_resident) umma_commit(bempty_bar(sb));
               if (r == 2) umma_commit(aempty_bar(sa));
-              if (last) umma_commit(tfull_bar(acc));
+              if (group_end) umma_commit(tfull_bar(acc));
             }
+            if (group_end) ++gi;
             if (++sb == SB) { sb = 0; pbp ^= 1; }
           }
           if (++sa == AH_STAGES) { sa = 0; pa ^= 1; }
         }
       }
     }
-  } else {
+  } else if (warp >= EPI_WARP0) {
     // =============================== epilogue warps ===============================
+    regs_grow_epilogue();
     epilogue_warps<BLOCK_N, true, POOL, CG, C::WIDE>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, worker, num_workers, cta_rank, is_leader);
   }
 
@@ -475,6 +499,9 @@ static int launch_halo(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb
 //   BLOCK_N = 128 (wide): max(128,90) + max(64,90) = 218 clk for 128 x 128 outputs
 //   BLOCK_N = 256       : 3 x 128                  = 384 clk for 128 x 256 outputs   (cta_group::2: same per CTA, half the B fill)
 // and a launch costs rounds x that, rounds = ceil(tiles / resident CTAs).
+// k-blocks (of 64) per TMEM accumulator group, see epilogue_tile: 1 = the partial sum is taken over by the epilogue warps after
+// every k-block (8-12 truncating MMA accumulations)
+constexpr int kGroupKBlocks = 1;
 struct TileCfg { int bn; int cg; };
 static TileCfg pick_tile(int num_sms, int N, int m_tiles128, bool lstm) {
   TileCfg best{64, 1};
@@ -527,6 +554,7 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
   Problem pb{};
   pb.M = M; pb.N = N; pb.K = K;
   pb.num_k_blocks = K / BLOCK_K;
+  pb.kb_per_group = kGroupKBlocks;
   const int m_tiles128 = DC_CEIL_DIV(M, BLOCK_M);
   const TileCfg tc_ = pick_tile(dc_launch_state(ctx)->num_sms, N, m_tiles128, ep.lstm_c != nullptr);
   const int bn = tc_.bn, cg = tc_.cg;
@@ -566,6 +594,7 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
   pb.kb_per_tap = Cin / BLOCK_K;
   pb.K = 9 * Cin;
   pb.num_k_blocks = 9 * pb.kb_per_tap;
+  pb.kb_per_group = kGroupKBlocks;
   pb.N = Cout;
   pb.tiles_w = DC_CEIL_DIV(W, TILE_W);
   const int m_tiles128 = N * DC_CEIL_DIV(H, TILE_H) * pb.tiles_w;

@@ -133,12 +133,16 @@ class DenseCaptioningEvaluator:
                 fp = np.cumsum(fp); tp = np.cumsum(tp)
                 rec = tp / max(self.npos, 1)
                 prec = tp / np.maximum(fp + tp, 1e-300)
-                ap = 0.0
-                for k in range(101):
-                    t = k * 0.01
+                # `for t=0,1,0.01` (eval_utils.lua:288) ACCUMULATES the step in double precision: after 100 additions
+                # t = 1.0000000000000007 > 1, so the reference averages over 100 thresholds (0 .. ~0.99), not 101, and the
+                # thresholds are the accumulated values (e.g. 0.060000000000000005), which decide `rec >= t` on exact ties.
+                ap, apn, t = 0.0, 0, 0.0
+                while t <= 1.0:
                     m = rec >= t
                     ap += float(prec[m].max()) if m.any() else 0.0
-                ap /= 101
+                    apn += 1
+                    t += 0.01
+                ap /= apn
                 if min_score == -1:
                     det_results["ov%s" % min_overlap] = ap
                 else:

@@ -59,3 +59,19 @@ def test_unmatched_detection_quirk_consumes_last_ground_truth():
     for ev in (faithful, intended):
         ev.addResult(np.array([0.9, 0.8, 0.7]), det, ["junk", "second", "first"], gt, texts)
     assert faithful.evaluate()["detmap"] < intended.evaluate()["detmap"]
+
+
+def test_ap_sweep_reproduces_the_lua_float_loop():
+    """eval_utils.lua:285-295: `for t=0,1,0.01` accumulates the step in double precision, so the sweep has 100 thresholds
+    (the last is ~0.99, 1.0000000000000007 > 1 ends the loop) and threshold #50 is 0.5000000000000002 > 0.5.
+    Hand-computed case: 2 ground-truth boxes; detections in score order = hit, miss, hit -> rec = [.5, .5, 1], prec = [1, .5, 2/3].
+    Thresholds 0..49 (<= 0.5) see max precision 1, thresholds 50..99 see 2/3: AP = (50 + 50 * 2/3) / 100 = 0.8333...
+    (a 101-point k*0.01 sweep would give (51 + 50 * 2/3) / 101 = 0.83498)."""
+    gt = np.array([[20, 20, 10, 10], [60, 60, 20, 20]], np.float32)
+    det = np.array([[20, 20, 10, 10], [300, 300, 10, 10], [60, 60, 20, 20]], np.float32)
+    ev = DenseCaptioningEvaluator(reference_quirks=False)
+    ev.addResult(np.array([0.9, 0.8, 0.7]), det, ["a", "b", "c"], gt, ["a", "c"])
+    res = ev.evaluate()
+    want = (50 + 50 * (2.0 / 3.0)) / 100
+    assert all(abs(v - want) < 1e-12 for v in res["det_breakdown"].values()), res["det_breakdown"]
+    assert abs(res["detmap"] - want) < 1e-12

@@ -61,6 +61,18 @@ def test_tc_linear_is_fp32_class_accurate(ctx):
     assert e < 2e-5, e   # fp32-accumulate class (a single fp16 pass would be ~5e-4)
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 25088), (300, 128, 25088), (130, 64, 4608)])
+def test_tc_linear_long_k_is_fp32_sgemm_class(ctx, M, N, K):
+    """The tensor core adds each MMA into its fp32 accumulator with truncation: over fc6's K = 25088 (4704 MMAs per output) a single
+    accumulator drifted by 1.2e-4 relative.  With hierarchical accumulation (partial sums of one k-block summed in registers with
+    round-to-nearest) the result must be in the class of an fp32 sgemm: a few 1e-7 of the output scale, for every tile shape
+    (256-column pair tiles, 128- and 64-column wide tiles)."""
+    y, ref = run_linear(ctx, M, N, K, 0, seed=K + N, bias=False)
+    e = rel_err(y, ref)
+    f32 = rel_err((torch.randn(1) * 0 + 1).cuda() * 0 + (y * 0 + (ref.float())), ref)       # rounding the exact result to fp32
+    assert e < 2e-6, "tcgen05 linear M=%d N=%d K=%d rel err %.3e (fp32 rounding alone: %.1e)" % (M, N, K, e, f32)
+
+
 def run_conv(ctx, N, Cin, Cout, H, W, pool, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     x = torch.randn(N, Cin, H, W, generator=g).cuda()
