@@ -44,11 +44,16 @@ SIGNATURES = {
     "dc_load_weights": (c_i, [c_vp, C.c_char_p, c_vp, C.POINTER(c_i64), c_i]),
     "dc_set_test_args": (c_i, [c_vp, c_f, c_f, c_i, c_i]),
     "dc_set_decode_all": (c_i, [c_vp, c_i]),
+    "dc_set_beam_size": (c_i, [c_vp, c_i]),
+    "dc_check_range": (c_i, [c_vp, c_vp]),
+    "dc_set_sampler": (c_i, [c_vp, c_i, C.c_uint64]),
     "dc_set_image_size": (c_i, [c_vp, c_i, c_i]),
     "dc_forward_test": (c_i, [c_vp, c_vp, c_i, c_i, c_i, C.POINTER(DcResult), c_vp]),
     "dc_forward_test_host": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_vp]),
     "dc_preprocess_u8": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp]),
     "dc_forward_test_host_u8": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp, c_vp]),
+    "dc_preprocess_u8_resize": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, C.POINTER(c_i), C.POINTER(c_i), c_vp]),
+    "dc_extract_features": (c_i, [c_vp, c_vp, c_i, c_i, c_vp, c_vp, c_vp, c_vp]),
     "dc_vgg_trunk_forward": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_vp]),
     "dc_localization_forward_test": (c_i, [c_vp, c_vp, c_i, c_i, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dc_rpn_proposals": (c_i, [c_vp, c_vp, c_vp, c_i, c_i, c_vp, c_vp, c_vp, c_vp]),
@@ -60,6 +65,9 @@ SIGNATURES = {
     "dc_get_grad_parameters": (c_i, [c_vp, C.c_char_p, c_vp, C.c_int64, c_vp]),
     "dc_recog_forward": (c_i, [c_vp, c_vp, c_vp, c_i, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dc_lm_sample": (c_i, [c_vp, c_vp, c_i, c_vp, c_vp, c_vp]),
+    "dc_lm_beamsearch": (c_i, [c_vp, c_vp, c_i, c_i, c_vp, c_vp]),
+    "dc_affine_grid_generator": (c_i, [c_vp, c_i, c_i, c_i, c_vp, c_vp]),
+    "dc_batch_bilinear_sampler": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_vp, c_i, c_i, c_i, c_vp, c_vp]),
     "dc_make_anchors": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_vp, c_vp]),
     "dc_reshape_box_features": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "dc_apply_box_transform": (c_i, [c_vp, c_vp, c_vp, c_i, c_vp]),
@@ -88,7 +96,8 @@ class DenseCapError(RuntimeError):
 
 
 def lib_path():
-    return _build.LIB_PATH
+    # DENSECAP_B200_LIB: development hook to load a variant build of the same library (see build.build_library(defines=...))
+    return os.environ.get("DENSECAP_B200_LIB") or _build.LIB_PATH
 
 
 def load(build_if_missing=True):
@@ -97,7 +106,7 @@ def load(build_if_missing=True):
     if _LIB is not None:
         return _LIB
     path = lib_path()
-    if build_if_missing and _build.is_stale() and _build._nvcc() is not None:
+    if build_if_missing and path == _build.LIB_PATH and _build.is_stale() and _build._nvcc() is not None:
         _build.build_library()
     if not os.path.exists(path):
         raise ImportError("libdensecap_b200.so not found at %s and could not be built; "

@@ -39,15 +39,17 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library.  Returns the library path."""
-    if not force and not is_stale():
+def build_library(force=False, verbose=False, defines=(), out_path=None):
+    """Compile every .cu under csrc/ into one shared library.  Returns the library path.
+    defines / out_path: development variant builds (e.g. -DDC_DISABLE_ROI_TMA to bisect a kernel problem on the GPU box)."""
+    if out_path is None and not defines and not force and not is_stale():
         return LIB_PATH
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libdensecap_b200.so")
-    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + sources()
+    target = out_path or LIB_PATH
+    tmp = target + ".tmp.%d" % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", tmp] + sources()
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     proc = subprocess.run(cmd, capture_output=True, text=True)
@@ -55,8 +57,8 @@ def build_library(force=False, verbose=False):
         if os.path.exists(tmp):
             os.remove(tmp)
         raise RuntimeError("nvcc failed:\n%s\n%s" % (proc.stdout, proc.stderr))
-    os.replace(tmp, LIB_PATH)
-    return LIB_PATH
+    os.replace(tmp, target)
+    return target
 
 
 if __name__ == "__main__":

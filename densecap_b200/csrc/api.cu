@@ -60,10 +60,21 @@ struct dc_ctx {
   float* lm_gate_table = nullptr;    // (V+2, 4H) fp32: b + lookup . Wx (gate-interleaved), rebuilt when an LM weight is loaded
   bool lm_gate_table_valid = false;
   int decode_all = 0;
+  int beam_size = 0;                 // 0 = greedy LanguageModel:sample, > 0 = LanguageModel:beamsearch in the full forward
+  struct BeamWs {                    // workspace of the beam search (allocated on first use)
+    char* mem = nullptr;
+    int rows_cap = 0;
+    float *logits = nullptr, *c[2] = {nullptr, nullptr}, *cand_lp = nullptr, *beam_lp = nullptr;
+    __half *h[2] = {nullptr, nullptr}, *x = nullptr;
+    int32_t *cand_ix = nullptr, *beams[2] = {nullptr, nullptr}, *src_row = nullptr, *tokens = nullptr;
+  } beam;
   int64_t *rpn_idx64 = nullptr, *fin_idx64 = nullptr, *seq64 = nullptr, *fin_seq = nullptr;
   float *fin_boxes = nullptr, *fin_scores = nullptr;
   unsigned long long* packed = nullptr;
   float* anchors_dev = nullptr;
+  unsigned int* overflow_flag = nullptr;   // device word, see GemmEpilogue::overflow and dc_check_range
+  float* splitk_ws = nullptr;        // partial-sum planes of the split-K convolutions (conv5_x / RPN 3x3 on small feature maps)
+  size_t splitk_elems = 0;
   float* scratch_f32 = nullptr;      // generic fp32 scratch (HWC features for dc_bilinear_roi_pool, ...)
   size_t scratch_elems = 0;
   void* roi_taps = nullptr;          // per-(roi,position) bilinear tap records, one block per batch image
@@ -78,6 +89,8 @@ struct dc_ctx {
   float* host_stage_f32 = nullptr;
   uint8_t* host_stage_u8 = nullptr;
   size_t host_stage_f32_elems = 0, host_stage_u8_elems = 0;
+  float* resize_tmp = nullptr;       // (3, H, out_w) intermediate of the two-pass image.scale, grown on demand
+  size_t resize_tmp_elems = 0;
   cudaStream_t fin_stream0 = nullptr;   // final NMS of image 0 (runs beside the caption decode, see run_final_nms)
   cudaEvent_t fin_done0 = nullptr;
   cudaEvent_t fork_ev = nullptr;
@@ -86,6 +99,8 @@ struct dc_ctx {
   float mid_box_reg_weight = 0.05f, mid_objectness_weight = 0.1f, box_reg_decay = 0.f;   // LocalizationLayer.lua:48-54
   float sampler_low = 0.5f, sampler_high = 0.7f;                                         // :79-82
   int sampler_batch = 256, remove_outbounds = 1;
+  int sampler_mode = 1;              // 1 = uniform random minibatch like torch.multinomial (BoxSampler.lua:138-152), 0 = first P / first M in index order
+  uint64_t sampler_seed = 0, sampler_calls = 0;
   void* train = nullptr;             // TrainBuffers (train_kernels.cu), allocated on the first training call
   char* train_mem = nullptr;
   int train_A = 0, train_B2max = 0, train_batch = 0;
@@ -116,6 +131,8 @@ int dc_set_error(dc_ctx* ctx, int code, const char* fmt, ...) {
   return code;
 }
 LaunchState* dc_launch_state(dc_ctx* ctx) { return &ctx->launch; }
+float* dc_splitk_workspace(dc_ctx* ctx, size_t* elems) { *elems = ctx->splitk_elems; return ctx->splitk_ws; }
+unsigned int* dc_overflow_flag(dc_ctx* ctx) { return ctx ? ctx->overflow_flag : nullptr; }
 void dc_count_launch(dc_ctx* ctx, int n) {
   if (ctx) ctx->launches += n;
 }
@@ -282,6 +299,9 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
   TRY(dev_alloc(ctx, &ctx->packed, B * P));
   TRY(dev_alloc(ctx, &ctx->anchors_dev, (size_t)2 * c.num_anchors));
   DC_CHECK_CUDA(ctx, cudaMemcpy(ctx->anchors_dev, c.anchors, sizeof(float) * 2 * c.num_anchors, cudaMemcpyHostToDevice));
+  TRY(dev_alloc(ctx, &ctx->overflow_flag, 1));
+  ctx->splitk_elems = 8 * cells * std::max(C5, F);                 // up to 8 K-splits of a conv5-sized map (batch 1-2 only, see k_tc_conv3x3)
+  TRY(dev_alloc(ctx, &ctx->splitk_ws, ctx->splitk_elems));
   ctx->scratch_elems = std::max(cells * C5, (size_t)1 << 20);
   TRY(dev_alloc(ctx, &ctx->scratch_f32, ctx->scratch_elems));
   const int nms_cap = (int)align_up(std::max(A, P), 64);
@@ -315,8 +335,10 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
     for (int i = 0; i < 13; ++i) {
       const int cout = c.widths[kConvStage[i]];
       const std::string n = kConvNames[i];
-      if (i == 0) TRY(weight_alloc_f32(ctx, n + ".weight", (size_t)cout * 27));
-      else TRY(weight_alloc_split(ctx, n + ".weight", (size_t)cout * 9 * cin));
+      if (i == 0) {
+        TRY(weight_alloc_f32(ctx, n + ".weight", (size_t)cout * 27));
+        if (cout == 64) TRY(weight_alloc_split(ctx, n + ".weight.tc", (size_t)64 * 64));      // tcgen05 filter bank, K padded 27 -> 64
+      } else TRY(weight_alloc_split(ctx, n + ".weight", (size_t)cout * 9 * cin));
       TRY(weight_alloc_f32(ctx, n + ".bias", cout));
       cin = cout;
     }
@@ -363,6 +385,8 @@ extern "C" int dc_destroy(dc_ctx* ctx) {
   if (ctx->fin_done0) cudaEventDestroy(ctx->fin_done0);
   if (ctx->host_stage_f32) cudaFree(ctx->host_stage_f32);
   if (ctx->host_stage_u8) cudaFree(ctx->host_stage_u8);
+  if (ctx->resize_tmp) cudaFree(ctx->resize_tmp);
+  if (ctx->beam.mem) cudaFree(ctx->beam.mem);
   if (ctx->train_mem) cudaFree(ctx->train_mem);
   if (ctx->bwd_mem) cudaFree(ctx->bwd_mem);
   free(ctx->train);
@@ -455,7 +479,18 @@ extern "C" int dc_load_weights(dc_ctx* ctx, const char* name, const float* data_
       const std::string base = kConvNames[i];
       if (n == base + ".weight") {
         if (!shape_is(shape, ndim, {cout, cin, 3, 3})) return bad_shape();
-        if (i == 0) return copy_f32(n, 0, numel);
+        if (i == 0) {
+          int rc = copy_f32(n, 0, numel);
+          if (rc || cout != 64) return rc;
+          Weight& wt = ctx->w[n + ".tc"];
+          Weight& wf = ctx->w[n];
+          float sc = 1.f;
+          if ((rc = weight_scale(ctx, wf.f32, numel, &sc, st))) return rc;
+          rc = k_conv_first_weight_to_split(ctx, wf.f32, wt.planes, wt.planes + wt.plane_elems, sc, st);
+          wt.inv_scale = 1.f / sc;
+          wt.loaded = true;
+          return finish(rc);
+        }
         int rc = stage();
         if (rc) return rc;
         Weight& w = ctx->w[n];
@@ -606,6 +641,30 @@ extern "C" int dc_set_decode_all(dc_ctx* ctx, int enable) {
   return DC_OK;
 }
 
+// Activations travel as split-fp16 planes (hi + lo), exact only for |x| < 65504; the kernels flag any value outside that range
+// (He-init / trained VGG activations stay below ~1e4, but nothing in the math forbids larger ones).  Reads and clears the sticky
+// flag after synchronising `stream`; returns DC_E_RANGE when a forward since the last check overflowed (its results are invalid).
+extern "C" int dc_check_range(dc_ctx* ctx, void* stream) {
+  if (!ctx) return dc_set_error(nullptr, DC_E_INVALID, "dc_check_range: null ctx");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  unsigned int flag = 0;
+  DC_CHECK_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->overflow_flag, sizeof(flag), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  DC_CHECK_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+  if (flag) {
+    DC_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->overflow_flag, 0, sizeof(flag), (cudaStream_t)stream));
+    return dc_set_error(ctx, DC_E_RANGE, "an activation left the fp16 range of the split hi+lo representation (|x| >= 65504 or NaN): "
+                                         "results of the forward passes since the last check are invalid; rescale the input or the weights");
+  }
+  return DC_OK;
+}
+
+extern "C" int dc_set_beam_size(dc_ctx* ctx, int beam_size) {
+  if (!ctx) return dc_set_error(nullptr, DC_E_INVALID, "dc_set_beam_size: null ctx");
+  DC_REQUIRE(ctx, beam_size >= 0 && beam_size <= 32, DC_E_INVALID, "beam_size must be in [0, 32] (0 = greedy sampling)");
+  ctx->beam_size = beam_size;
+  return DC_OK;
+}
+
 extern "C" int dc_set_image_size(dc_ctx* ctx, int image_h, int image_w) {
   if (!ctx) return dc_set_error(nullptr, DC_E_INVALID, "dc_set_image_size: null ctx");
   DC_REQUIRE(ctx, image_h > 0 && image_w > 0, DC_E_INVALID, "setImageSize: bad size %dx%d", image_h, image_w);
@@ -632,6 +691,18 @@ extern "C" int dc_set_train_args(dc_ctx* ctx, float mid_box_reg_weight, float mi
   return DC_OK;
 }
 
+// nn.BoxSampler minibatch selection: mode 1 = uniform random like the reference's torch.multinomial (default), seeded: the same seed
+// replays the same sequence of minibatches; mode 0 = the first P positives / first M negatives in index order (the reference's
+// debug_pos_sample_idx / debug_neg_sample_idx hook, BoxSampler.lua:154-159) -- what the parity tests inject into the oracle too.
+extern "C" int dc_set_sampler(dc_ctx* ctx, int mode, uint64_t seed) {
+  if (!ctx) return dc_set_error(nullptr, DC_E_INVALID, "dc_set_sampler: null ctx");
+  DC_REQUIRE(ctx, mode == 0 || mode == 1, DC_E_INVALID, "dc_set_sampler: mode must be 0 (deterministic) or 1 (random)");
+  ctx->sampler_mode = mode;
+  ctx->sampler_seed = seed;
+  ctx->sampler_calls = 0;
+  return DC_OK;
+}
+
 size_t train_buffers_struct_bytes();
 size_t train_buffers_carve(void* tb, char* base, int A, int B2max, int batch_size);
 float* train_buffers_roi_boxes(void* tb);
@@ -640,7 +711,8 @@ float* train_buffers_pos_target_boxes(void* tb);
 int32_t* train_buffers_counts(void* tb);
 int k_loc_train_sampler(dc_ctx* ctx, const float* head, int ld, int H, int W, int k, const float* anchors_dev, float x0, float y0, float sx,
                         float sy, const float* gt_boxes, int B2, float lo, float hi, int batch_size, int has_bounds, float img_w, float img_h,
-                        void* tb, int64_t* pos_target_idx, int64_t* pos_input_idx, int64_t* neg_input_idx, cudaStream_t st);
+                        void* tb, int64_t* pos_target_idx, int64_t* pos_input_idx, int64_t* neg_input_idx, int sampler_mode, uint32_t sampler_salt,
+                        cudaStream_t st);
 int k_loc_train_losses(dc_ctx* ctx, void* tb, int A, float w_obj, float w_box, float w_decay, float* losses, cudaStream_t st);
 
 static const int kMaxGtBoxes = 512;
@@ -783,7 +855,16 @@ static int run_trunk(dc_ctx* ctx, const float* img, int N, int H, int W, int* fh
   {
     __half* y = ctx->act[0].base;
     const size_t yp = (size_t)N * H * W * cin;
-    if ((rc = k_conv_first(ctx, img, w0->f32, b0->f32, y, y + yp, N, H, W, cin, st))) return rc;
+#ifndef DC_DISABLE_TC_CONV1
+    const bool tc_first = (cin == 64);
+#else
+    const bool tc_first = false;
+#endif
+    if (tc_first) {              // VGG-16 width: im2col + tcgen05 (tc_conv_first.cu); other widths: the generic CUDA-core kernel
+      Weight* wt;
+      if ((rc = need_weight(ctx, "conv1_1.weight.tc", &wt))) return rc;
+      if ((rc = k_tc_conv_first(ctx, img, wt->planes, wt->plane_elems, b0->f32, wt->inv_scale, y, y + yp, N, H, W, st))) return rc;
+    } else if ((rc = k_conv_first(ctx, img, w0->f32, b0->f32, y, y + yp, N, H, W, cin, st))) return rc;
   }
   for (int i = 1; i < 13; ++i) {
     const int cout = c.widths[kConvStage[i]];
@@ -958,31 +1039,39 @@ static int run_lm_encoder(dc_ctx* ctx, int rows, cudaStream_t st) {
   return gemm(ctx, ctx->fc7o.base, fplane, fc, *we, fc, rows, E, fc, ep, st);
 }
 
-// LanguageModel:sample, greedy (LanguageModel.lua:293-348), as one compaction launch + ONE persistent decoder launch (lm_decode.cu)
-// over the rows selected by (counts, idx32) of each of the B images (row stride P).
-static int run_lm_decode(dc_ctx* ctx, int B, int P, const int32_t* counts, const int32_t* idx32, int survivors, int64_t* fin_seq, float* logits,
-                         cudaStream_t st) {
+struct LmWeights { Weight *wl, *wlstm, *blstm, *wv, *bv; };
+static int lm_weights(dc_ctx* ctx, LmWeights& w, cudaStream_t st) {
   const dc_config& c = ctx->cfg;
-  Weight *wl, *wlstm, *blstm, *wv, *bv;
   int rc;
-  if ((rc = need_weight(ctx, "lm.lookup.weight", &wl))) return rc;
-  if ((rc = need_weight(ctx, "lm.lstm.weight", &wlstm))) return rc;
-  if ((rc = need_weight(ctx, "lm.lstm.bias", &blstm))) return rc;
-  if ((rc = need_weight(ctx, "lm.vocab.weight", &wv))) return rc;
-  if ((rc = need_weight(ctx, "lm.vocab.bias", &bv))) return rc;
+  if ((rc = need_weight(ctx, "lm.lookup.weight", &w.wl))) return rc;
+  if ((rc = need_weight(ctx, "lm.lstm.weight", &w.wlstm))) return rc;
+  if ((rc = need_weight(ctx, "lm.lstm.bias", &w.blstm))) return rc;
+  if ((rc = need_weight(ctx, "lm.vocab.weight", &w.wv))) return rc;
+  if ((rc = need_weight(ctx, "lm.vocab.bias", &w.bv))) return rc;
   // gate table = b + lookup . Wx for every token (the input half of the LSTM pre-activations), built on first use after a weight load
   const int E = c.encoding_size, H = c.rnn_size, V = c.vocab_size;
   if (!ctx->lm_gate_table_valid) {
     GemmEpilogue ep;
-    ep.bias = blstm->f32;
-    ep.acc_scale = wlstm->inv_scale;
+    ep.bias = w.blstm->f32;
+    ep.acc_scale = w.wlstm->inv_scale;
     ep.out_f32 = ctx->lm_gate_table;
     ep.ldf = 4 * H;
-    if ((rc = k_tc_gemm(ctx, wl->planes, wl->plane_elems, E, wlstm->planes, wlstm->plane_elems, E + H, V + 2, 4 * H, E, ep, st))) return rc;
+    if ((rc = k_tc_gemm(ctx, w.wl->planes, w.wl->plane_elems, E, w.wlstm->planes, w.wlstm->plane_elems, E + H, V + 2, 4 * H, E, ep, st))) return rc;
     ctx->lm_gate_table_valid = true;
   }
+  return DC_OK;
+}
+
+// LanguageModel:sample, greedy (LanguageModel.lua:293-348), as one compaction launch + ONE persistent decoder launch (lm_decode.cu)
+// over the rows selected by (counts, idx32) of each of the B images (row stride P).  compact_only: row maps only.
+static int run_lm_decode(dc_ctx* ctx, int B, int P, const int32_t* counts, const int32_t* idx32, int survivors, int64_t* fin_seq, float* logits,
+                         cudaStream_t st, bool compact_only = false) {
+  const dc_config& c = ctx->cfg;
+  LmWeights w;
+  int rc;
+  if ((rc = lm_weights(ctx, w, st))) return rc;
   LmDecodeArgs a{};
-  a.B = B; a.P = P; a.E = E; a.H = H; a.V = V; a.T = c.seq_length;
+  a.B = B; a.P = P; a.E = c.encoding_size; a.H = c.rnn_size; a.V = c.vocab_size; a.T = c.seq_length;
   a.counts = counts; a.idx32 = idx32; a.survivors = survivors;
   a.enc_planes = ctx->enc.base; a.enc_plane_elems = ctx->enc.cap_elems;
   a.x_planes = ctx->encx.base; a.x_plane_elems = ctx->encx.cap_elems;
@@ -990,15 +1079,98 @@ static int run_lm_decode(dc_ctx* ctx, int B, int P, const int32_t* counts, const
   a.cstate = ctx->cstate;
   a.gate_table = ctx->lm_gate_table;
   a.tokens = ctx->dec_tokens;
-  a.lstm_planes = wlstm->planes; a.lstm_plane_elems = wlstm->plane_elems; a.lstm_bias = blstm->f32; a.lstm_acc_scale = wlstm->inv_scale;
-  a.vocab_planes = wv->planes; a.vocab_plane_elems = wv->plane_elems; a.vocab_bias = bv->f32; a.vocab_acc_scale = wv->inv_scale;
+  a.lstm_planes = w.wlstm->planes; a.lstm_plane_elems = w.wlstm->plane_elems; a.lstm_bias = w.blstm->f32; a.lstm_acc_scale = w.wlstm->inv_scale;
+  a.vocab_planes = w.wv->planes; a.vocab_plane_elems = w.wv->plane_elems; a.vocab_bias = w.bv->f32; a.vocab_acc_scale = w.wv->inv_scale;
   a.packed = ctx->packed;
   a.counters = ctx->dec_counters;
   a.m_rows = ctx->dec_rows;
   a.dst_final = ctx->dec_dst_final; a.dst_all = ctx->dec_dst_all;
   a.fin_seq = fin_seq; a.all_seq = ctx->seq64;
   a.logits = logits;
-  return k_lm_decode(ctx, a, st);
+  return k_lm_decode(ctx, a, st, compact_only);
+}
+
+// LanguageModel:beamsearch (LanguageModel.lua:170-290) over M rows of ctx->enc listed in rows_src (device; null = rows 0..M-1), in chunks of
+// rows_cap / beam ROIs: row = roi * beam + b.  Tokens of the best beam of ROI r go to seq_a[dst_a[r]] and (optionally) seq_b[dst_b[r]].
+static int run_lm_beamsearch(dc_ctx* ctx, int M, int beam, const int32_t* rows_src, const int32_t* dst_a, int64_t* seq_a, const int32_t* dst_b,
+                             int64_t* seq_b, cudaStream_t st) {
+  const dc_config& c = ctx->cfg;
+  const int E = c.encoding_size, H = c.rnn_size, V = c.vocab_size, V1 = V + 1, T = c.seq_length;
+  DC_REQUIRE(ctx, beam >= 1 && beam <= 32 && beam <= V1, DC_E_INVALID, "beam_size must be in [1, 32]");
+  if (M <= 0) return DC_OK;
+  LmWeights w;
+  int rc;
+  if ((rc = lm_weights(ctx, w, st))) return rc;
+  dc_ctx::BeamWs& ws = ctx->beam;
+  const int rows_cap = 4096;
+  if (!ws.mem) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t o_log = take((size_t)rows_cap * V1 * 4), o_h0 = take((size_t)2 * rows_cap * H * 2), o_h1 = take((size_t)2 * rows_cap * H * 2),
+                 o_c0 = take((size_t)rows_cap * H * 4), o_c1 = take((size_t)rows_cap * H * 4), o_x = take((size_t)2 * rows_cap * E * 2),
+                 o_clp = take((size_t)rows_cap * 32 * 4), o_cix = take((size_t)rows_cap * 32 * 4), o_blp = take((size_t)rows_cap * 4),
+                 o_b0 = take((size_t)rows_cap * T * 4), o_b1 = take((size_t)rows_cap * T * 4), o_src = take((size_t)rows_cap * 4),
+                 o_tok = take((size_t)rows_cap * 4);
+    DC_CHECK_CUDA(ctx, cudaMalloc((void**)&ws.mem, off));
+    ws.rows_cap = rows_cap;
+    ws.logits = (float*)(ws.mem + o_log); ws.h[0] = (__half*)(ws.mem + o_h0); ws.h[1] = (__half*)(ws.mem + o_h1);
+    ws.c[0] = (float*)(ws.mem + o_c0); ws.c[1] = (float*)(ws.mem + o_c1); ws.x = (__half*)(ws.mem + o_x);
+    ws.cand_lp = (float*)(ws.mem + o_clp); ws.cand_ix = (int32_t*)(ws.mem + o_cix); ws.beam_lp = (float*)(ws.mem + o_blp);
+    ws.beams[0] = (int32_t*)(ws.mem + o_b0); ws.beams[1] = (int32_t*)(ws.mem + o_b1); ws.src_row = (int32_t*)(ws.mem + o_src);
+    ws.tokens = (int32_t*)(ws.mem + o_tok);
+  }
+  const size_t hplane = (size_t)rows_cap * H, xplane = (size_t)rows_cap * E;
+  const int chunk = rows_cap / beam;
+  for (int r0 = 0; r0 < M; r0 += chunk) {
+    const int R = std::min(chunk, M - r0), rows = R * beam;
+    // image time step (:198-201): encoded vector through the LSTM, h0 = c0 = 0
+    if ((rc = k_bs_gather_split(ctx, ctx->enc.base, ctx->enc.base + ctx->enc.cap_elems, E, rows_src, r0, R, ws.x, ws.x + xplane, st))) return rc;
+    {
+      GemmEpilogue ep;
+      ep.acc_scale = w.wlstm->inv_scale; ep.bias = w.blstm->f32;
+      ep.lstm_c = ws.c[0]; ep.lstm_H = H; ep.lstm_first = 1;
+      ep.out_hi = ws.h[0]; ep.out_lo = ws.h[0] + hplane; ep.ldo = H;
+      if ((rc = k_tc_gemm(ctx, ws.x, xplane, E, w.wlstm->planes, w.wlstm->plane_elems, E + H, R, 4 * H, E, ep, st))) return rc;
+    }
+    // START token (:203-206)
+    if ((rc = k_bs_fill_i32(ctx, ws.tokens, V + 1, R, st))) return rc;
+    auto lstm_step = [&](int nrows, const __half* h_in, float* cbuf, __half* h_out) -> int {
+      GemmEpilogue ep;
+      ep.acc_scale = w.wlstm->inv_scale;
+      ep.gather_tab = ctx->lm_gate_table; ep.gather_idx = ws.tokens; ep.gather_ld = 4 * H;
+      ep.lstm_c = cbuf; ep.lstm_H = H; ep.lstm_first = 0;
+      ep.out_hi = h_out; ep.out_lo = h_out + hplane; ep.ldo = H;
+      return k_tc_gemm(ctx, h_in, hplane, H, w.wlstm->planes + E, w.wlstm->plane_elems, E + H, nrows, 4 * H, H, ep, st);
+    };
+    auto vocab = [&](int nrows, const __half* h_in) -> int {
+      GemmEpilogue ep;
+      ep.acc_scale = w.wv->inv_scale; ep.bias = w.bv->f32;
+      ep.out_f32 = ws.logits; ep.ldf = V1;
+      return k_tc_gemm(ctx, h_in, hplane, H, w.wv->planes, w.wv->plane_elems, H, nrows, V1, H, ep, st);
+    };
+    if ((rc = lstm_step(R, ws.h[0], ws.c[0], ws.h[1]))) return rc;
+    if ((rc = vocab(R, ws.h[1]))) return rc;
+    // beams = top-beam words; states replicated (:208-227): h -> ws.h[0], c -> ws.c[1]
+    if ((rc = k_bs_first(ctx, ws.logits, R, V1, beam, T, H, ws.beam_lp, ws.beams[0], ws.tokens, ws.h[1], ws.h[1] + hplane, ws.c[0], ws.h[0],
+                         ws.h[0] + hplane, ws.c[1], st)))
+      return rc;
+    int cur_c = 1, cur_b = 0;
+    for (int t = 1; t < T; ++t) {
+      if ((rc = lstm_step(rows, ws.h[0], ws.c[cur_c], ws.h[1]))) return rc;
+      if ((rc = vocab(rows, ws.h[1]))) return rc;
+      if ((rc = k_bs_row_topk(ctx, ws.logits, rows, V1, beam, T, V + 1, ws.beams[cur_b], ws.cand_lp, ws.cand_ix, st))) return rc;
+      if ((rc = k_bs_merge(ctx, R, beam, T, t, ws.cand_lp, ws.cand_ix, ws.beam_lp, ws.beams[cur_b], ws.beams[cur_b ^ 1], ws.src_row, ws.tokens, st)))
+        return rc;
+      if ((rc = k_bs_reindex(ctx, rows, H, ws.src_row, ws.h[1], ws.h[1] + hplane, ws.c[cur_c], ws.h[0], ws.h[0] + hplane, ws.c[cur_c ^ 1], st)))
+        return rc;
+      cur_c ^= 1; cur_b ^= 1;
+    }
+    if (seq_a && (rc = k_bs_final(ctx, R, beam, T, ws.beam_lp, ws.beams[cur_b], dst_a ? dst_a + r0 : nullptr, seq_a + (dst_a ? 0 : (size_t)r0 * T), st)))
+      return rc;
+    if (seq_b && (rc = k_bs_final(ctx, R, beam, T, ws.beam_lp, ws.beams[cur_b], dst_b ? dst_b + r0 : nullptr, seq_b + (dst_b ? 0 : (size_t)r0 * T), st)))
+      return rc;
+  }
+  return DC_OK;
 }
 
 // Final NMS (DenseCapModel.lua:261-271) needs only the final boxes and objectness scores of the recognition head.  It is forked
@@ -1083,8 +1255,21 @@ extern "C" int dc_forward_test(dc_ctx* ctx, const float* img, int batch, int ima
   if ((rc = join_final_nms(ctx, batch, st))) return rc;
   phase_mark(ctx, "lm:sample", st);
   // decode only what the reference returns (the final-NMS survivors), or every proposal when all_seq was asked for
-  if (ctx->decode_all) rc = run_lm_decode(ctx, batch, ctx->P, ctx->rpn_count, nullptr, 0, nullptr, nullptr, st);
-  else rc = run_lm_decode(ctx, batch, ctx->P, ctx->fin_count, ctx->fin_idx32, 1, ctx->fin_seq, nullptr, st);
+  const int32_t* dcounts = ctx->decode_all ? ctx->rpn_count : ctx->fin_count;
+  const int32_t* didx = ctx->decode_all ? nullptr : ctx->fin_idx32;
+  if (ctx->beam_size > 0) {
+    // LanguageModel:beamsearch (self.beam_size ~= nil, LanguageModel.lua:129-132): row maps from the compaction kernel, then one host
+    // read of the row count (the beam search is sized by it; this optional path costs ~beam x the greedy decode anyway)
+    if ((rc = run_lm_decode(ctx, batch, ctx->P, dcounts, didx, ctx->decode_all ? 0 : 1, ctx->decode_all ? nullptr : ctx->fin_seq, nullptr, st, true)))
+      return rc;
+    int32_t m_rows = 0;
+    DC_CHECK_CUDA(ctx, cudaMemcpyAsync(&m_rows, ctx->dec_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DC_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    rc = run_lm_beamsearch(ctx, m_rows, ctx->beam_size, ctx->dec_dst_all, ctx->dec_dst_all, ctx->seq64, ctx->decode_all ? nullptr : ctx->dec_dst_final,
+                           ctx->decode_all ? nullptr : ctx->fin_seq, st);
+  } else {
+    rc = run_lm_decode(ctx, batch, ctx->P, dcounts, didx, ctx->decode_all ? 0 : 1, ctx->decode_all ? nullptr : ctx->fin_seq, nullptr, st);
+  }
   if (rc) return rc;
   phase_mark(ctx, "final_gather", st);
   if ((rc = run_final_gather(ctx, batch, ctx->decode_all != 0, st))) return rc;
@@ -1102,6 +1287,8 @@ static int ensure_host_stage(dc_ctx* ctx, size_t f32_elems, size_t u8_elems) {
   }
   if (ctx->host_stage_u8_elems < u8_elems) {
     if (ctx->host_stage_u8) cudaFree(ctx->host_stage_u8);
+  if (ctx->resize_tmp) cudaFree(ctx->resize_tmp);
+  if (ctx->beam.mem) cudaFree(ctx->beam.mem);
     ctx->host_stage_u8 = nullptr; ctx->host_stage_u8_elems = 0;
     DC_CHECK_CUDA(ctx, cudaMalloc((void**)&ctx->host_stage_u8, u8_elems));
     ctx->host_stage_u8_elems = u8_elems;
@@ -1129,8 +1316,7 @@ extern "C" int dc_forward_test_host(dc_ctx* ctx, const float* img_host, int batc
   if (final_boxes_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(final_boxes_host, r.final_boxes, rows * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (final_scores_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(final_scores_host, r.final_scores, rows * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (final_seq_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(final_seq_host, r.final_seq, rows * T * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  DC_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
-  return DC_OK;
+  return dc_check_range(ctx, st);          // synchronises; DC_E_RANGE if an activation overflowed the split-fp16 planes
 }
 
 // run_model.lua:66-74 preprocessing (no resize) on the device: uint8 RGB HWC (batch,H,W,3) -> fp32 BGR mean-subtracted NCHW
@@ -1163,8 +1349,7 @@ extern "C" int dc_forward_test_host_u8(dc_ctx* ctx, const uint8_t* img_host_u8, 
   if (final_boxes_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(final_boxes_host, r.final_boxes, rows * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (final_scores_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(final_scores_host, r.final_scores, rows * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (final_seq_host) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(final_seq_host, r.final_seq, rows * T * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  DC_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
-  return DC_OK;
+  return dc_check_range(ctx, st);          // synchronises; DC_E_RANGE if an activation overflowed the split-fp16 planes
 }
 
 extern "C" int dc_vgg_trunk_forward(dc_ctx* ctx, const float* img, int batch, int image_h, int image_w, float* feats_nchw, void* stream) {
@@ -1264,10 +1449,13 @@ extern "C" int dc_localization_forward_train(dc_ctx* ctx, const float* feats_nch
   phase_mark(ctx, "rpn:forward", st);
   if ((rc = run_rpn_head(ctx, 1, feat_h, feat_w, st))) return rc;
   phase_mark(ctx, "sampler:forward", st);
+  // torch.multinomial draws fresh samples on every call: the salt mixes the seed with a per-context call counter
+  uint32_t sampler_salt = (uint32_t)(ctx->sampler_seed ^ (ctx->sampler_seed >> 32)) * 0x9e3779b1u + (uint32_t)ctx->sampler_calls * 0x85ebca6bu + 1u;
+  if (ctx->sampler_mode == 1) ++ctx->sampler_calls;
   if ((rc = k_loc_train_sampler(ctx, ctx->rpn_head, 6 * k, feat_h, feat_w, k, ctx->anchors_dev, c.field_centers[0], c.field_centers[1],
                                 c.field_centers[2], c.field_centers[3], train_buffers_gt(ctx->train), ctx->gt_count, ctx->sampler_low,
                                 ctx->sampler_high, S, ctx->remove_outbounds, (float)ctx->image_w, (float)ctx->image_h, ctx->train, pos_target_idx, pos_input_idx,
-                                neg_input_idx, st)))
+                                neg_input_idx, ctx->sampler_mode, sampler_salt, st)))
     return rc;
   phase_mark(ctx, "roi_pooling:forward", st);
   const size_t rplane = (size_t)S * hw * C5;
@@ -1486,6 +1674,20 @@ extern "C" int dc_lm_sample(dc_ctx* ctx, const float* codes, int K, int64_t* seq
   return DC_OK;
 }
 
+// LanguageModel:beamsearch(image_vectors, beam_size) (LanguageModel.lua:170-290)
+extern "C" int dc_lm_beamsearch(dc_ctx* ctx, const float* codes, int K, int beam_size, int64_t* seq, void* stream) {
+  if (!ctx || !codes || !seq) return dc_set_error(ctx, DC_E_INVALID, "dc_lm_beamsearch: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  DC_REQUIRE(ctx, K >= 1 && K <= ctx->P * ctx->B, DC_E_INVALID, "K=%d exceeds capacity %d", K, ctx->P * ctx->B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int fc = ctx->cfg.fc_dim;
+  const size_t fplane = (size_t)K * fc;
+  int rc;
+  if ((rc = k_rowmajor_to_split(ctx, codes, ctx->fc7o.base, ctx->fc7o.base + fplane, fplane, st))) return rc;
+  if ((rc = run_lm_encoder(ctx, K, st))) return rc;
+  return run_lm_beamsearch(ctx, K, beam_size > 0 ? beam_size : 20, nullptr, nullptr, seq, nullptr, nullptr, st);
+}
+
 // ------------------------------------------------------------------------------------------------
 // leaf operators
 // ------------------------------------------------------------------------------------------------
@@ -1575,6 +1777,78 @@ extern "C" int dc_bilinear_roi_pool(dc_ctx* ctx, const float* feats_chw, int C, 
   return DC_OK;
 }
 
+// stnbhwd nn.AffineGridGeneratorBHWD(HH, WW):updateOutput (call site modules/BilinearRoiPooling.lua:52)
+extern "C" int dc_affine_grid_generator(const float* theta, int B, int HH, int WW, float* grids, void* stream) {
+  if (B > 0 && (!theta || !grids)) return dc_set_error(nullptr, DC_E_INVALID, "dc_affine_grid_generator: null");
+  if (HH < 2 || WW < 2) return dc_set_error(nullptr, DC_E_INVALID, "dc_affine_grid_generator: output size must be at least 2x2");
+  return k_affine_grid(nullptr, theta, B, HH, WW, grids, (cudaStream_t)stream);
+}
+
+// nn.BatchBilinearSamplerBHWD:updateOutput (modules/BatchBilinearSamplerBHWD.lua:104-122) on caller-supplied grids
+extern "C" int dc_batch_bilinear_sampler(dc_ctx* ctx, const float* feats_hwc, int feat_h, int feat_w, int C, const float* grids, int B, int HH, int WW,
+                                         float* out, void* stream) {
+  if (!ctx || !feats_hwc || !grids || !out) return dc_set_error(ctx, DC_E_INVALID, "dc_batch_bilinear_sampler: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  DC_REQUIRE(ctx, HH >= 1 && WW >= 1 && B >= 0, DC_E_INVALID, "dc_batch_bilinear_sampler: bad output size %dx%d", HH, WW);
+  const size_t records = (size_t)ctx->roi_taps_boxes * ctx->cfg.pool_hw * ctx->cfg.pool_hw;
+  const int chunk = (int)std::min<size_t>(records / ((size_t)HH * WW), (size_t)ctx->roi_taps_boxes);
+  DC_REQUIRE(ctx, chunk >= 1, DC_E_UNSUPPORTED, "dc_batch_bilinear_sampler: output grid %dx%d exceeds the tap workspace", HH, WW);
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
+    int rc = k_bilinear_sampler(ctx, feats_hwc, C, feat_h, feat_w, grids + (size_t)b0 * HH * WW * 2, nb, HH, WW, ctx->roi_taps,
+                                out + (size_t)b0 * HH * WW * C, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return DC_OK;
+}
+
+// DenseCapModel:extractFeatures (DenseCapModel.lua:285-304): the network without the language model, final NMS on the final boxes,
+// boxes and recog_base features (fc7 codes) of the kept rows in score order.
+extern "C" int dc_extract_features(dc_ctx* ctx, const float* img, int image_h, int image_w, float* boxes_xcycwh, float* feats, int32_t* num_out,
+                                   void* stream) {
+  if (!ctx || !img) return dc_set_error(ctx, DC_E_INVALID, "dc_extract_features: null argument");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = dc_set_image_size(ctx, image_h, image_w))) return rc;
+  ctx->timer.used = 0;
+  int fh, fw;
+  if ((rc = run_trunk(ctx, img, 1, image_h, image_w, &fh, &fw, st))) return rc;
+  ctx->size_consumed = true;
+  if ((rc = run_localization(ctx, 1, fh, fw, image_h, image_w, st))) return rc;
+  if ((rc = run_recog(ctx, ctx->P, st))) return rc;
+  if ((rc = run_final_nms(ctx, 1, st))) return rc;
+  if ((rc = join_final_nms(ctx, 1, st))) return rc;
+  const int P = ctx->P, fc = ctx->cfg.fc_dim;
+  if (boxes_xcycwh && (rc = k_gather_rows_f32(ctx, ctx->boxes_all, 4, ctx->fin_idx32, ctx->fin_count, P, boxes_xcycwh, st))) return rc;
+  if (feats && (rc = k_gather_rows_f32(ctx, ctx->codes, fc, ctx->fin_idx32, ctx->fin_count, P, feats, st))) return rc;
+  if (num_out) DC_CHECK_CUDA(ctx, cudaMemcpyAsync(num_out, ctx->fin_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return DC_OK;
+}
+
+// run_model.lua:66-74 WITH the resize: image.scale(img, image_size) (larger side -> image_size, bilinear) on the device
+extern "C" int dc_preprocess_u8_resize(dc_ctx* ctx, const uint8_t* img_u8, int image_h, int image_w, int image_size, float* img_nchw, int* out_h,
+                                       int* out_w, void* stream) {
+  if (!ctx || !img_u8 || !img_nchw || !out_h || !out_w) return dc_set_error(ctx, DC_E_INVALID, "dc_preprocess_u8_resize: null argument");
+  DC_REQUIRE(ctx, image_h > 0 && image_w > 0 && image_size > 0, DC_E_INVALID, "dc_preprocess_u8_resize: bad size");
+  DC_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int imax = std::max(image_h, image_w);
+  // image/init.lua: height = iheight*size/imax, width = iwidth*size/imax (Lua doubles), truncated by the tensor allocation
+  const int oh = (int)((double)image_h * (double)image_size / (double)imax);
+  const int ow = (int)((double)image_w * (double)image_size / (double)imax);
+  DC_REQUIRE(ctx, oh >= 1 && ow >= 1, DC_E_INVALID, "dc_preprocess_u8_resize: degenerate output %dx%d", oh, ow);
+  const size_t need = (size_t)3 * image_h * ow;
+  if (ctx->resize_tmp_elems < need) {
+    if (ctx->resize_tmp) cudaFree(ctx->resize_tmp);
+  if (ctx->beam.mem) cudaFree(ctx->beam.mem);
+    ctx->resize_tmp = nullptr; ctx->resize_tmp_elems = 0;
+    DC_CHECK_CUDA(ctx, cudaMalloc((void**)&ctx->resize_tmp, need * sizeof(float)));
+    ctx->resize_tmp_elems = need;
+  }
+  *out_h = oh; *out_w = ow;
+  return k_image_scale_preprocess(ctx, img_u8, image_h, image_w, oh, ow, ctx->resize_tmp, img_nchw, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 // dense test hooks
 // ------------------------------------------------------------------------------------------------
@@ -1647,5 +1921,5 @@ extern "C" int dc_conv3x3_relu(dc_ctx* ctx, const float* x, const float* w, cons
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc) return rc;
   if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "dc_conv3x3_relu: %s", cudaGetErrorString(e));
-  return DC_OK;
+  return dc_check_range(ctx, st);
 }

@@ -183,6 +183,28 @@ int k_box_to_affine(dc_ctx* ctx, const float* boxes, float* theta, int B, int H,
   return DC_OK;
 }
 
+// stnbhwd nn.AffineGridGeneratorBHWD(HH, WW) (call site modules/BilinearRoiPooling.lua:52):
+// grid[b][i][j] = baseGrid[i][j] . theta[b]^T with baseGrid = (y_i, x_j, 1), y_i = -1 + (i/(HH-1))*2 evaluated in double and stored as
+// float; the 3-term dot product is summed left to right (sgemm order), no FMA.  theta (B,2,3) -> grids (B,HH,WW,2) = (gy, gx).
+__global__ void affine_grid_kernel(const float* __restrict__ theta, int B, int HH, int WW, float2* __restrict__ grids) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * HH * WW) return;
+  const int b = idx / (HH * WW), p = idx % (HH * WW), i = p / WW, j = p % WW;
+  const float* t = theta + (size_t)b * 6;
+  const float yb = (float)(-1.0 + ((double)i / (double)(HH - 1)) * 2.0);
+  const float xb = (float)(-1.0 + ((double)j / (double)(WW - 1)) * 2.0);
+  float2 g;
+  g.x = __fadd_rn(__fadd_rn(__fmul_rn(t[0], yb), __fmul_rn(t[1], xb)), t[2]);
+  g.y = __fadd_rn(__fadd_rn(__fmul_rn(t[3], yb), __fmul_rn(t[4], xb)), t[5]);
+  grids[idx] = g;
+}
+int k_affine_grid(dc_ctx* ctx, const float* theta, int B, int HH, int WW, float* grids, cudaStream_t st) {
+  if (B <= 0) return DC_OK;
+  affine_grid_kernel<<<DC_CEIL_DIV(B * HH * WW, 256), 256, 0, st>>>(theta, B, HH, WW, (float2*)grids);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+
 // nn.BoxIoU (modules/BoxIoU.lua:40-73): area = w*h, corners from (w-1)/2, no +1.
 __global__ void box_iou_kernel(const float4* __restrict__ b1, const float4* __restrict__ b2, float* __restrict__ out, int B1, int B2) {
   __shared__ float4 s_lohi[128];

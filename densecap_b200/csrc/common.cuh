@@ -57,6 +57,10 @@ struct LaunchState {
   std::set<const void*> smem_attr_done;    // kernel function pointers
 };
 LaunchState* dc_launch_state(dc_ctx* ctx);
+// fp32 workspace of the split-K convolutions (partial-sum planes); null when the context has none
+float* dc_splitk_workspace(dc_ctx* ctx, size_t* elems);
+// sticky device flag: some split-fp16 activation left the fp16 range (see GemmEpilogue::overflow); null without a context
+unsigned int* dc_overflow_flag(dc_ctx* ctx);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (context, kernel)
 template <typename Kernel>
 static inline cudaError_t dc_ensure_smem(dc_ctx* ctx, Kernel kernel, size_t bytes) {
@@ -106,6 +110,7 @@ int k_clip_boxes(dc_ctx*, const float* boxes, float* out, uint8_t* valid, int n,
 int k_objectness_prob(dc_ctx*, const float* scores, float* prob, int n, cudaStream_t st);
 int k_box_to_affine(dc_ctx*, const float* boxes, float* theta, int B, int H, int W, cudaStream_t st);
 int k_box_iou(dc_ctx*, const float* b1, const float* b2, float* out, int B1, int B2, cudaStream_t st);
+int k_affine_grid(dc_ctx*, const float* theta, int B, int HH, int WW, float* grids, cudaStream_t st);
 
 // Fused RPN post-processing (MakeAnchors + ReshapeBoxFeatures + ApplyBoxTransform + clip_boxes +
 // objectness prob + clamp_data compaction).  head: (HW, ld) fp32 rows = pixels, columns
@@ -150,7 +155,12 @@ int k_roi_pool(dc_ctx*, const __half* feat_hi, const __half* feat_lo, const floa
                const float* boxes, const int32_t* nboxes_dev, int max_boxes, int img_h, int img_w, int HH, int WW,
                void* taps_ws, __half* out_hi, __half* out_lo, float* out_f32, int out_layout, cudaStream_t st);
 
+// nn.BatchBilinearSamplerBHWD on caller-supplied grids: feats (H',W',C) fp32, grids (B,HH,WW,2) -> out (B,HH,WW,C)
+int k_bilinear_sampler(dc_ctx*, const float* feats_hwc, int C, int fh, int fw, const float* grids, int B, int HH, int WW, void* taps_ws, float* out,
+                       cudaStream_t st);
+
 // layout_kernels.cu
+int k_image_scale_preprocess(dc_ctx*, const uint8_t* in_hwc, int H, int W, int oh, int ow, float* tmp, float* out_nchw, cudaStream_t st);
 int k_nchw_to_split_nhwc(dc_ctx*, const float* in, __half* hi, __half* lo, int N, int C, int H, int W, cudaStream_t st);
 int k_split_nhwc_to_nchw(dc_ctx*, const __half* hi, const __half* lo, float* out, int N, int C, int H, int W, cudaStream_t st);
 // scale: values are multiplied by it (a power of two) before the split -- used for weights, see weight_scale()
@@ -191,6 +201,9 @@ struct GemmEpilogue {
   const float* gather_tab = nullptr;
   const int32_t* gather_idx = nullptr;
   int gather_ld = 0;
+  // Range guard of the split-fp16 planes: an fp32 value with |x| >= 65504 (or NaN) cannot be represented as hi + lo fp16 (the
+  // conversion saturates); the epilogue ORs 1 into this word when it writes such a value (null = unchecked)
+  unsigned int* overflow = nullptr;
 };
 // small_dense_kernels.cu
 // conv1_1: NCHW fp32 (N,3,H,W) -> split NHWC (N,H,W,Cout), bias+ReLU fused.  w (Cout,3,3,3) fp32 reference layout.
@@ -199,6 +212,11 @@ int k_conv_first(dc_ctx*, const float* img, const float* w, const float* bias, _
 // objectness (1 row) + box regression (4 rows) heads in one pass over the codes: obj (M), trans (M,4)
 int k_recog_heads(dc_ctx*, const float* x, int ldx, const float* w_obj, const float* b_obj, const float* w_box, const float* b_box,
                   float* obj, float* trans, int M, int K, cudaStream_t st);
+
+// tc_conv_first.cu : conv1_1 (K = 27) on tcgen05; w_planes = split [64][64] bank from k_conv_first_weight_to_split
+int k_tc_conv_first(dc_ctx*, const float* img, const __half* w_planes, size_t w_plane_elems, const float* bias, float acc_scale, __half* y_hi, __half* y_lo,
+                    int N, int H, int W, cudaStream_t st);
+int k_conv_first_weight_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, float scale, cudaStream_t st);
 
 // tc_gemm.cu : tcgen05 engine
 int tc_init(dc_ctx*);   // resolves cuTensorMapEncodeTiled, sets smem attributes
@@ -231,7 +249,22 @@ struct LmDecodeArgs {
   float* logits;                            // optional (rows, T, V+1)
 };
 size_t lm_decode_counter_words(int T, int rows_cap);
-int k_lm_decode(dc_ctx*, const LmDecodeArgs& a, cudaStream_t st);
+// compact_only: build the row maps (m_rows, dst_final, dst_all, compacted x) without launching the greedy decoder
+int k_lm_decode(dc_ctx*, const LmDecodeArgs& a, cudaStream_t st, bool compact_only = false);
+
+// beam_search.cu : selection / bookkeeping kernels of LanguageModel:beamsearch (rows = roi * beam + b)
+int k_bs_first(dc_ctx*, const float* logits, int R, int V1, int Bm, int T, int H, float* beam_lp, int32_t* beams, int32_t* tokens, const __half* h_hi,
+               const __half* h_lo, const float* c, __half* hd_hi, __half* hd_lo, float* cd, cudaStream_t st);
+int k_bs_row_topk(dc_ctx*, const float* logits, int rows, int V1, int Bm, int T, int end_token, const int32_t* beams, float* cand_lp, int32_t* cand_ix,
+                  cudaStream_t st);
+int k_bs_merge(dc_ctx*, int R, int Bm, int T, int t, const float* cand_lp, const int32_t* cand_ix, float* beam_lp, const int32_t* beams_in,
+               int32_t* beams_out, int32_t* src_row, int32_t* tokens, cudaStream_t st);
+int k_bs_reindex(dc_ctx*, int rows, int H, const int32_t* src_row, const __half* hi_in, const __half* lo_in, const float* c_in, __half* hi_out,
+                 __half* lo_out, float* c_out, cudaStream_t st);
+int k_bs_final(dc_ctx*, int R, int Bm, int T, const float* beam_lp, const int32_t* beams, const int32_t* dst_row, int64_t* seq, cudaStream_t st);
+int k_bs_fill_i32(dc_ctx*, int32_t* p, int32_t v, int n, cudaStream_t st);
+int k_bs_gather_split(dc_ctx*, const __half* hi_in, const __half* lo_in, int E, const int32_t* rows_src, int first, int R, __half* hi_out,
+                      __half* lo_out, cudaStream_t st);
 
 // lm_kernels.cu
 int k_final_gather(dc_ctx*, const int32_t* idx32, const int32_t* count, int P, const float* boxes, const float* scores,

@@ -281,3 +281,79 @@ int k_preprocess_u8(dc_ctx* ctx, const uint8_t* in, float* out, int N, int H, in
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// image.scale(img, size), bilinear mode (run_model.lua:69, webcam/daemon.lua:70; torch `image` rock, restated in
+// oracle/densecap_oracle.py image_scale): two separable 1-D passes in fp32, width first.  One thread per output element;
+// the arithmetic (float index products, (1-f)*a + f*b without contraction, area average acc / n) follows the C routine
+// Main_scaleLinear_rowcol operation by operation.  Pass 1 reads the decoded uint8 RGB HWC image (image.load: byte / 255),
+// pass 2 applies the rest of run_model.lua:70-74 (RGB -> BGR, * 255, - VGG mean) and writes NCHW.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename Load>
+__device__ __forceinline__ float scale_1d(Load src, int src_len, int dst_len, int di) {
+  if (dst_len > src_len) {
+    if (src_len == 1) return src(0);
+    if (di == dst_len - 1) return src(src_len - 1);
+    const float scale = __fdiv_rn((float)(src_len - 1), (float)(dst_len - 1));
+    float sf = __fmul_rn((float)di, scale);
+    const int si = (int)sf;
+    sf = __fsub_rn(sf, (float)si);
+    return __fadd_rn(__fmul_rn(__fsub_rn(1.f, sf), src(si)), __fmul_rn(sf, src(si + 1)));
+  }
+  if (dst_len < src_len) {
+    const float scale = __fdiv_rn((float)src_len, (float)dst_len);
+    const float s0 = __fmul_rn((float)di, scale);
+    const int si0 = (int)s0;
+    const float f0 = (di == 0) ? 0.f : __fsub_rn(s0, (float)si0);
+    const float s1 = __fmul_rn((float)(di + 1), scale);
+    const int si1 = (int)s1;
+    const float f1 = __fsub_rn(s1, (float)si1);
+    float acc = __fmul_rn(__fsub_rn(1.f, f0), src(di == 0 ? 0 : si0));
+    float n = __fsub_rn(1.f, f0);
+    for (int si = (di == 0 ? 0 : si0) + 1; si < si1; ++si) { acc = __fadd_rn(acc, src(si)); n = __fadd_rn(n, 1.f); }
+    if (si1 < src_len) { acc = __fadd_rn(acc, __fmul_rn(f1, src(si1))); n = __fadd_rn(n, f1); }
+    return __fdiv_rn(acc, n);
+  }
+  return src(di);
+}
+__global__ void image_scale_w_kernel(const uint8_t* __restrict__ in_hwc, int H, int W, int ow, float* __restrict__ tmp) {
+  const size_t total = (size_t)3 * H * ow;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = i % ow, y = (i / ow) % H, c = i / ((size_t)ow * H);
+    const uint8_t* row = in_hwc + (size_t)y * W * 3 + c;
+    tmp[i] = scale_1d([&](int sx) { return __fdiv_rn((float)row[(size_t)sx * 3], 255.f); }, W, ow, x);
+  }
+}
+__global__ void image_scale_h_kernel(const float* __restrict__ tmp, int H, int oh, int ow, float* __restrict__ out_nchw) {
+  const size_t total = (size_t)3 * oh * ow;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = i % ow, y = (i / ow) % oh, c = i / ((size_t)ow * oh);          // c = OUTPUT channel (B, G, R)
+    const float* col = tmp + (size_t)(2 - c) * H * ow + x;
+    const float v = scale_1d([&](int sy) { return col[(size_t)sy * ow]; }, H, oh, y);
+    const float mean[3] = {103.939f, 116.779f, 123.68f};
+    out_nchw[i] = __fadd_rn(__fmul_rn(v, 255.f), __fmul_rn(-1.f, mean[c]));
+  }
+}
+int k_image_scale_preprocess(dc_ctx* ctx, const uint8_t* in_hwc, int H, int W, int oh, int ow, float* tmp, float* out_nchw, cudaStream_t st) {
+  if ((size_t)H * W == 0 || (size_t)oh * ow == 0) return DC_OK;
+  image_scale_w_kernel<<<(unsigned)std::min<size_t>(148 * 8, DC_CEIL_DIV((size_t)3 * H * ow, (size_t)256)), 256, 0, st>>>(in_hwc, H, W, ow, tmp);
+  DC_CHECK_LAUNCH(ctx);
+  image_scale_h_kernel<<<(unsigned)std::min<size_t>(148 * 8, DC_CEIL_DIV((size_t)3 * oh * ow, (size_t)256)), 256, 0, st>>>(tmp, H, oh, ow, out_nchw);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}
+
+// conv1_1 filter bank (64, 3, 3, 3) fp32 -> split [64][64] K-major rows: k = c*9 + r*3 + s (the natural flatten) for k < 27, zeros above
+__global__ void conv_first_weight_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 64) return;
+  const int co = i / 64, k = i % 64;
+  __half h = __float2half(0.f), l = __float2half(0.f);
+  if (k < 27) split_f32(w[co * 27 + k] * scale, h, l);
+  hi[i] = h; lo[i] = l;
+}
+int k_conv_first_weight_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, float scale, cudaStream_t st) {
+  conv_first_weight_kernel<<<16, 256, 0, st>>>(w, hi, lo, scale);
+  DC_CHECK_LAUNCH(ctx);
+  return DC_OK;
+}

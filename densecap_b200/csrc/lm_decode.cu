@@ -362,7 +362,7 @@ size_t lm_decode_counter_words(int T, int rows_cap) {
   return (size_t)(3 * T + 1) * mt_stride;
 }
 
-int k_lm_decode(dc_ctx* ctx, const LmDecodeArgs& a, cudaStream_t st) {
+int k_lm_decode(dc_ctx* ctx, const LmDecodeArgs& a, cudaStream_t st, bool compact_only) {
   using namespace tc;
   DC_REQUIRE(ctx, a.E % BLOCK_K == 0 && a.H % BLOCK_K == 0 && (4 * a.H) % DEC_BN == 0 && a.T >= 1 && a.B >= 1 && a.B <= 64, DC_E_UNSUPPORTED,
              "lm_decode: encoding / rnn size must be multiples of 64 (4H of 128), batch <= 64");
@@ -402,6 +402,7 @@ int k_lm_decode(dc_ctx* ctx, const LmDecodeArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "lm_compact launch: %s", cudaGetErrorString(e));
     DC_CHECK_LAUNCH(ctx);
   }
+  if (compact_only) return DC_OK;
   // ---- persistent decoder ----
   CUtensorMap mx, mh0, mh1, ml, mv;
   {

@@ -19,7 +19,7 @@
 //
 // The interpolation arithmetic follows the reference CPU kernel's operation order without FMA
 // contraction (mul/add intrinsics), so fp32 outputs are bit-identical to the oracle.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 constexpr int ROI_THREADS = 1024;
 constexpr int ROI_MAX_POS = 64;  // HH*WW <= 64
@@ -68,6 +68,38 @@ __global__ void roi_taps_kernel(const float4* __restrict__ boxes, const int32_t*
   const float wx = __fsub_rn(1.f, __fsub_rn(xcoord, xf));
   const float wy = __fsub_rn(1.f, __fsub_rn(ycoord, yf));
   // clamp before the int conversion so that huge/NaN coordinates simply fall outside
+  const int xl = (int)fminf(fmaxf(xf, -2.f), (float)fw + 1.f);
+  const int yt = (int)fminf(fmaxf(yf, -2.f), (float)fh + 1.f);
+  const float omx = __fsub_rn(1.f, wx), omy = __fsub_rn(1.f, wy);
+  t.w[0] = __fmul_rn(wx, wy);
+  t.w[1] = __fmul_rn(omx, wy);
+  t.w[2] = __fmul_rn(wx, omy);
+  t.w[3] = __fmul_rn(omx, omy);
+  const bool xin0 = xl >= 0 && xl <= fw - 1, xin1 = xl + 1 >= 0 && xl + 1 <= fw - 1;
+  const bool yin0 = yt >= 0 && yt <= fh - 1, yin1 = yt + 1 >= 0 && yt + 1 <= fh - 1;
+  const bool finite = (xcoord == xcoord) && (ycoord == ycoord);
+  t.off[0] = (finite && xin0 && yin0) ? (yt * fw + xl) * ch : zero_row;
+  t.off[1] = (finite && xin1 && yin0) ? (yt * fw + xl + 1) * ch : zero_row;
+  t.off[2] = (finite && xin0 && yin1) ? ((yt + 1) * fw + xl) * ch : zero_row;
+  t.off[3] = (finite && xin1 && yin1) ? ((yt + 1) * fw + xl + 1) * ch : zero_row;
+  taps[idx] = t;
+}
+
+// Tap records from CALLER-SUPPLIED sampling grids (stand-alone nn.BatchBilinearSamplerBHWD, modules/BatchBilinearSamplerBHWD.lua:104-122):
+// grids (B, HH, WW, 2) = (gy, gx) in [-1, 1]; same coordinate arithmetic as roi_taps_kernel from `xcoord` on.
+__global__ void roi_taps_from_grid_kernel(const float2* __restrict__ grids, int total, int fh, int fw, int ch, RoiTap* __restrict__ taps) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const float2 g = grids[idx];
+  const float gy = g.x, gx = g.y;
+  RoiTap t;
+  const int zero_row = fh * fw * ch;
+  const float xcoord = __fdiv_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)(fw - 1)), 2.f);
+  const float ycoord = __fdiv_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)(fh - 1)), 2.f);
+  const float xf = floorf(xcoord), yf = floorf(ycoord);
+  const float wx = __fsub_rn(1.f, __fsub_rn(xcoord, xf));
+  const float wy = __fsub_rn(1.f, __fsub_rn(ycoord, yf));
   const int xl = (int)fminf(fmaxf(xf, -2.f), (float)fw + 1.f);
   const int yt = (int)fminf(fmaxf(yf, -2.f), (float)fh + 1.f);
   const float omx = __fsub_rn(1.f, wx), omy = __fsub_rn(1.f, wy);
@@ -203,9 +235,109 @@ roi_pool_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ f
   }
 }
 
-int k_roi_pool(dc_ctx* ctx, const __half* feat_hi, const __half* feat_lo, const float* feats_f32, int C, int fh, int fw,
-               const float* boxes, const int32_t* nboxes_dev, int max_boxes, int img_h, int img_w, int HH, int WW,
-               void* taps_ws, __half* out_hi, __half* out_lo, float* out_f32, int out_layout, cudaStream_t st) {
+// ---------------------------------------------------------------------------------------------------------------------
+// Split-plane output through the TMA store engine (the hot path of the forward pass).
+// ncu on the kernel above (r06): LSU data pipe 76 % busy and the 16-byte-per-lane global stores (8 half-filled 128-byte lines
+// per warp instruction and plane) cost as many LSU cycles as the 32 LDS.128 corner wavefronts of an iteration.  Here a warp
+// writes its 8 positions x 32 channels x {hi, lo} into a 1 KB shared-memory tile (two conflict-free STS.128 per lane) and one
+// elected lane hands the tile to the TMA unit (cp.async.bulk.tensor.3d global <- shared, box {32 ch, 8 rows, 2 planes}); the
+// address generation and the 64-byte row writes leave the LSU.  Shared memory beyond the feature slice holds 12 such tiles, so
+// only the first 12 warps gather (all 32 stage the slice, then warps 12.. exit); tap records are prefetched two iterations ahead.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int ROI_TMA_WARPS = 12;
+__global__ void __launch_bounds__(ROI_THREADS, 1)
+roi_pool_tma_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ feat_lo, int C, int fh, int fw,
+                    const RoiTap* __restrict__ taps, int total_items, const __grid_constant__ CUtensorMap out_map) {
+  constexpr int CH = 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int cells = fh * fw;
+  float* slice = reinterpret_cast<float*>(smem_raw);                               // [cells + 1][CH], last row = zeros
+  const size_t slice_bytes = ((size_t)(cells + 1) * CH * 4 + 127) & ~(size_t)127;
+  unsigned char* tiles = smem_raw + slice_bytes;                                   // ROI_TMA_WARPS x [2 planes][8 rows][64 B]
+  const int c0 = blockIdx.x * CH;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) tc::prefetch_tmap(&out_map);
+  {
+    constexpr int QUADS = CH / 4;
+    for (int e = threadIdx.x; e < cells * QUADS; e += ROI_THREADS) {
+      const int cell = e / QUADS, cq4 = (e % QUADS) * 4;
+      const size_t g = (size_t)cell * C + c0 + cq4;
+      const uint2 h = *reinterpret_cast<const uint2*>(feat_hi + g);
+      const uint2 l = *reinterpret_cast<const uint2*>(feat_lo + g);
+      const __half2 h01 = *reinterpret_cast<const __half2*>(&h.x), h23 = *reinterpret_cast<const __half2*>(&h.y);
+      const __half2 l01 = *reinterpret_cast<const __half2*>(&l.x), l23 = *reinterpret_cast<const __half2*>(&l.y);
+      float4 v;
+      v.x = __low2float(h01) + __low2float(l01);
+      v.y = __high2float(h01) + __high2float(l01);
+      v.z = __low2float(h23) + __low2float(l23);
+      v.w = __high2float(h23) + __high2float(l23);
+      *reinterpret_cast<float4*>(slice + cell * CH + cq4) = v;
+    }
+    if (threadIdx.x < CH) slice[cells * CH + threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  if (warp >= ROI_TMA_WARPS) return;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int sub = lane >> 2, ql = lane & 3;
+  const int half = sub & 1;                               // odd positions read their two 4-channel halves in swapped order (bank spread)
+  const int cA = ql * 8 + 4 * half, cB = ql * 8 + 4 * (half ^ 1);
+  const int stride = gridDim.y * ROI_TMA_WARPS * 8;
+  unsigned char* tile = tiles + (size_t)warp * 1024;
+  const uint32_t tile_s = tc::smem_u32(tile);
+  auto blend4 = [&](const uint4& ta, const uint4& tb, int cc, float (&v)[4]) {
+    const float w0 = __uint_as_float(tb.x), w1 = __uint_as_float(tb.y), w2 = __uint_as_float(tb.z), w3 = __uint_as_float(tb.w);
+    const float4 tl = *reinterpret_cast<const float4*>(slice + ta.x + cc);
+    const float4 tr = *reinterpret_cast<const float4*>(slice + ta.y + cc);
+    const float4 bl = *reinterpret_cast<const float4*>(slice + ta.z + cc);
+    const float4 br = *reinterpret_cast<const float4*>(slice + ta.w + cc);
+    v[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.x), __fmul_rn(w1, tr.x)), __fmul_rn(w2, bl.x)), __fmul_rn(w3, br.x));
+    v[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.y), __fmul_rn(w1, tr.y)), __fmul_rn(w2, bl.y)), __fmul_rn(w3, br.y));
+    v[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.z), __fmul_rn(w1, tr.z)), __fmul_rn(w2, bl.z)), __fmul_rn(w3, br.z));
+    v[3] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.w), __fmul_rn(w1, tr.w)), __fmul_rn(w2, bl.w)), __fmul_rn(w3, br.w));
+  };
+  auto load_tap = [&](int it, uint4& a, uint4& b) {
+    a = make_uint4(0, 0, 0, 0); b = a;
+    if (it < total_items) { const uint4* tp = reinterpret_cast<const uint4*>(taps + it); a = __ldcg(tp); b = __ldcg(tp + 1); }
+  };
+  int it0 = (blockIdx.y * ROI_TMA_WARPS + warp) * 8;      // first item of this warp's current run of 8
+  uint4 t0a, t0b, t1a, t1b;
+  load_tap(it0 + sub, t0a, t0b);
+  load_tap(it0 + stride + sub, t1a, t1b);
+  while (it0 < total_items) {
+    uint4 t2a, t2b;
+    load_tap(it0 + 2 * stride + sub, t2a, t2b);
+    float va[4], vb[4];
+    blend4(t0a, t0b, cA, va);
+    blend4(t0a, t0b, cB, vb);
+    uint32_t ha0, la0, ha1, la1, hb0, lb0, hb1, lb1;
+    split_pair(va[0], va[1], ha0, la0);
+    split_pair(va[2], va[3], ha1, la1);
+    split_pair(vb[0], vb[1], hb0, lb0);
+    split_pair(vb[2], vb[3], hb1, lb1);
+    const uint4 ph = half ? make_uint4(hb0, hb1, ha0, ha1) : make_uint4(ha0, ha1, hb0, hb1);
+    const uint4 pl = half ? make_uint4(lb0, lb1, la0, la1) : make_uint4(la0, la1, lb0, lb1);
+    // the previous bulk store of this warp must have finished READING the tile before it is overwritten
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    *reinterpret_cast<uint4*>(tile + sub * 64 + ql * 16) = ph;                      // plane 0 (hi): rows of 64 B
+    *reinterpret_cast<uint4*>(tile + 512 + sub * 64 + ql * 16) = pl;                // plane 1 (lo)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                    // generic-proxy writes -> async proxy
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                   ::"l"(&out_map), "r"(c0), "r"(it0), "r"(0), "r"(tile_s) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    t0a = t1a; t0b = t1b; t1a = t2a; t1b = t2b;
+    it0 += stride;
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");        // stores complete before the CTA exits
+}
+
+// grids != nullptr: stand-alone sampler on caller-supplied (max_boxes, HH, WW, 2) grids (boxes / image size unused)
+static int roi_pool_impl(dc_ctx* ctx, const __half* feat_hi, const __half* feat_lo, const float* feats_f32, int C, int fh, int fw,
+                         const float* boxes, const float* grids, const int32_t* nboxes_dev, int max_boxes, int img_h, int img_w, int HH, int WW,
+                         void* taps_ws, __half* out_hi, __half* out_lo, float* out_f32, int out_layout, cudaStream_t st) {
   if (max_boxes <= 0) return DC_OK;
   DC_REQUIRE(ctx, HH * WW <= ROI_MAX_POS && HH > 1 && WW > 1, DC_E_UNSUPPORTED, "roi_pool: HH*WW must be in (1,64]");
   DC_REQUIRE(ctx, C % 8 == 0, DC_E_UNSUPPORTED, "roi_pool: C must be a multiple of 8");
@@ -216,14 +348,44 @@ int k_roi_pool(dc_ctx* ctx, const __half* feat_hi, const __half* feat_lo, const 
   int ch = 32;
   while (ch > 8 && ((size_t)(fh * fw + 1) * ch * 4 > limit || C % ch != 0)) ch >>= 1;
   const size_t smem = (size_t)(fh * fw + 1) * ch * 4;
-  roi_taps_kernel<<<DC_CEIL_DIV(total, 256), 256, 0, st>>>((const float4*)boxes, nboxes_dev, max_boxes, (float)img_h, (float)img_w, fh, fw,
-                                                          HH, WW, ch, taps);
+  if (grids) roi_taps_from_grid_kernel<<<DC_CEIL_DIV(total, 256), 256, 0, st>>>((const float2*)grids, total, fh, fw, ch, taps);
+  else roi_taps_kernel<<<DC_CEIL_DIV(total, 256), 256, 0, st>>>((const float4*)boxes, nboxes_dev, max_boxes, (float)img_h, (float)img_w, fh, fw,
+                                                               HH, WW, ch, taps);
   DC_CHECK_LAUNCH(ctx);
   DC_REQUIRE(ctx, smem <= limit && C % ch == 0, DC_E_UNSUPPORTED, "roi_pool: feature map %dx%d too large for the shared-memory slice", fh, fw);
   const int slices = C / ch;
   int groups = dc_launch_state(ctx)->num_sms / slices;
   if (groups < 1) groups = 1;
   dim3 grid(slices, groups);
+  const size_t slice_bytes = (smem + 127) & ~(size_t)127;
+#ifdef DC_DISABLE_ROI_TMA
+  const bool tma_ok = false;
+#else
+  const bool tma_ok = true;
+#endif
+  if (tma_ok && out_hi && !out_f32 && !feats_f32 && ch == 32 && out_lo > out_hi && slice_bytes + ROI_TMA_WARPS * 1024 <= limit &&
+      (((size_t)(out_lo - out_hi) * 2) % 16) == 0 && dc_launch_state(ctx)->encode_tiled) {
+    // TMA-store variant: output viewed as (planes, rows = boxes * positions, C) fp16
+    CUtensorMap omap;
+    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)total, 2};
+    const uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)(out_lo - out_hi) * 2};
+    const uint32_t box[3] = {32, 8, 2};
+    int rc = tc::encode_map(ctx, &omap, out_hi, 3, dims, str, box, /*swizzle=*/false);
+    if (rc) return rc;
+    const size_t smem_t = slice_bytes + ROI_TMA_WARPS * 1024;
+    cudaError_t e = dc_ensure_smem(ctx, roi_pool_tma_kernel, limit);
+    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "roi_pool smem attribute: %s", cudaGetErrorString(e));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = grid; lc.blockDim = dim3(ROI_THREADS); lc.dynamicSmemBytes = smem_t; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    e = cudaLaunchKernelEx(&lc, roi_pool_tma_kernel, feat_hi, feat_lo, C, fh, fw, (const RoiTap*)taps, total, omap);
+    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "roi_pool launch: %s", cudaGetErrorString(e));
+    DC_CHECK_LAUNCH(ctx);
+    return DC_OK;
+  }
 #define ROI_LAUNCH(CHV)                                                                                              \
   do {                                                                                                               \
     cudaError_t e = dc_ensure_smem(ctx, roi_pool_kernel<CHV>, limit);                                                  \
@@ -244,6 +406,18 @@ int k_roi_pool(dc_ctx* ctx, const __half* feat_hi, const __half* feat_lo, const 
 #undef ROI_LAUNCH
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
+}
+
+int k_roi_pool(dc_ctx* ctx, const __half* feat_hi, const __half* feat_lo, const float* feats_f32, int C, int fh, int fw,
+               const float* boxes, const int32_t* nboxes_dev, int max_boxes, int img_h, int img_w, int HH, int WW,
+               void* taps_ws, __half* out_hi, __half* out_lo, float* out_f32, int out_layout, cudaStream_t st) {
+  return roi_pool_impl(ctx, feat_hi, feat_lo, feats_f32, C, fh, fw, boxes, nullptr, nboxes_dev, max_boxes, img_h, img_w, HH, WW, taps_ws, out_hi, out_lo,
+                       out_f32, out_layout, st);
+}
+// nn.BatchBilinearSamplerBHWD:updateOutput: feats (H', W', C) fp32 HWC, grids (B, HH, WW, 2) -> out (B, HH, WW, C) fp32
+int k_bilinear_sampler(dc_ctx* ctx, const float* feats_hwc, int C, int fh, int fw, const float* grids, int B, int HH, int WW, void* taps_ws, float* out,
+                       cudaStream_t st) {
+  return roi_pool_impl(ctx, nullptr, nullptr, feats_hwc, C, fh, fw, nullptr, grids, nullptr, B, 0, 0, HH, WW, taps_ws, nullptr, nullptr, out, 1, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------

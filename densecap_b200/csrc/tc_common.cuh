@@ -16,7 +16,7 @@ constexpr int EPI_THREAD0 = 32 * EPI_WARP0;
 // start warpgroup 0 shrinks to 40 registers and the epilogue warpgroups grow to 232, which is what lets an epilogue thread keep the
 // 128 running sums of a 256-column tile (hierarchical accumulation, see epilogue_tile) in registers.
 constexpr int NUM_THREADS = EPI_THREAD0 + 32 * EPI_WARPS;
-constexpr int REGS_CONTROL = 80, REGS_EPILOGUE = 216;
+constexpr int REGS_CONTROL = 80, REGS_EPILOGUE = 208;    // 128 * 80 + 256 * 208 = 63488 <= 384 * 168 (the registers the CTA owns)
 __device__ __forceinline__ void regs_shrink_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL)); }
 __device__ __forceinline__ void regs_grow_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE)); }
 constexpr int TILE_H = 8, TILE_W = 16;   // conv M tile = 8x16 output pixels
@@ -216,6 +216,8 @@ struct Problem {
   int M, N, K;                 // GEMM view (conv: M = tiles*128 is implicit, N = Cout, K = 9*Cin)
   int num_k_blocks;
   int kb_per_group;            // k-blocks accumulated in TMEM before the partial sum is taken over by the epilogue (>= 1)
+  int split_k;                 // convolution only: K splits per output tile (>= 1), partial sums to out_f32 + split * split_stride
+  size_t split_stride;
   int m_tiles, n_tiles;
   int m_fastest;               // tile order
   // conv geometry
@@ -267,7 +269,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
   // decoder gate tiles: the input half of the pre-activations comes from a table row per output row (token); it is requested
   // when the first group arrives (the token is final by then) and added after the last one
   float4 gath[CHUNKS_PER_WARP][8];
-  const bool use_gather = !CONV && ep.gather_tab != nullptr;
+  const bool use_gather = !CONV && WIDE && ep.gather_tab != nullptr;      // only the wide (<= 128-column) tiles carry the table gather
 #pragma unroll 1
   for (int g = 0; g < num_groups; ++g, ++gi) {
     const int acc = gi & 1;
@@ -334,6 +336,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
   }
   float best_v = -INFINITY;
   int best_c = 0x7fffffff;
+  bool out_of_range = false;
 
   // Stage this tile's bias slice in shared memory (one coalesced load per thread) -- per-element global loads in the column
   // loop would serialise on L2 latency.  Two buffers used alternately by consecutive tiles, so one named barrier per tile suffices.
@@ -358,6 +361,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
       } else if (ep.bias) x += sbias[c * 32 + j];
       if (ep.relu) x = fmaxf(x, 0.f);
       v[j] = x;
+      out_of_range |= !(fabsf(x) < 65504.f);          // true for |x| >= 65504 and for NaN
     }
     if (POOL) {
       // ReLU output is >= 0, so 0 is the identity of max for out-of-image pixels (ceil-mode windows)
@@ -462,6 +466,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
   }
   if (ep.argmax && out_row >= 0 && best_c != 0x7fffffff)
     atomicMax(ep.argmax + out_row, pack_argmax_tc(best_v, best_c));
+  if (ep.overflow && ep.out_hi && !ep.lstm_c && out_of_range && (POOL ? in_bounds : out_row >= 0)) atomicOr(ep.overflow, 1u);
 }
 
 // Epilogue warps of the GEMM / convolution kernels: drain the accumulator groups of every tile this CTA owns.
@@ -480,7 +485,7 @@ __device__ __forceinline__ void epilogue_warps(const Problem& pb, const GemmEpil
 }
 
 static int encode_map(dc_ctx* ctx, CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box) {
+                      const uint32_t* box, bool swizzle128 = true) {
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
@@ -488,7 +493,7 @@ static int encode_map(dc_ctx* ctx, CUtensorMap* map, const void* base, int rank,
   const PFN_encodeTiled encode = (PFN_encodeTiled)dc_launch_state(ctx)->encode_tiled;
   DC_REQUIRE(ctx, encode != nullptr, DC_E_CUDA, "cuTensorMapEncodeTiled unavailable (tc_init not run)");
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DC_REQUIRE(ctx, r == CUDA_SUCCESS, DC_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
   return DC_OK;

@@ -306,10 +306,15 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  const int num_tiles = pb.m_tiles * pb.n_tiles;
-  const int groups = 3 * pb.kb_per_tap;                                 // (s, channel block) groups per tile
+  // Work item = (output tile, K split).  split_k > 1 (layers whose tile count cannot fill the GPU: conv5_x, the RPN 3x3): the
+  // (tap column, channel block) groups of a tile are divided among split_k items; each writes its raw fp32 partial sums to its own
+  // plane of a workspace, and a small finalize kernel adds the planes in a fixed order (+ bias, ReLU, fp16 split).
+  const int S = pb.split_k;
+  const int num_tiles = pb.m_tiles * pb.n_tiles * S;
+  const int groups_all = 3 * pb.kb_per_tap;                             // (s, channel block) groups per output tile
+  auto group_begin = [&](int sp) { return (int)(((long)groups_all * sp) / S); };
   // whole filter bank of the (single) N tile fits the B ring: load it once, keep it
-  const bool b_resident = (pb.n_tiles == 1) && (pb.num_k_blocks == SB);
+  const bool b_resident = (pb.n_tiles == 1) && (pb.num_k_blocks == SB) && S == 1;
 
   if (warp < EPI_WARP0) {
     regs_shrink_control();
@@ -320,7 +325,8 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int sa = 0; uint32_t pa = 0;
       int sb = 0; uint32_t pbp = 0;
       bool first = true;
-      for (int tile = worker; tile < num_tiles; tile += num_workers, first = false) {
+      for (int item = worker; item < num_tiles; item += num_workers, first = false) {
+        const int sp = item % S, tile = item / S;
         const int nt = tile % pb.n_tiles, mt = tile / pb.n_tiles;
         const int n0 = nt * BLOCK_N + (int)cta_rank * C::B_ROWS;
         const int per_img = pb.tiles_h * pb.tiles_w;
@@ -328,7 +334,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int rr = mt % per_img;
         const int h0 = ((rr / pb.tiles_w) * CG + (int)cta_rank) * TILE_H;
         const int w0 = (rr % pb.tiles_w) * TILE_W;
-        for (int g = 0; g < groups; ++g) {
+        for (int g = group_begin(sp); g < group_begin(sp + 1); ++g) {
           const int s = g / pb.kb_per_tap, cb = g % pb.kb_per_tap;
           mbar_wait(aempty_bar(sa), pa ^ 1);
           const uint32_t a_dst = a_ring + sa * AH_STAGE_BYTES;
@@ -369,11 +375,14 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int gi = 0;                                     // accumulator groups issued so far (TMEM stage = gi & 1)
       const int G = pb.kb_per_group;
       bool first_tile = true;
-      for (int tile = worker; tile < num_tiles; tile += num_workers, first_tile = false) {
+      for (int item = worker; item < num_tiles; item += num_workers, first_tile = false) {
+        const int sp = item % S;
+        const int g_begin = group_begin(sp), g_end = group_begin(sp + 1);
+        const int nkb = (g_end - g_begin) * 3;        // k-blocks of this item
         uint32_t d_tmem = 0;
         int acc = 0;
-        int kb = 0;                                   // (group, vertical tap) counter = k-block index of the tile
-        for (int g = 0; g < groups; ++g) {
+        int kb = 0;                                   // (group, vertical tap) counter = k-block index inside the item
+        for (int g = g_begin; g < g_end; ++g) {
           mbar_wait(afull_bar(sa), pa);
           const uint32_t a_base = a_ring + sa * AH_STAGE_BYTES;
 #pragma unroll 1
@@ -411,7 +420,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
               }
             }
-            const bool group_end = (kb % G) == G - 1 || kb == pb.num_k_blocks - 1;
+            const bool group_end = (kb % G) == G - 1 || kb == nkb - 1;
             if (CG == 2) {
               if (!b_resident) umma2_commit_mc(bempty_bar(sb));
               if (r == 2) umma2_commit_mc(aempty_bar(sa));
@@ -431,7 +440,17 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp >= EPI_WARP0) {
     // =============================== epilogue warps ===============================
     regs_grow_epilogue();
-    epilogue_warps<BLOCK_N, true, POOL, CG, C::WIDE>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, worker, num_workers, cta_rank, is_leader);
+    const int G = pb.kb_per_group;
+    int gi = 0, iter = 0;
+    for (int item = worker; item < num_tiles; item += num_workers, ++iter) {
+      const int sp = item % S, tile = item / S;
+      const int nt = tile % pb.n_tiles, mt = tile / pb.n_tiles;
+      const int nkb = (group_begin(sp + 1) - group_begin(sp)) * 3;
+      GemmEpilogue e2 = ep;
+      if (S > 1) e2.out_f32 = ep.out_f32 + (size_t)sp * pb.split_stride;      // this split's partial-sum plane
+      epilogue_tile<BLOCK_N, true, POOL, CG, C::WIDE>(pb, e2, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, mt, nt, (nkb + G - 1) / G, gi, iter, cta_rank,
+                                                      is_leader);
+    }
   }
 
   __syncwarp();
@@ -454,7 +473,7 @@ static int launch_kernel(dc_ctx* ctx, Kernel kernel, size_t smem_bytes, int cg, 
     cudaError_t e = dc_ensure_smem(ctx, kernel, smem_bytes);
     if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "tc_gemm smem attribute: %s", cudaGetErrorString(e));
   }
-  const int tiles = pb.m_tiles * pb.n_tiles;
+  const int tiles = pb.m_tiles * pb.n_tiles * (pb.split_k > 1 ? pb.split_k : 1);
   const int slots = dc_launch_state(ctx)->num_sms / cg;                        // CTAs (CG=1) or CTA pairs (CG=2) resident at once
   const int workers = tiles < slots ? tiles : slots;
   cudaLaunchConfig_t cfg = {};
@@ -521,6 +540,42 @@ static TileCfg pick_tile(int num_sms, int N, int m_tiles128, bool lstm) {
   return best;
 }
 
+// out = relu(sum_s ws[s] + bias) as split-fp16 planes; the S partial planes are added in index order (deterministic)
+__global__ void splitk_finalize_kernel(const float* __restrict__ ws, int S, size_t stride, size_t rows, int N, const float* __restrict__ bias, int relu,
+                                       __half* __restrict__ out_hi, __half* __restrict__ out_lo, unsigned int* __restrict__ overflow) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const size_t total8 = rows * (size_t)N / 8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total8; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i * 8;
+    const int n = (int)(e % N);
+    float v[8];
+    {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(ws + e)), b = __ldcg(reinterpret_cast<const float4*>(ws + e) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    for (int s2 = 1; s2 < S; ++s2) {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(ws + s2 * stride + e)), b = __ldcg(reinterpret_cast<const float4*>(ws + s2 * stride + e) + 1);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    uint32_t hh[4], ll[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x0 = v[2 * j], x1 = v[2 * j + 1];
+      if (bias) { x0 += __ldg(bias + n + 2 * j); x1 += __ldg(bias + n + 2 * j + 1); }
+      if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+      if (overflow && (!(fabsf(x0) < 65504.f) || !(fabsf(x1) < 65504.f))) atomicOr(overflow, 1u);
+      __half h0, l0, h1, l1;
+      split_f32(x0, h0, l0);
+      split_f32(x1, h1, l1);
+      hh[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      ll[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4*>(out_hi + e) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    *reinterpret_cast<uint4*>(out_lo + e) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+  }
+}
+
 }  // namespace tc
 
 int tc_init(dc_ctx* ctx) {
@@ -555,12 +610,15 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
   pb.M = M; pb.N = N; pb.K = K;
   pb.num_k_blocks = K / BLOCK_K;
   pb.kb_per_group = kGroupKBlocks;
+  pb.split_k = 1;
   const int m_tiles128 = DC_CEIL_DIV(M, BLOCK_M);
-  const TileCfg tc_ = pick_tile(dc_launch_state(ctx)->num_sms, N, m_tiles128, ep.lstm_c != nullptr);
+  TileCfg tc_ = pick_tile(dc_launch_state(ctx)->num_sms, N, m_tiles128, ep.lstm_c != nullptr);
+  if (ep.gather_tab && tc_.bn == 256) tc_ = TileCfg{128, 1};          // the table-gather epilogue exists for the wide tiles only
   const int bn = tc_.bn, cg = tc_.cg;
   pb.m_tiles = DC_CEIL_DIV(m_tiles128, cg);
   pb.n_tiles = DC_CEIL_DIV(N, bn);
   pb.m_fastest = pb.m_tiles <= pb.n_tiles;
+  if (ep.out_hi && !ep.overflow) ep.overflow = dc_overflow_flag(ctx);
   CUtensorMap ma, mb;
   {
     const uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, 2};
@@ -598,8 +656,28 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
   pb.N = Cout;
   pb.tiles_w = DC_CEIL_DIV(W, TILE_W);
   const int m_tiles128 = N * DC_CEIL_DIV(H, TILE_H) * pb.tiles_w;
-  const TileCfg tc_ = pick_tile(dc_launch_state(ctx)->num_sms, Cout, m_tiles128, false);
+  TileCfg tc_ = pick_tile(dc_launch_state(ctx)->num_sms, Cout, m_tiles128, false);
+  // Small feature maps (conv5_x, RPN 3x3 at batch 1-2) have too few 256 x 256 pair tiles to fill the GPU and were run as 128 x 64 tiles at
+  // ~51 % tensor-pipe activity.  Split K instead: every pair tile is divided into S items over the (tap column, channel block) groups.
+  int split = 1;
+  size_t ws_elems = 0;
+  float* ws = dc_splitk_workspace(ctx, &ws_elems);
+#ifdef DC_DISABLE_SPLITK
+  ws = nullptr;
+#endif
+  if (!fuse_pool && Cout >= 256 && Cout % 8 == 0 && ws) {
+    const int slots = dc_launch_state(ctx)->num_sms / 2;
+    const long pair_tiles = (long)N * DC_CEIL_DIV(H, 2 * TILE_H) * pb.tiles_w * DC_CEIL_DIV(Cout, 256);
+    const int groups_all = 3 * pb.kb_per_tap;
+    if (pair_tiles * 2 <= slots) {
+      int S = (int)std::min<long>(std::min<long>(slots / pair_tiles, groups_all / 2), 8);
+      while (S >= 2 && (size_t)S * N * H * W * Cout > ws_elems) --S;
+      if (S >= 2) { split = S; tc_ = TileCfg{256, 2}; }
+    }
+  }
   const int bn = tc_.bn, cg = tc_.cg;
+  pb.split_k = split;
+  pb.split_stride = (size_t)N * H * W * Cout;
   pb.tiles_h = DC_CEIL_DIV(H, TILE_H * cg);          // cg == 2: a pair tile covers 16 image rows (two stacked 8x16 patches)
   pb.m_tiles = N * pb.tiles_h * pb.tiles_w;
   pb.M = pb.m_tiles * BLOCK_M * cg;
@@ -608,12 +686,18 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
   pb.n_tiles = DC_CEIL_DIV(Cout, bn);
   pb.m_fastest = 0;   // n fastest: CTAs sharing an activation patch run together, the patch stays in L2
   GemmEpilogue ep;
-  ep.bias = bias;
   ep.acc_scale = acc_scale;
-  ep.relu = relu;
-  ep.out_hi = y_hi;
-  ep.out_lo = y_lo;
-  ep.ldo = Cout;
+  if (split > 1) {             // raw partial sums; bias / ReLU / fp16 split happen in splitk_finalize_kernel
+    ep.out_f32 = ws;
+    ep.ldf = Cout;
+  } else {
+    ep.bias = bias;
+    ep.relu = relu;
+    ep.out_hi = y_hi;
+    ep.out_lo = y_lo;
+    ep.ldo = Cout;
+    ep.overflow = dc_overflow_flag(ctx);
+  }
   CUtensorMap ma, mb;
   {
     const uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N, 2};
@@ -634,6 +718,23 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
     if (bn == 64) return launch_halo<64, true, 1>(ctx, ma, mb, pb, ep, st);
     if (bn == 256) return launch_halo<256, true, 1>(ctx, ma, mb, pb, ep, st);
     return launch_halo<128, true, 1>(ctx, ma, mb, pb, ep, st);
+  }
+  if (split > 1) {
+    int rc = launch_halo<256, false, 2>(ctx, ma, mb, pb, ep, st);
+    if (rc) return rc;
+    const size_t rows = (size_t)N * H * W;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::min<size_t>((size_t)dc_launch_state(ctx)->num_sms * 4, DC_CEIL_DIV(rows * Cout / 8, (size_t)256)));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, splitk_finalize_kernel, (const float*)ws, split, pb.split_stride, rows, Cout, bias, relu, y_hi, y_lo, dc_overflow_flag(ctx));
+    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "splitk_finalize launch: %s", cudaGetErrorString(e));
+    DC_CHECK_LAUNCH(ctx);
+    return DC_OK;
   }
   if (cg == 2) return launch_halo<256, false, 2>(ctx, ma, mb, pb, ep, st);
   if (bn == 64) return launch_halo<64, false, 1>(ctx, ma, mb, pb, ep, st);

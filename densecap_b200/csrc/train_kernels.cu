@@ -132,22 +132,113 @@ __device__ int block_first_nonzero(const uint8_t* __restrict__ mask, bool invert
     }
     __syncthreads();
   }
-  return running;
+  const int total = running;       // every thread reads the final value ...
+  __syncthreads();                 // ... before the next call of this function can reset it
+  return total;
 }
 
-// counts: [0] total_pos, [1] total_neg, [2] P, [3] M
+// ---- uniform sampling (torch.multinomial over a constant probability vector, BoxSampler.lua:138-152) --------------------------
+// A keyed bijection of the row index gives every candidate a UNIQUE pseudo-random 32-bit key; "n candidates without replacement"
+// = the n candidates with the smallest keys.  The n-th smallest key is found by bisection on the key value (one block-wide count
+// per bit), then the selected rows are compacted in index order.  With replacement (only when there are fewer negatives than
+// requested, like the reference) draw j takes candidate hash(j) mod total.
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {       // murmur3 finaliser: a bijection on 32-bit words
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+__device__ int block_count_le(const uint8_t* __restrict__ mask, bool invert_of, const uint8_t* __restrict__ other, int A, uint32_t salt, uint32_t thr) {
+  __shared__ int warp_cnt[32];
+  __shared__ int total;
+  int c = 0;
+  for (int r = threadIdx.x; r < A; r += blockDim.x) {
+    const bool f = invert_of ? (other[r] == 0) : (mask[r] != 0);
+    c += (f && fmix32((uint32_t)r ^ salt) <= thr) ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_cnt[w];
+    total = t;
+  }
+  __syncthreads();
+  return total;
+}
+// ordered compaction of the candidates whose key is <= thr (at most cap of them); returns nothing
+__device__ void block_compact_le(const uint8_t* __restrict__ mask, bool invert_of, const uint8_t* __restrict__ other, int A, uint32_t salt, uint32_t thr,
+                                 int cap, int32_t* __restrict__ out) {
+  __shared__ int warp_cnt[32];
+  __shared__ int running;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  for (int base = 0; base < A; base += blockDim.x) {
+    const int r = base + threadIdx.x;
+    bool f = false;
+    if (r < A) f = (invert_of ? (other[r] == 0) : (mask[r] != 0)) && fmix32((uint32_t)r ^ salt) <= thr;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = running;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    off += __popc(bal & ((1u << lane) - 1u));
+    if (f && off < cap) out[off] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int c = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) c += warp_cnt[w];
+      running += c;
+    }
+    __syncthreads();
+  }
+}
+// n <= total candidates, n >= 1: smallest key value thr with #(key <= thr) >= n  (keys are unique, so the count is exactly n)
+__device__ uint32_t block_nth_key(const uint8_t* __restrict__ mask, bool invert_of, const uint8_t* __restrict__ other, int A, uint32_t salt, int n) {
+  uint32_t lo = 0u, hi = 0xFFFFFFFFu;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (block_count_le(mask, invert_of, other, A, salt, mid) >= n) hi = mid; else lo = mid + 1u;
+  }
+  return lo;
+}
+
+// counts: [0] total_pos, [1] total_neg, [2] P, [3] M.  mode 0: the first P positives / first M negatives in index order (the
+// reference's debug_pos_sample_idx / debug_neg_sample_idx injection, BoxSampler.lua:154-159); mode 1: uniform random (seeded).
 __global__ void __launch_bounds__(1024)
-sampler_select_kernel(const uint8_t* __restrict__ pos, const uint8_t* __restrict__ neg, int A, int batch_size, int32_t* __restrict__ pos_idx,
-                      int32_t* __restrict__ neg_idx, int32_t* __restrict__ counts) {
+sampler_select_kernel(const uint8_t* __restrict__ pos, const uint8_t* __restrict__ neg, int A, int batch_size, int mode, uint32_t salt,
+                      int32_t* __restrict__ pos_idx, int32_t* __restrict__ neg_idx, int32_t* __restrict__ counts) {
+  __shared__ int32_t s_list[1024];
   const int total_pos = block_first_nonzero(pos, false, nullptr, A, batch_size, pos_idx);
   int total_neg = block_first_nonzero(neg, false, nullptr, A, batch_size, neg_idx);
-  if (total_neg == 0) total_neg = block_first_nonzero(nullptr, true, pos, A, batch_size, neg_idx);   // neg = not pos (BoxSampler.lua:111-128)
+  const bool neg_is_not_pos = (total_neg == 0);
+  if (neg_is_not_pos) total_neg = block_first_nonzero(nullptr, true, pos, A, batch_size, neg_idx);   // neg = not pos (BoxSampler.lua:111-128)
   const int P = min(batch_size / 2, total_pos);
   const int M = batch_size - P;
   __syncthreads();
-  // too few negatives: sampled with replacement -> deterministic cyclic reuse
-  const int have = min(total_neg, batch_size);
-  for (int j = have + threadIdx.x; j < M; j += blockDim.x) neg_idx[j] = have > 0 ? neg_idx[j % have] : 0;
+  if (mode == 1) {
+    const uint32_t salt_p = fmix32(salt ^ 0x9e3779b9u), salt_n = fmix32(salt ^ 0x7f4a7c15u);
+    if (P > 0 && total_pos > P) {                                     // all positives are taken when total_pos <= P
+      const uint32_t thr = block_nth_key(pos, false, nullptr, A, salt_p, P);
+      block_compact_le(pos, false, nullptr, A, salt_p, thr, P, pos_idx);
+    }
+    if (total_neg > M) {                                              // without replacement
+      const uint32_t thr = block_nth_key(neg, neg_is_not_pos, pos, A, salt_n, M);
+      block_compact_le(neg, neg_is_not_pos, pos, A, salt_n, thr, M, neg_idx);
+    } else if (total_neg > 0 && total_neg < M) {                      // with replacement: neg_idx[0, total_neg) holds every negative
+      __syncthreads();
+      for (int j = threadIdx.x; j < total_neg; j += blockDim.x) s_list[j] = neg_idx[j];
+      __syncthreads();
+      for (int j = threadIdx.x; j < M; j += blockDim.x) neg_idx[j] = s_list[fmix32((uint32_t)j * 0x9e3779b1u ^ salt_n) % (uint32_t)total_neg];
+    }
+  } else {
+    // too few negatives: sampled with replacement -> deterministic cyclic reuse
+    const int have = min(total_neg, batch_size);
+    __syncthreads();
+    for (int j = have + threadIdx.x; j < M; j += blockDim.x) neg_idx[j] = have > 0 ? neg_idx[j % have] : 0;
+  }
   if (threadIdx.x == 0) { counts[0] = total_pos; counts[1] = total_neg; counts[2] = P; counts[3] = M; }
 }
 
@@ -279,7 +370,8 @@ struct TrainBuffers {
 
 int k_loc_train_sampler(dc_ctx* ctx, const float* head, int ld, int H, int W, int k, const float* anchors_dev, float x0, float y0, float sx,
                         float sy, const float* gt_boxes, int B2, float lo, float hi, int batch_size, int has_bounds, float img_w, float img_h,
-                        void* tb_, int64_t* pos_target_idx, int64_t* pos_input_idx, int64_t* neg_input_idx, cudaStream_t st) {
+                        void* tb_, int64_t* pos_target_idx, int64_t* pos_input_idx, int64_t* neg_input_idx, int sampler_mode, uint32_t sampler_salt,
+                        cudaStream_t st) {
   TrainBuffers& tb = *reinterpret_cast<TrainBuffers*>(tb_);
   const int A = k * H * W;
   rpn_rows_kernel<<<DC_CEIL_DIV(A, 256), 256, 0, st>>>(head, ld, H, W, k, anchors_dev, x0, y0, sx, sy, tb.boxes, tb.anc, tb.trans, tb.scores);
@@ -293,7 +385,7 @@ int k_loc_train_sampler(dc_ctx* ctx, const float* head, int ld, int H, int W, in
   DC_CHECK_LAUNCH(ctx);
   sampler_force_kernel<<<DC_CEIL_DIV(B2, 128), 128, 0, st>>>(tb.target_idx, B2, tb.pos, tb.neg);
   DC_CHECK_LAUNCH(ctx);
-  sampler_select_kernel<<<1, 1024, 0, st>>>(tb.pos, tb.neg, A, batch_size, tb.pos_idx, tb.neg_idx, tb.counts);
+  sampler_select_kernel<<<1, 1024, 0, st>>>(tb.pos, tb.neg, A, batch_size, sampler_mode, sampler_salt, tb.pos_idx, tb.neg_idx, tb.counts);
   DC_CHECK_LAUNCH(ctx);
   sampler_gather_kernel<<<DC_CEIL_DIV(batch_size, 128), 128, 0, st>>>(tb.counts, tb.pos_idx, tb.neg_idx, tb.argmax, tb.boxes, tb.anc, tb.trans,
                                                                     tb.scores, (const float4*)gt_boxes, batch_size, tb.roi_boxes, tb.pos_anchors,

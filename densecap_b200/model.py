@@ -34,6 +34,9 @@ class LocalizationLayer:
                     "train_remove_outbounds_boxes": opt.get("train_remove_outbounds_boxes", 1),
                     "mid_box_reg_weight": opt.get("mid_box_reg_weight", 0.05), "mid_objectness_weight": opt.get("mid_objectness_weight", 0.1),
                     "box_reg_decay": opt.get("box_reg_decay", 0.0)}
+        # torch.multinomial minibatch draws by default (BoxSampler.lua:138-152); {"sampler_mode": "deterministic"} selects the first
+        # P / first M candidates in index order (the reference's debug_*_sample_idx hook)
+        self.ctx.set_sampler(opt.get("sampler_mode", "random"), opt.get("sampler_seed", 0))
         self._push_train_args()
         self.setTestArgs()
 
@@ -160,6 +163,16 @@ class LanguageModel:
         self.END_TOKEN = d.vocab_size + 1
         self.NULL_TOKEN = d.vocab_size + 2
         self.idx_to_token = idx_to_token or {}
+        self.beam_size = None                   # like the reference: set it to run beam search in forward()
+
+    def beamsearch(self, image_vectors, beam_size=20):
+        """LanguageModel:beamsearch (LanguageModel.lua:170-290)."""
+        v = _check_cuda_f32(image_vectors)
+        N = v.shape[0]
+        seq = torch.zeros((N, self.seq_length), dtype=torch.int64, device=v.device)
+        self.ctx.check(self.ctx._lib.dc_lm_beamsearch(self.ctx.handle, ptr(v), N, int(beam_size or 20), ptr(seq), stream_ptr()))
+        self.output = seq
+        return seq
 
     def sample(self, image_vectors, return_logits=False):
         v = _check_cuda_f32(image_vectors)
@@ -175,6 +188,8 @@ class LanguageModel:
         image_vectors, gt_sequence = input
         if gt_sequence is not None and gt_sequence.numel() > 0:
             raise NotImplementedError("training-time LanguageModel forward is outside the test-time hot path")
+        if self.beam_size is not None:          # LanguageModel.lua:129-132
+            return self.beamsearch(image_vectors, self.beam_size)
         return self.sample(image_vectors)
 
     def decodeSequence(self, seq):
@@ -261,6 +276,20 @@ class DenseCapModel:
         self._last = r
         return self.output
 
+    def extractFeatures(self, input):
+        """DenseCapModel:extractFeatures (DenseCapModel.lua:285-304): boxes (K',4) xcycwh and recog_base features (K',fc_dim) of the
+        boxes kept by the final NMS, in score order; the language model does not run."""
+        x = _check_cuda_f32(input)
+        assert x.dim() == 4 and x.shape[0] == 1 and x.shape[1] == 3
+        P = self.ctx.max_proposals
+        boxes = torch.empty((P, 4), dtype=torch.float32, device=x.device)
+        feats = torch.empty((P, self.dims.fc_dim), dtype=torch.float32, device=x.device)
+        n = torch.zeros((1,), dtype=torch.int32, device=x.device)
+        self.ctx.check(self.ctx._lib.dc_extract_features(self.ctx.handle, ptr(x), x.shape[2], x.shape[3], ptr(boxes), ptr(feats), ptr(n),
+                                                         stream_ptr()))
+        k = int(n.item())
+        return boxes[:k], feats[:k]
+
     def forward_test(self, input):
         """DenseCapModel:forward_test (DenseCapModel.lua:319-327)."""
         self.evaluate()
@@ -269,12 +298,22 @@ class DenseCapModel:
         return out[3], out[0], captions
 
 
-def preprocess_image(ctx, img_u8):
-    """run_model.lua:66-74 without the resize, on the device: uint8 RGB (N,H,W,3) or (H,W,3) CUDA tensor -> (N,3,H,W) fp32
-    BGR, mean-subtracted -- what DenseCapModel:forward_test expects."""
+def preprocess_image(ctx, img_u8, image_size=None):
+    """run_model.lua:66-74 on the device: uint8 RGB (N,H,W,3) or (H,W,3) CUDA tensor -> (N,3,H,W) fp32 BGR, mean-subtracted -- what
+    DenseCapModel:forward_test expects.  image_size: image.scale(img, image_size) first (one image; larger side -> image_size)."""
     if not isinstance(img_u8, torch.Tensor) or not img_u8.is_cuda or img_u8.dtype != torch.uint8:
         raise TypeError("preprocess_image takes a CUDA uint8 tensor")
     x = img_u8.contiguous()
+    if image_size is not None:
+        if x.dim() == 4:
+            assert x.shape[0] == 1, "the resizing path takes one image"
+            x = x[0]
+        H, W, C_ = x.shape
+        assert C_ == 3
+        out = torch.empty((3 * int(image_size) * int(image_size),), dtype=torch.float32, device=x.device)
+        oh, ow = C.c_int(0), C.c_int(0)
+        ctx.check(ctx._lib.dc_preprocess_u8_resize(ctx.handle, ptr(x), H, W, int(image_size), ptr(out), C.byref(oh), C.byref(ow), stream_ptr()))
+        return out[:3 * oh.value * ow.value].view(1, 3, oh.value, ow.value)
     if x.dim() == 3:
         x = x[None]
     N, H, W, C_ = x.shape

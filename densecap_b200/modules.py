@@ -88,6 +88,40 @@ class BoxToAffine:
         return out
 
 
+class AffineGridGeneratorBHWD:
+    """stnbhwd nn.AffineGridGeneratorBHWD(height, width) (call site densecap/modules/BilinearRoiPooling.lua:52):
+    forward(theta (B,2,3)) -> grids (B,height,width,2), last dimension (y, x)."""
+
+    def __init__(self, height, width):
+        self.height, self.width = int(height), int(width)
+
+    def forward(self, theta):
+        t = _check_cuda_f32(theta)
+        assert t.dim() == 3 and t.shape[1] == 2 and t.shape[2] == 3, "Expected input of shape B x 2 x 3"
+        out = torch.empty((t.shape[0], self.height, self.width, 2), dtype=torch.float32, device=t.device)
+        _lib.check(_lib.load().dc_affine_grid_generator(ptr(t), t.shape[0], self.height, self.width, ptr(out), stream_ptr()))
+        return out
+
+
+class BatchBilinearSamplerBHWD:
+    """nn.BatchBilinearSamplerBHWD (densecap/modules/BatchBilinearSamplerBHWD.lua:104-122): forward({feats (H,W,C), grids (B,HH,WW,2)})
+    -> (B,HH,WW,C); one feature image shared by every grid."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx
+
+    def forward(self, input):
+        feats, grids = input
+        f = _check_cuda_f32(feats); g = _check_cuda_f32(grids)
+        assert g.dim() == 4 and f.dim() == 3
+        H, W, C_ = f.shape
+        B, HH, WW, _ = g.shape
+        ctx = self.ctx or default_context(f.device.index or 0)
+        out = torch.empty((B, HH, WW, C_), dtype=torch.float32, device=f.device)
+        _lib.check(_lib.load().dc_batch_bilinear_sampler(ctx.handle, ptr(f), H, W, C_, ptr(g), B, HH, WW, ptr(out), stream_ptr()), ctx.handle)
+        return out
+
+
 class BoxIoU:
     """nn.BoxIoU (densecap/modules/BoxIoU.lua:40-73).  forward({box1 (N,B1,4), box2 (N,B2,4)}) with N == 1."""
 

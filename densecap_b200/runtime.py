@@ -108,6 +108,14 @@ class Context:
         """Decode a caption for every proposal (fills `all_seq`) instead of only for the rows kept by the final NMS."""
         self.check(self._lib.dc_set_decode_all(self.handle, 1 if on else 0))
 
+    def set_beam_size(self, beam_size):
+        """0 = greedy LanguageModel:sample, n > 0 = LanguageModel:beamsearch(beam_size n) in the full forward."""
+        self.check(self._lib.dc_set_beam_size(self.handle, int(beam_size or 0)))
+
+    def set_sampler(self, mode="random", seed=0):
+        """nn.BoxSampler minibatch draw: 'random' (torch.multinomial-like, seeded) or 'deterministic' (first P / first M)."""
+        self.check(self._lib.dc_set_sampler(self.handle, 1 if mode == "random" else 0, int(seed)))
+
     def enable_timing(self, on=True):
         self.check(self._lib.dc_enable_timing(self.handle, 1 if on else 0))
 

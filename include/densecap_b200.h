@@ -35,6 +35,7 @@ extern "C" {
 #define DC_E_NOMEM      -4
 #define DC_E_UNSUPPORTED -5
 #define DC_E_NOTFOUND   -6   /* unknown weight name                                     */
+#define DC_E_RANGE      -7   /* an activation left the fp16 range of the split hi+lo planes */
 
 #define DC_MAX_ANCHORS 32
 
@@ -110,6 +111,14 @@ int dc_set_test_args(dc_ctx* ctx, float rpn_nms_thresh, float final_nms_thresh,
  * independent, so output[5] is identical).  enable = 1 decodes every proposal, which fills dc_result.all_seq completely
  * (debugging / parity of the unfiltered LM output). */
 int dc_set_decode_all(dc_ctx* ctx, int enable);
+/* LanguageModel decode mode of the full forward: 0 = greedy LanguageModel:sample (default), n > 0 = LanguageModel:beamsearch with
+ * beam_size n <= 32 (the reference dispatches on self.beam_size, LanguageModel.lua:129-132). */
+int dc_set_beam_size(dc_ctx* ctx, int beam_size);
+/* Range guard.  Dense activations travel as split-fp16 planes (hi + lo), exact only for |x| < 65504; every kernel that writes such
+ * planes flags values outside that range (or NaN) in a sticky device word.  dc_check_range synchronises `stream`, returns DC_E_RANGE if
+ * a forward since the last check overflowed (its results are invalid) and clears the flag.  The host-boundary calls
+ * (dc_forward_test_host / _u8) check it themselves. */
+int dc_check_range(dc_ctx* ctx, void* stream);
 /* LocalizationLayer:setImageSize (LocalizationLayer.lua:167-172): must precede each forward. */
 int dc_set_image_size(dc_ctx* ctx, int image_h, int image_w);
 
@@ -136,6 +145,17 @@ int dc_preprocess_u8(dc_ctx* ctx, const uint8_t* img_u8, int batch, int image_h,
 int dc_forward_test_host_u8(dc_ctx* ctx, const uint8_t* img_host_u8, int batch, int image_h, int image_w,
                             int32_t* num_final_host, float* final_boxes_host, float* final_scores_host,
                             int64_t* final_seq_host);
+/* The same preprocessing WITH the resize of run_model.lua:69 / webcam/daemon.lua:70, image.scale(img, image_size): the larger side
+ * becomes image_size (aspect kept, fractions truncated), bilinear mode = two separable fp32 passes (torch `image` rock, restated in
+ * oracle.image_scale; third-party arithmetic, parity unpinned).  img_u8 (image_h, image_w, 3) DEVICE uint8 RGB; img_nchw must hold
+ * 3 * image_size * image_size floats; the output size is returned through the HOST ints out_h / out_w. */
+int dc_preprocess_u8_resize(dc_ctx* ctx, const uint8_t* img_u8, int image_h, int image_w, int image_size, float* img_nchw,
+                            int* out_h, int* out_w, void* stream);
+/* DenseCapModel:extractFeatures (DenseCapModel.lua:285-304): the network without the language model; final NMS of the final boxes
+ * by objectness; boxes_xcycwh (K',4) and feats (K',fc_dim) = recog_base output of the kept rows in score order; num_out (1) int32.
+ * Capacity max_proposals rows each; any output may be NULL. */
+int dc_extract_features(dc_ctx* ctx, const float* img, int image_h, int image_w, float* boxes_xcycwh, float* feats,
+                        int32_t* num_out, void* stream);
 
 /* ---- stages of the path (each mirrors one reference entry point; used for per-stage parity) */
 
@@ -167,6 +187,11 @@ int dc_rpn_proposals(dc_ctx* ctx, const float* rpn_trans_nchw, const float* rpn_
 int dc_set_train_args(dc_ctx* ctx, float mid_box_reg_weight, float mid_objectness_weight,
                       float box_reg_decay, float sampler_low_thresh, float sampler_high_thresh,
                       int sampler_batch_size, int train_remove_outbounds_boxes);
+/* nn.BoxSampler minibatch selection (BoxSampler.lua:138-159).  mode 1 (default): uniform random like torch.multinomial -- positives
+ * without replacement, negatives without replacement unless there are fewer than requested -- from a counter-based generator:
+ * the same seed replays the same sequence of minibatches.  mode 0: the first P positives / first M negatives in index order, i.e.
+ * the reference's debug_pos_sample_idx / debug_neg_sample_idx injection (what the parity tests feed the oracle). */
+int dc_set_sampler(dc_ctx* ctx, int mode, uint64_t seed);
 /* LocalizationLayer:setGroundTruth (LocalizationLayer.lua:181-186): gt_boxes (B1,4) xcycwh fp32, host or
  * device memory; must precede every training-time forward.  gt_labels stay with the caller: the layer
  * only indexes them with pos_target_idx (:455-457). */
@@ -175,9 +200,7 @@ int dc_set_ground_truth(dc_ctx* ctx, const float* gt_boxes, int num_gt, void* st
  * nn.BoxSampler (modules/BoxSampler.lua:64-167) with the out-of-bounds exclusion, BoxSamplerHelper
  * gathers, ROI pooling of the S = sampler_batch_size sampled boxes (positives first), and the mid-level
  * losses (objectness cross-entropy, SmoothL1 on InvertBoxTransform targets with the |t|>10 mask hack,
- * box_reg_decay regulariser).  torch.multinomial is replaced by a deterministic selection -- the first P
- * positives / first M negatives in index order -- the same injection point as the reference's
- * debug_pos_sample_idx / debug_neg_sample_idx hooks (BoxSampler.lua:154-159).
+ * box_reg_decay regulariser).  The minibatch is drawn as configured by dc_set_sampler (uniform random by default).
  * Errors: DC_E_PROTOCOL 'Must call setGroundTruth before training-time forward pass' /
  * 'Must call setImageSize before each forward pass' (same order as the reference's asserts).
  * Outputs (device, any may be NULL): roi_features (S,C,HH,WW); roi_boxes (S,4); pos_target_boxes (S,4;
@@ -217,6 +240,10 @@ int dc_recog_forward(dc_ctx* ctx, const float* roi_features, const float* roi_bo
 /* LanguageModel:sample (LanguageModel.lua:293-348), greedy argmax.  codes (K,fc_dim).
  * seq (K,T) int64 tokens in [1,V+1].  logits (optional, may be NULL): (K,T,V+1) fp32. */
 int dc_lm_sample(dc_ctx* ctx, const float* codes, int K, int64_t* seq, float* logits, void* stream);
+/* LanguageModel:beamsearch(image_vectors, beam_size) (LanguageModel.lua:170-290): per image vector the beam_size best partial
+ * captions are extended token by token (log-softmax scores, END-token masking by multiplication, state re-indexing), the best beam
+ * is returned.  beam_size <= 32 (<= 0: the reference default 20).  seq (K,T) int64. */
+int dc_lm_beamsearch(dc_ctx* ctx, const float* codes, int K, int beam_size, int64_t* seq, void* stream);
 
 /* ---- leaf operators (stateless; one per reference module) ------------------------------- */
 
@@ -251,6 +278,14 @@ int dc_box_to_affine(const float* boxes, float* theta, int B, int image_h, int i
 int dc_bilinear_roi_pool(dc_ctx* ctx, const float* feats_chw, int C, int feat_h, int feat_w,
                          const float* boxes, int B, int image_h, int image_w, int HH, int WW,
                          float* out, int out_layout, void* stream);
+/* stnbhwd nn.AffineGridGeneratorBHWD(HH,WW):updateOutput (call site modules/BilinearRoiPooling.lua:52): theta (B,2,3) ->
+ * grids (B,HH,WW,2), last dimension (y, x) in [-1,1] normalised coordinates. */
+int dc_affine_grid_generator(const float* theta, int B, int HH, int WW, float* grids, void* stream);
+/* nn.BatchBilinearSamplerBHWD:updateOutput (modules/BatchBilinearSamplerBHWD.lua:104-122) = stnbhwd BilinearSamplerBHWD_updateOutput
+ * on ONE image shared by all grids (the reference expands it with a 0-stride batch dimension, :114): feats_hwc (H',W',C) fp32,
+ * grids (B,HH,WW,2) caller-supplied -> out (B,HH,WW,C).  HH*WW <= 64. */
+int dc_batch_bilinear_sampler(dc_ctx* ctx, const float* feats_hwc, int feat_h, int feat_w, int C, const float* grids, int B,
+                              int HH, int WW, float* out, void* stream);
 /* nn.BoxIoU:updateOutput (modules/BoxIoU.lua:40-73): (B1,4),(B2,4) -> (B1,B2) */
 int dc_box_iou(const float* box1, const float* box2, float* out, int B1, int B2, void* stream);
 

@@ -664,11 +664,14 @@ def smooth_l1(x, t):
 # densecap/LocalizationLayer.lua:383-526  _forward_train (losses in stats.losses)
 def localization_layer_forward_train(feats, weights, gt_boxes, image_h, image_w, mid_box_reg_weight=0.05,
                                      mid_objectness_weight=0.1, box_reg_decay=0.0, sampler_low=0.5, sampler_high=0.7,
-                                     batch_size=256, anchors=DEFAULT_ANCHORS, field_centers=FIELD_CENTERS, HH=7, WW=7):
-    """feats (1,C,H',W'), gt_boxes (1,B1,4).  Deterministic sampling = first P positives / first M negatives."""
+                                     batch_size=256, anchors=DEFAULT_ANCHORS, field_centers=FIELD_CENTERS, HH=7, WW=7,
+                                     pos_sample_idx=None, neg_sample_idx=None):
+    """feats (1,C,H',W'), gt_boxes (1,B1,4).  Default sampling = first P positives / first M negatives; pos_sample_idx /
+    neg_sample_idx inject other draws (0-based indices into the candidate lists), like BoxSampler.lua:154-159."""
     boxes, anc, trans, scores, _ = rpn_forward(feats, weights, anchors, field_centers)
     bounds = {"x_min": 1, "y_min": 1, "x_max": image_w, "y_max": image_h}          # :414-422
-    pi, pt, ni, pos_mask, neg_mask = box_sampler(boxes, gt_boxes, sampler_low, sampler_high, batch_size, bounds)
+    pi, pt, ni, pos_mask, neg_mask = box_sampler(boxes, gt_boxes, sampler_low, sampler_high, batch_size, bounds,
+                                                 pos_sample_idx=pos_sample_idx, neg_sample_idx=neg_sample_idx)
     pos, tgt, neg = box_sampler_helper_forward([boxes, anc, trans, scores], [gt_boxes], pi, pt, ni)
     pos_boxes, pos_anchors, pos_trans, pos_scores = pos
     pos_target_boxes = tgt[0]
@@ -767,6 +770,83 @@ def preprocess_u8(img_u8_hwc):
     img = np.asarray(img_u8_hwc, np.uint8)
     x = img.astype(np.float32) / f32(255)                       # image.load
     x = np.ascontiguousarray(x.transpose(2, 0, 1)[::-1])        # CHW, BGR
+    x = x * f32(255)
+    x = x + (f32(-1) * VGG_MEAN_BGR)[:, None, None]
+    return x[None].astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------
+# [3P-recalled, parity unpinned] torch/image `image.scale(src, size)` as called by run_model.lua:69 and
+# webcam/daemon.lua:70 (the `image` rock is not under /root/reference; restated from its published source
+# image/init.lua `scale` + generic/image.c `scaleBilinear` / `Main_scaleLinear_rowcol`):
+#   * a NUMBER size rescales so that the LARGER side equals size: height = iheight*size/imax, width = iwidth*size/imax,
+#     the tensor allocation truncates the fractions;
+#   * bilinear mode = two separable 1-D passes in float (width first into a (C, srcH, dstW) temporary, then height):
+#       upscaling   (dst_len > src_len): scale = (src_len-1)/(dst_len-1); dst[di] = (1-f)*src[i] + f*src[i+1] with
+#                   i = floor(di*scale), f = di*scale - i; the last element is copied;
+#       downscaling (dst_len < src_len): scale = src_len/dst_len; area average of the source span [di*scale, (di+1)*scale)
+#                   with fractional end weights, acc / n;
+#       equal length: copy.
+# ----------------------------------------------------------------------------------------
+def image_scaled_size(h, w, size):
+    imax = max(h, w)
+    return int(h * size / imax), int(w * size / imax)
+
+
+def _scale_linear_1d(src, dst_len):
+    """src (..., src_len) float32 -> (..., dst_len), the rowcol routine applied along the last axis."""
+    src = np.asarray(src, np.float32)
+    src_len = src.shape[-1]
+    out = np.empty(src.shape[:-1] + (dst_len,), np.float32)
+    if dst_len > src_len:
+        if src_len == 1:
+            out[...] = src[..., :1]
+            return out
+        scale = np.float32(src_len - 1) / np.float32(dst_len - 1)
+        for di in range(dst_len - 1):
+            sf = np.float32(di) * scale
+            si = int(sf)
+            sf = np.float32(sf - np.float32(si))
+            out[..., di] = (np.float32(1) - sf) * src[..., si] + sf * src[..., si + 1]
+        out[..., dst_len - 1] = src[..., src_len - 1]
+    elif dst_len < src_len:
+        scale = np.float32(src_len) / np.float32(dst_len)
+        si0_i, si0_f = 0, np.float32(0)
+        for di in range(dst_len):
+            s1 = np.float32(di + 1) * scale
+            si1_i = int(s1)
+            si1_f = np.float32(s1 - np.float32(si1_i))
+            acc = (np.float32(1) - si0_f) * src[..., si0_i]
+            n = np.float32(1) - si0_f
+            for si in range(si0_i + 1, si1_i):
+                acc = acc + src[..., si]
+                n = np.float32(n + np.float32(1))
+            if si1_i < src_len:
+                acc = acc + si1_f * src[..., si1_i]
+                n = np.float32(n + si1_f)
+            out[..., di] = acc / n
+            si0_i, si0_f = si1_i, si1_f
+    else:
+        out[...] = src
+    return out
+
+
+def image_scale(src_chw, size):
+    """image.scale(src, size) for a (C,H,W) float image and a NUMBER size, bilinear mode (the default)."""
+    src = np.asarray(src_chw, np.float32)
+    C, H, W = src.shape
+    oh, ow = image_scaled_size(H, W, size)
+    tmp = _scale_linear_1d(src, ow)                                   # (C, H, ow): width pass
+    out = _scale_linear_1d(tmp.transpose(0, 2, 1), oh).transpose(0, 2, 1)   # height pass
+    return np.ascontiguousarray(out)
+
+
+# run_model.lua:66-74: image.load (byte/255) -> image.scale(img, image_size) -> BGR -> *255 -> minus the VGG mean
+def preprocess_u8_resize(img_u8_hwc, image_size):
+    img = np.asarray(img_u8_hwc, np.uint8)
+    x = (img.astype(np.float32) / f32(255)).transpose(2, 0, 1)       # image.load: (3,H,W) RGB in [0,1]
+    x = image_scale(x, image_size)
+    x = np.ascontiguousarray(x[::-1])                                # index(1, {3,2,1}): BGR
     x = x * f32(255)
     x = x + (f32(-1) * VGG_MEAN_BGR)[:, None, None]
     return x[None].astype(np.float32)

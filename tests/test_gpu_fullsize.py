@@ -125,7 +125,8 @@ def run_proposals(model, case):
     n = torch.zeros((1,), dtype=torch.int32, device="cuda")
     ctx.set_test_args(0.7, 0.3, NPROP, True)
     ctx.check(ctx._lib.dc_set_image_size(ctx.handle, IMG_H, IMG_W))
-    ctx.check(ctx._lib.dc_rpn_proposals(ctx.handle, p(dev(t)), p(dev(s)), case.fh, case.fw, p(boxes), p(idx), p(n), None))
+    td, sd = dev(t), dev(s)              # named: two temporaries would be freed (and their memory reused) before the kernel reads them
+    ctx.check(ctx._lib.dc_rpn_proposals(ctx.handle, p(td), p(sd), case.fh, case.fw, p(boxes), p(idx), p(n), None))
     k = int(n.item())
     return boxes[:k].cpu().numpy(), idx[:k].cpu().numpy()
 
@@ -156,7 +157,8 @@ def test_roi_pooling_full_size_bit_exact(model_c, case_c):
     oll = case_c.ref["ll"]
     K = oll["boxes"].shape[0]
     out = torch.empty((K, 512, 7, 7), device="cuda")
-    ctx.check(ctx._lib.dc_bilinear_roi_pool(ctx.handle, p(dev(case_c.ref["feats"][0])), 512, case_c.fh, case_c.fw, p(dev(oll["boxes"])), K,
+    fd, bd = dev(case_c.ref["feats"][0]), dev(oll["boxes"])
+    ctx.check(ctx._lib.dc_bilinear_roi_pool(ctx.handle, p(fd), 512, case_c.fh, case_c.fw, p(bd), K,
                                             IMG_H, IMG_W, 7, 7, p(out), 0, None))
     assert np.array_equal(out.cpu().numpy(), oll["roi_features"])
 
@@ -185,7 +187,8 @@ def test_recognition_head_k25088(model_c, case_c):
     K = oll["roi_features"].shape[0]
     codes = torch.empty((K, 4096), device="cuda"); obj = torch.empty((K,), device="cuda")
     trans = torch.empty((K, 4), device="cuda"); fb = torch.empty((K, 4), device="cuda")
-    ctx.check(ctx._lib.dc_recog_forward(ctx.handle, p(dev(oll["roi_features"])), p(dev(oll["boxes"])), K, p(codes), p(obj), p(trans), p(fb), None))
+    rd, bd = dev(oll["roi_features"]), dev(oll["boxes"])
+    ctx.check(ctx._lib.dc_recog_forward(ctx.handle, p(rd), p(bd), K, p(codes), p(obj), p(trans), p(fb), None))
     ocodes, oobj, otrans, ofb = O.recog_head(oll["roi_features"], oll["boxes"], case_c.weights)
     with O.precision(np.float64):
         gcodes, gobj, gtrans, gfb = O.recog_head(oll["roi_features"], oll["boxes"], case_c.weights)

@@ -195,6 +195,54 @@ def test_survivor_decode_equals_full_decode(model, small):
     assert full_final.tolist() == ref["seq"].tolist()
 
 
+def test_extract_features(model, small):
+    """DenseCapModel:extractFeatures (DenseCapModel.lua:285-304): boxes and fc7 codes of the final-NMS survivors, no language model."""
+    dims, weights, img, cfg, ref = small
+    boxes, feats = model.extractFeatures(dev(img))
+    fidx = ref["final_idx"] - 1
+    assert boxes.shape[0] == len(fidx)
+    gold = gold_of(img, weights, cfg)
+    assert_within_fp32_noise(boxes.cpu().numpy(), ref["pre_nms"]["final_boxes"][fidx], gold["pre_nms"]["final_boxes"][fidx], "extractFeatures boxes")
+    assert_within_fp32_noise(feats.cpu().numpy(), ref["codes"][fidx], gold["codes"][fidx], "extractFeatures codes")
+
+
+def test_beamsearch_matches_oracle(model, small):
+    """LanguageModel:beamsearch (LanguageModel.lua:170-290) on the oracle's codes: same tokens as the restated reference algorithm
+    (END masking by multiplication, beam*beam re-ranking, parent state re-indexing), for two beam widths."""
+    dims, weights, img, cfg, ref = small
+    codes = ref["codes"][:12]
+    lm = model.nets["language_model"]
+    for beam in (3, 7):
+        want = O.lm_beamsearch(codes, weights, dims.seq_length, beam)
+        got = lm.beamsearch(dev(codes), beam).cpu().numpy()
+        assert got.shape == want.shape and got.dtype == np.int64
+        same = (got == want).all(axis=1)
+        assert same.mean() >= 0.9, "beam %d: %d of %d captions differ from the oracle" % (beam, int((~same).sum()), len(same))
+    # the reference's own shape test (test/LanguageModel_test.lua:125-133): N x T tokens in [1, V+1]
+    out = lm.beamsearch(dev(ref["codes"][:3]), 7)
+    assert tuple(out.shape) == (3, dims.seq_length) and int(out.min()) >= 1 and int(out.max()) <= dims.vocab_size + 1
+    # forward() dispatches on beam_size like LanguageModel.lua:129-132
+    lm.beam_size = 3
+    assert np.array_equal(lm.forward([dev(codes), None]).cpu().numpy(), lm.beamsearch(dev(codes), 3).cpu().numpy())
+    lm.beam_size = None
+
+
+def test_full_forward_with_beam_search(model, small):
+    """dc_set_beam_size: the full forward decodes the final-NMS survivors with beam search; rows equal the stand-alone call."""
+    dims, weights, img, cfg, ref = small
+    model.ctx.set_beam_size(3)
+    try:
+        out = model.forward(dev(img))
+        Kf = out[4].shape[0]
+        r = model._last
+        codes = r["codes"][(r["final_idx"][:Kf] - 1)].clone()
+        seq = out[4].cpu().numpy().copy()
+    finally:
+        model.ctx.set_beam_size(0)
+    want = model.nets["language_model"].beamsearch(codes, 3).cpu().numpy()
+    assert np.array_equal(seq, want)
+
+
 def test_host_boundary_call_matches_device_call(model, small):
     import ctypes as C
     dims, weights, img, cfg, ref = small

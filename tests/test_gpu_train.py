@@ -91,7 +91,8 @@ def layer(small):
     dims, weights = small
     ctx = Context(dims, max_image_hw=(IMG_H, IMG_W), max_proposals=64)
     ctx.load_weights({k: v for k, v in weights.items() if k.startswith("rpn.")})
-    ll = LocalizationLayer(ctx, {"sampler_batch_size": 32, "mid_box_reg_weight": 0.05, "mid_objectness_weight": 0.1, "box_reg_decay": 5e-5})
+    ll = LocalizationLayer(ctx, {"sampler_batch_size": 32, "mid_box_reg_weight": 0.05, "mid_objectness_weight": 0.1, "box_reg_decay": 5e-5,
+                                 "sampler_mode": "deterministic"})
     yield ll
     ctx.close()
 
@@ -161,7 +162,7 @@ def test_train_forward_full_size():
     ctx = Context(dims, max_image_hw=(H, W), max_proposals=256)
     try:
         ctx.load_weights(weights)
-        ll = LocalizationLayer(ctx, {"sampler_batch_size": 256, "sampler_low_thresh": 0.3, "box_reg_decay": 5e-5})
+        ll = LocalizationLayer(ctx, {"sampler_batch_size": 256, "sampler_low_thresh": 0.3, "box_reg_decay": 5e-5, "sampler_mode": "deterministic"})
         out, labels = run_case(ll, feats, gt, H, W)
         P, M = ll.stats["vars"]["num_pos"], ll.stats["vars"]["num_neg"]
         assert P + M == 256 and 1 <= P <= 128
@@ -247,8 +248,51 @@ def test_train_backward_full_size():
     ctx = Context(dims, max_image_hw=(H, W), max_proposals=256)
     try:
         ctx.load_weights(weights)
-        ll = LocalizationLayer(ctx, {"sampler_batch_size": 256, "sampler_low_thresh": 0.3, "box_reg_decay": 5e-5})
+        ll = LocalizationLayer(ctx, {"sampler_batch_size": 256, "sampler_low_thresh": 0.3, "box_reg_decay": 5e-5, "sampler_mode": "deterministic"})
         gin, gparams, ref = run_backward_case(ll, dims, weights, feats, gt, H, W, 256, kw, 3)
         check_backward(gin, gparams, ref)
+    finally:
+        ctx.close()
+
+
+def test_random_sampler_draws_uniform_minibatches_the_oracle_accepts(small):
+    """nn.BoxSampler draws its minibatch with torch.multinomial (BoxSampler.lua:138-152).  The library's default does the same with a
+    seeded generator: every draw is a set of DISTINCT positives / negatives from the oracle's candidate masks, different seeds and
+    consecutive calls give different minibatches, the same seed replays, and -- injected into the oracle through the reference's
+    debug_*_sample_idx hook -- the whole forward matches."""
+    from densecap_b200.model import LocalizationLayer
+    from densecap_b200.runtime import Context
+    dims, weights = small
+    feats, gt = make_case(dims, weights, IMG_H, IMG_W, 6, 0)
+    ctx = Context(dims, max_image_hw=(IMG_H, IMG_W), max_proposals=64)
+    ctx.load_weights({k: v for k, v in weights.items() if k.startswith("rpn.")})
+    try:
+        ll = LocalizationLayer(ctx, {"sampler_batch_size": 32, "mid_box_reg_weight": 0.05, "mid_objectness_weight": 0.1, "box_reg_decay": 5e-5,
+                                     "sampler_mode": "random", "sampler_seed": 7})
+        base = O.localization_layer_forward_train(feats, weights, gt, IMG_H, IMG_W, mid_box_reg_weight=0.05, mid_objectness_weight=0.1,
+                                                 box_reg_decay=5e-5, batch_size=32)
+        pos_nz = np.nonzero(base["pos_mask"])[0]; neg_nz = np.nonzero(base["neg_mask"])[0]
+        draws = []
+        for call in range(3):
+            out, labels = run_case(ll, feats, gt, IMG_H, IMG_W)
+            pi = ll.pos_input_idx.cpu().numpy() - 1; ni = ll.neg_input_idx.cpu().numpy() - 1
+            assert len(pi) == base["num_pos"] and len(ni) == base["num_neg"]
+            assert set(pi.tolist()) <= set(pos_nz.tolist()) and len(set(pi.tolist())) == len(pi)
+            assert set(ni.tolist()) <= set(neg_nz.tolist())
+            if neg_nz.size >= len(ni):
+                assert len(set(ni.tolist())) == len(ni), "negatives are drawn without replacement when there are enough"
+            # the same draw injected into the oracle -> identical forward
+            ref = O.localization_layer_forward_train(feats, weights, gt, IMG_H, IMG_W, mid_box_reg_weight=0.05, mid_objectness_weight=0.1,
+                                                     box_reg_decay=5e-5, batch_size=32, pos_sample_idx=np.searchsorted(pos_nz, pi),
+                                                     neg_sample_idx=np.searchsorted(neg_nz, ni))
+            check_case(ll, out, labels, ref)
+            draws.append((tuple(pi.tolist()), tuple(ni.tolist())))
+        assert len(set(d[1] for d in draws)) > 1, "consecutive calls must draw different minibatches"
+        ctx.set_sampler("random", 7)                      # same seed: the sequence replays
+        run_case(ll, feats, gt, IMG_H, IMG_W)
+        assert (tuple((ll.pos_input_idx.cpu().numpy() - 1).tolist()), tuple((ll.neg_input_idx.cpu().numpy() - 1).tolist())) == draws[0]
+        ctx.set_sampler("random", 8)
+        run_case(ll, feats, gt, IMG_H, IMG_W)
+        assert tuple((ll.neg_input_idx.cpu().numpy() - 1).tolist()) != draws[0][1]
     finally:
         ctx.close()

@@ -8,7 +8,9 @@ phases() { grep -o '"phases_ms": {[^}]*}' gpurun_out/$1.log; grep -o '"e2e[_u8]*
 for step in "$@"; do
   case $step in
     tests)      TAIL=15 run 900 tests python -m pytest tests -m gpu -q --tb=short -x ;;
-    tests_noexit) TAIL=40 run 900 tests python -m pytest tests -m gpu -q --tb=short ;;
+    tests_noexit) TAIL=60 run 900 tests python -m pytest tests -m gpu -q --tb=short --maxfail=12 ;;
+    safe)       # the same suite against the variant build without the newest hot-path kernels (bisecting a failure on the box)
+                TAIL=40 DENSECAP_B200_LIB=$PWD/densecap_b200/libdensecap_b200_safe.so run 600 tests_safe python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_fullsize.py tests/test_gpu_dense.py -m gpu -q --tb=short --maxfail=12 ;;
     test:*)     TAIL=30 run 600 test_${step#test:} python -m pytest tests -m gpu -q --tb=short -x -k "${step#test:}" ;;
     file:*)     TAIL=30 run 600 tfile python -m pytest "tests/${step#file:}" -m gpu -q --tb=short -x ;;
     smoke)      run 200 smoke python __graft_entry__.py smoke ;;
