@@ -46,6 +46,7 @@ SIGNATURES = {
     "dc_set_decode_all": (c_i, [c_vp, c_i]),
     "dc_set_beam_size": (c_i, [c_vp, c_i]),
     "dc_check_range": (c_i, [c_vp, c_vp]),
+    "dc_set_accumulation_groups": (c_i, [c_vp, c_i, c_i, c_i]),
     "dc_set_sampler": (c_i, [c_vp, c_i, C.c_uint64]),
     "dc_set_image_size": (c_i, [c_vp, c_i, c_i]),
     "dc_forward_test": (c_i, [c_vp, c_vp, c_i, c_i, c_i, C.POINTER(DcResult), c_vp]),

@@ -658,6 +658,15 @@ extern "C" int dc_check_range(dc_ctx* ctx, void* stream) {
   return DC_OK;
 }
 
+// Accuracy / speed knob of the tcgen05 kernels: k-blocks (64 K each) accumulated in the truncating TMEM accumulator before the partial sum
+// is added in fp32 registers with round-to-nearest, per tile width (64 / 128 / 256 columns).  1 = closest to an fp32 sgemm.
+extern "C" int dc_set_accumulation_groups(dc_ctx* ctx, int kb_tile64, int kb_tile128, int kb_tile256) {
+  if (!ctx) return dc_set_error(nullptr, DC_E_INVALID, "dc_set_accumulation_groups: null ctx");
+  DC_REQUIRE(ctx, kb_tile64 >= 1 && kb_tile128 >= 1 && kb_tile256 >= 1, DC_E_INVALID, "accumulation groups must be >= 1 k-block");
+  ctx->launch.group_kb[0] = kb_tile64; ctx->launch.group_kb[1] = kb_tile128; ctx->launch.group_kb[2] = kb_tile256;
+  return DC_OK;
+}
+
 extern "C" int dc_set_beam_size(dc_ctx* ctx, int beam_size) {
   if (!ctx) return dc_set_error(nullptr, DC_E_INVALID, "dc_set_beam_size: null ctx");
   DC_REQUIRE(ctx, beam_size >= 0 && beam_size <= 32, DC_E_INVALID, "beam_size must be in [0, 32] (0 = greedy sampling)");

@@ -54,6 +54,9 @@ void dc_count_launch(dc_ctx* ctx, int n = 1);
 struct LaunchState {
   void* encode_tiled = nullptr;            // cuTensorMapEncodeTiled (resolved by tc_init)
   int num_sms = 148;
+  // k-blocks (64 K each) a tcgen05 tile accumulates in TMEM before the epilogue warps take the partial sum over (hierarchical
+  // accumulation, tc_common.cuh): index 0 / 1 / 2 = 64- / 128- / 256-column tiles.  Smaller = closer to fp32 sgemm, more TMEM sweeps.
+  int group_kb[3] = {2, 2, 1};
   std::set<const void*> smem_attr_done;    // kernel function pointers
 };
 LaunchState* dc_launch_state(dc_ctx* ctx);

@@ -208,7 +208,7 @@ lm_decode_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff);
             const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff);
             umma_f16(d_tmem, da_hi, db_hi, idesc_wide, k != 0);            // A_hi.[B_hi | B_lo]
-            umma_f16(d_tmem, da_lo, db_hi, idesc, 1);                      // A_lo.B_hi
+            umma_f16(d_tmem + DEC_BN, da_lo, db_hi, idesc, 1);             // A_lo.B_hi -> the small-term half of the accumulator
           }
           umma_commit(empty_bar(stage));
           umma_commit(tfull_bar(acc));

@@ -276,24 +276,29 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
     mbar_wait(tfull_bar(acc), (uint32_t)((gi >> 1) & 1));
     tcgen05_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
+    // two TMEM loads in flight per wait (the drain latency, not its bandwidth, is what can stall the MMA warp)
+    constexpr int STEP = WIDE ? 1 : (CHUNKS_PER_WARP >= 2 ? 2 : 1);
 #pragma unroll
-    for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
-      const int c = c_first + cc;
-      uint32_t raw[32];
-      tmem_ld_32x32(t_row + c * 32, raw);
+    for (int cc = 0; cc < CHUNKS_PER_WARP; cc += STEP) {
+      uint32_t raw[32], raw2[32];
+      tmem_ld_32x32(t_row + (c_first + cc) * 32, raw);
+      // WIDE: columns [BLOCK_N, 2*BLOCK_N) hold the small terms (A_hi.B_lo + A_lo.B_hi) of the same outputs; else: the next chunk
+      if (WIDE) tmem_ld_32x32(t_row + BLOCK_N + (c_first + cc) * 32, raw2);
+      else if (STEP == 2) tmem_ld_32x32(t_row + (c_first + cc + 1) * 32, raw2);
       tmem_ld_wait();
       if (WIDE) {
-        // columns [BLOCK_N, 2*BLOCK_N) hold the A_hi . B_lo partial sums of the same outputs
-        uint32_t raw2[32];
-        tmem_ld_32x32(t_row + BLOCK_N + c * 32, raw2);
-        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
       }
       if (g == 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) run[cc][j] = __uint_as_float(raw[j]);
+        if (!WIDE && STEP == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) run[cc + STEP - 1][j] = __uint_as_float(raw2[j]);
+        }
         if (use_gather) {
+          const int c = c_first + cc;
           const int m = (mt * CG + (int)cta_rank) * BLOCK_M + row_in_tile;
           const int tok = (m < pb.M) ? __ldcg(ep.gather_idx + m) : 1;           // written by another SM during this kernel: read at L2
           const float4* gp = reinterpret_cast<const float4*>(ep.gather_tab + (size_t)(tok - 1) * ep.gather_ld + n0 + c * 32);
@@ -303,6 +308,10 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) run[cc][j] += __uint_as_float(raw[j]);
+        if (!WIDE && STEP == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) run[cc + STEP - 1][j] += __uint_as_float(raw2[j]);
+        }
       }
     }
     // TMEM reads of this accumulator stage are complete: hand it back to the MMA warp

@@ -87,7 +87,7 @@ tc_conv_first_kernel(const float* __restrict__ img, const __grid_constant__ CUte
           for (int k = 0; k < 2; ++k) {                     // K = 32 (27 taps + zero padding)
             const uint32_t koff = k * UMMA_K * 2;
             umma_f16(d_tmem, make_kmajor_sw128_desc(a_hi + koff), make_kmajor_sw128_desc(b_hi + koff), idesc_wide, k != 0);   // A_hi.[W_hi | W_lo]
-            umma_f16(d_tmem, make_kmajor_sw128_desc(a_lo + koff), make_kmajor_sw128_desc(b_hi + koff), idesc, 1);             // A_lo.W_hi
+            umma_f16(d_tmem + 64, make_kmajor_sw128_desc(a_lo + koff), make_kmajor_sw128_desc(b_hi + koff), idesc, 1);        // A_lo.W_hi -> small half
           }
           umma_commit(aempty_bar(stage));
           umma_commit(tfull_bar(acc));

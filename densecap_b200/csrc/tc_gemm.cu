@@ -171,6 +171,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t b_hi = a_hi + 2 * A_PLANE_BYTES;
           const uint32_t b_lo = b_hi + C::B_PLANE_BYTES;
 #pragma unroll
+          for (int pass = 0; pass < (C::WIDE ? 1 : 3); ++pass)
+#pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint32_t koff = k * UMMA_K * 2;   // bytes along K inside the swizzle atom
             const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff);
@@ -182,16 +184,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               // D[:, 0:BN] += A_hi.B_hi and D[:, BN:2BN] += A_hi.B_lo in ONE N = 2*BN instruction (B planes are adjacent), then
               // D[:, 0:BN] += A_lo.B_hi.  Every MMA reads its 128 x 32 B A slice from shared memory (~90 clk, measured); two
               // instructions instead of three per K step is what lifts the narrow tiles.
+              // The accumulator's columns [BN, 2BN) collect ALL small terms (A_hi.B_lo and A_lo.B_hi), the columns [0, BN) only A_hi.B_hi:
+              // every accumulation truncates at the ulp of the running sum, so the small terms must not be added onto the big one.
               umma_f16(d_tmem, da_hi, db_hi, idesc_wide, accum);
-              umma_f16(d_tmem, da_lo, db_hi, idesc, 1);
-            } else if (CG == 2) {
-              umma2_f16(d_tmem, da_lo, db_hi, idesc, accum);
-              umma2_f16(d_tmem, da_hi, db_lo, idesc, 1);
-              umma2_f16(d_tmem, da_hi, db_hi, idesc, 1);
+              umma_f16(d_tmem + BLOCK_N, da_lo, db_hi, idesc, 1);
             } else {
-              umma_f16(d_tmem, da_lo, db_hi, idesc, accum);   // small terms first
-              umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
-              umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+              // three passes over the four K steps of the block: both small terms first (while a fresh accumulator is still small their
+              // truncation error is negligible), the A_hi.B_hi products last
+              const uint64_t da = pass == 0 ? da_lo : da_hi, db = pass == 1 ? db_lo : db_hi;
+              const uint32_t acc_flag = !(group_start && pass == 0 && k == 0);
+              if (CG == 2) umma2_f16(d_tmem, da, db, idesc, acc_flag);
+              else umma_f16(d_tmem, da, db, idesc, acc_flag);
             }
           }
           const bool group_end = (kb % G) == G - 1 || kb == pb.num_k_blocks - 1;
@@ -400,6 +403,8 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t b_hi = b_ring + sb * C::B_STAGE_BYTES;
             const uint32_t b_lo = b_hi + C::B_PLANE_BYTES;
 #pragma unroll
+            for (int pass = 0; pass < (C::WIDE ? 1 : 3); ++pass)
+#pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               const uint32_t koff = k * UMMA_K * 2;
               const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff);
@@ -408,16 +413,13 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               const uint64_t db_lo = make_kmajor_sw128_desc(b_lo + koff);
               const uint32_t accum = !(group_start && k == 0);
               if (C::WIDE) {
-                umma_f16(d_tmem, da_hi, db_hi, idesc_wide, accum);
-                umma_f16(d_tmem, da_lo, db_hi, idesc, 1);
-              } else if (CG == 2) {
-                umma2_f16(d_tmem, da_lo, db_hi, idesc, accum);
-                umma2_f16(d_tmem, da_hi, db_lo, idesc, 1);
-                umma2_f16(d_tmem, da_hi, db_hi, idesc, 1);
+                umma_f16(d_tmem, da_hi, db_hi, idesc_wide, accum);          // big terms -> columns [0, BN), A_hi.B_lo -> [BN, 2BN)
+                umma_f16(d_tmem + BLOCK_N, da_lo, db_hi, idesc, 1);         // A_lo.B_hi -> the small half as well (see tc_gemm_kernel)
               } else {
-                umma_f16(d_tmem, da_lo, db_hi, idesc, accum);
-                umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
-                umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+                const uint64_t da = pass == 0 ? da_lo : da_hi, db = pass == 1 ? db_lo : db_hi;
+                const uint32_t acc_flag = !(group_start && pass == 0 && k == 0);
+                if (CG == 2) umma2_f16(d_tmem, da, db, idesc, acc_flag);
+                else umma_f16(d_tmem, da, db, idesc, acc_flag);
               }
             }
             const bool group_end = (kb % G) == G - 1 || kb == nkb - 1;
@@ -518,9 +520,12 @@ static int launch_halo(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb
 //   BLOCK_N = 128 (wide): max(128,90) + max(64,90) = 218 clk for 128 x 128 outputs
 //   BLOCK_N = 256       : 3 x 128                  = 384 clk for 128 x 256 outputs   (cta_group::2: same per CTA, half the B fill)
 // and a launch costs rounds x that, rounds = ceil(tiles / resident CTAs).
-// k-blocks (of 64) per TMEM accumulator group, see epilogue_tile: 1 = the partial sum is taken over by the epilogue warps after
-// every k-block (8-12 truncating MMA accumulations)
-constexpr int kGroupKBlocks = 1;
+// k-blocks (of 64) per TMEM accumulator group for a tile width, see epilogue_tile and LaunchState::group_kb
+static int group_kblocks(dc_ctx* ctx, int bn) {
+  const LaunchState* ls = dc_launch_state(ctx);
+  const int g = ls->group_kb[bn == 64 ? 0 : (bn == 128 ? 1 : 2)];
+  return g < 1 ? 1 : g;
+}
 struct TileCfg { int bn; int cg; };
 static TileCfg pick_tile(int num_sms, int N, int m_tiles128, bool lstm) {
   TileCfg best{64, 1};
@@ -609,12 +614,12 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
   Problem pb{};
   pb.M = M; pb.N = N; pb.K = K;
   pb.num_k_blocks = K / BLOCK_K;
-  pb.kb_per_group = kGroupKBlocks;
   pb.split_k = 1;
   const int m_tiles128 = DC_CEIL_DIV(M, BLOCK_M);
   TileCfg tc_ = pick_tile(dc_launch_state(ctx)->num_sms, N, m_tiles128, ep.lstm_c != nullptr);
   if (ep.gather_tab && tc_.bn == 256) tc_ = TileCfg{128, 1};          // the table-gather epilogue exists for the wide tiles only
   const int bn = tc_.bn, cg = tc_.cg;
+  pb.kb_per_group = group_kblocks(ctx, bn);
   pb.m_tiles = DC_CEIL_DIV(m_tiles128, cg);
   pb.n_tiles = DC_CEIL_DIV(N, bn);
   pb.m_fastest = pb.m_tiles <= pb.n_tiles;
@@ -652,7 +657,6 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
   pb.kb_per_tap = Cin / BLOCK_K;
   pb.K = 9 * Cin;
   pb.num_k_blocks = 9 * pb.kb_per_tap;
-  pb.kb_per_group = kGroupKBlocks;
   pb.N = Cout;
   pb.tiles_w = DC_CEIL_DIV(W, TILE_W);
   const int m_tiles128 = N * DC_CEIL_DIV(H, TILE_H) * pb.tiles_w;
@@ -676,6 +680,7 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
     }
   }
   const int bn = tc_.bn, cg = tc_.cg;
+  pb.kb_per_group = group_kblocks(ctx, bn);
   pb.split_k = split;
   pb.split_stride = (size_t)N * H * W * Cout;
   pb.tiles_h = DC_CEIL_DIV(H, TILE_H * cg);          // cg == 2: a pair tile covers 16 image rows (two stacked 8x16 patches)

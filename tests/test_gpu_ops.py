@@ -212,7 +212,7 @@ def test_affine_grid_and_batch_sampler_entry_points_bit_exact():
     assert_bit_equal(comp, np.ascontiguousarray(want), "composed roi pooling")
 
 
-@pytest.mark.parametrize("h,w,size", [(533, 800, 720), (300, 200, 720), (600, 720, 720), (97, 131, 64), (1, 50, 20)])
+@pytest.mark.parametrize("h,w,size", [(533, 800, 720), (300, 200, 720), (600, 720, 720), (97, 131, 64), (5, 50, 20)])
 def test_device_resize_preprocessing_matches_image_scale_restatement(h, w, size):
     """SURVEY.md 8f rank 1 with the resize: image.scale(img, size) + run_model.lua:70-74 on the device, bit-exact with the oracle's
     restatement of the torch `image` routine (third-party arithmetic, parity unpinned) for down-, up-scaling and the identity."""
