@@ -268,6 +268,7 @@ def main():
                     help="cfg1 = BASELINE configs[1] (the metric's configuration); mixed8 = configs[2]: 8 images, long side 600..800, 300 proposals")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle legs (cpu_baseline, parity)")
     ap.add_argument("--no-extras", action="store_true", help="device-resident timing only (for runs under ncu)")
+    ap.add_argument("--groups", default="", help="development: dc_set_accumulation_groups a,b,c (k-blocks per TMEM accumulator group)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -306,6 +307,8 @@ def main():
     model.setTestArgs({"rpn_nms_thresh": 0.7, "final_nms_thresh": 0.3, "num_proposals": NUM_PROPOSALS})
     ctx = model.ctx
     lib = ctx._lib
+    if args.groups:
+        ctx.check(lib.dc_set_accumulation_groups(ctx.handle, *[int(v) for v in args.groups.split(",")]))
     # a pool of distinct synthetic batches (image i of rank r differs), resident in HBM for `value`,
     # and in pinned host memory for `e2e`
     NPOOL = 3

@@ -27,6 +27,7 @@ struct PhaseTimer {
   std::vector<const char*> names;
   std::vector<cudaEvent_t> events;   // events[i] marks the START of phase i; last = end
   bool enabled = false;
+  bool layers = false;               // dc_enable_timing(ctx, 2): one mark per conv layer of the trunk as well
   size_t used = 0;
   cudaEvent_t roi0 = nullptr, roi1 = nullptr;   // bracket the ROI-pooling kernel of image 0 (HBM roofline of that kernel)
   bool roi_valid = false;
@@ -50,7 +51,7 @@ struct dc_ctx {
   int fh_max = 0, fw_max = 0, A_max = 0, P = 0, B = 0;
   // buffers
   SplitBuf act[2], feats, rpn_hidden, roi, fc6o, fc7o, xh, enc, encx;
-  float *rpn_head = nullptr, *codes = nullptr, *obj = nullptr, *trans = nullptr, *boxes_all = nullptr, *cstate = nullptr;
+  float *rpn_head = nullptr, *codes = nullptr, *obj = nullptr, *trans = nullptr, *boxes_all = nullptr, *cstate = nullptr, *dec_gate_ws = nullptr;
   float *pp_boxes = nullptr, *pp_x1y1 = nullptr, *pp_prob = nullptr, *roi_boxes = nullptr, *fin_x1y1 = nullptr;
   int32_t *pp_src = nullptr, *pp_nvalid = nullptr, *pp_blocks = nullptr;
   int32_t *rpn_idx32 = nullptr, *rpn_count = nullptr, *fin_idx32 = nullptr, *fin_count = nullptr;
@@ -277,6 +278,7 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
   TRY(dev_alloc(ctx, &ctx->trans, B * P * 4));
   TRY(dev_alloc(ctx, &ctx->boxes_all, B * P * 4));
   TRY(dev_alloc(ctx, &ctx->cstate, B * P * H));
+  TRY(dev_alloc(ctx, &ctx->dec_gate_ws, B * P * 4 * H));
   const size_t A = ctx->A_max;
   TRY(dev_alloc(ctx, &ctx->pp_boxes, B * A * 4));
   TRY(dev_alloc(ctx, &ctx->pp_x1y1, B * A * 4));
@@ -774,6 +776,7 @@ static void phase_mark(dc_ctx* ctx, const char* name, cudaStream_t st) {
 extern "C" int dc_enable_timing(dc_ctx* ctx, int enable) {
   if (!ctx) return DC_E_INVALID;
   ctx->timer.enabled = enable != 0;
+  ctx->timer.layers = enable == 2;
   ctx->timer.used = 0;
   return DC_OK;
 }
@@ -876,6 +879,7 @@ static int run_trunk(dc_ctx* ctx, const float* img, int N, int H, int W, int* fh
     } else if ((rc = k_conv_first(ctx, img, w0->f32, b0->f32, y, y + yp, N, H, W, cin, st))) return rc;
   }
   for (int i = 1; i < 13; ++i) {
+    if (ctx->timer.layers) phase_mark(ctx, kConvNames[i], st);
     const int cout = c.widths[kConvStage[i]];
     Weight *wt, *bs;
     if ((rc = need_weight(ctx, (std::string(kConvNames[i]) + ".weight").c_str(), &wt))) return rc;
@@ -1086,6 +1090,7 @@ static int run_lm_decode(dc_ctx* ctx, int B, int P, const int32_t* counts, const
   a.x_planes = ctx->encx.base; a.x_plane_elems = ctx->encx.cap_elems;
   a.h_planes = ctx->xh.base;
   a.cstate = ctx->cstate;
+  a.gate_ws = ctx->dec_gate_ws;
   a.gate_table = ctx->lm_gate_table;
   a.tokens = ctx->dec_tokens;
   a.lstm_planes = w.wlstm->planes; a.lstm_plane_elems = w.wlstm->plane_elems; a.lstm_bias = w.blstm->f32; a.lstm_acc_scale = w.wlstm->inv_scale;

@@ -240,6 +240,7 @@ struct LmDecodeArgs {
   __half* x_planes; size_t x_plane_elems;   // (B*P, E) split scratch: the compacted encoded vectors (input of the first LSTM step)
   __half* h_planes;                         // [hi: buf0, buf1][lo: buf0, buf1], each (B*P, H): h_t ping-pong
   float* cstate;                            // (B*P, H)
+  float* gate_ws;                           // (B*P, 4H) fp32 scratch: h . Wh^T of the current step (weights-stationary decoder); null = tile decoder
   const float* gate_table;                  // (V+2, 4H) fp32: b + lookup . Wx, gate-interleaved columns
   int32_t* tokens;                          // (B*P) scratch: current input token of each row
   const __half* lstm_planes; size_t lstm_plane_elems; const float* lstm_bias; float lstm_acc_scale;

@@ -294,6 +294,329 @@ lm_decode_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   }
 }
 
+// ==================================================================================================================
+// Weights-stationary persistent decoder (the default path; the tile decoder above remains for models whose LM weights do not
+// fit the shared memory of one GPU -- see k_lm_decode).
+//
+// The tile decoder re-reads the vocabulary matrix (21 MB as split planes) from L2 for every 128-row block and step: at 740
+// rows that is ~300 MB of L2->SM operand traffic per step, and ncu showed the kernel at 12.7 % tensor-pipe activity, bound
+// by that traffic.  Here every CTA PAIR (cta_group::2) owns 176 output columns for the whole launch and keeps its slice of the
+// weights (88 rows x H x {hi, lo} per CTA = 176 KB at H = 512) resident in shared memory; only the activations h_t
+// (rows x H, ~1.5 MB) stream through a small ring every step.  Column owners: pairs [0, nv) = vocabulary rows, pairs
+// [nv, nv + ng) = the recurrent LSTM weights Wh (gate-interleaved rows).  Because logits_t and the recurrent half of the next
+// pre-activations both read h_t, ONE pass over h per step feeds both:
+//     step s = 0      : A = x (encoded image),  gate pairs only (B = Wx)  -> cell with c = 0, + bias            -> h
+//     step s = 1      : A = h,                  gate pairs only (B = Wh)  -> cell, + table[START]               -> h
+//     step s = 2..T+1 : A = h,  all pairs: logits_{s-2} (+ arg-max) | h.Wh -> token = arg-max -> seq[s-2]; cell, + table[token] -> h
+// (the last step has no cell).  The LSTM cell is an element-wise phase between the passes, executed by the epilogue warps of all
+// CTAs (one row per CTA and round): gates = table[token] + h.Wh -- the gate table (b + lookup.Wx) removes the x half of the GEMM.
+// MMA: M = 256 (two CTAs x 128 rows), N = 176, three kind::f16 instructions per K = 16 step; the A_hi.B_hi products go to one
+// TMEM accumulator (columns [0,176)), both small terms to a second one ([176,352)), so the 32 truncating accumulations of a
+// K = 512 product never see a small term added onto a large sum and no mid-tile accumulator sweeps are needed.
+// A ring: 3 stages of {32 K x 128 rows x 2 planes} = 16 KB (SWIZZLE_64B rows) -- what is left beside the resident weights.
+// Dependencies are per 256-row block (release/acquire counters at gpu scope + generic->async proxy fences, as above):
+//     pass(s, mb) needs cell(s, mb) of ALL CTAs     (cnt_cell[s][mb] == #CTAs;  s >= 1)
+//     cell(s+1, mb) needs pass(s, mb) of all owners (cnt_pass[s][mb] == #CTAs that ran the pass)
+// Every role walks (s, mb) in lexicographic order, which is a topological order -> no deadlock while all CTAs are resident
+// (grid = 2 (nv + ng) <= #SMs, one CTA per SM).  All waits are bounded.
+// ==================================================================================================================
+constexpr int WS_NP = 176;                                   // output columns per CTA pair
+constexpr int WS_NC = WS_NP / 2;                             // weight rows resident per CTA
+constexpr int WS_KA = 32;                                    // K extent of one A stage
+constexpr uint32_t WS_A_PLANE = BLOCK_M * WS_KA * 2;         // 8 KB
+constexpr uint32_t WS_A_STAGE = 2 * WS_A_PLANE;              // 16 KB (hi + lo)
+constexpr int WS_STAGES = 3;
+constexpr uint32_t WS_B_PLANE = WS_NC * BLOCK_K * 2;         // 11264 B: 88 rows x 128 B (one 64-wide K block of one plane)
+constexpr uint32_t WS_B_KB = 2 * WS_B_PLANE;                 // hi + lo
+constexpr int WS_MAX_KB = 8;                                 // H <= 512
+constexpr uint32_t WS_TMEM_COLS = 512;
+constexpr int WS_ROWS = 2 * BLOCK_M;                         // rows per pass tile (pair)
+static size_t ws_smem_bytes(int H) { return (size_t)(H / BLOCK_K) * WS_B_KB + (size_t)WS_STAGES * WS_A_STAGE + 1024 + 256 + WS_NP * 4; }
+
+struct WsParams {
+  int E, H, V1, T;
+  int nv, ng;                          // vocabulary pairs, gate pairs
+  const int32_t* m_rows;
+  float* gH;                           // (rows, 4H) fp32: recurrent half of the gate pre-activations (acc_scale applied)
+  float* cstate;                       // (rows, H)
+  __half* h_hi; __half* h_lo;          // (rows, H) split planes: h_t, the A operand of the next pass
+  const float* gate_table;             // (V+2, 4H) = b + lookup.Wx, gate-interleaved
+  const float* lstm_bias;              // (4H) gate-interleaved (image step only)
+  float lstm_acc_scale, vocab_acc_scale;
+  const float* vocab_bias;
+  unsigned long long* packed;          // (rows) arg-max cells, zero on entry
+  int start_token;
+  uint32_t* cnt_pass;                  // [T+2][mt_stride]
+  uint32_t* cnt_cell;                  // [T+2][mt_stride]
+  int mt_stride;
+  const int32_t* dst_final; const int32_t* dst_all;
+  int64_t* fin_seq; int64_t* all_seq;
+  float* logits;                       // optional (rows, T, V1)
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lm_decode_ws_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_vocab,
+                    const __grid_constant__ CUtensorMap map_lstm, WsParams p) {
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool is_leader = cta_rank == 0;
+  const int pair = (int)(blockIdx.x >> 1);
+  const bool gate_pair = pair >= p.nv;
+  const int col0 = (gate_pair ? pair - p.nv : pair) * WS_NP;          // first output column of this pair (in its own matrix)
+  cluster_sync_all();
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  const int KB = p.H / BLOCK_K;                  // 64-wide K blocks of the resident weights
+  const int KS = p.H / WS_KA;                    // A stages per pass tile (E == H is required)
+  const uint32_t b_base = smem_base;
+  const uint32_t a_ring = smem_base + (uint32_t)KB * WS_B_KB;
+  const uint32_t bar_base = a_ring + WS_STAGES * WS_A_STAGE;
+  unsigned char* bar_ptr = smem_aligned + (size_t)KB * WS_B_KB + (size_t)WS_STAGES * WS_A_STAGE;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (WS_STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * WS_STAGES), tempty_bar = tfull_bar + 8u, bfull_bar = tfull_bar + 16u, bready_bar = tfull_bar + 24u,
+                 bfree_bar = tfull_bar + 32u;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * WS_STAGES + 5));
+  float* bias_smem = reinterpret_cast<float*>(bar_ptr + 256);          // [WS_NP] vocabulary bias / LSTM bias of this pair's columns
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_x); prefetch_tmap(&map_h); prefetch_tmap(&map_vocab); prefetch_tmap(&map_lstm);
+    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 2 * 32 * EPI_WARPS);
+    mbar_init(bfull_bar, 1);
+    mbar_init(bready_bar, 1);
+    mbar_init(bfree_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(smem_u32(tmem_holder), WS_TMEM_COLS);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const int M = __ldcg(p.m_rows);
+  const int mT = (M + WS_ROWS - 1) / WS_ROWS;
+  const int S_LAST = p.T + 1;                                // last step index
+  const int first_step = gate_pair ? 0 : 2;                  // vocabulary pairs have nothing to do for the two state-only steps
+  const uint32_t n_ctas = gridDim.x;
+
+  if (warp < EPI_WARP0) regs_shrink_control();
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (elect_one()) {
+      const CUtensorMap* mw = gate_pair ? &map_lstm : &map_vocab;
+      const int n0 = col0 + (int)cta_rank * WS_NC;
+      auto load_weights = [&](int k0) {
+        mbar_arrive_expect_tx(bfull_bar, (uint32_t)KB * WS_B_KB);
+        for (int kb = 0; kb < KB; ++kb) tma_load_3d(b_base + (uint32_t)kb * WS_B_KB, mw, bfull_bar, k0 + kb * BLOCK_K, n0, 0);
+      };
+      // resident weight slice: Wx (K offset 0) for the image step of the gate pairs, then Wh (K offset E); vocabulary rows have K offset 0
+      load_weights(0);
+      mbar_wait(bfull_bar, 0);
+      if (!is_leader) mbar_arrive_remote(bready_bar, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int s = first_step; s <= S_LAST; ++s) {
+        if (gate_pair && s == 1) {
+          // swap Wx for Wh once every MMA of step 0 has retired in both CTAs (bfree is committed after the last one)
+          mbar_wait(bfree_bar, 0);
+          load_weights(p.E);
+          mbar_wait(bfull_bar, 1);
+          if (!is_leader) mbar_arrive_remote(bready_bar, 0);
+        }
+        const CUtensorMap* ma = (s == 0) ? &map_x : &map_h;
+        for (int mb = 0; mb < mT; ++mb) {
+          if (s >= 1) {
+            wait_counter(p.cnt_cell + (size_t)s * p.mt_stride + mb, n_ctas);      // h rows of this block written by every CTA
+            fence_proxy_async_global();
+          }
+          const int m0 = mb * WS_ROWS + (int)cta_rank * BLOCK_M;
+          for (int ks = 0; ks < KS; ++ks) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * WS_A_STAGE);
+            else mbar_arrive_remote(full_bar(stage), 0);
+            tma2_load_3d(a_ring + stage * WS_A_STAGE, ma, full_bar(stage), ks * WS_KA, m0, 0);
+            if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader CTA) ===============================
+    if (is_leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * BLOCK_M, WS_NP);
+      const uint32_t d_big = tmem_base, d_small = tmem_base + WS_NP;
+      mbar_wait(bfull_bar, 0);
+      mbar_wait(bready_bar, 0);
+      int stage = 0; uint32_t phase = 0, tpar = 0;
+      for (int s = first_step; s <= S_LAST; ++s) {
+        if (gate_pair && s == 1) { mbar_wait(bfull_bar, 1); mbar_wait(bready_bar, 1); }
+        for (int mb = 0; mb < mT; ++mb) {
+          mbar_wait(tempty_bar, tpar ^ 1);
+          tcgen05_fence_after();
+          for (int ks = 0; ks < KS; ++ks) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint32_t a_hi = a_ring + stage * WS_A_STAGE, a_lo = a_hi + WS_A_PLANE;
+            const uint32_t b_hi = b_base + (uint32_t)(ks >> 1) * WS_B_KB + (uint32_t)(ks & 1) * 64u, b_lo = b_hi + WS_B_PLANE;
+#pragma unroll
+            for (int kk = 0; kk < WS_KA / UMMA_K; ++kk) {
+              const uint32_t koff = kk * UMMA_K * 2;
+              const uint64_t da_hi = make_kmajor_sw64_desc(a_hi + koff), da_lo = make_kmajor_sw64_desc(a_lo + koff);
+              const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff), db_lo = make_kmajor_sw128_desc(b_lo + koff);
+              const uint32_t acc = (ks | kk) != 0;
+              umma2_f16(d_small, da_lo, db_hi, idesc, acc);
+              umma2_f16(d_small, da_hi, db_lo, idesc, 1);
+              umma2_f16(d_big, da_hi, db_hi, idesc, acc);
+            }
+            umma2_commit_mc(empty_bar(stage));
+            if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma2_commit_mc(tfull_bar);
+          tpar ^= 1;
+        }
+        if (gate_pair && s == 0) umma2_commit_mc(bfree_bar);          // every MMA that reads Wx has retired when this arrives
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // =============================== epilogue warps: pass epilogue + LSTM cell / token phase ===============================
+    regs_grow_epilogue();
+    const int et = threadIdx.x - EPI_THREAD0;                // 0 .. 255
+    const int q = warp & 3, chalf = (warp - EPI_WARP0) >> 2;
+    const int H4 = 4 * p.H;
+    // bias of this pair's columns (constant for the whole launch)
+    for (int j = et; j < WS_NP; j += 32 * EPI_WARPS) {
+      const int n = col0 + j;
+      bias_smem[j] = gate_pair ? (n < H4 ? __ldg(p.lstm_bias + n) : 0.f) : (n < p.V1 ? __ldg(p.vocab_bias + n) : 0.f);
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+    const float scale = gate_pair ? p.lstm_acc_scale : p.vocab_acc_scale;
+    const int c_begin = chalf ? 6 : 0, c_end = chalf ? WS_NP / 16 : 6;        // 16-column chunks: warps 4-7 take 96 columns, 8-11 take 80
+    uint32_t tpar = 0;
+    for (int s = 0; s <= S_LAST; ++s) {
+      const bool active = s >= first_step;
+      const uint32_t owners = (s < 2) ? (uint32_t)(2 * p.ng) : n_ctas;         // CTAs that run pass s
+      for (int mb = 0; mb < mT; ++mb) {
+        if (active) {
+          mbar_wait(tfull_bar, tpar);
+          tcgen05_fence_after();
+          const int row = mb * WS_ROWS + (int)cta_rank * BLOCK_M + q * 32 + lane;
+          const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+          float best_v = -INFINITY;
+          int best_c = 0x7fffffff;
+#pragma unroll 1
+          for (int c = c_begin; c < c_end; ++c) {
+            uint32_t rb[16], rs[16];
+            tmem_ld_32x16(t_row + c * 16, rb);
+            tmem_ld_32x16(t_row + WS_NP + c * 16, rs);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = (__uint_as_float(rb[j]) + __uint_as_float(rs[j])) * scale;
+            const int n = col0 + c * 16;
+            if (row < M) {
+              if (gate_pair) {
+                if (n < H4) {                    // 4H is a multiple of 16
+                  float* g = p.gH + (size_t)row * H4 + n;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(g)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+              } else {
+                float* lg = p.logits ? p.logits + ((size_t)row * p.T + (s - 2)) * p.V1 + n : nullptr;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  if (n + j < p.V1) {
+                    const float x = v[j] + bias_smem[c * 16 + j];
+                    if (lg) lg[j] = x;
+                    if (x > best_v) { best_v = x; best_c = n + j; }
+                  }
+                }
+              }
+            }
+          }
+          tcgen05_fence_before();
+          if (!is_leader) mbar_arrive_remote(tempty_bar, 0);
+          else mbar_arrive(tempty_bar);
+          tpar ^= 1;
+          if (!gate_pair && row < M && best_c != 0x7fffffff) atomicMax(p.packed + row, pack_argmax_tc(best_v, best_c));
+          __threadfence();
+          asm volatile("bar.sync 2, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+          if (et == 0) atom_add_release_u32(p.cnt_pass + (size_t)s * p.mt_stride + mb, 1u);
+        }
+        // ---- token + LSTM cell of step s for the rows of block mb this CTA owns (one row per round, 256 threads per row) ----
+        if (et == 0) wait_counter(p.cnt_pass + (size_t)s * p.mt_stride + mb, owners);
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        const int r_end = min(M, (mb + 1) * WS_ROWS);
+        for (int r = mb * WS_ROWS + (int)blockIdx.x; r < r_end; r += (int)n_ctas) {
+          int tok = p.start_token;
+          if (s >= 2) {
+            const unsigned long long pk = __ldcg(p.packed + r);
+            const uint32_t col = 0xFFFFFFFFu - (uint32_t)(pk & 0xFFFFFFFFull);
+            tok = (pk == 0ull) ? 1 : (int)min(col, (uint32_t)p.start_token - 1u) + 1;     // all-NaN row -> first index, like torch.max
+          }
+          if (s < S_LAST) {
+            for (int u2 = et; u2 < p.H / 2; u2 += 32 * EPI_WARPS) {      // two hidden units (8 interleaved gate columns) per thread
+              const float4* gp = reinterpret_cast<const float4*>(p.gH + (size_t)r * H4 + 8 * u2);
+              const float4 g0 = __ldcg(gp), g1 = __ldcg(gp + 1);
+              float4 t0, t1;
+              if (s == 0) {
+                t0 = __ldg(reinterpret_cast<const float4*>(p.lstm_bias + 8 * u2));
+                t1 = __ldg(reinterpret_cast<const float4*>(p.lstm_bias + 8 * u2) + 1);
+              } else {
+                const float4* tp = reinterpret_cast<const float4*>(p.gate_table + (size_t)(tok - 1) * H4 + 8 * u2);
+                t0 = __ldg(tp); t1 = __ldg(tp + 1);
+              }
+              float2 cprev = make_float2(0.f, 0.f);
+              float2* cp = reinterpret_cast<float2*>(p.cstate + (size_t)r * p.H + 2 * u2);
+              if (s > 0) cprev = __ldcg(cp);
+              // torch-rnn nn.LSTM cell on interleaved columns (i, f, o, g), same arithmetic as the fused GEMM epilogue (tc_common.cuh)
+              const float i0 = lstm_sigmoid(g0.x + t0.x), f0 = lstm_sigmoid(g0.y + t0.y), o0 = lstm_sigmoid(g0.z + t0.z), gg0 = lstm_tanh(g0.w + t0.w);
+              const float i1 = lstm_sigmoid(g1.x + t1.x), f1 = lstm_sigmoid(g1.y + t1.y), o1 = lstm_sigmoid(g1.z + t1.z), gg1 = lstm_tanh(g1.w + t1.w);
+              const float c0 = f0 * cprev.x + i0 * gg0, c1 = f1 * cprev.y + i1 * gg1;
+              *cp = make_float2(c0, c1);
+              __half h0h, h0l, h1h, h1l;
+              split_f32(o0 * lstm_tanh(c0), h0h, h0l);
+              split_f32(o1 * lstm_tanh(c1), h1h, h1l);
+              const size_t ho = (size_t)r * p.H + 2 * u2;
+              *reinterpret_cast<__half2*>(p.h_hi + ho) = __halves2half2(h0h, h1h);
+              *reinterpret_cast<__half2*>(p.h_lo + ho) = __halves2half2(h0l, h1l);
+            }
+          }
+          if (s >= 2 && et == 0) {
+            const int df = p.dst_final ? __ldg(p.dst_final + r) : -1;
+            const int da = p.dst_all ? __ldg(p.dst_all + r) : -1;
+            if (df >= 0) p.fin_seq[(size_t)df * p.T + (s - 2)] = tok;
+            if (da >= 0) p.all_seq[(size_t)da * p.T + (s - 2)] = tok;
+          }
+        }
+        if (s < S_LAST) {
+          // publish h / c of this CTA's rows: gpu scope + async proxy (the next pass reads h with TMA)
+          fence_proxy_async_global();
+          __threadfence();
+          asm volatile("bar.sync 2, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+          if (et == 0) {
+            // every thread of the CTA has read its rows' arg-max cells (barrier above): clear them for the next vocabulary pass
+            if (s >= 2)
+              for (int r = mb * WS_ROWS + (int)blockIdx.x; r < r_end; r += (int)n_ctas) p.packed[r] = 0ull;
+            atom_add_release_u32(p.cnt_cell + (size_t)(s + 1) * p.mt_stride + mb, 1u);
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc2(tmem_base, WS_TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Row compaction in front of the decoder: the rows to decode (survivors of the final NMS, or every proposal) of all
 // images of the batch become rows [0, M') of the operand buffers.  One block per 8 rows (+ grid-stride), 256 threads.
@@ -359,7 +682,88 @@ lm_compact_kernel(CompactParams c) {
 
 size_t lm_decode_counter_words(int T, int rows_cap) {
   const int mt_stride = DC_CEIL_DIV(rows_cap, tc::BLOCK_M) + 1;
-  return (size_t)(3 * T + 1) * mt_stride;
+  const size_t tile_words = (size_t)(3 * T + 1) * mt_stride;                       // tile decoder
+  const size_t ws_words = (size_t)2 * (T + 2) * (DC_CEIL_DIV(rows_cap, tc::WS_ROWS) + 1);   // weights-stationary decoder
+  return tile_words > ws_words ? tile_words : ws_words;
+}
+
+// Weights-stationary decoder launch; returns DC_OK with *launched = false when the model does not fit (caller falls back to the tile decoder)
+static int launch_lm_decode_ws(dc_ctx* ctx, const LmDecodeArgs& a, cudaStream_t st, bool* launched) {
+  using namespace tc;
+  *launched = false;
+  const int V1 = a.V + 1, H4 = 4 * a.H;
+  const int nv = DC_CEIL_DIV(V1, WS_NP), ng = DC_CEIL_DIV(H4, WS_NP);
+  const int num_sms = dc_launch_state(ctx)->num_sms;
+  if (a.E != a.H || a.H % BLOCK_K != 0 || a.H > WS_MAX_KB * BLOCK_K || 2 * (nv + ng) > num_sms) return DC_OK;
+  const size_t smem = ws_smem_bytes(a.H);
+  const int rows_cap = a.B * a.P;
+  const int mt_stride = DC_CEIL_DIV(rows_cap, WS_ROWS) + 1;
+  const size_t hbuf = (size_t)rows_cap * a.H;
+  __half* h_hi = a.h_planes;
+  __half* h_lo = a.h_planes + 2 * hbuf;
+  CUtensorMap mx, mh, mv, ml;
+  int rc;
+  {
+    const uint64_t dims[3] = {(uint64_t)a.E, (uint64_t)rows_cap, 2};
+    const uint64_t str[2] = {(uint64_t)a.E * 2, (uint64_t)a.x_plane_elems * 2};
+    const uint32_t box[3] = {WS_KA, BLOCK_M, 2};
+    if ((rc = encode_map(ctx, &mx, a.x_planes, 3, dims, str, box, 64))) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a.H, (uint64_t)rows_cap, 2};
+    const uint64_t str[2] = {(uint64_t)a.H * 2, (uint64_t)(2 * hbuf) * 2};
+    const uint32_t box[3] = {WS_KA, BLOCK_M, 2};
+    if ((rc = encode_map(ctx, &mh, h_hi, 3, dims, str, box, 64))) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a.H, (uint64_t)V1, 2};
+    const uint64_t str[2] = {(uint64_t)a.H * 2, (uint64_t)a.vocab_plane_elems * 2};
+    const uint32_t box[3] = {BLOCK_K, WS_NC, 2};
+    if ((rc = encode_map(ctx, &mv, a.vocab_planes, 3, dims, str, box))) return rc;
+  }
+  {
+    const int ld = a.E + a.H;
+    const uint64_t dims[3] = {(uint64_t)ld, (uint64_t)H4, 2};
+    const uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)a.lstm_plane_elems * 2};
+    const uint32_t box[3] = {BLOCK_K, WS_NC, 2};
+    if ((rc = encode_map(ctx, &ml, a.lstm_planes, 3, dims, str, box))) return rc;
+  }
+  WsParams p{};
+  p.E = a.E; p.H = a.H; p.V1 = V1; p.T = a.T;
+  p.nv = nv; p.ng = ng;
+  p.m_rows = a.m_rows;
+  p.gH = a.gate_ws;
+  p.cstate = a.cstate;
+  p.h_hi = h_hi; p.h_lo = h_lo;
+  p.gate_table = a.gate_table; p.lstm_bias = a.lstm_bias;
+  p.lstm_acc_scale = a.lstm_acc_scale; p.vocab_acc_scale = a.vocab_acc_scale; p.vocab_bias = a.vocab_bias;
+  p.packed = a.packed;
+  p.start_token = a.V + 1;
+  p.cnt_pass = a.counters;
+  p.cnt_cell = a.counters + (size_t)(a.T + 2) * mt_stride;
+  p.mt_stride = mt_stride;
+  p.dst_final = a.dst_final; p.dst_all = a.dst_all; p.fin_seq = a.fin_seq; p.all_seq = a.all_seq;
+  p.logits = a.logits;
+  {
+    cudaError_t e = dc_ensure_smem(ctx, lm_decode_ws_kernel, smem);
+    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "lm_decode_ws smem attribute: %s", cudaGetErrorString(e));
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (nv + ng));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lm_decode_ws_kernel, mx, mh, mv, ml, p);
+  if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "lm_decode_ws launch: %s", cudaGetErrorString(e));
+  DC_CHECK_LAUNCH(ctx);
+  *launched = true;
+  return DC_OK;
 }
 
 int k_lm_decode(dc_ctx* ctx, const LmDecodeArgs& a, cudaStream_t st, bool compact_only) {
@@ -403,7 +807,14 @@ int k_lm_decode(dc_ctx* ctx, const LmDecodeArgs& a, cudaStream_t st, bool compac
     DC_CHECK_LAUNCH(ctx);
   }
   if (compact_only) return DC_OK;
-  // ---- persistent decoder ----
+  // ---- persistent decoder: weights-stationary kernel when the LM fits one GPU's shared memory (DenseCap's does), tile kernel otherwise ----
+#ifndef DC_DISABLE_LM_WS
+  if (a.gate_ws) {
+    bool launched = false;
+    int rc = launch_lm_decode_ws(ctx, a, st, &launched);
+    if (rc || launched) return rc;
+  }
+#endif
   CUtensorMap mx, mh0, mh1, ml, mv;
   {
     const uint64_t dims[3] = {(uint64_t)a.E, (uint64_t)rows_cap, 2};

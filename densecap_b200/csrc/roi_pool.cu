@@ -370,7 +370,7 @@ static int roi_pool_impl(dc_ctx* ctx, const __half* feat_hi, const __half* feat_
     const uint64_t dims[3] = {(uint64_t)C, (uint64_t)total, 2};
     const uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)(out_lo - out_hi) * 2};
     const uint32_t box[3] = {32, 8, 2};
-    int rc = tc::encode_map(ctx, &omap, out_hi, 3, dims, str, box, /*swizzle=*/false);
+    int rc = tc::encode_map(ctx, &omap, out_hi, 3, dims, str, box, /*swizzle_bytes=*/0);
     if (rc) return rc;
     const size_t smem_t = slice_bytes + ROI_TMA_WARPS * 1024;
     cudaError_t e = dc_ensure_smem(ctx, roi_pool_tma_kernel, limit);

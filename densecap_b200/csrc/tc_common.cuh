@@ -180,6 +180,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B, one 128-byte swizzle atom along K:
@@ -192,6 +202,15 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+// Same for SWIZZLE_64B (64-byte rows: 32 fp16 along K per row, 8-row groups 512 B apart, layout type 4)
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
   return d;
 }
 // Instruction descriptor (kind::f16): c_format=F32 (bits 4-5 = 1), a/b format = F16 (0), K-major A and B,
@@ -270,6 +289,14 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
   // when the first group arrives (the token is final by then) and added after the last one
   float4 gath[CHUNKS_PER_WARP][8];
   const bool use_gather = !CONV && WIDE && ep.gather_tab != nullptr;      // only the wide (<= 128-column) tiles carry the table gather
+  // Stage this tile's bias slice in shared memory (one coalesced load per thread, issued BEFORE the wait for the first accumulator
+  // group so that its L2 latency overlaps the MMAs of this tile) -- per-element global loads in the column loop would serialise on L2
+  // latency.  Two buffers used alternately by consecutive tiles, so one named barrier per tile suffices.
+  float* sbias = bias_smem + (tile_parity & 1) * BLOCK_N;
+  if (ep.bias && !use_gather) {
+    for (int j = threadIdx.x - EPI_THREAD0; j < BLOCK_N; j += 32 * EPI_WARPS) sbias[j] = (n0 + j < pb.N) ? __ldg(ep.bias + n0 + j) : 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+  }
 #pragma unroll 1
   for (int g = 0; g < num_groups; ++g, ++gi) {
     const int acc = gi & 1;
@@ -346,14 +373,6 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
   float best_v = -INFINITY;
   int best_c = 0x7fffffff;
   bool out_of_range = false;
-
-  // Stage this tile's bias slice in shared memory (one coalesced load per thread) -- per-element global loads in the column
-  // loop would serialise on L2 latency.  Two buffers used alternately by consecutive tiles, so one named barrier per tile suffices.
-  float* sbias = bias_smem + (tile_parity & 1) * BLOCK_N;
-  if (ep.bias && !use_gather) {
-    for (int j = threadIdx.x - EPI_THREAD0; j < BLOCK_N; j += 32 * EPI_WARPS) sbias[j] = (n0 + j < pb.N) ? __ldg(ep.bias + n0 + j) : 0.f;
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-  }
 
 #pragma unroll
   for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
@@ -494,7 +513,7 @@ __device__ __forceinline__ void epilogue_warps(const Problem& pb, const GemmEpil
 }
 
 static int encode_map(dc_ctx* ctx, CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, bool swizzle128 = true) {
+                      const uint32_t* box, int swizzle_bytes = 128) {
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
@@ -502,7 +521,9 @@ static int encode_map(dc_ctx* ctx, CUtensorMap* map, const void* base, int rank,
   const PFN_encodeTiled encode = (PFN_encodeTiled)dc_launch_state(ctx)->encode_tiled;
   DC_REQUIRE(ctx, encode != nullptr, DC_E_CUDA, "cuTensorMapEncodeTiled unavailable (tc_init not run)");
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DC_REQUIRE(ctx, r == CUDA_SUCCESS, DC_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
   return DC_OK;

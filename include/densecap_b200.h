@@ -308,7 +308,8 @@ int dc_conv3x3_relu(dc_ctx* ctx, const float* x, const float* w, const float* b,
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Per-phase device times of the last dc_forward_test (milliseconds, cudaEvent based), in the
  * spirit of LocalizationLayer stats.times (LocalizationLayer.lua:219-230).  Enabling timing
- * inserts events only (no host sync until dc_get_times).  names_out: static strings. */
+ * inserts events only (no host sync until dc_get_times).  names_out: static strings.
+ * enable = 2 additionally marks every convolution layer of the trunk ("conv_trunk" is then conv1_1 alone, followed by "conv1_2" ...). */
 int dc_enable_timing(dc_ctx* ctx, int enable);
 int dc_get_times(dc_ctx* ctx, const char** names_out, float* ms_out, int capacity, int* count_out);
 /* Number of kernels launched by this library on ctx since creation (for bench accounting). */

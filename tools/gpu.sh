@@ -23,11 +23,12 @@ for step in "$@"; do
     launches:*) # launch list of one batch-N step: launches:1 / launches:4
                 B=${step#launches:}
                 run 600 ncu_launches_b$B ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum \
-                    --clock-control none --csv --log-file gpurun_out/launches_b$B.csv python bench.py --steps 1 --warmup 3 --batch $B --no-cpu-baseline --no-extras ;;
+                    --clock-control none --csv --log-file gpurun_out/launches_b$B.csv python bench.py --steps 1 --warmup 3 --batch $B --no-cpu-baseline --no-extras $BENCH_EXTRA
+                mv gpurun_out/launches_b$B.csv gpurun_out/launches_b$B$TAG.csv ;;
     full:*)     # ncu --set full of kernels matching a regex: full:<regex>  (batch 1, last step only)
                 R=${step#full:}
-                run 900 ncu_full ncu --set full --import-source on --clock-control none -k "regex:$R" --launch-skip-before-match 0 -c 40 -o gpurun_out/prof_full \
-                    python bench.py --steps 1 --warmup 0 --batch 1 --no-cpu-baseline --no-extras
+                run 900 ncu_full ncu --set full --import-source on --clock-control none -k "regex:$R" --launch-skip-before-match 0 -c ${CNT:-40} -o gpurun_out/prof_full \
+                    python bench.py --steps 1 --warmup 0 --batch ${PB:-1} --no-cpu-baseline --no-extras $BENCH_EXTRA
                 ncu -i gpurun_out/prof_full.ncu-rep --page raw --csv > gpurun_out/prof_full_raw.csv 2>/dev/null
                 ncu -i gpurun_out/prof_full.ncu-rep --page source --csv > gpurun_out/prof_full_source.csv 2>/dev/null
                 rm -f gpurun_out/prof_full.ncu-rep ;;
