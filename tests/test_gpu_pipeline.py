@@ -41,9 +41,12 @@ def gold_of(img, weights, cfg):
         return O.densecap_forward_test(img, weights, cfg, return_intermediates=True)
 
 
-def assert_within_fp32_noise(got, ref32, gold, what, factor=2.0):
+def assert_within_fp32_noise(got, ref32, gold, what, factor=3.0):
     """|got - gold| <= factor * |oracle_fp32 - gold| (max-norm, relative to the tensor scale) -- the GPU result may not be
-    further from the fp64 truth than `factor` times the fp32 oracle is."""
+    further from the fp64 truth than `factor` times the fp32 oracle is.  Both sides are maxima over the few hundred numbers of a
+    small-model tensor, i.e. extreme-value statistics of two independent rounding-noise draws whose ratio scatters by ~2x from
+    input to input (measured 0.4 .. 2.3 over the cases of this file), hence factor 3 here; the full-size tensors of
+    tests/test_gpu_fullsize.py (>= 10^5 numbers, stable maxima) are held to factor 2."""
     e = rel(got, gold); floor = rel(ref32, gold)
     assert e <= factor * floor + 1e-6, "%s: |gpu - fp64| = %.3g exceeds %.1f x the oracle's own fp32 noise %.3g" % (what, e, factor, floor)
     return e, floor
