@@ -47,6 +47,7 @@ SIGNATURES = {
     "dc_set_beam_size": (c_i, [c_vp, c_i]),
     "dc_check_range": (c_i, [c_vp, c_vp]),
     "dc_set_accumulation_groups": (c_i, [c_vp, c_i, c_i, c_i]),
+    "dc_debug_peek_cuda_error": (c_i, [C.c_char_p, c_i]),
     "dc_set_sampler": (c_i, [c_vp, c_i, C.c_uint64]),
     "dc_set_image_size": (c_i, [c_vp, c_i, c_i]),
     "dc_forward_test": (c_i, [c_vp, c_vp, c_i, c_i, c_i, C.POINTER(DcResult), c_vp]),
@@ -117,8 +118,32 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("DENSECAP_B200_DEBUG"):
+        lib = _DebugLib(lib)
     _LIB = lib
     return lib
+
+
+class _DebugLib:
+    """DENSECAP_B200_DEBUG=1: after every entry point, synchronise and report a CUDA error the call left unreported."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if name in ("dc_debug_peek_cuda_error", "dc_last_error"):
+            return fn
+        peek = self._lib.dc_debug_peek_cuda_error
+
+        def wrapped(*a):
+            rc = fn(*a)
+            buf = C.create_string_buffer(256)
+            if peek(buf, 256) != 0:
+                import sys
+                print("DENSECAP_B200_DEBUG: %s returned %r but left CUDA error: %s" % (name, rc, buf.value.decode()), file=sys.stderr, flush=True)
+            return rc
+        return wrapped
 
 
 def check(rc, ctx=None):

@@ -140,6 +140,12 @@ void dc_count_launch(dc_ctx* ctx, int n) {
 
 extern "C" const char* dc_last_error(const dc_ctx* ctx) { return ctx ? ctx->err : g_err; }
 extern "C" int dc_version(void) { return 100; }
+extern "C" int dc_debug_peek_cuda_error(char* msg, int capacity) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaGetLastError(); else cudaGetLastError();
+  if (msg && capacity > 0) snprintf(msg, (size_t)capacity, "%s", e == cudaSuccess ? "" : cudaGetErrorString(e));
+  return e == cudaSuccess ? 0 : (int)e;
+}
 extern "C" int64_t dc_kernel_launches(const dc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int dc_config_default(dc_config* c) {
@@ -1301,8 +1307,6 @@ static int ensure_host_stage(dc_ctx* ctx, size_t f32_elems, size_t u8_elems) {
   }
   if (ctx->host_stage_u8_elems < u8_elems) {
     if (ctx->host_stage_u8) cudaFree(ctx->host_stage_u8);
-  if (ctx->resize_tmp) cudaFree(ctx->resize_tmp);
-  if (ctx->beam.mem) cudaFree(ctx->beam.mem);
     ctx->host_stage_u8 = nullptr; ctx->host_stage_u8_elems = 0;
     DC_CHECK_CUDA(ctx, cudaMalloc((void**)&ctx->host_stage_u8, u8_elems));
     ctx->host_stage_u8_elems = u8_elems;
@@ -1854,7 +1858,6 @@ extern "C" int dc_preprocess_u8_resize(dc_ctx* ctx, const uint8_t* img_u8, int i
   const size_t need = (size_t)3 * image_h * ow;
   if (ctx->resize_tmp_elems < need) {
     if (ctx->resize_tmp) cudaFree(ctx->resize_tmp);
-  if (ctx->beam.mem) cudaFree(ctx->beam.mem);
     ctx->resize_tmp = nullptr; ctx->resize_tmp_elems = 0;
     DC_CHECK_CUDA(ctx, cudaMalloc((void**)&ctx->resize_tmp, need * sizeof(float)));
     ctx->resize_tmp_elems = need;

@@ -246,7 +246,7 @@ lm_decode_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         ep.ldo = p.H;
         ep.out_col0 = 0;
       }
-      epilogue_tile<DEC_BN, false, false, 1, true>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, it.mt, it.nt, kblocks(it), gi, iter,
+      epilogue_tile<DEC_BN, false, false, 1, true, FEAT_DECODE>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, it.mt, it.nt, kblocks(it), gi, iter,
                                                    0u, true);
       // publish: this thread's global writes (h / c / arg-max cells / logits) -> gpu scope and the async proxy
       fence_proxy_async_global();

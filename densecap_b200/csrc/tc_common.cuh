@@ -190,6 +190,12 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+// 256-bit global store (STG.256): p must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
+               "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B, one 128-byte swizzle atom along K:
@@ -259,6 +265,17 @@ struct Cfg {
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
 };
 
+// Compile-time feature mask of the epilogue.  The output phase of a tile is straight-line code executed once per tile; with every feature
+// compiled into every kernel the 256-column convolution kernel was 10,216 SASS instructions (163 KB, more than the instruction cache) and an ncu
+// source profile showed its output phase stalled on instruction fetch (~13 us per tile).  Each kernel is therefore instantiated only with
+// the epilogue features its callers use.
+enum : int { F_SPLIT = 1, F_F32 = 2, F_LSTM = 4, F_ARGMAX = 8, F_GATHER = 16 };
+constexpr int FEAT_CONV = F_SPLIT;                                   // bias + ReLU (+ pool) -> split planes
+constexpr int FEAT_PARTIAL = F_F32;                                  // raw fp32 partial sums (split-K)
+constexpr int FEAT_DENSE = F_SPLIT | F_F32;                          // linear layers: split planes and / or fp32
+constexpr int FEAT_LSTM = F_LSTM | F_GATHER;                         // LSTM gate GEMM with the fused cell (beam search)
+constexpr int FEAT_DECODE = F_LSTM | F_GATHER | F_ARGMAX | F_F32;    // tile decoder (lm_decode_kernel)
+
 // Epilogue of ONE output tile (mt, nt) by the 8 epilogue warps (threads 128..383) of a CTA.
 //
 // Hierarchical accumulation.  The tensor core adds every MMA result into the fp32 TMEM accumulator with TRUNCATION (round toward
@@ -269,7 +286,7 @@ struct Cfg {
 // then bounded by the MMAs of ONE group (<= 4e-7), i.e. fp32-sgemm class, at the cost of one tcgen05.ld sweep per group.
 // gi = running count of accumulator groups of this CTA (selects the TMEM stage and its barrier parity); advanced here.
 // tfull0 / tempty0: shared addresses of the two tmem_full / tmem_empty barriers.
-template <int BLOCK_N, bool CONV, bool POOL, int CG, bool WIDE>
+template <int BLOCK_N, bool CONV, bool POOL, int CG, bool WIDE, int FEAT>
 __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilogue& ep, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                               float* bias_smem, int mt, int nt, int num_groups, int& gi, int tile_parity, uint32_t cta_rank, bool is_leader) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -288,7 +305,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
   // decoder gate tiles: the input half of the pre-activations comes from a table row per output row (token); it is requested
   // when the first group arrives (the token is final by then) and added after the last one
   float4 gath[CHUNKS_PER_WARP][8];
-  const bool use_gather = !CONV && WIDE && ep.gather_tab != nullptr;      // only the wide (<= 128-column) tiles carry the table gather
+  const bool use_gather = (FEAT & F_GATHER) && !CONV && WIDE && ep.gather_tab != nullptr;      // only the wide (<= 128-column) tiles carry the table gather
   // Stage this tile's bias slice in shared memory (one coalesced load per thread, issued BEFORE the wait for the first accumulator
   // group so that its L2 latency overlaps the MMAs of this tile) -- per-element global loads in the column loop would serialise on L2
   // latency.  Two buffers used alternately by consecutive tiles, so one named barrier per tile suffices.
@@ -401,7 +418,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
         v[j] = x;
       }
     }
-    if (ep.lstm_c) {
+    if ((FEAT & F_LSTM) && ep.lstm_c) {
       // torch-rnn nn.LSTM cell on interleaved gate columns: 8 hidden units per 32-column chunk
       if (out_row >= 0) {
         const int j0 = nc >> 2;
@@ -443,37 +460,30 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
       }
     } else if (out_row >= 0) {
       const bool full = (nc + 32 <= pb.N);
-      if (ep.out_hi) {
+      if ((FEAT & F_SPLIT) && ep.out_hi) {
+        // N is a multiple of 8 for split outputs (checked on the host): 16-byte stores, predicated per 8-column group
         __half* ph = ep.out_hi + (size_t)out_row * ep.ldo + ep.out_col0 + nc;
         __half* pl = ep.out_lo + (size_t)out_row * ep.ldo + ep.out_col0 + nc;
-        if (full) {
-          uint32_t hh[16], ll[16];
+        uint32_t hh[16], ll[16];
   #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            __half h0, l0, h1, l1;
-            split_f32(v[2 * j], h0, l0);
-            split_f32(v[2 * j + 1], h1, l1);
-            hh[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            ll[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-          }
+        for (int j = 0; j < 16; ++j) {
+          __half h0, l0, h1, l1;
+          split_f32(v[2 * j], h0, l0);
+          split_f32(v[2 * j + 1], h1, l1);
+          hh[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          ll[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+#ifndef DC_EPI_NO_STORE
   #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 4; ++j) {
+          if (full || nc + 8 * j + 8 <= pb.N) {
             reinterpret_cast<uint4*>(ph)[j] = make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
             reinterpret_cast<uint4*>(pl)[j] = make_uint4(ll[4 * j], ll[4 * j + 1], ll[4 * j + 2], ll[4 * j + 3]);
           }
-        } else {
-  #pragma unroll
-          for (int j = 0; j < 32; ++j) {      // fully unrolled + predicated: v[] must stay in registers
-            if (nc + j < pb.N) {
-              __half h0, l0;
-              split_f32(v[j], h0, l0);
-              ph[j] = h0;
-              pl[j] = l0;
-            }
-          }
         }
+#endif
       }
-      if (ep.out_f32) {
+      if ((FEAT & F_F32) && ep.out_f32) {
         float* pf = ep.out_f32 + (size_t)out_row * ep.ldf + nc;
         if (full && (ep.ldf & 3) == 0) {
   #pragma unroll
@@ -485,20 +495,20 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
             if (nc + j < pb.N) pf[j] = v[j];
         }
       }
-      if (ep.argmax) {
+      if ((FEAT & F_ARGMAX) && ep.argmax) {
   #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (nc + j < pb.N && v[j] > best_v) { best_v = v[j]; best_c = nc + j; }
       }
     }
   }
-  if (ep.argmax && out_row >= 0 && best_c != 0x7fffffff)
+  if ((FEAT & F_ARGMAX) && ep.argmax && out_row >= 0 && best_c != 0x7fffffff)
     atomicMax(ep.argmax + out_row, pack_argmax_tc(best_v, best_c));
-  if (ep.overflow && ep.out_hi && !ep.lstm_c && out_of_range && (POOL ? in_bounds : out_row >= 0)) atomicOr(ep.overflow, 1u);
+  if ((FEAT & F_SPLIT) && ep.overflow && ep.out_hi && out_of_range && (POOL ? in_bounds : out_row >= 0)) atomicOr(ep.overflow, 1u);
 }
 
 // Epilogue warps of the GEMM / convolution kernels: drain the accumulator groups of every tile this CTA owns.
-template <int BLOCK_N, bool CONV, bool POOL, int CG, bool WIDE>
+template <int BLOCK_N, bool CONV, bool POOL, int CG, bool WIDE, int FEAT>
 __device__ __forceinline__ void epilogue_warps(const Problem& pb, const GemmEpilogue& ep, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                                float* bias_smem, int worker, int num_workers, uint32_t cta_rank, bool is_leader) {
   const int num_tiles = pb.m_tiles * pb.n_tiles;
@@ -508,7 +518,7 @@ __device__ __forceinline__ void epilogue_warps(const Problem& pb, const GemmEpil
     int mt, nt;
     if (pb.m_fastest) { mt = tile % pb.m_tiles; nt = tile / pb.m_tiles; }
     else { nt = tile % pb.n_tiles; mt = tile / pb.n_tiles; }
-    epilogue_tile<BLOCK_N, CONV, POOL, CG, WIDE>(pb, ep, tmem_base, tfull0, tempty0, bias_smem, mt, nt, num_groups, gi, iter, cta_rank, is_leader);
+    epilogue_tile<BLOCK_N, CONV, POOL, CG, WIDE, FEAT>(pb, ep, tmem_base, tfull0, tempty0, bias_smem, mt, nt, num_groups, gi, iter, cta_rank, is_leader);
   }
 }
 

@@ -100,7 +100,7 @@ tc_conv_first_kernel(const float* __restrict__ img, const __grid_constant__ CUte
     asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     int gi = 0, iter = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter)
-      epilogue_tile<64, true, false, 1, true>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, tile, 0, 1, gi, iter, 0u, true);
+      epilogue_tile<64, true, false, 1, true, FEAT_CONV>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, tile, 0, 1, gi, iter, 0u, true);
   } else {
     // ---- builders: im2col rows of the 8 x 16 patch ----
     asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");

@@ -37,7 +37,7 @@
 
 namespace tc {
 
-template <int BLOCK_N, bool CONV, bool POOL, int CG>
+template <int BLOCK_N, bool CONV, bool POOL, int CG, int FEAT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Problem pb, GemmEpilogue ep) {
   using C = Cfg<BLOCK_N, CG>;
@@ -223,7 +223,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp >= EPI_WARP0) {
     // =============================== epilogue warps ===============================
     regs_grow_epilogue();
-    epilogue_warps<BLOCK_N, CONV, POOL, CG, C::WIDE>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, worker, num_workers, cta_rank, is_leader);
+    epilogue_warps<BLOCK_N, CONV, POOL, CG, C::WIDE, FEAT>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, worker, num_workers, cta_rank, is_leader);
   }
 
   __syncwarp();     // lanes of the single-thread roles rejoin their warp before the aligned barriers below
@@ -268,7 +268,7 @@ struct HaloCfg {
   static constexpr size_t SMEM_BYTES = (size_t)RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
 };
 
-template <int BLOCK_N, bool POOL, int CG>
+template <int BLOCK_N, bool POOL, int CG, int FEAT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Problem pb, GemmEpilogue ep) {
   using C = HaloCfg<BLOCK_N, CG>;
@@ -469,7 +469,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int nkb = (group_begin(sp + 1) - group_begin(sp)) * 3;
       GemmEpilogue e2 = ep;
       if (S > 1) e2.out_f32 = ep.out_f32 + (size_t)sp * pb.split_stride;      // this split's partial-sum plane
-      epilogue_tile<BLOCK_N, true, POOL, CG, C::WIDE>(pb, e2, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, mt, nt, (nkb + G - 1) / G, gi, iter, cta_rank,
+      epilogue_tile<BLOCK_N, true, POOL, CG, C::WIDE, FEAT>(pb, e2, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, mt, nt, (nkb + G - 1) / G, gi, iter, cta_rank,
                                                       is_leader);
     }
   }
@@ -522,14 +522,16 @@ static int launch_kernel(dc_ctx* ctx, Kernel kernel, size_t smem_bytes, int cg, 
   return DC_OK;
 }
 
-template <int BLOCK_N, bool CONV, bool POOL, int CG>
+template <int BLOCK_N, int CG>
 static int launch(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const Problem& pb, const GemmEpilogue& ep, cudaStream_t st) {
-  return launch_kernel(ctx, tc_gemm_kernel<BLOCK_N, CONV, POOL, CG>, Cfg<BLOCK_N, CG>::SMEM_BYTES, CG, ma, mb, pb, ep, st);
+  // linear layers write split planes and / or fp32; the LSTM gate GEMM with the fused cell is its own instantiation (epilogue feature mask)
+  if (ep.lstm_c || ep.gather_tab) return launch_kernel(ctx, tc_gemm_kernel<BLOCK_N, false, false, CG, FEAT_LSTM>, Cfg<BLOCK_N, CG>::SMEM_BYTES, CG, ma, mb, pb, ep, st);
+  return launch_kernel(ctx, tc_gemm_kernel<BLOCK_N, false, false, CG, FEAT_DENSE>, Cfg<BLOCK_N, CG>::SMEM_BYTES, CG, ma, mb, pb, ep, st);
 }
 
-template <int BLOCK_N, bool POOL, int CG>
+template <int BLOCK_N, bool POOL, int CG, int FEAT = FEAT_CONV>
 static int launch_halo(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const Problem& pb, const GemmEpilogue& ep, cudaStream_t st) {
-  return launch_kernel(ctx, tc_conv_halo_kernel<BLOCK_N, POOL, CG>, HaloCfg<BLOCK_N, CG>::SMEM_BYTES, CG, ma, mb, pb, ep, st);
+  return launch_kernel(ctx, tc_conv_halo_kernel<BLOCK_N, POOL, CG, FEAT>, HaloCfg<BLOCK_N, CG>::SMEM_BYTES, CG, ma, mb, pb, ep, st);
 }
 
 // Tile shape by an MMA-issue model (ncu, r06): a tcgen05.mma of this kernel cannot retire faster than ~90 clk because it
@@ -628,7 +630,9 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
   DC_REQUIRE(ctx, K > 0 && K % BLOCK_K == 0, DC_E_UNSUPPORTED, "tc_gemm: K=%d must be a positive multiple of 64", K);
   DC_REQUIRE(ctx, lda % 8 == 0 && ldb % 8 == 0 && a_plane_elems % 8 == 0 && b_plane_elems % 8 == 0, DC_E_UNSUPPORTED,
              "tc_gemm: leading dimensions / plane sizes must be multiples of 8 elements");
-  DC_REQUIRE(ctx, !ep.out_hi || (ep.ldo % 8 == 0 && ep.out_col0 % 8 == 0), DC_E_UNSUPPORTED, "tc_gemm: split output alignment");
+  DC_REQUIRE(ctx, !ep.out_hi || (ep.ldo % 8 == 0 && ep.out_col0 % 8 == 0 && (N % 8 == 0 || ep.lstm_c)), DC_E_UNSUPPORTED,
+             "tc_gemm: split outputs need N, ld and the column offset to be multiples of 8");
+  DC_REQUIRE(ctx, !ep.argmax, DC_E_UNSUPPORTED, "tc_gemm: the arg-max epilogue belongs to the decoder kernels");
   DC_REQUIRE(ctx, !ep.lstm_c || (ep.out_hi && N == 4 * ep.lstm_H && ep.lstm_H % 8 == 0), DC_E_UNSUPPORTED, "tc_gemm: LSTM epilogue shape");
   Problem pb{};
   pb.M = M; pb.N = N; pb.K = K;
@@ -658,10 +662,10 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
     int rc = encode_map(ctx, &mb, b_planes, 3, dims, str, box);
     if (rc) return rc;
   }
-  if (cg == 2) return launch<256, false, false, 2>(ctx, ma, mb, pb, ep, st);
-  if (bn == 64) return launch<64, false, false, 1>(ctx, ma, mb, pb, ep, st);
-  if (bn == 256) return launch<256, false, false, 1>(ctx, ma, mb, pb, ep, st);
-  return launch<128, false, false, 1>(ctx, ma, mb, pb, ep, st);
+  if (cg == 2) return launch<256, 2>(ctx, ma, mb, pb, ep, st);
+  if (bn == 64) return launch<64, 1>(ctx, ma, mb, pb, ep, st);
+  if (bn == 256) return launch<256, 1>(ctx, ma, mb, pb, ep, st);
+  return launch<128, 1>(ctx, ma, mb, pb, ep, st);
 }
 
 int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, const __half* w_planes, size_t w_plane_elems,
@@ -744,7 +748,7 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
     return launch_halo<128, true, 1>(ctx, ma, mb, pb, ep, st);
   }
   if (split > 1) {
-    int rc = launch_halo<256, false, 2>(ctx, ma, mb, pb, ep, st);
+    int rc = launch_halo<256, false, 2, FEAT_PARTIAL>(ctx, ma, mb, pb, ep, st);
     if (rc) return rc;
     const size_t rows = (size_t)N * H * W;
     cudaLaunchConfig_t cfg = {};

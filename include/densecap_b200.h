@@ -93,6 +93,9 @@ int dc_create(const dc_config* cfg, int device, dc_ctx** out);
 int dc_destroy(dc_ctx* ctx);
 const char* dc_last_error(const dc_ctx* ctx);      /* ctx may be NULL: last ctx-less error    */
 int dc_version(void);
+/* Debugging aid: synchronises the current device and pops the CUDA runtime's last error (0 = none; msg receives its text).  With
+ * DENSECAP_B200_DEBUG=1 the Python binding calls it after every entry point and reports the first call that leaves an error behind. */
+int dc_debug_peek_cuda_error(char* msg, int capacity);
 
 /* Weights arrive in the reference's own layouts (host fp32) and are re-laid-out on the device:
  *   "convI_J.weight" (Cout,Cin,3,3) / ".bias";  "rpn.conv|box|score.weight/.bias";
