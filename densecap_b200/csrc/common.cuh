@@ -175,6 +175,15 @@ int k_maxpool2x2_split(dc_ctx*, const __half* ihi, const __half* ilo, __half* oh
 // weight re-layout: conv (Cout,Cin,3,3) -> [Cout][(r*3+s)*Cin + ci] split; fc6 (out, C*HH*WW) (c,y,x) -> (y,x,c);
 // lstm ((D+H),4H) -> [4H][D+H]
 int k_conv_weight_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int Cout, int Cin, cudaStream_t st, float scale = 1.f);
+// Order of the (channel, position) pairs inside one row of the pooled ROI features = the K order of fc6's A operand.
+// The pooling kernel gives every CTA one 32-channel slice of the feature map, so a row is laid out slice-major:
+// [slice s][position p][32 channels] -- the 49 positions x 32 channels x 2 B a CTA produces for one ROI are then 3136 contiguous
+// bytes per plane and a warp's store of 8 positions covers four full 128-byte lines (with plain (p, c) order every store was a
+// 64-byte fragment of a 1 KB row).  fc6's weight columns are permuted to the same order once at load time.
+__host__ __device__ inline size_t roi_feature_index(int c, int pos, int C, int hw) {
+  const int cs = (C % 32 == 0) ? 32 : C;
+  return ((size_t)(c / cs) * hw + pos) * cs + (size_t)(c % cs);
+}
 int k_fc6_weight_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int out, int C, int hw, cudaStream_t st, float scale = 1.f);
 // interleave_h > 0: output row of input column c is 4*(c % H) + c / H (LSTM gate interleave, H = interleave_h)
 int k_transpose_to_split(dc_ctx*, const float* w, __half* hi, __half* lo, int rows, int cols, int interleave_h, cudaStream_t st, float scale = 1.f);

@@ -152,19 +152,20 @@ int k_conv_weight_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, 
   return DC_OK;
 }
 
-// fc6 weight (out, C*hw) with input order (c, pos) -> split (out, hw*C) with input order (pos, c),
-// so that the BHWC output of the ROI pooling feeds fc6 without the reference's nn.Transpose/View.
+// fc6 weight (out, C*hw) with input order (c, pos) -> split (out, hw*C) in the order of the pooled ROI rows (roi_feature_index),
+// so that the output of the ROI pooling feeds fc6 without the reference's nn.Transpose/View.
 __global__ void fc6_weight_to_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int out, int C, int hw, float scale) {
   const size_t K = (size_t)C * hw;
   const size_t total = (size_t)out * K;
   for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
-    const int c = o % C;
-    const int pos = (o / C) % hw;
+    const int pos = o % hw;                      // o walks the reference order (row, c, pos): coalesced reads
+    const int c = (o / hw) % C;
     const size_t row = o / K;
     __half h, l;
-    split_f32(w[row * K + (size_t)c * hw + pos] * scale, h, l);
-    hi[o] = h;
-    lo[o] = l;
+    split_f32(w[o] * scale, h, l);
+    const size_t d = row * K + roi_feature_index(c, pos, C, hw);
+    hi[d] = h;
+    lo[d] = l;
   }
 }
 int k_fc6_weight_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, int out, int C, int hw, cudaStream_t st, float scale) {
@@ -204,17 +205,18 @@ int k_transpose_to_split(dc_ctx* ctx, const float* w, __half* hi, __half* lo, in
   return DC_OK;
 }
 
-// (K,C,hw) fp32 BCHW -> split rows (K, hw*C) in (pos, c) order
+// (K,C,hw) fp32 BCHW -> split rows (K, hw*C) in roi_feature_index order
 __global__ void bchw_to_split_rows_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, int K, int C, int hw) {
   const size_t total = (size_t)K * C * hw;
   for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
-    const int c = o % C;
-    const int pos = (o / C) % hw;
+    const int pos = o % hw;
+    const int c = (o / hw) % C;
     const size_t b = o / ((size_t)C * hw);
     __half h, l;
-    split_f32(in[(b * C + c) * hw + pos], h, l);
-    hi[o] = h;
-    lo[o] = l;
+    split_f32(in[o], h, l);
+    const size_t d = b * ((size_t)C * hw) + roi_feature_index(c, pos, C, hw);
+    hi[d] = h;
+    lo[d] = l;
   }
 }
 int k_bchw_to_split_rows(dc_ctx* ctx, const float* in, __half* hi, __half* lo, int K, int C, int hw, cudaStream_t st) {
@@ -230,7 +232,7 @@ __global__ void bhwc_split_to_bchw_kernel(const __half* __restrict__ hi, const _
     const int pos = o % hw;
     const int c = (o / hw) % C;
     const size_t b = o / ((size_t)C * hw);
-    const size_t g = (b * hw + pos) * C + c;
+    const size_t g = b * ((size_t)C * hw) + roi_feature_index(c, pos, C, hw);
     out[o] = join_f32(hi[g], lo[g]);
   }
 }

@@ -33,8 +33,10 @@ size_t roi_taps_bytes(int max_boxes, int npos) { return (size_t)max_boxes * npos
 
 __global__ void roi_taps_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ nboxes_dev, int max_boxes,
                                 float img_h, float img_w, int fh, int fw, int HH, int WW, int ch, RoiTap* __restrict__ taps) {
-  // let the dependent roi_pool_kernel start staging its feature slice right away (it waits before reading taps)
+  // let the dependent roi_pool_kernel start staging its feature slice right away (it waits before reading taps); this kernel is itself
+  // launched with programmatic stream serialisation, so wait for the producer of `boxes` / `nboxes_dev` before reading them
   asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int npos = HH * WW;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= max_boxes * npos) return;
@@ -133,11 +135,32 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 
+// Packed fp32x2 arithmetic (sm_100 FMUL2 / FADD2 / FFMA2): two IEEE single-precision operations per issue slot.  The blend must keep
+// the reference's unfused operation order, and ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (also when the product is spelled
+// fma(a, b, -0.0) with a literal -0), so the product is fma(a, b, nz) with nz = (-0.0, -0.0) passed in as a KERNEL ARGUMENT: adding -0
+// leaves every product (and the sign of a zero product) unchanged, and an opaque addend leaves nothing to contract.
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b, unsigned long long nz) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 template <int CH>
 __global__ void __launch_bounds__(ROI_THREADS, 1)
 roi_pool_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ feat_lo, const float* __restrict__ feats_f32,
                 int C, int fh, int fw, const RoiTap* __restrict__ taps, int total_items, int npos,
-                __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_f32, int out_layout) {
+                __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_f32, int out_layout, unsigned long long nz2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* slice = reinterpret_cast<float*>(smem_raw);                               // [fh*fw + 1][CH], last row = zeros
   constexpr int LPP = CH / 8;                   // lanes per output position (8 channels per lane)
@@ -149,6 +172,7 @@ roi_pool_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ f
   // ---- stage the channel slice (4 channels per thread and step) ---------------------------------
   {
     constexpr int QUADS = CH / 4;
+#pragma unroll 4                                   // several independent L2 round trips in flight per thread
     for (int e = threadIdx.x; e < cells * QUADS; e += ROI_THREADS) {
       const int cell = e / QUADS, cq4 = (e % QUADS) * 4;
       const size_t g = (size_t)cell * C + c0 + cq4;
@@ -177,19 +201,26 @@ roi_pool_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ f
   const int cA = (lane % LPP) * 8 + 4 * half, cB = (lane % LPP) * 8 + 4 * (half ^ 1);
   // items (roi*npos + pos) are dealt in contiguous runs of POS_PER_WARP to (blockIdx.y, warp)
   const int stride = gridDim.y * NWARPS * POS_PER_WARP;
+  // 4 channels of one output position: ((w0 tl + w1 tr) + w2 bl) + w3 br per channel, every product and sum rounded separately
+  // (reference operation order), evaluated two channels per instruction
   auto blend4 = [&](const uint4& ta, const uint4& tb, int cc, float (&v)[4]) {
     const float w0 = __uint_as_float(tb.x), w1 = __uint_as_float(tb.y), w2 = __uint_as_float(tb.z), w3 = __uint_as_float(tb.w);
-    const float4 tl = *reinterpret_cast<const float4*>(slice + ta.x + cc);
-    const float4 tr = *reinterpret_cast<const float4*>(slice + ta.y + cc);
-    const float4 bl = *reinterpret_cast<const float4*>(slice + ta.z + cc);
-    const float4 br = *reinterpret_cast<const float4*>(slice + ta.w + cc);
-    v[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.x), __fmul_rn(w1, tr.x)), __fmul_rn(w2, bl.x)), __fmul_rn(w3, br.x));
-    v[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.y), __fmul_rn(w1, tr.y)), __fmul_rn(w2, bl.y)), __fmul_rn(w3, br.y));
-    v[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.z), __fmul_rn(w1, tr.z)), __fmul_rn(w2, bl.z)), __fmul_rn(w3, br.z));
-    v[3] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.w), __fmul_rn(w1, tr.w)), __fmul_rn(w2, bl.w)), __fmul_rn(w3, br.w));
+    const unsigned long long p0 = f2_pack(w0, w0), p1 = f2_pack(w1, w1), p2 = f2_pack(w2, w2), p3 = f2_pack(w3, w3);
+    const ulonglong2 tl = *reinterpret_cast<const ulonglong2*>(slice + ta.x + cc);
+    const ulonglong2 tr = *reinterpret_cast<const ulonglong2*>(slice + ta.y + cc);
+    const ulonglong2 bl = *reinterpret_cast<const ulonglong2*>(slice + ta.z + cc);
+    const ulonglong2 br = *reinterpret_cast<const ulonglong2*>(slice + ta.w + cc);
+    const unsigned long long a01 = f2_add(f2_add(f2_add(f2_mul(p0, tl.x, nz2), f2_mul(p1, tr.x, nz2)), f2_mul(p2, bl.x, nz2)), f2_mul(p3, br.x, nz2));
+    const unsigned long long a23 = f2_add(f2_add(f2_add(f2_mul(p0, tl.y, nz2), f2_mul(p1, tr.y, nz2)), f2_mul(p2, bl.y, nz2)), f2_mul(p3, br.y, nz2));
+    f2_unpack(a01, v[0], v[1]);
+    f2_unpack(a23, v[2], v[3]);
   };
   const int c8 = (lane % LPP) * 8;
-  auto emit = [&](int it, const uint4& ta, const uint4& tb) {
+  // split output rows are laid out slice-major (roi_feature_index): the 8 positions a warp emits per step are 8 x 64 contiguous bytes per plane
+  const size_t row_elems = (size_t)npos * C;
+  const size_t col_base = roi_feature_index(c0 + c8, 0, C, npos);
+  const int cs = (C % 32 == 0) ? 32 : C;
+  auto emit = [&](int it, int roi, int pos, const uint4& ta, const uint4& tb) {
     float va[4], vb[4];
     blend4(ta, tb, cA, va);
     blend4(ta, tb, cB, vb);
@@ -202,7 +233,7 @@ roi_pool_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ f
       split_pair(vb[2], vb[3], hb1, lb1);
       const uint4 ph = half ? make_uint4(hb0, hb1, ha0, ha1) : make_uint4(ha0, ha1, hb0, hb1);
       const uint4 pl = half ? make_uint4(lb0, lb1, la0, la1) : make_uint4(la0, la1, lb0, lb1);
-      const size_t o = (size_t)it * C + c0 + c8;
+      const size_t o = (size_t)roi * row_elems + col_base + (size_t)pos * cs;
       *reinterpret_cast<uint4*>(out_hi + o) = ph;
       *reinterpret_cast<uint4*>(out_lo + o) = pl;
     }
@@ -211,9 +242,8 @@ roi_pool_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ f
         *reinterpret_cast<float4*>(out_f32 + (size_t)it * C + c0 + cA) = make_float4(va[0], va[1], va[2], va[3]);
         *reinterpret_cast<float4*>(out_f32 + (size_t)it * C + c0 + cB) = make_float4(vb[0], vb[1], vb[2], vb[3]);
       } else {
-        const int b = it / npos, p = it % npos;
-        float* oa = out_f32 + ((size_t)b * C + c0 + cA) * npos + p;
-        float* ob = out_f32 + ((size_t)b * C + c0 + cB) * npos + p;
+        float* oa = out_f32 + ((size_t)roi * C + c0 + cA) * npos + pos;
+        float* ob = out_f32 + ((size_t)roi * C + c0 + cB) * npos + pos;
 #pragma unroll
         for (int j = 0; j < 4; ++j) { oa[(size_t)j * npos] = va[j]; ob[(size_t)j * npos] = vb[j]; }
       }
@@ -224,114 +254,25 @@ roi_pool_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ f
   // software pipeline of depth one: the tap record of the next item is requested before the current item is gathered,
   // so the L2 latency of the tap load is covered by this warp's own work
   int it = (blockIdx.y * NWARPS + warp) * POS_PER_WARP + sub;
-  uint4 t0 = make_uint4(0, 0, 0, 0), t1 = t0;
-  if (it < total_items) { const uint4* tp = reinterpret_cast<const uint4*>(taps + it); t0 = __ldcg(tp); t1 = __ldcg(tp + 1); }
-  while (it < total_items) {
-    const int nx = it + stride;
-    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-    if (nx < total_items) { const uint4* tp = reinterpret_cast<const uint4*>(taps + nx); n0 = __ldcg(tp); n1 = __ldcg(tp + 1); }
-    emit(it, t0, t1);
-    t0 = n0; t1 = n1; it = nx;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Split-plane output through the TMA store engine (the hot path of the forward pass).
-// ncu on the kernel above (r06): LSU data pipe 76 % busy and the 16-byte-per-lane global stores (8 half-filled 128-byte lines
-// per warp instruction and plane) cost as many LSU cycles as the 32 LDS.128 corner wavefronts of an iteration.  Here a warp
-// writes its 8 positions x 32 channels x {hi, lo} into a 1 KB shared-memory tile (two conflict-free STS.128 per lane) and one
-// elected lane hands the tile to the TMA unit (cp.async.bulk.tensor.3d global <- shared, box {32 ch, 8 rows, 2 planes}); the
-// address generation and the 64-byte row writes leave the LSU.  Shared memory beyond the feature slice holds 12 such tiles, so
-// only the first 12 warps gather (all 32 stage the slice, then warps 12.. exit); tap records are prefetched two iterations ahead.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int ROI_TMA_WARPS = 12;
-__global__ void __launch_bounds__(ROI_THREADS, 1)
-roi_pool_tma_kernel(const __half* __restrict__ feat_hi, const __half* __restrict__ feat_lo, int C, int fh, int fw,
-                    const RoiTap* __restrict__ taps, int total_items, const __grid_constant__ CUtensorMap out_map) {
-  constexpr int CH = 32;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int cells = fh * fw;
-  float* slice = reinterpret_cast<float*>(smem_raw);                               // [cells + 1][CH], last row = zeros
-  const size_t slice_bytes = ((size_t)(cells + 1) * CH * 4 + 127) & ~(size_t)127;
-  unsigned char* tiles = smem_raw + slice_bytes;                                   // ROI_TMA_WARPS x [2 planes][8 rows][64 B]
-  const int c0 = blockIdx.x * CH;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) tc::prefetch_tmap(&out_map);
-  {
-    constexpr int QUADS = CH / 4;
-    for (int e = threadIdx.x; e < cells * QUADS; e += ROI_THREADS) {
-      const int cell = e / QUADS, cq4 = (e % QUADS) * 4;
-      const size_t g = (size_t)cell * C + c0 + cq4;
-      const uint2 h = *reinterpret_cast<const uint2*>(feat_hi + g);
-      const uint2 l = *reinterpret_cast<const uint2*>(feat_lo + g);
-      const __half2 h01 = *reinterpret_cast<const __half2*>(&h.x), h23 = *reinterpret_cast<const __half2*>(&h.y);
-      const __half2 l01 = *reinterpret_cast<const __half2*>(&l.x), l23 = *reinterpret_cast<const __half2*>(&l.y);
-      float4 v;
-      v.x = __low2float(h01) + __low2float(l01);
-      v.y = __high2float(h01) + __high2float(l01);
-      v.z = __low2float(h23) + __low2float(l23);
-      v.w = __high2float(h23) + __high2float(l23);
-      *reinterpret_cast<float4*>(slice + cell * CH + cq4) = v;
-    }
-    if (threadIdx.x < CH) slice[cells * CH + threadIdx.x] = 0.f;
-  }
-  __syncthreads();
-  if (warp >= ROI_TMA_WARPS) return;
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int sub = lane >> 2, ql = lane & 3;
-  const int half = sub & 1;                               // odd positions read their two 4-channel halves in swapped order (bank spread)
-  const int cA = ql * 8 + 4 * half, cB = ql * 8 + 4 * (half ^ 1);
-  const int stride = gridDim.y * ROI_TMA_WARPS * 8;
-  unsigned char* tile = tiles + (size_t)warp * 1024;
-  const uint32_t tile_s = tc::smem_u32(tile);
-  auto blend4 = [&](const uint4& ta, const uint4& tb, int cc, float (&v)[4]) {
-    const float w0 = __uint_as_float(tb.x), w1 = __uint_as_float(tb.y), w2 = __uint_as_float(tb.z), w3 = __uint_as_float(tb.w);
-    const float4 tl = *reinterpret_cast<const float4*>(slice + ta.x + cc);
-    const float4 tr = *reinterpret_cast<const float4*>(slice + ta.y + cc);
-    const float4 bl = *reinterpret_cast<const float4*>(slice + ta.z + cc);
-    const float4 br = *reinterpret_cast<const float4*>(slice + ta.w + cc);
-    v[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.x), __fmul_rn(w1, tr.x)), __fmul_rn(w2, bl.x)), __fmul_rn(w3, br.x));
-    v[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.y), __fmul_rn(w1, tr.y)), __fmul_rn(w2, bl.y)), __fmul_rn(w3, br.y));
-    v[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.z), __fmul_rn(w1, tr.z)), __fmul_rn(w2, bl.z)), __fmul_rn(w3, br.z));
-    v[3] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, tl.w), __fmul_rn(w1, tr.w)), __fmul_rn(w2, bl.w)), __fmul_rn(w3, br.w));
-  };
-  auto load_tap = [&](int it, uint4& a, uint4& b) {
+  int roi = it / npos, pos = it - roi * npos;                   // advanced incrementally (no division in the loop)
+  const int step_roi = stride / npos, step_pos = stride - step_roi * npos;
+  auto load_tap = [&](int i, uint4& a, uint4& b) {
     a = make_uint4(0, 0, 0, 0); b = a;
-    if (it < total_items) { const uint4* tp = reinterpret_cast<const uint4*>(taps + it); a = __ldcg(tp); b = __ldcg(tp + 1); }
+    if (i < total_items) { const uint4* tp = reinterpret_cast<const uint4*>(taps + i); a = __ldcg(tp); b = __ldcg(tp + 1); }
   };
-  int it0 = (blockIdx.y * ROI_TMA_WARPS + warp) * 8;      // first item of this warp's current run of 8
-  uint4 t0a, t0b, t1a, t1b;
-  load_tap(it0 + sub, t0a, t0b);
-  load_tap(it0 + stride + sub, t1a, t1b);
-  while (it0 < total_items) {
-    uint4 t2a, t2b;
-    load_tap(it0 + 2 * stride + sub, t2a, t2b);
-    float va[4], vb[4];
-    blend4(t0a, t0b, cA, va);
-    blend4(t0a, t0b, cB, vb);
-    uint32_t ha0, la0, ha1, la1, hb0, lb0, hb1, lb1;
-    split_pair(va[0], va[1], ha0, la0);
-    split_pair(va[2], va[3], ha1, la1);
-    split_pair(vb[0], vb[1], hb0, lb0);
-    split_pair(vb[2], vb[3], hb1, lb1);
-    const uint4 ph = half ? make_uint4(hb0, hb1, ha0, ha1) : make_uint4(ha0, ha1, hb0, hb1);
-    const uint4 pl = half ? make_uint4(lb0, lb1, la0, la1) : make_uint4(la0, la1, lb0, lb1);
-    // the previous bulk store of this warp must have finished READING the tile before it is overwritten
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    __syncwarp();
-    *reinterpret_cast<uint4*>(tile + sub * 64 + ql * 16) = ph;                      // plane 0 (hi): rows of 64 B
-    *reinterpret_cast<uint4*>(tile + 512 + sub * 64 + ql * 16) = pl;                // plane 1 (lo)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                    // generic-proxy writes -> async proxy
-    __syncwarp();
-    if (lane == 0) {
-      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
-                   ::"l"(&out_map), "r"(c0), "r"(it0), "r"(0), "r"(tile_s) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-    t0a = t1a; t0b = t1b; t1a = t2a; t1b = t2b;
-    it0 += stride;
+  // software pipeline of depth two: tap records are requested two steps ahead of their use (L2 latency ~ one step of this warp)
+  uint4 t0, t1, u0, u1;
+  load_tap(it, t0, t1);
+  load_tap(it + stride, u0, u1);
+  while (it < total_items) {
+    uint4 n0, n1;
+    load_tap(it + 2 * stride, n0, n1);
+    emit(it, roi, pos, t0, t1);
+    t0 = u0; t1 = u1; u0 = n0; u1 = n1;
+    it += stride;
+    roi += step_roi; pos += step_pos;
+    if (pos >= npos) { pos -= npos; ++roi; }
   }
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");        // stores complete before the CTA exits
 }
 
 // grids != nullptr: stand-alone sampler on caller-supplied (max_boxes, HH, WW, 2) grids (boxes / image size unused)
@@ -349,43 +290,22 @@ static int roi_pool_impl(dc_ctx* ctx, const __half* feat_hi, const __half* feat_
   while (ch > 8 && ((size_t)(fh * fw + 1) * ch * 4 > limit || C % ch != 0)) ch >>= 1;
   const size_t smem = (size_t)(fh * fw + 1) * ch * 4;
   if (grids) roi_taps_from_grid_kernel<<<DC_CEIL_DIV(total, 256), 256, 0, st>>>((const float2*)grids, total, fh, fw, ch, taps);
-  else roi_taps_kernel<<<DC_CEIL_DIV(total, 256), 256, 0, st>>>((const float4*)boxes, nboxes_dev, max_boxes, (float)img_h, (float)img_w, fh, fw,
-                                                               HH, WW, ch, taps);
+  else {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(DC_CEIL_DIV(total, 256)); lc.blockDim = dim3(256); lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&lc, roi_taps_kernel, (const float4*)boxes, nboxes_dev, max_boxes, (float)img_h, (float)img_w, fh, fw, HH, WW, ch, taps);
+    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "roi_taps launch: %s", cudaGetErrorString(e));
+  }
   DC_CHECK_LAUNCH(ctx);
   DC_REQUIRE(ctx, smem <= limit && C % ch == 0, DC_E_UNSUPPORTED, "roi_pool: feature map %dx%d too large for the shared-memory slice", fh, fw);
   const int slices = C / ch;
   int groups = dc_launch_state(ctx)->num_sms / slices;
   if (groups < 1) groups = 1;
   dim3 grid(slices, groups);
-  const size_t slice_bytes = (smem + 127) & ~(size_t)127;
-#ifdef DC_DISABLE_ROI_TMA
-  const bool tma_ok = false;
-#else
-  const bool tma_ok = true;
-#endif
-  if (tma_ok && out_hi && !out_f32 && !feats_f32 && ch == 32 && out_lo > out_hi && slice_bytes + ROI_TMA_WARPS * 1024 <= limit &&
-      (((size_t)(out_lo - out_hi) * 2) % 16) == 0 && dc_launch_state(ctx)->encode_tiled) {
-    // TMA-store variant: output viewed as (planes, rows = boxes * positions, C) fp16
-    CUtensorMap omap;
-    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)total, 2};
-    const uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)(out_lo - out_hi) * 2};
-    const uint32_t box[3] = {32, 8, 2};
-    int rc = tc::encode_map(ctx, &omap, out_hi, 3, dims, str, box, /*swizzle_bytes=*/0);
-    if (rc) return rc;
-    const size_t smem_t = slice_bytes + ROI_TMA_WARPS * 1024;
-    cudaError_t e = dc_ensure_smem(ctx, roi_pool_tma_kernel, limit);
-    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "roi_pool smem attribute: %s", cudaGetErrorString(e));
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = grid; lc.blockDim = dim3(ROI_THREADS); lc.dynamicSmemBytes = smem_t; lc.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = at; lc.numAttrs = 1;
-    e = cudaLaunchKernelEx(&lc, roi_pool_tma_kernel, feat_hi, feat_lo, C, fh, fw, (const RoiTap*)taps, total, omap);
-    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "roi_pool launch: %s", cudaGetErrorString(e));
-    DC_CHECK_LAUNCH(ctx);
-    return DC_OK;
-  }
 #define ROI_LAUNCH(CHV)                                                                                              \
   do {                                                                                                               \
     cudaError_t e = dc_ensure_smem(ctx, roi_pool_kernel<CHV>, limit);                                                  \
@@ -397,7 +317,7 @@ static int roi_pool_impl(dc_ctx* ctx, const __half* feat_hi, const __half* feat_
     at[0].val.programmaticStreamSerializationAllowed = 1;                                                            \
     lc.attrs = at; lc.numAttrs = 1;                                                                                  \
     e = cudaLaunchKernelEx(&lc, roi_pool_kernel<CHV>, feat_hi, feat_lo, feats_f32, C, fh, fw, (const RoiTap*)taps, total, npos, \
-                           out_hi, out_lo, out_f32, out_layout);                                                     \
+                           out_hi, out_lo, out_f32, out_layout, 0x8000000080000000ULL);                              \
     if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "roi_pool launch: %s", cudaGetErrorString(e));          \
   } while (0)
   if (ch == 32) ROI_LAUNCH(32);

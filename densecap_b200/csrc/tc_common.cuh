@@ -389,7 +389,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
   }
   float best_v = -INFINITY;
   int best_c = 0x7fffffff;
-  bool out_of_range = false;
+  uint32_t absmax_bits = 0;           // range guard of the split-fp16 planes: largest |x| written (as IEEE bits)
 
 #pragma unroll
   for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
@@ -397,16 +397,20 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
     const int nc = n0 + c * 32;
     if (nc >= pb.N) continue;           // whole chunk outside N (uniform across the CTA)
     float v[32];
+    // acc_scale is a power of two, so run * acc_scale is exact and the fused form rounds exactly like (run * acc_scale) + bias
   #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = run[cc][j] * ep.acc_scale;
-      if (use_gather) {
-        const float4 gq = gath[cc][j >> 2];
-        x += (j & 3) == 0 ? gq.x : ((j & 3) == 1 ? gq.y : ((j & 3) == 2 ? gq.z : gq.w));
-      } else if (ep.bias) x += sbias[c * 32 + j];
-      if (ep.relu) x = fmaxf(x, 0.f);
-      v[j] = x;
-      out_of_range |= !(fabsf(x) < 65504.f);          // true for |x| >= 65504 and for NaN
+    for (int j4 = 0; j4 < 8; ++j4) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (use_gather) b4 = gath[cc][j4];
+      else if (ep.bias) b4 = *reinterpret_cast<const float4*>(sbias + c * 32 + 4 * j4);
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+  #pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float x = fmaf(run[cc][4 * j4 + u], ep.acc_scale, bb[u]);
+        if (ep.relu) x = fmaxf(x, 0.f);
+        v[4 * j4 + u] = x;
+        absmax_bits = max(absmax_bits, __float_as_uint(x) & 0x7fffffffu);      // |x| as ordered bits: inf and NaN sort above every finite value
+      }
     }
     if (POOL) {
       // ReLU output is >= 0, so 0 is the identity of max for out-of-image pixels (ceil-mode windows)
@@ -504,6 +508,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
   }
   if ((FEAT & F_ARGMAX) && ep.argmax && out_row >= 0 && best_c != 0x7fffffff)
     atomicMax(ep.argmax + out_row, pack_argmax_tc(best_v, best_c));
+  const bool out_of_range = absmax_bits >= 0x477fe000u;      // |x| >= 65504 (fp16 max), inf or NaN
   if ((FEAT & F_SPLIT) && ep.overflow && ep.out_hi && out_of_range && (POOL ? in_bounds : out_row >= 0)) atomicOr(ep.overflow, 1u);
 }
 

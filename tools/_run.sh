@@ -1,3 +1,6 @@
 cd /root/repo
-DENSECAP_B200_DEBUG=1 timeout 900 python -m pytest tests -m gpu -q --tb=line -x -s 2>&1 | grep -B2 -A2 -m 6 "DENSECAP_B200_DEBUG" | cut -c1-300
-bash tools/gpu.sh b1 b4
+bash tools/gpu.sh tests_noexit b4
+grep -o '"roi_pool": {[^}]*}' gpurun_out/bench_b4.log
+bash tools/ab.sh "2 2 1" default
+bash tools/ab.sh "4 4 1" default
+bash tools/ab.sh "4 4 2" default
