@@ -480,7 +480,12 @@ __device__ __forceinline__ void epilogue_tile(const Problem& pb, const GemmEpilo
 #ifndef DC_EPI_NO_STORE
   #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (full || nc + 8 * j + 8 <= pb.N) {
+#ifdef DC_EPI_FAKE_STORE
+          if (ep.ldo == -12345)              // experiment: all the output math, no store traffic
+#else
+          if (full || nc + 8 * j + 8 <= pb.N)
+#endif
+          {
             reinterpret_cast<uint4*>(ph)[j] = make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
             reinterpret_cast<uint4*>(pl)[j] = make_uint4(ll[4 * j], ll[4 * j + 1], ll[4 * j + 2], ll[4 * j + 3]);
           }

@@ -643,6 +643,9 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
   if (ep.gather_tab && tc_.bn == 256) tc_ = TileCfg{128, 1};          // the table-gather epilogue exists for the wide tiles only
   const int bn = tc_.bn, cg = tc_.cg;
   pb.kb_per_group = group_kblocks(ctx, bn);
+  // short reductions (the RPN 1x1 heads, K = 256; the LM encoder / gate table, K = 512): an accumulator sweep per k-block costs nothing
+  // measurable there and these outputs feed discrete decisions (NMS order, arg-max), so take the most accurate setting
+  if (pb.num_k_blocks <= 8) pb.kb_per_group = 1;
   pb.m_tiles = DC_CEIL_DIV(m_tiles128, cg);
   pb.n_tiles = DC_CEIL_DIV(N, bn);
   pb.m_fastest = pb.m_tiles <= pb.n_tiles;

@@ -188,8 +188,12 @@ def test_localization_layer_on_oracle_features(model_c, case_c):
     report("C.ll_on_oracle_feats", {"picks_in_common": common, "same_order": same, "order_valid_within_2e-6": ok,
                                     "positions_differing": int((got_idx != oll["idx"]).sum())})
     assert common == len(oll["idx"]) and ok
-    assert rel(out[1].cpu().numpy(), oll["boxes"]) < 1e-4
-    assert rel(out[0].cpu().numpy(), oll["roi_features"]) < 1e-4
+    # values are compared pick by pick (aligned on the anchor index): where two candidates tie within the score noise their POSITIONS may be
+    # swapped (accepted above), which must not be mistaken for a wrong box
+    pos_of = {int(a): i for i, a in enumerate(got_idx.tolist())}
+    perm = np.array([pos_of[int(a)] for a in oll["idx"].tolist()])
+    assert rel(out[1].cpu().numpy()[perm], oll["boxes"]) < 1e-4
+    assert rel(out[0].cpu().numpy()[perm], oll["roi_features"]) < 1e-4
     model_c.setTestArgs(CFG)
 
 
