@@ -39,7 +39,8 @@ namespace tc {
 
 template <int BLOCK_N, bool CONV, bool POOL, int CG, int FEAT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Problem pb, GemmEpilogue ep) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
+               Problem pb, GemmEpilogue ep) {
   using C = Cfg<BLOCK_N, CG>;
   // CG == 2: the two CTAs of a cluster form one 256-row tile; rank 0 (leader) issues the MMAs
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -52,21 +53,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // 1024-byte alignment required by SWIZZLE_128B
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_aligned + (size_t)STAGES * C::STAGE_BYTES);
+  // [operand ring][8 epilogue staging slots of 4 KB][barriers][bias]
+  const uint32_t staging = smem_base + STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_aligned + (size_t)STAGES * C::STAGE_BYTES + C::STAGING_BYTES);
   // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem base address holder
-  const uint32_t bar_base = smem_base + STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = staging + C::STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* bias_smem = reinterpret_cast<float*>(smem_aligned + (size_t)STAGES * C::STAGE_BYTES + 256);   // [2][BLOCK_N]
+  float* bias_smem = reinterpret_cast<float*>(smem_aligned + (size_t)STAGES * C::STAGE_BYTES + C::STAGING_BYTES + 256);   // [2][BLOCK_N] ([1] at 256 columns)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_out);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), CG);          // one producer arrival per CTA of the pair (leader's barrier is the live one)
       mbar_init(empty_bar(s), 1);
@@ -223,7 +227,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp >= EPI_WARP0) {
     // =============================== epilogue warps ===============================
     regs_grow_epilogue();
-    epilogue_warps<BLOCK_N, CONV, POOL, CG, C::WIDE, FEAT>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, worker, num_workers, cta_rank, is_leader);
+    epilogue_warps<BLOCK_N, CONV, POOL, CG, C::WIDE, FEAT, C::TMAS>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, worker, num_workers, cta_rank,
+                                                                    is_leader, OutStage{&tmap_out, staging});
   }
 
   __syncwarp();     // lanes of the single-thread roles rejoin their warp before the aligned barriers below
@@ -260,17 +265,22 @@ struct HaloCfg {
   static constexpr int B_ROWS = BLOCK_N / CG;
   static constexpr uint32_t B_PLANE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr uint32_t B_STAGE_BYTES = 2 * B_PLANE_BYTES;
-  static constexpr int SB = (B_STAGE_BYTES <= 16384) ? 9 : (B_STAGE_BYTES <= 32768 ? 4 : 2);
+  // split-plane outputs through TMA stores where 32 KB of staging fit beside the rings (a B stage less); the 64-column configuration keeps the
+  // whole conv1_2 filter bank resident and the 1-CTA 256-column one needs 2 x 64 KB of B: both keep direct stores
+  static constexpr bool TMAS = (B_STAGE_BYTES == 32768);
+  static constexpr int SB = (B_STAGE_BYTES <= 16384) ? 9 : (B_STAGE_BYTES <= 32768 ? 3 : 2);
   static constexpr bool WIDE = (CG == 1 && BLOCK_N <= 128);
   static constexpr int ACC_COLS = WIDE ? 2 * BLOCK_N : BLOCK_N;
   static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
   static constexpr uint32_t RING_BYTES = AH_STAGES * AH_STAGE_BYTES + SB * B_STAGE_BYTES;
-  static constexpr size_t SMEM_BYTES = (size_t)RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
+  static constexpr uint32_t STAGING_BYTES = TMAS ? 8 * 4096 : 0;
+  static constexpr size_t SMEM_BYTES = (size_t)RING_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
 };
 
 template <int BLOCK_N, bool POOL, int CG, int FEAT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Problem pb, GemmEpilogue ep) {
+tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
+                    Problem pb, GemmEpilogue ep) {
   using C = HaloCfg<BLOCK_N, CG>;
   constexpr int SB = C::SB;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -283,9 +293,11 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
   const uint32_t a_ring = smem_base;
   const uint32_t b_ring = smem_base + AH_STAGES * AH_STAGE_BYTES;
+  // [A ring][B ring][epilogue staging slots (TMAS)][barriers][bias]
   // bars: a_full[2], a_empty[2], b_full[SB], b_empty[SB], tmem_full[2], tmem_empty[2], tmem base holder
-  const uint32_t bar_base = smem_base + C::RING_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_aligned + C::RING_BYTES);
+  const uint32_t staging = smem_base + C::RING_BYTES;
+  const uint32_t bar_base = staging + C::STAGING_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_aligned + C::RING_BYTES + C::STAGING_BYTES);
   auto afull_bar = [&](int s) { return bar_base + 8u * s; };
   auto aempty_bar = [&](int s) { return bar_base + 8u * (AH_STAGES + s); };
   auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * AH_STAGES + s); };
@@ -294,12 +306,13 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * AH_STAGES + 2 * SB + 2 + s); };
   static_assert((2 * AH_STAGES + 2 * SB + 4) * 8 + 8 <= 256, "barrier block overflow");
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * AH_STAGES + 2 * SB + 4);
-  float* bias_smem = reinterpret_cast<float*>(smem_aligned + C::RING_BYTES + 256);
+  float* bias_smem = reinterpret_cast<float*>(smem_aligned + C::RING_BYTES + C::STAGING_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_out);
     for (int s = 0; s < AH_STAGES; ++s) { mbar_init(afull_bar(s), CG); mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(bfull_bar(s), CG); mbar_init(bempty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 32 * EPI_WARPS * CG); }
@@ -469,9 +482,10 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int nkb = (group_begin(sp + 1) - group_begin(sp)) * 3;
       GemmEpilogue e2 = ep;
       if (S > 1) e2.out_f32 = ep.out_f32 + (size_t)sp * pb.split_stride;      // this split's partial-sum plane
-      epilogue_tile<BLOCK_N, true, POOL, CG, C::WIDE, FEAT>(pb, e2, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, mt, nt, (nkb + G - 1) / G, gi, iter, cta_rank,
-                                                      is_leader);
+      epilogue_tile<BLOCK_N, true, POOL, CG, C::WIDE, FEAT, C::TMAS>(pb, e2, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, mt, nt, (nkb + G - 1) / G, gi, iter,
+                                                               cta_rank, is_leader, OutStage{&tmap_out, staging});
     }
+    if (C::TMAS && (threadIdx.x & 31) == 0) bulk_wait0();        // the staging slots must outlive the last bulk stores
   }
 
   __syncwarp();
@@ -488,7 +502,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // host side
 // ------------------------------------------------------------------------------------------------
 template <typename Kernel>
-static int launch_kernel(dc_ctx* ctx, Kernel kernel, size_t smem_bytes, int cg, const CUtensorMap& ma, const CUtensorMap& mb,
+static int launch_kernel(dc_ctx* ctx, Kernel kernel, size_t smem_bytes, int cg, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
                          const Problem& pb, const GemmEpilogue& ep, cudaStream_t st) {
   {
     cudaError_t e = dc_ensure_smem(ctx, kernel, smem_bytes);
@@ -516,22 +530,24 @@ static int launch_kernel(dc_ctx* ctx, Kernel kernel, size_t smem_bytes, int cg, 
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ma, mb, pb, ep);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ma, mb, mo, pb, ep);
   if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "tc_gemm launch: %s", cudaGetErrorString(e));
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;
 }
 
 template <int BLOCK_N, int CG>
-static int launch(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const Problem& pb, const GemmEpilogue& ep, cudaStream_t st) {
+static int launch(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const Problem& pb, const GemmEpilogue& ep, cudaStream_t st) {
   // linear layers write split planes and / or fp32; the LSTM gate GEMM with the fused cell is its own instantiation (epilogue feature mask)
-  if (ep.lstm_c || ep.gather_tab) return launch_kernel(ctx, tc_gemm_kernel<BLOCK_N, false, false, CG, FEAT_LSTM>, Cfg<BLOCK_N, CG>::SMEM_BYTES, CG, ma, mb, pb, ep, st);
-  return launch_kernel(ctx, tc_gemm_kernel<BLOCK_N, false, false, CG, FEAT_DENSE>, Cfg<BLOCK_N, CG>::SMEM_BYTES, CG, ma, mb, pb, ep, st);
+  if (ep.lstm_c || ep.gather_tab)
+    return launch_kernel(ctx, tc_gemm_kernel<BLOCK_N, false, false, CG, FEAT_LSTM>, Cfg<BLOCK_N, CG>::SMEM_BYTES, CG, ma, mb, mo, pb, ep, st);
+  return launch_kernel(ctx, tc_gemm_kernel<BLOCK_N, false, false, CG, FEAT_DENSE>, Cfg<BLOCK_N, CG>::SMEM_BYTES, CG, ma, mb, mo, pb, ep, st);
 }
 
 template <int BLOCK_N, bool POOL, int CG, int FEAT = FEAT_CONV>
-static int launch_halo(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const Problem& pb, const GemmEpilogue& ep, cudaStream_t st) {
-  return launch_kernel(ctx, tc_conv_halo_kernel<BLOCK_N, POOL, CG, FEAT>, HaloCfg<BLOCK_N, CG>::SMEM_BYTES, CG, ma, mb, pb, ep, st);
+static int launch_halo(dc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const Problem& pb, const GemmEpilogue& ep,
+                       cudaStream_t st) {
+  return launch_kernel(ctx, tc_conv_halo_kernel<BLOCK_N, POOL, CG, FEAT>, HaloCfg<BLOCK_N, CG>::SMEM_BYTES, CG, ma, mb, mo, pb, ep, st);
 }
 
 // Tile shape by an MMA-issue model (ncu, r06): a tcgen05.mma of this kernel cannot retire faster than ~90 clk because it
@@ -665,10 +681,21 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
     int rc = encode_map(ctx, &mb, b_planes, 3, dims, str, box);
     if (rc) return rc;
   }
-  if (cg == 2) return launch<256, 2>(ctx, ma, mb, pb, ep, st);
-  if (bn == 64) return launch<64, 1>(ctx, ma, mb, pb, ep, st);
-  if (bn == 256) return launch<256, 1>(ctx, ma, mb, pb, ep, st);
-  return launch<128, 1>(ctx, ma, mb, pb, ep, st);
+  // output map of the TMA-store epilogue: (planes, M rows, out_col0 + N columns) fp16, box {32 columns, 32 rows, 2 planes}, SWIZZLE_64B
+  CUtensorMap mo = ma;
+  if (ep.out_hi && !ep.lstm_c) {
+    DC_REQUIRE(ctx, ep.out_lo > ep.out_hi && ((size_t)(ep.out_lo - ep.out_hi) * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out_hi) & 15) == 0,
+               DC_E_UNSUPPORTED, "tc_gemm: split output planes must be 16-byte aligned, lo plane after the hi plane");
+    const uint64_t dims[3] = {(uint64_t)(ep.out_col0 + N), (uint64_t)M, 2};
+    const uint64_t str[2] = {(uint64_t)ep.ldo * 2, (uint64_t)(ep.out_lo - ep.out_hi) * 2};
+    const uint32_t box[3] = {32, 32, 2};
+    int rc = encode_map(ctx, &mo, ep.out_hi, 3, dims, str, box, 64);
+    if (rc) return rc;
+  }
+  if (cg == 2) return launch<256, 2>(ctx, ma, mb, mo, pb, ep, st);
+  if (bn == 64) return launch<64, 1>(ctx, ma, mb, mo, pb, ep, st);
+  if (bn == 256) return launch<256, 1>(ctx, ma, mb, mo, pb, ep, st);
+  return launch<128, 1>(ctx, ma, mb, mo, pb, ep, st);
 }
 
 int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, const __half* w_planes, size_t w_plane_elems,
@@ -744,14 +771,25 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
     int rc = encode_map(ctx, &mb, w_planes, 3, dims, str, box);
     if (rc) return rc;
   }
+  // output map of the TMA-store epilogue: (planes, N, OH, OW, Cout) fp16 NHWC; box = the 2 image rows x 16 pixels (pooled: 1 x 8) x 32 channels
+  // x 2 planes one epilogue warp produces per 32-column chunk, SWIZZLE_64B
+  CUtensorMap mo = ma;
+  if (split == 1) {
+    DC_REQUIRE(ctx, y_lo > y_hi && ((size_t)(y_lo - y_hi) * 2) % 16 == 0, DC_E_UNSUPPORTED, "tc_conv3x3: lo plane must follow the hi plane (16-byte aligned)");
+    const uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)pb.OW, (uint64_t)pb.OH, (uint64_t)N, 2};
+    const uint64_t str[4] = {(uint64_t)Cout * 2, (uint64_t)pb.OW * Cout * 2, (uint64_t)pb.OH * pb.OW * Cout * 2, (uint64_t)(y_lo - y_hi) * 2};
+    const uint32_t box[5] = {32, fuse_pool ? 8u : 16u, fuse_pool ? 1u : 2u, 1, 2};
+    int rc = encode_map(ctx, &mo, y_hi, 5, dims, str, box, 64);
+    if (rc) return rc;
+  }
   if (fuse_pool) {
-    if (cg == 2) return launch_halo<256, true, 2>(ctx, ma, mb, pb, ep, st);
-    if (bn == 64) return launch_halo<64, true, 1>(ctx, ma, mb, pb, ep, st);
-    if (bn == 256) return launch_halo<256, true, 1>(ctx, ma, mb, pb, ep, st);
-    return launch_halo<128, true, 1>(ctx, ma, mb, pb, ep, st);
+    if (cg == 2) return launch_halo<256, true, 2>(ctx, ma, mb, mo, pb, ep, st);
+    if (bn == 64) return launch_halo<64, true, 1>(ctx, ma, mb, mo, pb, ep, st);
+    if (bn == 256) return launch_halo<256, true, 1>(ctx, ma, mb, mo, pb, ep, st);
+    return launch_halo<128, true, 1>(ctx, ma, mb, mo, pb, ep, st);
   }
   if (split > 1) {
-    int rc = launch_halo<256, false, 2, FEAT_PARTIAL>(ctx, ma, mb, pb, ep, st);
+    int rc = launch_halo<256, false, 2, FEAT_PARTIAL>(ctx, ma, mb, mo, pb, ep, st);
     if (rc) return rc;
     const size_t rows = (size_t)N * H * W;
     cudaLaunchConfig_t cfg = {};
@@ -767,8 +805,8 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
     DC_CHECK_LAUNCH(ctx);
     return DC_OK;
   }
-  if (cg == 2) return launch_halo<256, false, 2>(ctx, ma, mb, pb, ep, st);
-  if (bn == 64) return launch_halo<64, false, 1>(ctx, ma, mb, pb, ep, st);
-  if (bn == 256) return launch_halo<256, false, 1>(ctx, ma, mb, pb, ep, st);
-  return launch_halo<128, false, 1>(ctx, ma, mb, pb, ep, st);
+  if (cg == 2) return launch_halo<256, false, 2>(ctx, ma, mb, mo, pb, ep, st);
+  if (bn == 64) return launch_halo<64, false, 1>(ctx, ma, mb, mo, pb, ep, st);
+  if (bn == 256) return launch_halo<256, false, 1>(ctx, ma, mb, mo, pb, ep, st);
+  return launch_halo<128, false, 1>(ctx, ma, mb, mo, pb, ep, st);
 }
