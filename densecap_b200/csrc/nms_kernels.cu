@@ -350,11 +350,15 @@ __device__ __forceinline__ void nms_scan_chunk(uint64_t* smem_mask, uint64_t* s_
   }
   if (tid == 0) *s_cnt = kept0;
   __syncthreads();
+  // every thread carries its own copy of the running count, refreshed BETWEEN the two barriers of an iteration: reading *s_cnt at the top
+  // of the loop raced with warp 0's update of the same iteration (compute-sanitizer racecheck), and a late reader could have left the loop
+  // ahead of the barriers its siblings still wait at
+  int cnt = kept0;
   for (int c = 0; c < cwords; ++c) {
-    if (*s_cnt >= cap) break;                       // uniform: s_cnt is only written before the barrier below
+    if (cnt >= cap) break;                          // uniform
     const int lim = min(64, cn_total - c * 64);
     if (warp == 0) {
-      const int before = *s_cnt;
+      const int before = cnt;
       const uint64_t d0 = (lane < lim) ? smem_mask[(size_t)(c * 64 + lane) * NMS_W + c] : 0ull;
       const uint64_t d1 = (lane + 32 < lim) ? smem_mask[(size_t)(c * 64 + 32 + lane) * NMS_W + c] : 0ull;
       const uint64_t cur = s_removed[c];
@@ -396,6 +400,7 @@ __device__ __forceinline__ void nms_scan_chunk(uint64_t* smem_mask, uint64_t* s_
       if (lane == 0) { s_keep[0] = keep; *s_cnt = before + nk; }
     }
     __syncthreads();
+    cnt = *s_cnt;                                   // settled: written before the barrier above, next written after the barrier below
     // the other warps: rows of block c's survivors -> removed words c+2 .. cwords-1, one word per warp (warp 0 joins late)
     {
       const uint64_t keep = s_keep[0];

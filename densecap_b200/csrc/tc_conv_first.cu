@@ -18,17 +18,20 @@ constexpr int CF_STAGES = 4;
 constexpr uint32_t CF_A_STAGE_BYTES = 2 * A_PLANE_BYTES;                 // hi + lo planes, 128 rows x 128 B (first 64 B of a row used)
 constexpr uint32_t CF_B_BYTES = 2 * 64 * BLOCK_K * 2;                    // 64 filters x 64 k (32 used) x {hi, lo}
 constexpr int CF_BUILD_WARP0 = 12;
-constexpr size_t CF_SMEM_BYTES = (size_t)CF_STAGES * CF_A_STAGE_BYTES + CF_B_BYTES + 1024 + 256 + 2 * 64 * 4;
+constexpr size_t CF_SMEM_USED = (size_t)CF_STAGES * CF_A_STAGE_BYTES + CF_B_BYTES + EPI_STAGING_BYTES + 256 + 2 * 64 * 4;   // before the input patches
+constexpr size_t CF_SMEM_BYTES = CF_SMEM_USED + 2 * 3 * (TILE_H + 2) * (TILE_W + 2) * 4 + 1024;
 
 __global__ void __launch_bounds__(CF_THREADS, 1)
-tc_conv_first_kernel(const float* __restrict__ img, const __grid_constant__ CUtensorMap tmap_w, Problem pb, GemmEpilogue ep) {
+tc_conv_first_kernel(const float* __restrict__ img, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out, Problem pb,
+                     GemmEpilogue ep) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
   const uint32_t a_ring = smem_base;
   const uint32_t b_base = smem_base + CF_STAGES * CF_A_STAGE_BYTES;
-  const uint32_t bar_base = b_base + CF_B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_aligned + (size_t)CF_STAGES * CF_A_STAGE_BYTES + CF_B_BYTES);
+  const uint32_t staging = b_base + CF_B_BYTES;                            // 8 epilogue staging slots (TMA-store epilogue, tc_common.cuh)
+  const uint32_t bar_base = staging + EPI_STAGING_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_aligned + (size_t)CF_STAGES * CF_A_STAGE_BYTES + CF_B_BYTES + EPI_STAGING_BYTES);
   // bars: a_full[4], a_empty[4], b_full, tmem_full[2], tmem_empty[2], tmem holder
   auto afull_bar = [&](int s) { return bar_base + 8u * s; };
   auto aempty_bar = [&](int s) { return bar_base + 8u * (CF_STAGES + s); };
@@ -36,12 +39,13 @@ tc_conv_first_kernel(const float* __restrict__ img, const __grid_constant__ CUte
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * CF_STAGES + 1 + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * CF_STAGES + 3 + s); };
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * CF_STAGES + 5);
-  float* bias_smem = reinterpret_cast<float*>(smem_aligned + (size_t)CF_STAGES * CF_A_STAGE_BYTES + CF_B_BYTES + 256);
+  float* bias_smem = reinterpret_cast<float*>(smem_aligned + (size_t)CF_STAGES * CF_A_STAGE_BYTES + CF_B_BYTES + EPI_STAGING_BYTES + 256);
   using C = Cfg<64, 1>;                                   // wide 64-column tile: accumulator 128 columns, 2 stages = 256 TMEM columns
 
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_out);
     for (int s = 0; s < CF_STAGES; ++s) { mbar_init(afull_bar(s), 128); mbar_init(aempty_bar(s), 1); }
     mbar_init(bfull_bar, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 32 * EPI_WARPS); }
@@ -100,7 +104,9 @@ tc_conv_first_kernel(const float* __restrict__ img, const __grid_constant__ CUte
     asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     int gi = 0, iter = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter)
-      epilogue_tile<64, true, false, 1, true, FEAT_CONV>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, tile, 0, 1, gi, iter, 0u, true);
+      epilogue_tile<64, true, false, 1, true, FEAT_CONV, true>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, tile, 0, 1, gi, iter, 0u, true,
+                                                              OutStage{&tmap_out, staging});
+    if ((threadIdx.x & 31) == 0) bulk_wait0();               // the staging slots must outlive the last bulk stores
   } else {
     // ---- builders: im2col rows of the 8 x 16 patch ----
     asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
@@ -108,17 +114,45 @@ tc_conv_first_kernel(const float* __restrict__ img, const __grid_constant__ CUte
     const int py = t / TILE_W, px = t % TILE_W;
     const int per_img = pb.tiles_h * pb.tiles_w;
     const size_t plane = (size_t)H * W;
-    int stage = 0; uint32_t phase = 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+    // The 128 im2col rows of a tile overlap almost completely (3456 taps, 540 distinct input values): the builders stage the
+    // 3 x 10 x 18 input halo of the tile in shared memory (coalesced row loads, zero padding by predication) and every thread reads its
+    // 27 taps from there.  Two patch buffers: the halo of the NEXT tile is requested (registers) before the current tile is assembled.
+    constexpr int PATCH = 3 * (TILE_H + 2) * (TILE_W + 2);   // 540 floats
+    constexpr int PLOADS = (PATCH + 127) / 128;              // 5 loads per thread
+    float* patch = reinterpret_cast<float*>(smem_aligned + CF_SMEM_USED);      // [2][PATCH]
+    auto fetch = [&](int tile, float (&r)[PLOADS]) {
       const int n = tile / per_img, rr = tile % per_img;
-      const int h = (rr / pb.tiles_w) * TILE_H + py, w = (rr % pb.tiles_w) * TILE_W + px;
+      const int h0 = (rr / pb.tiles_w) * TILE_H - 1, w0 = (rr % pb.tiles_w) * TILE_W - 1;
       const float* base = img + (size_t)n * 3 * plane;
+#pragma unroll
+      for (int i = 0; i < PLOADS; ++i) {
+        const int e = t + 128 * i;
+        const int c = e / ((TILE_H + 2) * (TILE_W + 2)), rem = e % ((TILE_H + 2) * (TILE_W + 2));
+        const int yy = h0 + rem / (TILE_W + 2), xx = w0 + rem % (TILE_W + 2);
+        r[i] = (e < PATCH && tile < num_tiles && yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(base + (size_t)c * plane + (size_t)yy * W + xx) : 0.f;
+      }
+    };
+    auto deposit = [&](int buf, const float (&r)[PLOADS]) {
+#pragma unroll
+      for (int i = 0; i < PLOADS; ++i) {
+        const int e = t + 128 * i;
+        if (e < PATCH) patch[buf * PATCH + e] = r[i];
+      }
+    };
+    int stage = 0; uint32_t phase = 0;
+    float nxt[PLOADS];
+    fetch(worker, nxt);
+    deposit(0, nxt);
+    asm volatile("bar.sync 3, 128;" ::: "memory");
+    int buf = 0;
+    for (int tile = worker; tile < num_tiles; tile += num_workers, buf ^= 1) {
+      fetch(tile + num_workers, nxt);                        // in flight while this tile is assembled
+      const float* pt = patch + buf * PATCH + py * (TILE_W + 2) + px;
       float v[32];
 #pragma unroll
       for (int k = 0; k < 27; ++k) {
         const int c = k / 9, r = (k % 9) / 3, s = k % 3;
-        const int yy = h + r - 1, xx = w + s - 1;
-        v[k] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(base + (size_t)c * plane + (size_t)yy * W + xx) : 0.f;
+        v[k] = pt[c * ((TILE_H + 2) * (TILE_W + 2)) + r * (TILE_W + 2) + s];
       }
 #pragma unroll
       for (int k = 27; k < 32; ++k) v[k] = 0.f;
@@ -143,6 +177,8 @@ tc_conv_first_kernel(const float* __restrict__ img, const __grid_constant__ CUte
       fence_proxy_async();                                   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(afull_bar(stage));
       if (++stage == CF_STAGES) { stage = 0; phase ^= 1; }
+      deposit(buf ^ 1, nxt);                                 // the other buffer was last read one tile ago (barrier below, previous iteration)
+      asm volatile("bar.sync 3, 128;" ::: "memory");
     }
   }
 
@@ -183,6 +219,15 @@ int k_tc_conv_first(dc_ctx* ctx, const float* img, const __half* w_planes, size_
     int rc = encode_map(ctx, &mw, w_planes, 3, dims, str, box);
     if (rc) return rc;
   }
+  CUtensorMap mo;
+  {
+    DC_REQUIRE(ctx, y_lo > y_hi && ((size_t)(y_lo - y_hi) * 2) % 16 == 0, DC_E_UNSUPPORTED, "tc_conv_first: lo plane must follow the hi plane (16-byte aligned)");
+    const uint64_t dims[5] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)N, 2};
+    const uint64_t str[4] = {64 * 2, (uint64_t)W * 64 * 2, (uint64_t)H * W * 64 * 2, (uint64_t)(y_lo - y_hi) * 2};
+    const uint32_t box[5] = {32, 16, 2, 1, 2};
+    int rc = encode_map(ctx, &mo, y_hi, 5, dims, str, box, 64);
+    if (rc) return rc;
+  }
   cudaError_t e = dc_ensure_smem(ctx, tc_conv_first_kernel, CF_SMEM_BYTES);
   if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "tc_conv_first smem attribute: %s", cudaGetErrorString(e));
   const int sms = dc_launch_state(ctx)->num_sms;
@@ -195,7 +240,7 @@ int k_tc_conv_first(dc_ctx* ctx, const float* img, const __half* w_planes, size_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, tc_conv_first_kernel, img, mw, pb, ep);
+  e = cudaLaunchKernelEx(&cfg, tc_conv_first_kernel, img, mw, mo, pb, ep);
   if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "tc_conv_first launch: %s", cudaGetErrorString(e));
   DC_CHECK_LAUNCH(ctx);
   return DC_OK;

@@ -164,6 +164,35 @@ def test_language_model_many_rows_full_width():
         ctx.close()
 
 
+def test_language_model_tile_decoder_fallback():
+    """Models whose LM does not fit the weights-stationary decoder (here: encoding size != rnn size) take the tile decoder
+    (lm_decode_kernel): same outputs as the oracle.  Keeps the capacity fallback exercised."""
+    from densecap_b200.model import LanguageModel
+    from densecap_b200.runtime import Context
+    dims = ModelDims(widths=(64, 64, 64, 64, 64), rpn_filters=64, fc_dim=128, rnn_size=64, encoding_size=128, vocab_size=300, seq_length=6)
+    rng = np.random.RandomState(5)
+    E, H, V, fc = dims.encoding_size, dims.rnn_size, dims.vocab_size, dims.fc_dim
+    w = {"lm.encoder.weight": (rng.randn(E, fc) * np.sqrt(2.0 / fc)).astype(np.float32), "lm.encoder.bias": np.zeros(E, np.float32),
+         "lm.lookup.weight": (rng.randn(V + 2, E) * 0.5).astype(np.float32),
+         "lm.lstm.weight": (rng.randn(E + H, 4 * H) / np.sqrt(E + H)).astype(np.float32), "lm.lstm.bias": (rng.randn(4 * H) * 0.1).astype(np.float32),
+         "lm.vocab.weight": (rng.randn(V + 1, H) / np.sqrt(H)).astype(np.float32), "lm.vocab.bias": (rng.randn(V + 1) * 0.1).astype(np.float32)}
+    K = 200
+    codes = np.maximum(rng.randn(K, fc), 0).astype(np.float32)
+    oseq, ologits = O.lm_sample(codes, w, dims.seq_length, return_logits=True)
+    ctx = Context(dims, max_image_hw=(64, 64), max_proposals=K)
+    try:
+        ctx.load_weights(w)
+        seq, logits = LanguageModel(ctx).sample(dev(codes), return_logits=True)
+        got = logits.cpu().numpy()
+        agree = np.ones(K, bool)
+        for t in range(dims.seq_length):
+            assert agree.mean() > 0.98
+            assert rel(got[agree, t], ologits[agree, t]) < 1e-4, "logits of step %d differ" % t
+            agree &= (seq[:, t].cpu().numpy() == oseq[:, t])
+    finally:
+        ctx.close()
+
+
 def test_full_forward_matches_oracle(model, small):
     dims, weights, img, cfg, ref = small
     out = model.forward(dev(img))

@@ -32,8 +32,13 @@ for step in "$@"; do
                 ncu -i gpurun_out/prof_full.ncu-rep --page raw --csv > gpurun_out/prof_full_raw.csv 2>/dev/null
                 ncu -i gpurun_out/prof_full.ncu-rep --page source --csv > gpurun_out/prof_full_source.csv 2>/dev/null
                 rm -f gpurun_out/prof_full.ncu-rep ;;
-    sanitizer)  TAIL=25 run 1500 sanitizer_memcheck compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -m gpu -q --tb=line -x -k "small_pipeline or sanitizer"
-                TAIL=25 run 1500 sanitizer_racecheck compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests -m gpu -q --tb=line -x -k "sanitizer" ;;
+    sanitizer)  # compute-sanitizer over the small-model end-to-end tests (every kernel of the forward path incl. the persistent decoder, TMA-store epilogues,
+                # cluster kernels) and the dense-layer tests; summaries are copied to profiles/ by hand
+                SEL="full_forward_matches_oracle or batched_forward_equals_single or beamsearch_matches_oracle or test_tc_conv or test_tc_linear"
+                TAIL=25 run 1500 sanitizer_memcheck compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_dense.py -m gpu -q --tb=line -x -k "$SEL"
+                TAIL=25 run 1500 sanitizer_racecheck compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_dense.py -m gpu -q --tb=line -x -k "full_forward_matches_oracle or test_tc_conv"
+                TAIL=25 run 1500 sanitizer_synccheck compute-sanitizer --tool synccheck --error-exitcode 9 python -m pytest tests/test_gpu_pipeline.py -m gpu -q --tb=line -x -k "full_forward_matches_oracle" ;;
+    racecheck)  TAIL=25 run 1500 sanitizer_racecheck compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_dense.py -m gpu -q --tb=line -x -k "full_forward_matches_oracle or test_tc_conv" ;;
     py:*)       TAIL=60 run 600 py python "${step#py:}" ;;
     *) echo "unknown step $step" ;;
   esac

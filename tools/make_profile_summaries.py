@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Turns the ncu launch lists of tools/gpu.sh launches:N (gpurun_out/launches_b1.csv, launches_b4.csv) into the tracked summaries under profiles/:
+  profiles/launches_<tag>_b<N>_summary.md   per-launch table of one forward step (time, tensor-pipe %, DRAM MB) + conv-trunk aggregate
+  profiles/roofline_traffic_<tag>.json      DRAM bytes of the fc6 launch per batch size (read by bench.py for roofline.traffic)
+usage: python tools/make_profile_summaries.py r08"""
+import collections, csv, json, os, re, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CONV_NAMES = ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_3", "conv4_1", "conv4_2", "conv4_3", "conv5_1", "conv5_2", "conv5_3"]
+
+
+def load(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    L = collections.OrderedDict()
+    for r in csv.DictReader(lines):
+        d = L.setdefault(r["ID"], {"name": re.sub(r"^void ", "", re.sub(r"\(.*", "", r["Kernel Name"])).strip(), "grid": r["Grid Size"]})
+        v = float(r["Metric Value"].replace(",", ""))
+        u = r["Metric Unit"]
+        if r["Metric Name"].startswith("gpu__time"):
+            v = v / 1000.0 if u.startswith("n") else (v * 1000.0 if u.startswith("m") else v)
+        d[r["Metric Name"]] = v
+    ids = list(L)
+    starts = [i for i, k in enumerate(ids) if "conv_first" in L[k]["name"]]
+    return [L[k] for k in ids[starts[-1]:]]
+
+
+def main():
+    tag = sys.argv[1]
+    traffic = {"fc6": {}}
+    for B in (1, 4):
+        path = os.path.join(ROOT, "gpurun_out", "launches_b%d.csv" % B)
+        if not os.path.exists(path):
+            continue
+        step = load(path)
+        T, TP, RD, WR = "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum"
+        total = sum(d[T] for d in step)
+        out = ["# Launch list of one forward step, batch %d (%s)\n" % (B, tag),
+               "Command (B200 box): `ncu --metrics %s,%s,%s,%s --clock-control none --csv python bench.py --steps 1 --warmup 3 --batch %d "
+               "--no-cpu-baseline --no-extras` (tools/gpu.sh launches:%d; raw CSV in gpurun_out/, not tracked).  720x600 images, 1000 proposals, 15 tokens.  "
+               "Per-launch times under ncu are cold-cache and serialised (side-stream overlap and programmatic dependent launch are lost): compare SHARES with "
+               "the live CUDA-event phase times of bench.py.\n" % (T, TP, RD, WR, B, B),
+               "%d launches, %.1f us serialised under ncu.\n" % (len(step), total)]
+        # conv trunk aggregate: conv_first + the halo launches before the first non-conv kernel (split-K finalize launches belong to their conv)
+        convs, i = [], 0
+        for d in step:
+            if "conv_first" in d["name"] or "tc_conv_halo" in d["name"] or "splitk_finalize" in d["name"]:
+                convs.append(d)
+            else:
+                break
+        # the RPN 3x3 conv (+ its finalize) is the last halo launch: not part of the VGG trunk
+        trunk, k, rpn_seen = [], 0, False
+        for d in convs:
+            if "splitk_finalize" in d["name"]:
+                if trunk and k <= 13 and trunk[-1]["name"].rstrip(">").endswith(", 2") and not rpn_seen:      # follows a split-K (FEAT_PARTIAL) launch of the trunk
+                    trunk[-1]["extra_us"] = trunk[-1].get("extra_us", 0.0) + d[T]
+                continue
+            if k < 13:
+                trunk.append(dict(d)); k += 1
+            else:
+                rpn_seen = True
+        tw = sum(d[T] * d.get(TP, 0.0) for d in trunk) / max(sum(d[T] for d in trunk), 1e-9)
+        tsum = sum(d[T] + d.get("extra_us", 0.0) for d in trunk)
+        out.append("## VGG-16 conv trunk (13 layers)\n")
+        out.append("| layer | kernel | us (+ split-K finalize) | tensor-pipe active % |")
+        out.append("|---|---|---:|---:|")
+        for n, d in zip(CONV_NAMES, trunk):
+            out.append("| %s | `%s` | %.1f%s | %.1f |" % (n, d["name"], d[T], (" + %.1f" % d["extra_us"]) if d.get("extra_us") else "", d.get(TP, 0.0)))
+        out.append("\nTime-weighted tensor-pipe activity over all 13 conv launches: **%.1f %%** (%.1f us of kernels; the tensor pipe executes 3 fp16 MMAs per "
+                   "fp32-class product).\n" % (tw, tsum))
+        out.append("## All launches\n")
+        out.append("| # | kernel | grid | us | share %% | tensor-pipe %% | DRAM read MB | DRAM write MB |".replace("%%", "%"))
+        out.append("|---:|---|---|---:|---:|---:|---:|---:|")
+        for i, d in enumerate(step):
+            out.append("| %d | `%s` | %s | %.1f | %.1f | %.1f | %.1f | %.1f |" % (i, d["name"], d["grid"].strip("()"), d[T], 100.0 * d[T] / total, d.get(TP, 0.0),
+                                                                                 d.get(RD, 0.0) / 1e6, d.get(WR, 0.0) / 1e6))
+        open(os.path.join(ROOT, "profiles", "launches_%s_b%d_summary.md" % (tag, B)), "w").write("\n".join(out) + "\n")
+        # fc6 = the longest tc_gemm launch
+        g = [d for d in step if "tc_gemm_kernel" in d["name"]]
+        if g:
+            f = max(g, key=lambda d: d[T])
+            traffic["fc6"]["batch%d" % B] = {"kernel": f["name"], "dram_bytes_read": f.get(RD, 0.0), "dram_bytes_write": f.get(WR, 0.0),
+                                             "duration_us_under_ncu": f[T], "tensor_pipe_active_pct": f.get(TP, 0.0),
+                                             "source": "profiles/launches_%s_b%d_summary.md" % (tag, B)}
+        print("batch %d: %d launches, trunk tensor-pipe %.1f %% time-weighted" % (B, len(step), tw))
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", "roofline_traffic_%s.json" % tag), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
