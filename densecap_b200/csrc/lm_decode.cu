@@ -140,7 +140,7 @@ lm_decode_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const int worker = blockIdx.x, num_workers = gridDim.x;
 
   if (warp < EPI_WARP0) {
-    regs_shrink_control();
+    regs_shrink_control<REGS_CONTROL>();
   }
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -218,7 +218,7 @@ lm_decode_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
   } else if (warp >= EPI_WARP0) {
     // =============================== epilogue warps ===============================
-    regs_grow_epilogue();
+    regs_grow_epilogue<REGS_EPILOGUE>();
     const int et = threadIdx.x - EPI_THREAD0;                // 0 .. 255
     int iter = 0, gi = 0;
     for (int g = worker; g < total_items; g += num_workers, ++iter) {
@@ -404,7 +404,7 @@ lm_decode_ws_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   const int first_step = gate_pair ? 0 : 2;                  // vocabulary pairs have nothing to do for the two state-only steps
   const uint32_t n_ctas = gridDim.x;
 
-  if (warp < EPI_WARP0) regs_shrink_control();
+  if (warp < EPI_WARP0) regs_shrink_control<REGS_CONTROL>();
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (elect_one()) {
@@ -483,7 +483,7 @@ lm_decode_ws_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
   } else if (warp >= EPI_WARP0) {
     // =============================== epilogue warps: pass epilogue + LSTM cell / token phase ===============================
-    regs_grow_epilogue();
+    regs_grow_epilogue<REGS_EPILOGUE>();
     const int et = threadIdx.x - EPI_THREAD0;                // 0 .. 255
     const int q = warp & 3, chalf = (warp - EPI_WARP0) >> 2;
     const int H4 = 4 * p.H;

@@ -13,12 +13,19 @@ constexpr int EPI_WARP0 = 4;                       // first epilogue warp
 constexpr int EPI_THREAD0 = 32 * EPI_WARP0;
 // Warp roles by WARPGROUP (setmaxnreg works on groups of 4 warps): warpgroup 0 = {warp 0: TMA producer, warp 1: MMA issuer + TMEM
 // allocator, warps 2-3: idle}, warpgroups 1-2 = the 8 epilogue warps.  The kernels are compiled for 384 threads (168 registers); at
-// start warpgroup 0 shrinks to 40 registers and the epilogue warpgroups grow to 232, which is what lets an epilogue thread keep the
-// 128 running sums of a 256-column tile (hierarchical accumulation, see epilogue_tile) in registers.
+// start warpgroup 0 shrinks and the epilogue warpgroups grow (setmaxnreg), which is what lets an epilogue thread keep the 128 running sums of a
+// 256-column tile (hierarchical accumulation, see epilogue_tile) in registers.
 constexpr int NUM_THREADS = EPI_THREAD0 + 32 * EPI_WARPS;
-constexpr int REGS_CONTROL = 80, REGS_EPILOGUE = 208;    // 128 * 80 + 256 * 208 = 63488 <= 384 * 168 (the registers the CTA owns)
-__device__ __forceinline__ void regs_shrink_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL)); }
-__device__ __forceinline__ void regs_grow_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE)); }
+// (128 control threads x C + 256 epilogue threads x E <= 384 x 168 = 64512 registers.)  ptxas allocates each role's code against the value its
+// setmaxnreg announces.  Measured (A/B on B200): 56 / 224 removes the epilogue spills of the 256-column kernels (240 -> 24 bytes) at no cost to the
+// control warps; 40 / 232 is another 1-5 % faster on the long-K pair-tile GEMM (fc6 / fc7) but makes the producer / issuer of the narrow convolution
+// tiles spill (conv1_2 +6 %), so only tc_gemm_kernel<256, cta_group::2> uses it.
+template <int REGS>
+__device__ __forceinline__ void regs_shrink_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void regs_grow_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+constexpr int REGS_CONTROL = 56, REGS_EPILOGUE = 224;
+constexpr int REGS_CONTROL_LONGK = 40, REGS_EPILOGUE_LONGK = 232;
 constexpr int TILE_H = 8, TILE_W = 16;   // conv M tile = 8x16 output pixels
 constexpr uint32_t A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 

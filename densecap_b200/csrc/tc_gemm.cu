@@ -103,7 +103,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   };
 
   if (warp < EPI_WARP0) {
-    regs_shrink_control();
+    regs_shrink_control<(BLOCK_N == 256 && CG == 2) ? REGS_CONTROL_LONGK : REGS_CONTROL>();
   }
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -226,7 +226,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp >= EPI_WARP0) {
     // =============================== epilogue warps ===============================
-    regs_grow_epilogue();
+    regs_grow_epilogue<(BLOCK_N == 256 && CG == 2) ? REGS_EPILOGUE_LONGK : REGS_EPILOGUE>();
     epilogue_warps<BLOCK_N, CONV, POOL, CG, C::WIDE, FEAT, C::TMAS>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, worker, num_workers, cta_rank,
                                                                     is_leader, OutStage{&tmap_out, staging});
   }
@@ -343,7 +343,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const bool b_resident = (pb.n_tiles == 1) && (pb.num_k_blocks == SB) && S == 1;
 
   if (warp < EPI_WARP0) {
-    regs_shrink_control();
+    regs_shrink_control<REGS_CONTROL>();
   }
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -473,7 +473,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp >= EPI_WARP0) {
     // =============================== epilogue warps ===============================
-    regs_grow_epilogue();
+    regs_grow_epilogue<REGS_EPILOGUE>();
     const int G = pb.kb_per_group;
     int gi = 0, iter = 0;
     for (int item = worker; item < num_tiles; item += num_workers, ++iter) {

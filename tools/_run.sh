@@ -1,3 +1,3 @@
 cd /root/repo
-bash tools/gpu.sh tests_noexit b1 b4 racecheck
-DC_LAYERS=1 bash tools/ab.sh "2 2 1" default
+bash tools/gpu.sh tests_noexit smoke bench ref mixed8 train launches:1
+PB=4 bash tools/gpu.sh launches:4
