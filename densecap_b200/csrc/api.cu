@@ -309,6 +309,7 @@ extern "C" int dc_create(const dc_config* cfg, int device, dc_ctx** out) {
   DC_CHECK_CUDA(ctx, cudaMemcpy(ctx->anchors_dev, c.anchors, sizeof(float) * 2 * c.num_anchors, cudaMemcpyHostToDevice));
   TRY(dev_alloc(ctx, &ctx->overflow_flag, 1));
   ctx->splitk_elems = 8 * cells * std::max(C5, F);                 // up to 8 K-splits of a conv5-sized map (batch 1-2 only, see k_tc_conv3x3)
+  ctx->splitk_elems = std::max<size_t>(ctx->splitk_elems, (size_t)(148 / 2) * 256 * 256);   // K-range partials of the GEMM tail tiles (k_tc_gemm): <= one item per SM pair
   TRY(dev_alloc(ctx, &ctx->splitk_ws, ctx->splitk_elems));
   ctx->scratch_elems = std::max(cells * C5, (size_t)1 << 20);
   TRY(dev_alloc(ctx, &ctx->scratch_f32, ctx->scratch_elems));

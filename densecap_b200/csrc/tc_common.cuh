@@ -264,6 +264,9 @@ struct Problem {
   int kb_per_group;            // k-blocks accumulated in TMEM before the partial sum is taken over by the epilogue (>= 1)
   int split_k;                 // convolution only: K splits per output tile (>= 1), partial sums to out_f32 + split * split_stride
   size_t split_stride;
+  // GEMM kernel: this launch covers the tiles [tile_begin, tile_end) of the m_tiles x n_tiles grid (whole grid by default).  The TAIL
+  // instantiation cuts each of its tiles into tail_split K-ranges and writes raw partial sums, see k_tc_gemm.
+  int tile_begin, tile_end, tail_split;
   int m_tiles, n_tiles;
   int m_fastest;               // tile order
   // conv geometry
@@ -595,10 +598,9 @@ template <int BLOCK_N, bool CONV, bool POOL, int CG, bool WIDE, int FEAT, bool T
 __device__ __forceinline__ void epilogue_warps(const Problem& pb, const GemmEpilogue& ep, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                                float* bias_smem, int worker, int num_workers, uint32_t cta_rank, bool is_leader,
                                                OutStage ost = OutStage{nullptr, 0u}) {
-  const int num_tiles = pb.m_tiles * pb.n_tiles;
   const int num_groups = (pb.num_k_blocks + pb.kb_per_group - 1) / pb.kb_per_group;
   int gi = 0, iter = 0;
-  for (int tile = worker; tile < num_tiles; tile += num_workers, ++iter) {
+  for (int tile = pb.tile_begin + worker; tile < pb.tile_end; tile += num_workers, ++iter) {
     int mt, nt;
     if (pb.m_fastest) { mt = tile % pb.m_tiles; nt = tile / pb.m_tiles; }
     else { nt = tile % pb.n_tiles; mt = tile / pb.n_tiles; }

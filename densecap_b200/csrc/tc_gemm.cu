@@ -37,7 +37,7 @@
 
 namespace tc {
 
-template <int BLOCK_N, bool CONV, bool POOL, int CG, int FEAT>
+template <int BLOCK_N, bool CONV, bool POOL, int CG, int FEAT, bool TAIL = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
                Problem pb, GemmEpilogue ep) {
@@ -95,7 +95,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  const int num_tiles = pb.m_tiles * pb.n_tiles;
+  // Work items.  Normal launch: the tiles [tile_begin, tile_end), whole.  TAIL instantiation (k_tc_gemm: the leftover tiles of a mostly idle last
+  // round): every tile in pb.tail_split K-ranges, item = (tile - tile_begin) * tail_split + part; the epilogue writes raw partial sums to the item's
+  // 256 x 256 block of ep.out_f32 and gemm_tail_finalize_kernel adds the ranges.
+  const int num_items = TAIL ? (pb.tile_end - pb.tile_begin) * pb.tail_split : (pb.tile_end - pb.tile_begin);
+  auto item_decode = [&](int item, int& tile, int& kb0, int& kb1) {
+    if (TAIL) {
+      const int part = item % pb.tail_split;
+      tile = pb.tile_begin + item / pb.tail_split;
+      kb0 = (pb.num_k_blocks * part) / pb.tail_split;
+      kb1 = (pb.num_k_blocks * (part + 1)) / pb.tail_split;
+    } else {
+      tile = pb.tile_begin + item; kb0 = 0; kb1 = pb.num_k_blocks;
+    }
+  };
 
   auto tile_coords = [&](int tile, int& mt, int& nt) {
     if (pb.m_fastest) { mt = tile % pb.m_tiles; nt = tile / pb.m_tiles; }
@@ -109,7 +122,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // =============================== TMA producer ===============================
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      for (int item = worker; item < num_items; item += num_workers) {
+        int tile, kb_begin, kb_end;
+        item_decode(item, tile, kb_begin, kb_end);
         int mt, nt;
         tile_coords(tile, mt, nt);
         const int n0 = nt * BLOCK_N + (int)cta_rank * C::B_ROWS;     // this CTA's slice of the B tile
@@ -122,7 +137,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           w0 = (r % pb.tiles_w) * TILE_W;
         }
         const int m0 = (mt * CG + (int)cta_rank) * BLOCK_M;
-        for (int kb = 0; kb < pb.num_k_blocks; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + 2 * A_PLANE_BYTES;
@@ -158,11 +173,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int G = pb.kb_per_group;
       // This loop is executed by ONE thread and paces the tensor pipe: no integer division, no modulo (an ncu source profile showed
       // the issuer ~80 % busy on address arithmetic when the group position was computed as kb % G).
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      for (int item = worker; item < num_items; item += num_workers) {
+        int tile, kb_begin, kb_end;
+        item_decode(item, tile, kb_begin, kb_end);
         uint32_t d_tmem = 0;
         int acc = 0;
         int kb_in_group = 0;
-        for (int kb = 0; kb < pb.num_k_blocks; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           const bool group_start = kb_in_group == 0;
           if (group_start) {
             // a fresh accumulator every G k-blocks: the epilogue warps sum the groups in registers (see epilogue_tile)
@@ -211,7 +228,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               else umma_f16(d_tmem, da, db, idesc, acc_flag);
             }
           }
-          const bool group_end = kb_in_group == G - 1 || kb == pb.num_k_blocks - 1;
+          const bool group_end = kb_in_group == G - 1 || kb == kb_end - 1;
           if (CG == 2) {
             umma2_commit_mc(empty_bar(stage));                              // frees this stage in BOTH CTAs
             if (group_end) umma2_commit_mc(tfull_bar(acc));                 // partial accumulators of both CTAs complete
@@ -227,8 +244,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp >= EPI_WARP0) {
     // =============================== epilogue warps ===============================
     regs_grow_epilogue<(BLOCK_N == 256 && CG == 2) ? REGS_EPILOGUE_LONGK : REGS_EPILOGUE>();
-    epilogue_warps<BLOCK_N, CONV, POOL, CG, C::WIDE, FEAT, C::TMAS>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, worker, num_workers, cta_rank,
-                                                                    is_leader, OutStage{&tmap_out, staging});
+    if (!TAIL) {
+      epilogue_warps<BLOCK_N, CONV, POOL, CG, C::WIDE, FEAT, C::TMAS>(pb, ep, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, worker, num_workers, cta_rank,
+                                                                      is_leader, OutStage{&tmap_out, staging});
+    } else {
+      const int G = pb.kb_per_group;
+      int gi = 0, iter = 0;
+      for (int item = worker; item < num_items; item += num_workers, ++iter) {
+        int tile, kb_begin, kb_end;
+        item_decode(item, tile, kb_begin, kb_end);
+        GemmEpilogue e2 = ep;                                   // raw scaled partial sums into this item's 256 x 256 block (rows 0..255 of a 256-wide matrix)
+        e2.out_f32 = ep.out_f32 + (size_t)item * (size_t)(CG * BLOCK_M) * BLOCK_N;
+        epilogue_tile<BLOCK_N, CONV, POOL, CG, C::WIDE, FEAT, false>(pb, e2, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, 0, 0, (kb_end - kb_begin + G - 1) / G,
+                                                                     gi, iter, cta_rank, is_leader);
+      }
+    }
   }
 
   __syncwarp();     // lanes of the single-thread roles rejoin their warp before the aligned barriers below
@@ -508,7 +538,7 @@ static int launch_kernel(dc_ctx* ctx, Kernel kernel, size_t smem_bytes, int cg, 
     cudaError_t e = dc_ensure_smem(ctx, kernel, smem_bytes);
     if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "tc_gemm smem attribute: %s", cudaGetErrorString(e));
   }
-  const int tiles = pb.m_tiles * pb.n_tiles * (pb.split_k > 1 ? pb.split_k : 1);
+  const int tiles = (pb.tile_end - pb.tile_begin) * (pb.split_k > 1 ? pb.split_k : 1) * (pb.tail_split > 1 ? pb.tail_split : 1);
   const int slots = dc_launch_state(ctx)->num_sms / cg;                        // CTAs (CG=1) or CTA pairs (CG=2) resident at once
   const int workers = tiles < slots ? tiles : slots;
   cudaLaunchConfig_t cfg = {};
@@ -618,6 +648,65 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int S, size
   }
 }
 
+// Tail tiles of the pair-tile GEMM: out = epilogue(sum of the K-range partial sums); the ranges are added in index order (deterministic)
+__global__ void __launch_bounds__(256)
+gemm_tail_finalize_kernel(const float* __restrict__ ws, int tile_begin, int n_tail, int S, int m_tiles, int n_tiles, int m_fastest, int M, int N,
+                          GemmEpilogue ep) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  constexpr int TR = 2 * BLOCK_M, TC = 256;
+  const size_t per_tile = (size_t)TR * TC;
+  const size_t total8 = (size_t)n_tail * per_tile / 8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total8; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i * 8;
+    const int j = (int)(e / per_tile);
+    const int r = (int)((e % per_tile) / TC), c = (int)(e % TC);
+    const int tile = tile_begin + j;
+    const int mt = m_fastest ? tile % m_tiles : tile / n_tiles, nt = m_fastest ? tile / m_tiles : tile % n_tiles;
+    const int m = mt * TR + r, n = nt * TC + c;
+    if (m >= M || n >= N) continue;
+    float v[8];
+    const float* p0 = ws + ((size_t)j * S) * per_tile + (size_t)r * TC + c;
+    {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(p0)), b = __ldcg(reinterpret_cast<const float4*>(p0) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    for (int s2 = 1; s2 < S; ++s2) {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(p0 + s2 * per_tile)), b = __ldcg(reinterpret_cast<const float4*>(p0 + s2 * per_tile) + 1);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    bool oor = false;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float x = v[q];
+      if (ep.bias && n + q < N) x += __ldg(ep.bias + n + q);
+      if (ep.relu) x = fmaxf(x, 0.f);
+      v[q] = x;
+      oor |= !(fabsf(x) < 65504.f);
+    }
+    if (ep.out_f32) {
+      float* pf = ep.out_f32 + (size_t)m * ep.ldf + n;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (n + q < N) pf[q] = v[q];
+    }
+    if (ep.out_hi) {            // N is a multiple of 8 for split outputs
+      uint32_t hh[4], ll[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        __half h0, l0, h1, l1;
+        split_f32(v[2 * q], h0, l0);
+        split_f32(v[2 * q + 1], h1, l1);
+        hh[q] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        ll[q] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      }
+      const size_t o = (size_t)m * ep.ldo + ep.out_col0 + n;
+      *reinterpret_cast<uint4*>(ep.out_hi + o) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+      *reinterpret_cast<uint4*>(ep.out_lo + o) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+      if (ep.overflow && oor) atomicOr(ep.overflow, 1u);
+    }
+  }
+}
+
 }  // namespace tc
 
 int tc_init(dc_ctx* ctx) {
@@ -665,7 +754,27 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
   pb.m_tiles = DC_CEIL_DIV(m_tiles128, cg);
   pb.n_tiles = DC_CEIL_DIV(N, bn);
   pb.m_fastest = pb.m_tiles <= pb.n_tiles;
+  pb.tile_begin = 0; pb.tile_end = pb.m_tiles * pb.n_tiles; pb.tail_split = 1;
   if (ep.out_hi && !ep.overflow) ep.overflow = dc_overflow_flag(ctx);
+  // Tail split (fc6 / fc7 at batch 4: 256 pair tiles on 74 SM pairs = three full rounds + a round of 34 tiles).  The full rounds run as one
+  // launch; the leftover tiles run as a second launch of the TAIL instantiation, each cut into S K-ranges so that this last round fills the
+  // machine and lasts 1/S of a round, followed by a small kernel that adds the ranges and applies the real epilogue.
+  int n_tail = 0, tail_S = 1;
+  float* tail_ws = nullptr;
+#ifndef DC_DISABLE_TAIL_SPLIT
+  if (cg == 2 && !ep.lstm_c && !ep.gather_tab && !ep.argmax && pb.num_k_blocks >= 128) {   // long K only: at K = 4096 (fc7) the two extra launches cost more than the idle half round
+    const int slots = dc_launch_state(ctx)->num_sms / 2;
+    const int tiles = pb.m_tiles * pb.n_tiles;
+    const int left = tiles % slots;
+    size_t ws_elems = 0;
+    float* ws = dc_splitk_workspace(ctx, &ws_elems);
+    if (tiles > slots && left > 0 && 2 * left <= slots && ws) {
+      int S = std::min(4, slots / left);
+      while (S >= 2 && (size_t)left * S * (2 * BLOCK_M) * 256 > ws_elems) --S;
+      if (S >= 2) { n_tail = left; tail_S = S; tail_ws = ws; pb.tile_end = tiles - left; }
+    }
+  }
+#endif
   CUtensorMap ma, mb;
   {
     const uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, 2};
@@ -692,7 +801,28 @@ int k_tc_gemm(dc_ctx* ctx, const __half* a_planes, size_t a_plane_elems, int lda
     int rc = encode_map(ctx, &mo, ep.out_hi, 3, dims, str, box, 64);
     if (rc) return rc;
   }
-  if (cg == 2) return launch<256, 2>(ctx, ma, mb, mo, pb, ep, st);
+  if (cg == 2) {
+    int rc = launch<256, 2>(ctx, ma, mb, mo, pb, ep, st);
+    if (rc || n_tail == 0) return rc;
+    Problem pt = pb;
+    pt.tile_begin = pb.tile_end; pt.tile_end = pb.tile_end + n_tail; pt.tail_split = tail_S;
+    GemmEpilogue et;                                        // raw partial sums, scaled
+    et.acc_scale = ep.acc_scale; et.out_f32 = tail_ws; et.ldf = 256;
+    if ((rc = launch_kernel(ctx, tc_gemm_kernel<256, false, false, 2, FEAT_PARTIAL, true>, Cfg<256, 2>::SMEM_BYTES, 2, ma, mb, mo, pt, et, st))) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::min<size_t>((size_t)dc_launch_state(ctx)->num_sms * 4, DC_CEIL_DIV((size_t)n_tail * 2 * BLOCK_M * 256 / 8, (size_t)256)));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tail_finalize_kernel, (const float*)tail_ws, pt.tile_begin, n_tail, tail_S, pb.m_tiles, pb.n_tiles, pb.m_fastest,
+                                       M, N, ep);
+    if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "gemm_tail_finalize launch: %s", cudaGetErrorString(e));
+    DC_CHECK_LAUNCH(ctx);
+    return DC_OK;
+  }
   if (bn == 64) return launch<64, 1>(ctx, ma, mb, mo, pb, ep, st);
   if (bn == 256) return launch<256, 1>(ctx, ma, mb, mo, pb, ep, st);
   return launch<128, 1>(ctx, ma, mb, mo, pb, ep, st);
@@ -743,6 +873,7 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
   pb.OW = fuse_pool ? (W + 1) / 2 : W;
   pb.n_tiles = DC_CEIL_DIV(Cout, bn);
   pb.m_fastest = 0;   // n fastest: CTAs sharing an activation patch run together, the patch stays in L2
+  pb.tile_begin = 0; pb.tile_end = pb.m_tiles * pb.n_tiles; pb.tail_split = 1;
   GemmEpilogue ep;
   ep.acc_scale = acc_scale;
   if (split > 1) {             // raw partial sums; bias / ReLU / fp16 split happen in splitk_finalize_kernel

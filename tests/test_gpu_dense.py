@@ -54,6 +54,16 @@ def test_tc_linear(ctx, M, N, K, relu):
     assert e < 2e-5, "tcgen05 linear M=%d N=%d K=%d rel err %.3e" % (M, N, K, e)
 
 
+@pytest.mark.parametrize("M,N,K,relu", [(4000, 4096, 8192, 1), (3900, 4000, 8192, 0)])
+def test_tc_linear_tail_split(ctx, M, N, K, relu):
+    """256 pair tiles on 74 SM pairs: the 34 tiles of the last round run as a second launch, each cut into two K-ranges, and
+    gemm_tail_finalize_kernel adds the ranges (fc6 / fc7 at batch 4).  Ragged M and N in the second case."""
+    y, ref = run_linear(ctx, M, N, K, relu, seed=M + N + K)
+    assert not torch.isnan(y).any(), "output rows left unwritten"
+    e = rel_err(y, ref)
+    assert e < 2e-5, "tcgen05 linear M=%d N=%d K=%d rel err %.3e" % (M, N, K, e)
+
+
 def test_tc_linear_is_fp32_class_accurate(ctx):
     # the split scheme must beat a single fp16 pass by orders of magnitude
     y, ref = run_linear(ctx, 256, 256, 2048, 0, seed=7, bias=False)
