@@ -262,6 +262,7 @@ struct Problem {
   int M, N, K;                 // GEMM view (conv: M = tiles*128 is implicit, N = Cout, K = 9*Cin)
   int num_k_blocks;
   int kb_per_group;            // k-blocks accumulated in TMEM before the partial sum is taken over by the epilogue (>= 1)
+  int kb_first;                // convolution kernel: size of the first two groups of every tile (>= kb_per_group)
   int split_k;                 // convolution only: K splits per output tile (>= 1), partial sums to out_f32 + split * split_stride
   size_t split_stride;
   // GEMM kernel: this launch covers the tiles [tile_begin, tile_end) of the m_tiles x n_tiles grid (whole grid by default).  The TAIL

@@ -440,6 +440,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int acc = 0;
         int kb = 0;                                   // (group, vertical tap) counter = k-block index inside the item
         int kb_in_group = 0;                          // position inside the accumulator group (no division in this single-thread loop)
+        int gsz = pb.kb_first, grp = 0;               // the first two groups of a tile may be longer (pb.kb_first), see k_tc_conv3x3
         for (int g = g_begin; g < g_end; ++g) {
           mbar_wait(afull_bar(sa), pa);
           const uint32_t a_base = a_ring + sa * AH_STAGE_BYTES;
@@ -484,7 +485,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 else umma_f16(d_tmem, da, db, idesc, acc_flag);
               }
             }
-            const bool group_end = kb_in_group == G - 1 || kb == nkb - 1;
+            const bool group_end = kb_in_group == gsz - 1 || kb == nkb - 1;
             if (CG == 2) {
               if (!b_resident) umma2_commit_mc(bempty_bar(sb));
               if (r == 2) umma2_commit_mc(aempty_bar(sa));
@@ -494,7 +495,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               if (r == 2) umma_commit(aempty_bar(sa));
               if (group_end) umma_commit(tfull_bar(acc));
             }
-            if (group_end) { ++gi; kb_in_group = 0; } else ++kb_in_group;
+            if (group_end) { ++gi; kb_in_group = 0; if (++grp == 2) gsz = G; } else ++kb_in_group;
             if (++sb == SB) { sb = 0; pbp ^= 1; }
           }
           if (++sa == AH_STAGES) { sa = 0; pa ^= 1; }
@@ -512,7 +513,10 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int nkb = (group_begin(sp + 1) - group_begin(sp)) * 3;
       GemmEpilogue e2 = ep;
       if (S > 1) e2.out_f32 = ep.out_f32 + (size_t)sp * pb.split_stride;      // this split's partial-sum plane
-      epilogue_tile<BLOCK_N, true, POOL, CG, C::WIDE, FEAT, C::TMAS>(pb, e2, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, mt, nt, (nkb + G - 1) / G, gi, iter,
+      int ngroups = 0, rem = nkb;
+      for (int z = 0; z < 2 && rem > 0; ++z) { rem -= min(pb.kb_first, rem); ++ngroups; }
+      ngroups += (rem + G - 1) / G;
+      epilogue_tile<BLOCK_N, true, POOL, CG, C::WIDE, FEAT, C::TMAS>(pb, e2, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, mt, nt, ngroups, gi, iter,
                                                                cta_rank, is_leader, OutStage{&tmap_out, staging});
     }
     if (C::TMAS && (threadIdx.x & 31) == 0) bulk_wait0();        // the staging slots must outlive the last bulk stores
@@ -864,6 +868,15 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
   }
   const int bn = tc_.bn, cg = tc_.cg;
   pb.kb_per_group = group_kblocks(ctx, bn);
+  // The output phase of tile i keeps the epilogue warps away from the accumulator sweeps of tile i+1, and the issuer can run only two groups
+  // ahead (two TMEM stages): with one-k-block groups it stalls at every tile boundary.  The first two groups of a tile are therefore longer; their
+  // partial sums are the smallest of the tile, so the extra truncating accumulations cost the least accuracy there.  Measured (A/B, batch 4):
+  // 2 k-blocks: conv3_x / conv4_x -3..5 %, trunk features 1.57e-6 -> 1.73e-6 from the fp64 oracle (fp32 oracle: 8.5e-7); 3 k-blocks: no
+  // further speed-up and 2.67e-6 (over the 2x-noise budget of tests/test_gpu_fullsize.py).
+#ifndef DC_FIRST_GROUP_KB
+#define DC_FIRST_GROUP_KB 2
+#endif
+  pb.kb_first = std::max(pb.kb_per_group, (bn == 256 && pb.kb_per_group < DC_FIRST_GROUP_KB) ? DC_FIRST_GROUP_KB : pb.kb_per_group);
   pb.split_k = split;
   pb.split_stride = (size_t)N * H * W * Cout;
   pb.tiles_h = DC_CEIL_DIV(H, TILE_H * cg);          // cg == 2: a pair tile covers 16 image rows (two stacked 8x16 patches)
