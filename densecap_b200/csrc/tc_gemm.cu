@@ -307,7 +307,7 @@ struct HaloCfg {
   static constexpr size_t SMEM_BYTES = (size_t)RING_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
 };
 
-template <int BLOCK_N, bool POOL, int CG, int FEAT>
+template <int BLOCK_N, bool POOL, int CG, int FEAT, bool TAIL = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
                     Problem pb, GemmEpilogue ep) {
@@ -365,8 +365,10 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // Work item = (output tile, K split).  split_k > 1 (layers whose tile count cannot fill the GPU: conv5_x, the RPN 3x3): the
   // (tap column, channel block) groups of a tile are divided among split_k items; each writes its raw fp32 partial sums to its own
   // plane of a workspace, and a small finalize kernel adds the planes in a fixed order (+ bias, ReLU, fp16 split).
+  // The launch covers the tiles [tile_begin, tile_end).  TAIL instantiation (k_tc_conv3x3: the leftover tiles of a mostly idle last round, each in
+  // split_k K-ranges): the items write raw partial sums to compact 256 x 256 blocks, conv_tail_finalize_kernel maps them back to pixels.
   const int S = pb.split_k;
-  const int num_tiles = pb.m_tiles * pb.n_tiles * S;
+  const int num_tiles = (pb.tile_end - pb.tile_begin) * S;
   const int groups_all = 3 * pb.kb_per_tap;                             // (s, channel block) groups per output tile
   auto group_begin = [&](int sp) { return S == 1 ? sp * groups_all : (groups_all * sp) / S; };       // 32-bit; S == 1 needs no division
   // whole filter bank of the (single) N tile fits the B ring: load it once, keep it
@@ -382,7 +384,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int sb = 0; uint32_t pbp = 0;
       bool first = true;
       for (int item = worker; item < num_tiles; item += num_workers, first = false) {
-        const int sp = S == 1 ? 0 : item % S, tile = S == 1 ? item : item / S;
+        const int sp = S == 1 ? 0 : item % S, tile = pb.tile_begin + (S == 1 ? item : item / S);
         const int nt = tile % pb.n_tiles, mt = tile / pb.n_tiles;
         const int n0 = nt * BLOCK_N + (int)cta_rank * C::B_ROWS;
         const int per_img = pb.tiles_h * pb.tiles_w;
@@ -508,16 +510,21 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int G = pb.kb_per_group;
     int gi = 0, iter = 0;
     for (int item = worker; item < num_tiles; item += num_workers, ++iter) {
-      const int sp = S == 1 ? 0 : item % S, tile = S == 1 ? item : item / S;
+      const int sp = S == 1 ? 0 : item % S, tile = pb.tile_begin + (S == 1 ? item : item / S);
       const int nt = tile % pb.n_tiles, mt = tile / pb.n_tiles;
       const int nkb = (group_begin(sp + 1) - group_begin(sp)) * 3;
       GemmEpilogue e2 = ep;
-      if (S > 1) e2.out_f32 = ep.out_f32 + (size_t)sp * pb.split_stride;      // this split's partial-sum plane
+      if (TAIL) e2.out_f32 = ep.out_f32 + (size_t)item * (size_t)(CG * BLOCK_M) * BLOCK_N;     // this item's 256 x 256 block
+      else if (S > 1) e2.out_f32 = ep.out_f32 + (size_t)sp * pb.split_stride;                   // this split's partial-sum plane
       int ngroups = 0, rem = nkb;
       for (int z = 0; z < 2 && rem > 0; ++z) { rem -= min(pb.kb_first, rem); ++ngroups; }
       ngroups += (rem + G - 1) / G;
-      epilogue_tile<BLOCK_N, true, POOL, CG, C::WIDE, FEAT, C::TMAS>(pb, e2, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, mt, nt, ngroups, gi, iter,
-                                                               cta_rank, is_leader, OutStage{&tmap_out, staging});
+      if (TAIL)      // rows 0..255 of a 256-wide fp32 matrix: the GEMM form of the epilogue (no pixel mapping, no pooling)
+        epilogue_tile<BLOCK_N, false, false, CG, C::WIDE, FEAT, false>(pb, e2, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, 0, 0, ngroups, gi, iter, cta_rank,
+                                                                       is_leader);
+      else
+        epilogue_tile<BLOCK_N, true, POOL, CG, C::WIDE, FEAT, C::TMAS>(pb, e2, tmem_base, tfull_bar(0), tempty_bar(0), bias_smem, mt, nt, ngroups, gi, iter,
+                                                                 cta_rank, is_leader, OutStage{&tmap_out, staging});
     }
     if (C::TMAS && (threadIdx.x & 31) == 0) bulk_wait0();        // the staging slots must outlive the last bulk stores
   }
@@ -708,6 +715,76 @@ gemm_tail_finalize_kernel(const float* __restrict__ ws, int tile_begin, int n_ta
       *reinterpret_cast<uint4*>(ep.out_lo + o) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
       if (ep.overflow && oor) atomicOr(ep.overflow, 1u);
     }
+  }
+}
+
+// Tail tiles of a pair-tile convolution: partial blocks [(tile - tile_begin) * S + part][256 rows = 2 x (8 x 16 pixels)][256 channels] -> bias, ReLU,
+// optional 2x2 ceil-mode max-pool, split NHWC planes.  One thread = one output pixel (pooled: one pooled pixel) x 8 channels.
+__global__ void __launch_bounds__(256)
+conv_tail_finalize_kernel(const float* __restrict__ ws, int tile_begin, int n_tail, int S, int n_tiles, int tiles_h, int tiles_w, int H, int W, int Cout,
+                          int pool, const float* __restrict__ bias, int relu, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                          unsigned int* __restrict__ overflow) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  constexpr int TC = 256;
+  const size_t per_tile = (size_t)(2 * BLOCK_M) * TC;
+  const int OH = pool ? (H + 1) / 2 : H, OW = pool ? (W + 1) / 2 : W;
+  const int px_per_tile = pool ? 64 : 256;                     // 16 x 16 pixels, pooled 8 x 8
+  const size_t total = (size_t)n_tail * px_per_tile * (TC / 8);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % (TC / 8)) * 8;
+    const int px = (int)((i / (TC / 8)) % px_per_tile);
+    const int j = (int)(i / ((size_t)(TC / 8) * px_per_tile));
+    const int tile = tile_begin + j;
+    const int nt = tile % n_tiles, mt = tile / n_tiles;
+    const int per_img = tiles_h * tiles_w;
+    const int img = mt / per_img, rem = mt % per_img;
+    const int h0 = (rem / tiles_w) * 2 * TILE_H, w0 = (rem % tiles_w) * TILE_W;       // top-left pixel of the 16 x 16 pair tile
+    const int n = nt * TC + c8;
+    if (n >= Cout) continue;
+    float best[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) best[q] = 0.f;                 // pooled outputs follow a ReLU (>= 0): 0 is the identity of max
+    const int oy = pool ? (px / 8) : (px / 16), ox = pool ? (px % 8) : (px % 16);
+    const int oh = (pool ? h0 / 2 : h0) + oy, ow = (pool ? w0 / 2 : w0) + ox;
+    if (oh >= OH || ow >= OW) continue;
+    const int taps = pool ? 4 : 1;
+    for (int t = 0; t < taps; ++t) {
+      const int ly = pool ? 2 * oy + (t >> 1) : oy, lx = pool ? 2 * ox + (t & 1) : ox;      // pixel inside the 16 x 16 tile
+      if (h0 + ly >= H || w0 + lx >= W) continue;
+      const int r = (ly / TILE_H) * BLOCK_M + (ly % TILE_H) * TILE_W + lx;                  // row of the partial block: CTA rank * 128 + patch row
+      const float* p0 = ws + ((size_t)j * S) * per_tile + (size_t)r * TC + c8;
+      float v[8];
+      {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(p0)), b = __ldcg(reinterpret_cast<const float4*>(p0) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      }
+      for (int s2 = 1; s2 < S; ++s2) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(p0 + s2 * per_tile)), b = __ldcg(reinterpret_cast<const float4*>(p0 + s2 * per_tile) + 1);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float x = v[q] + (bias ? __ldg(bias + n + q) : 0.f);
+        if (relu) x = fmaxf(x, 0.f);
+        best[q] = (pool && t > 0) ? fmaxf(best[q], x) : ((pool && t == 0) ? fmaxf(x, 0.f) : x);
+      }
+    }
+    uint32_t hh[4], ll[4];
+    bool oor = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __half a0, b0, a1, b1;
+      split_f32(best[2 * q], a0, b0);
+      split_f32(best[2 * q + 1], a1, b1);
+      oor |= !(fabsf(best[2 * q]) < 65504.f) || !(fabsf(best[2 * q + 1]) < 65504.f);
+      hh[q] = (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(a1) << 16);
+      ll[q] = (uint32_t)__half_as_ushort(b0) | ((uint32_t)__half_as_ushort(b1) << 16);
+    }
+    const size_t o = (((size_t)img * OH + oh) * OW + ow) * Cout + n;
+    *reinterpret_cast<uint4*>(out_hi + o) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    *reinterpret_cast<uint4*>(out_lo + o) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+    if (overflow && oor) atomicOr(overflow, 1u);
   }
 }
 
@@ -926,6 +1003,47 @@ int k_tc_conv3x3(dc_ctx* ctx, const __half* x_planes, size_t x_plane_elems, cons
     int rc = encode_map(ctx, &mo, y_hi, 5, dims, str, box, 64);
     if (rc) return rc;
   }
+  // Tail split (conv4_x at batch 4: 240 pair tiles on 74 SM pairs = three full rounds + a round of 18): the full rounds run as one launch, the
+  // leftover tiles as a second launch of the TAIL instantiation, each cut into S ranges of its (tap column, channel block) groups, so that the last
+  // round fills the machine and lasts 1/S of a round; conv_tail_finalize_kernel adds the ranges (+ bias, ReLU, pool, fp16 split).
+#ifndef DC_DISABLE_TAIL_SPLIT
+  if (cg == 2 && split == 1) {
+    const int slots = dc_launch_state(ctx)->num_sms / 2;
+    const int tiles = pb.m_tiles * pb.n_tiles;
+    const int left = tiles % slots;
+    const int groups_all = 3 * pb.kb_per_tap;
+    // only when the tail is at most a quarter round (S = 4): with half a round left (conv3_x at batch 4, S = 2) the two extra launches and the
+    // finalize pass cost what the split saves (A/B: conv4_x -8 %, conv3_x +-0)
+    if (tiles > slots && left > 0 && 4 * left <= slots && ws && groups_all >= 12) {
+      int S = std::min(std::min(4, slots / left), groups_all / 3);
+      while (S >= 2 && (size_t)left * S * (2 * BLOCK_M) * 256 > ws_elems) --S;
+      if (S >= 2) {
+        pb.tile_end = tiles - left;
+        int rc = fuse_pool ? launch_halo<256, true, 2>(ctx, ma, mb, mo, pb, ep, st) : launch_halo<256, false, 2>(ctx, ma, mb, mo, pb, ep, st);
+        if (rc) return rc;
+        Problem pt = pb;
+        pt.tile_begin = pb.tile_end; pt.tile_end = tiles; pt.split_k = S;
+        GemmEpilogue et;
+        et.acc_scale = acc_scale; et.out_f32 = ws; et.ldf = 256;
+        if ((rc = launch_kernel(ctx, tc_conv_halo_kernel<256, false, 2, FEAT_PARTIAL, true>, HaloCfg<256, 2>::SMEM_BYTES, 2, ma, mb, mo, pt, et, st))) return rc;
+        const size_t work = (size_t)left * (fuse_pool ? 64 : 256) * 32;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)std::min<size_t>((size_t)dc_launch_state(ctx)->num_sms * 4, DC_CEIL_DIV(work, (size_t)256)));
+        cfg.blockDim = dim3(256);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tail_finalize_kernel, (const float*)ws, pt.tile_begin, left, S, pb.n_tiles, pb.tiles_h, pb.tiles_w, H, W, Cout,
+                                           fuse_pool ? 1 : 0, bias, relu, y_hi, y_lo, dc_overflow_flag(ctx));
+        if (e != cudaSuccess) return dc_set_error(ctx, DC_E_CUDA, "conv_tail_finalize launch: %s", cudaGetErrorString(e));
+        DC_CHECK_LAUNCH(ctx);
+        return DC_OK;
+      }
+    }
+  }
+#endif
   if (fuse_pool) {
     if (cg == 2) return launch_halo<256, true, 2>(ctx, ma, mb, mo, pb, ep, st);
     if (bn == 64) return launch_halo<64, true, 1>(ctx, ma, mb, mo, pb, ep, st);

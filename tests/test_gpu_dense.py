@@ -110,6 +110,9 @@ def run_conv(ctx, N, Cin, Cout, H, W, pool, seed=0):
     (2, 64, 64, 120, 130, 0),     # same, batch 2, no pool
     (1, 128, 256, 150, 180, 0),   # cta_group::2 pair tiles, several rounds, 2 k-blocks per tap
     (1, 512, 512, 38, 45, 0),     # conv5 shape: 8 channel blocks per tap through the 9-stage B ring
+    (1, 256, 256, 144, 160, 0),   # 90 pair tiles on 74 SM pairs: the 16 leftover tiles run as the K-split tail launch + conv_tail_finalize
+    (1, 256, 256, 139, 157, 2),   # same with the fused ceil-mode pool (odd sizes) done by the finalize kernel
+    (2, 256, 512, 75, 90, 0),     # conv4-like: 120 pair tiles, tail of 46 -> no split (more than half a round), plain path
 ])
 def test_tc_conv(ctx, N, Cin, Cout, H, W, pool):
     y, ref = run_conv(ctx, N, Cin, Cout, H, W, pool, seed=H * W + Cin)
