@@ -216,7 +216,7 @@ class DenseCapModel:
         self.opt.setdefault("final_nms_thresh", 0.3)
         self.ctx = Context(dims, device=device, max_batch=max_batch, max_image_hw=max_image_hw,
                            max_proposals=opt.get("max_proposals", 1000), fuse_pool=fuse_pool,
-                           pool_ceil=opt.get("pool_ceil", True))
+                           pool_ceil=opt.get("pool_ceil", True), anchors=opt.get("anchors"), field_centers=opt.get("field_centers"))
         self.train = False
         self.nets = {"localization_layer": LocalizationLayer(self.ctx),
                      "language_model": LanguageModel(self.ctx, opt.get("idx_to_token"))}
@@ -241,8 +241,12 @@ class DenseCapModel:
         tok = info.get("idx_to_token")
         if isinstance(tok, dict):
             tok = {int(k): v for k, v in tok.items()}
-        return cls({"dims": dims, "max_proposals": max_proposals, "idx_to_token": tok}, weights=weights, device=device, max_batch=max_batch,
-                   max_image_hw=max_image_hw)
+        opt = {"dims": dims, "max_proposals": max_proposals, "idx_to_token": tok}
+        # model state stored in the checkpoint overrides the library defaults: MakeAnchors' anchor table and field centres, pooling mode
+        for key in ("anchors", "field_centers", "pool_ceil"):
+            if key in info:
+                opt[key] = info[key]
+        return cls(opt, weights=weights, device=device, max_batch=max_batch, max_image_hw=max_image_hw)
 
     def evaluate(self):
         self.train = False

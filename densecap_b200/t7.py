@@ -344,7 +344,50 @@ def extract_densecap_weights(checkpoint):
     opt = model.fields.get("opt") if isinstance(model, T7Object) else None
     info = {"vocab_size": int(lf.get("vocab_size", w["lm.vocab.weight"].shape[0] - 1)), "seq_length": lf.get("seq_length"),
             "idx_to_token": lf.get("idx_to_token"), "opt": opt}
+    info.update(_model_state(nets))
     return w, info
+
+
+def _walk_all(obj, out, seen=None):
+    """Every T7Object of a module tree (tables and nn.Sequential-like `modules` lists included), each once."""
+    seen = seen if seen is not None else set()
+    if id(obj) in seen:
+        return out
+    seen.add(id(obj))
+    if isinstance(obj, T7Object):
+        out.append(obj)
+        _walk_all(obj.fields, out, seen)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _walk_all(v, out, seen)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _walk_all(v, out, seen)
+    return out
+
+
+def _model_state(nets):
+    """Non-weight state a checkpoint carries and the context must honour instead of its defaults:
+      anchors (2, k) and the receptive-field centres x0, y0, sx, sy of nn.MakeAnchors (MakeAnchors.lua:31-38, LocalizationLayer.lua:653-655),
+      ceil_mode of the VGG nn.SpatialMaxPooling layers (DenseCapModel.lua:61-76 sets it on the loaded VGG-16).
+    Missing fields (e.g. a tree written by densecap_checkpoint_tree without them) leave the entry out -> library defaults."""
+    st = {}
+    mods = _walk_all(nets.get("localization_layer"), [])
+    for m in mods:
+        if m.classname.endswith("MakeAnchors"):
+            f = m.fields
+            if "anchors" in f and f["anchors"] is not None:
+                st["anchors"] = np.asarray(f["anchors"], np.float32).reshape(2, -1)
+            if all(k in f for k in ("x0", "y0", "sx", "sy")):
+                st["field_centers"] = tuple(float(f[k]) for k in ("x0", "y0", "sx", "sy"))
+            break
+    pools = [m for m in _walk_all(nets.get("conv_net1"), []) + _walk_all(nets.get("conv_net2"), []) if m.classname.endswith("SpatialMaxPooling")]
+    modes = {bool(m.fields.get("ceil_mode", False)) for m in pools}
+    if len(modes) == 1:
+        st["pool_ceil"] = modes.pop()
+    elif len(modes) > 1:
+        raise ValueError("checkpoint: the VGG pooling layers mix ceil and floor mode, which the trunk kernels do not support")
+    return st
 
 
 # ---------------------------------------------------------------------------------------------------------

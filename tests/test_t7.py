@@ -93,3 +93,33 @@ def test_results_json_matches_run_model_format(tmp_path):
     assert back == doc and back["results"][0]["img_name"] == "elephant.jpg" and set(back) == {"results", "opt"}
     with pytest.raises(ValueError):
         R.result_to_json(boxes, [0.5], ["x", "y"])
+
+
+def test_checkpoint_model_state_is_extracted():
+    """MakeAnchors' anchor table / field centres and the pooling mode stored in the module tree are reported (they were
+    silently replaced by library defaults)."""
+    from densecap_b200.synth import ModelDims, make_weights
+    dims = ModelDims(widths=(8, 8, 8, 8, 8), rpn_filters=8, fc_dim=16, rnn_size=8, encoding_size=8, vocab_size=10, seq_length=3)
+    w = make_weights(dims, seed=1)
+    tree = t7.densecap_checkpoint_tree(dims, w)
+    _, info = t7.extract_densecap_weights(tree)
+    assert info["pool_ceil"] is True and "anchors" not in info          # the synthetic tree carries no MakeAnchors state
+    loc = tree["model"].fields["nets"]["localization_layer"]
+    ma = [m for m in t7._walk_all(loc, []) if m.classname == "nn.MakeAnchors"][0]
+    anchors = np.arange(2 * dims.num_anchors, dtype=np.float32).reshape(2, -1) + 10
+    ma.fields.update({"anchors": anchors, "x0": 7.5, "y0": 7.5, "sx": 16.0, "sy": 16.0})
+    for m in t7._walk_all(tree["model"].fields["nets"]["conv_net1"], []):
+        if m.classname == "nn.SpatialMaxPooling":
+            m.fields["ceil_mode"] = False
+    for m in t7._walk_all(tree["model"].fields["nets"]["conv_net2"], []):
+        if m.classname == "nn.SpatialMaxPooling":
+            m.fields["ceil_mode"] = False
+    blob_path = None
+    import io, tempfile, os
+    with tempfile.TemporaryDirectory() as d:
+        blob_path = os.path.join(d, "m.t7")
+        t7.save(tree, blob_path)
+        _, info2 = t7.extract_densecap_weights(t7.load(blob_path))
+    assert np.array_equal(info2["anchors"], anchors)
+    assert info2["field_centers"] == (7.5, 7.5, 16.0, 16.0)
+    assert info2["pool_ceil"] is False
