@@ -40,33 +40,30 @@ def main():
                "Per-launch times under ncu are cold-cache and serialised (side-stream overlap and programmatic dependent launch are lost): compare SHARES with "
                "the live CUDA-event phase times of bench.py.\n" % (T, TP, RD, WR, B, B),
                "%d launches, %.1f us serialised under ncu.\n" % (len(step), total)]
-        # conv trunk aggregate: conv_first + the halo launches before the first non-conv kernel (split-K finalize launches belong to their conv)
-        convs, i = [], 0
+        # conv trunk aggregate: a layer = conv_first / a halo launch, plus the launches that finish it (split-K finalize; the K-split TAIL launch of the
+        # leftover tiles, template argument TAIL = 1, and its conv_tail_finalize).  The 14th layer is the RPN 3x3 conv, not part of the VGG trunk.
+        layers = []
         for d in step:
-            if "conv_first" in d["name"] or "tc_conv_halo" in d["name"] or "splitk_finalize" in d["name"]:
-                convs.append(d)
-            else:
+            nm = d["name"]
+            is_tail = "tc_conv_halo" in nm and nm.rstrip(">").endswith(", 1")
+            if "conv_first" in nm or ("tc_conv_halo" in nm and not is_tail):
+                layers.append([d])
+            elif layers and (is_tail or "splitk_finalize" in nm or "conv_tail_finalize" in nm):
+                layers[-1].append(d)
+            elif layers:
                 break
-        # the RPN 3x3 conv (+ its finalize) is the last halo launch: not part of the VGG trunk
-        trunk, k, rpn_seen = [], 0, False
-        for d in convs:
-            if "splitk_finalize" in d["name"]:
-                if trunk and k <= 13 and trunk[-1]["name"].rstrip(">").endswith(", 2") and not rpn_seen:      # follows a split-K (FEAT_PARTIAL) launch of the trunk
-                    trunk[-1]["extra_us"] = trunk[-1].get("extra_us", 0.0) + d[T]
-                continue
-            if k < 13:
-                trunk.append(dict(d)); k += 1
-            else:
-                rpn_seen = True
-        tw = sum(d[T] * d.get(TP, 0.0) for d in trunk) / max(sum(d[T] for d in trunk), 1e-9)
-        tsum = sum(d[T] + d.get("extra_us", 0.0) for d in trunk)
+        trunk = layers[:13]
+        all_t = sum(d[T] for L in trunk for d in L)
+        tw = sum(d[T] * d.get(TP, 0.0) for L in trunk for d in L) / max(all_t, 1e-9)
         out.append("## VGG-16 conv trunk (13 layers)\n")
-        out.append("| layer | kernel | us (+ split-K finalize) | tensor-pipe active % |")
+        out.append("| layer | kernels | us | tensor-pipe active % (time-weighted over the layer's launches) |")
         out.append("|---|---|---:|---:|")
-        for n, d in zip(CONV_NAMES, trunk):
-            out.append("| %s | `%s` | %.1f%s | %.1f |" % (n, d["name"], d[T], (" + %.1f" % d["extra_us"]) if d.get("extra_us") else "", d.get(TP, 0.0)))
-        out.append("\nTime-weighted tensor-pipe activity over all 13 conv launches: **%.1f %%** (%.1f us of kernels; the tensor pipe executes 3 fp16 MMAs per "
-                   "fp32-class product).\n" % (tw, tsum))
+        for n, L in zip(CONV_NAMES, trunk):
+            t = sum(d[T] for d in L)
+            tp = sum(d[T] * d.get(TP, 0.0) for d in L) / max(t, 1e-9)
+            out.append("| %s | %s | %s | %.1f |" % (n, " + ".join("`%s`" % d["name"] for d in L), " + ".join("%.1f" % d[T] for d in L), tp))
+        out.append("\nTime-weighted tensor-pipe activity over all conv-trunk launches (13 layers incl. their tail / finalize launches): **%.1f %%** "
+                   "(%.1f us of kernels; the tensor pipe executes 3 fp16 MMAs per fp32-class product).\n" % (tw, all_t))
         out.append("## All launches\n")
         out.append("| # | kernel | grid | us | share %% | tensor-pipe %% | DRAM read MB | DRAM write MB |".replace("%%", "%"))
         out.append("|---:|---|---|---:|---:|---:|---:|---:|")
