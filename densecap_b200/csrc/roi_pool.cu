@@ -16,6 +16,9 @@
 // half2 pairs (cvt.rn.f16x2.f32).  grid = (C/32 slices) x (148/(C/32) ROI groups), 1024 threads.
 // The slice staging does not depend on the taps, so the kernel is launched with programmatic stream
 // serialisation and overlaps roi_taps_kernel; it waits (griddepcontrol.wait) only before the first tap read.
+// Output rows are slice-major (roi_feature_index, common.cuh): the 8 positions a warp emits per step are 512 contiguous
+// bytes per plane, so the plain 16-byte stores are fully coalesced.  ncu (profiles/kernels_r08_notes.md): shared-memory
+// wavefronts = ideal, LSU data pipe 72 % busy, issue slots 57 % -- the gather is bound by shared-memory bandwidth, not HBM.
 //
 // The interpolation arithmetic follows the reference CPU kernel's operation order without FMA
 // contraction (mul/add intrinsics), so fp32 outputs are bit-identical to the oracle.

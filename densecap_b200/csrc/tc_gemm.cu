@@ -12,12 +12,15 @@
 //   warp 0   : TMA producer -- cp.async.bulk.tensor loads of the A and B stage tiles (both planes in one
 //              box) into 128B-swizzled shared memory, signalled through full[] mbarriers;
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases the smem stage
-//              (empty[]) and publishes the finished accumulator (tmem_full[]);
-//   warps 4-11: epilogue -- tcgen05.ld of the 128xBLOCK_N fp32 accumulator (two warps per TMEM lane quarter, half of the columns each;
-//              warp), bias + ReLU (+ fused 2x2 ceil-mode max-pool through warp shuffles for the VGG
-//              layers that precede a pool), re-split to fp16 planes / fp32 / row arg-max, vectorised stores.
-//   The accumulator is double buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps
-//   the MMAs of tile i+1.
+//              (empty[]) and publishes a finished accumulator GROUP (tmem_full[]) every kb_per_group k-blocks
+//              (hierarchical accumulation: the tensor core accumulates with truncation, tc_common.cuh);
+//   warps 4-11: epilogue -- tcgen05.ld sweeps of the accumulator groups (two warps per TMEM lane quarter, half of
+//              the columns each) summed in registers, then bias + ReLU (+ fused 2x2 ceil-mode max-pool through warp
+//              shuffles), re-split to fp16 planes, staged per warp in shared memory and written with TMA tensor
+//              stores (fp32 / partial-sum outputs: direct stores).
+//   The accumulator is double buffered in TMEM so the sweeps of group i overlap the MMAs of group i+1.
+//   Instantiations: epilogue feature mask FEAT (which output paths are compiled in) and TAIL (K-split items of the
+//   leftover tiles of a mostly idle last round, see k_tc_gemm / k_tc_conv3x3).
 //
 // CG = 2 variant (cta_group::2): two CTAs of a cluster (an SM pair) compute one 256 x 256 tile.  Each CTA
 // loads its own 128 rows of A and HALF of the B tile (128 of the 256 rows); the leader CTA's single thread
@@ -194,17 +197,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t a_lo = a_hi + A_PLANE_BYTES;
           const uint32_t b_hi = a_hi + 2 * A_PLANE_BYTES;
           const uint32_t b_lo = b_hi + C::B_PLANE_BYTES;
-#ifdef DC_MMA_INTERLEAVED
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-#pragma unroll
-          for (int pass = 0; pass < (C::WIDE ? 1 : 3); ++pass) {
-#else
 #pragma unroll
           for (int pass = 0; pass < (C::WIDE ? 1 : 3); ++pass)
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-#endif
             const uint32_t koff = k * UMMA_K * 2;   // bytes along K inside the swizzle atom
             const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff);
             const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff);
@@ -460,17 +456,10 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t a_lo = a_hi + AH_PLANE_BYTES;
             const uint32_t b_hi = b_ring + sb * C::B_STAGE_BYTES;
             const uint32_t b_lo = b_hi + C::B_PLANE_BYTES;
-#ifdef DC_MMA_INTERLEAVED
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-#pragma unroll
-            for (int pass = 0; pass < (C::WIDE ? 1 : 3); ++pass) {
-#else
 #pragma unroll
             for (int pass = 0; pass < (C::WIDE ? 1 : 3); ++pass)
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-#endif
               const uint32_t koff = k * UMMA_K * 2;
               const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff);
               const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff);
