@@ -132,7 +132,12 @@ int dc_set_image_size(dc_ctx* ctx, int image_h, int image_w);
 
 /* DenseCapModel:forward (test mode).  img: (batch,3,H,W) fp32 NCHW, BGR, mean-subtracted
  * (run_model.lua:70-74).  dc_forward_test calls dc_set_image_size(H,W) itself exactly like
- * DenseCapModel:updateOutput (DenseCapModel.lua:245-246). */
+ * DenseCapModel:updateOutput (DenseCapModel.lua:245-246).
+ * Concurrency: a context is used by one host thread at a time, and ONE forward runs per device at a time.  The caption decoder is a
+ * persistent kernel whose CTAs (2 per 176 output columns, 144 for DenseCap's LM) wait for each other through device-side counters and
+ * therefore need to be co-resident; forwards of two contexts interleaved on the same GPU could each hold part of the SMs.  The waits are
+ * bounded (a violated assumption surfaces as DC_E_CUDA after ~2 s, never as a hung GPU).  Use one process / context per GPU and batch the
+ * images (max_batch) instead -- which is also faster. */
 int dc_forward_test(dc_ctx* ctx, const float* img, int batch, int image_h, int image_w,
                     dc_result* out, void* stream);
 
