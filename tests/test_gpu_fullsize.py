@@ -320,3 +320,47 @@ def test_chain_bench_workload_agreement_is_at_the_oracle_noise_level(model_a, ca
     # final selection = oracle NMS of the device's own pre-NMS boxes / scores (exact order)
     ref_idx = O.nms(np.concatenate([O.xcycwh_to_x1y1x2y2(g["boxes"]), g["scores"][:, None]], 1), 0.3)
     assert g["final_idx"].tolist() == ref_idx.tolist()
+
+
+def test_batch4_forward_matches_single_image_forwards(case_c):
+    """BASELINE configs[1] as benched (4 images per step): the batched forward takes code paths a single image does not -- 256 pair tiles
+    per fc6 launch with the K-split tail launch + gemm_tail_finalize_kernel, conv4_x tail launches + conv_tail_finalize_kernel, no split-K
+    in conv5 / the RPN conv, three 256-row blocks per decoder pass -- i.e. other summation orders, and must reproduce the single-image
+    forwards of the same images.  Candidates whose scores tie within the fp32 noise may swap POSITIONS between the two runs (measured:
+    two neighbours with scores 3.6645815 / 3.6645834), so everything is compared per proposal, keyed by its anchor index: same proposals,
+    same final selection, same captions, fc7 codes / scores / boxes within 1e-5."""
+    from densecap_b200.model import DenseCapModel
+    m = DenseCapModel({"dims": case_c.dims}, weights=case_c.weights, max_batch=4)
+    m.setTestArgs(CFG)
+
+    def per_anchor(r, o, kp, k):
+        anchors = r["proposal_idx"][o:o + kp].cpu().numpy()
+        pos = {int(a): i for i, a in enumerate(anchors.tolist())}
+        fin_rows = r["final_idx"][o:o + k].cpu().numpy() - 1                    # 1-based rows of the proposal list
+        fin = {int(anchors[row]): tuple(seq) for row, seq in zip(fin_rows.tolist(), r["final_seq"][o:o + k].cpu().numpy().tolist())}
+        return pos, fin, {key: r[key][o:o + kp].cpu().numpy().copy() for key in ("codes", "all_scores", "all_boxes", "roi_boxes")}
+
+    try:
+        imgs = [make_image(IMG_H, IMG_W, seed=s) for s in (0, 3, 5, 8)]
+        singles = []
+        for im in imgs:
+            r = m.forward_device(dev(im))
+            k = int(r["num_final"][0]); kp = int(r["num_proposals"][0])
+            singles.append((k, kp) + per_anchor(r, 0, kp, k))
+        r = m.forward_device(dev(np.concatenate(imgs, 0)))
+        P = r["max_proposals"]
+        nf = r["num_final"].cpu().numpy(); npr = r["num_proposals"].cpu().numpy()
+        worst = {}
+        for b, (k, kp, pos1, fin1, t1) in enumerate(singles):
+            assert int(nf[b]) == k and int(npr[b]) == kp, (b, nf[b], k)
+            pos4, fin4, t4 = per_anchor(r, b * P, kp, k)
+            assert set(pos4) == set(pos1), "image %d: the batched forward proposes other boxes" % b
+            assert fin4 == fin1, "image %d: final selection or captions differ" % b
+            perm = np.array([pos4[a] for a in sorted(pos1)]); base = np.array([pos1[a] for a in sorted(pos1)])
+            for key in t1:
+                e = rel(t4[key][perm], t1[key][base])
+                worst[key] = max(worst.get(key, 0.0), e)
+                assert e < 1e-5, "image %d: %s differs by %.3g" % (b, key, e)
+        report("C.batch4_vs_single", worst)
+    finally:
+        m.ctx.close()
