@@ -464,10 +464,13 @@ def main():
         # DRAM traffic of the fc6 launch from an `ncu --set full` capture AT THE BENCHED BATCH (profiles/roofline_traffic_*.json holds one
         # record per batch size; null when no capture exists for this batch)
         traffic = None
+        trunk_ncu = None
         for fn in sorted([f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("roofline_traffic_")], reverse=True):
             try:
                 tj = json.load(open(os.path.join(ROOT, "profiles", fn)))
                 rec = tj.get("fc6", {}).get("batch%d" % B)
+                if trunk_ncu is None and tj.get("conv_trunk", {}).get("batch%d" % B):
+                    trunk_ncu = dict(tj["conv_trunk"]["batch%d" % B], file="profiles/" + fn)
                 if rec:
                     traffic = {"bytes_per_launch": int(rec["dram_bytes_read"] + rec["dram_bytes_write"]), "file": "profiles/" + fn, "batch": B,
                                "algorithmic_bytes_per_launch": int(2 * 2 * (dims.fc_dim * dims.feat_dim * 49 + B * P * dims.feat_dim * 49) + 2 * 2 * B * P * dims.fc_dim)}
@@ -482,7 +485,9 @@ def main():
                             "so the tensor pipe does 3x this work (hw_flops_factor); tensor-pipe activity per kernel: profiles/ (ncu)",
                     "hw_flops_factor": 3, "tensor_pipe_frac_3x": (3 * fc6_tflops / peak) if fc6_tflops else None,
                     "conv_trunk": {"ms": trunk_ms, "algorithmic_tflops": trunk_tflops, "frac": (trunk_tflops / peak) if trunk_tflops else None,
-                                   "tensor_pipe_frac_3x": (3 * trunk_tflops / peak) if trunk_tflops else None},
+                                   "tensor_pipe_frac_3x": (3 * trunk_tflops / peak) if trunk_tflops else None,
+                                   # ncu sm__pipe_tensor_cycles_active, time-weighted over every launch of the 13 conv layers (committed capture, not this run)
+                                   "tensor_pipe_active_ncu": trunk_ncu},
                     "roi_pool": {"bound": "hbm", "ms": roi_ms, "timed": "ROI-pooling kernel(s) of one image, batch-1 forward, CUDA events",
                                  "algorithmic_bytes": 103870080,
                                  "achieved_GBps": (103870080 / 1e9) / (roi_ms / 1e3) if roi_ms > 0 else None, "peak_GBps": peaks["hbm"],

@@ -78,6 +78,8 @@ def main():
             traffic["fc6"]["batch%d" % B] = {"kernel": f["name"], "dram_bytes_read": f.get(RD, 0.0), "dram_bytes_write": f.get(WR, 0.0),
                                              "duration_us_under_ncu": f[T], "tensor_pipe_active_pct": f.get(TP, 0.0),
                                              "source": "profiles/launches_%s_b%d_summary.md" % (tag, B)}
+        traffic.setdefault("conv_trunk", {})["batch%d" % B] = {"tensor_pipe_active_pct_time_weighted": round(tw, 2), "kernel_us_under_ncu": round(all_t, 1),
+                                                               "launches": sum(len(L) for L in trunk), "source": "profiles/launches_%s_b%d_summary.md" % (tag, B)}
         print("batch %d: %d launches, trunk tensor-pipe %.1f %% time-weighted" % (B, len(step), tw))
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "roofline_traffic_%s.json" % tag), "w"), indent=1)
 
