@@ -56,12 +56,7 @@ struct LaunchState {
   int num_sms = 148;
   // k-blocks (64 K each) a tcgen05 tile accumulates in TMEM before the epilogue warps take the partial sum over (hierarchical
   // accumulation, tc_common.cuh): index 0 / 1 / 2 = 64- / 128- / 256-column tiles.  Smaller = closer to fp32 sgemm, more TMEM sweeps.
-#ifndef DC_G64
-#define DC_G64 3      // A/B (profiles/ab_r08_experiments.md): 3,3,1 vs 2,2,1 = trunk -3 % at 1.97e-6 vs 1.73e-6 from the fp64 oracle (fp32 oracle: 8.5e-7);
-#define DC_G128 3     // the 9 k-blocks of conv1_2 / conv2_1 become three equal groups
-#define DC_G256 1
-#endif
-  int group_kb[3] = {DC_G64, DC_G128, DC_G256};
+  int group_kb[3] = {2, 2, 1};
   std::set<const void*> smem_attr_done;    // kernel function pointers
 };
 LaunchState* dc_launch_state(dc_ctx* ctx);
