@@ -15,7 +15,7 @@ ffi.cdef[[
 typedef struct dc_ctx dc_ctx;
 typedef struct dc_config { int32_t widths[5]; int32_t rpn_filters, num_anchors, fc_dim, pool_hw, rnn_size,
   encoding_size, vocab_size, seq_length, pool_ceil, max_batch, max_image_h, max_image_w, max_proposals,
-  engine, fuse_pool; float anchors[64]; float field_centers[4]; } dc_config;
+  reserved0, fuse_pool; float anchors[64]; float field_centers[4]; } dc_config;
 int dc_config_default(dc_config*);
 int dc_create(const dc_config*, int device, dc_ctx**);
 int dc_destroy(dc_ctx*);
@@ -24,6 +24,10 @@ int dc_load_weights(dc_ctx*, const char* name, const float* host, const int64_t*
 int dc_set_test_args(dc_ctx*, float rpn_nms_thresh, float final_nms_thresh, int num_proposals, int clip_boxes);
 int dc_forward_test_host(dc_ctx*, const float* img_host, int batch, int H, int W,
                          int32_t* num_final, float* final_boxes, float* final_scores, int64_t* final_seq);
+int dc_forward_test_host_u8(dc_ctx*, const uint8_t* img_host_u8, int batch, int H, int W,
+                            int32_t* num_final, float* final_boxes, float* final_scores, int64_t* final_seq);   -- decoded RGB bytes, run_model.lua:66-74 on the device
+int dc_set_beam_size(dc_ctx*, int beam_size);      -- 0 = LanguageModel:sample, n > 0 = :beamsearch (LanguageModel.lua:129-132)
+int dc_set_decode_all(dc_ctx*, int enable);       -- captions for every proposal, not only the final-NMS survivors
 ]]
 
 local C = ffi.load('densecap_b200')
@@ -100,6 +104,9 @@ function M:setTestArgs(kwargs)                                           -- Dens
 end
 
 function M:evaluate() end
+
+-- run_model.lua's `-beam_size` option (LanguageModel.lua:129-132 dispatches on self.beam_size)
+function M:setBeamSize(n) check(self.ctx, C.dc_set_beam_size(self.ctx, n or 0)) end
 
 function M:forward_test(img)                                             -- DenseCapModel.lua:319-327
   assert(img:dim() == 4 and img:size(1) == 1 and img:size(2) == 3, 'input must be 1 x 3 x H x W')
