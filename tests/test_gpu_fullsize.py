@@ -364,3 +364,42 @@ def test_batch4_forward_matches_single_image_forwards(case_c):
         report("C.batch4_vs_single", worst)
     finally:
         m.ctx.close()
+
+
+def test_configs2_image_size_800x600_300_proposals_chain_parity():
+    """BASELINE configs[2] member: an 800-pixel image (feature map 38 x 50 = 1900 cells: the ROI-pooling slice no longer fits shared memory at
+    32 channels, so the 16-channel kernel runs with the slice-major output rows) with 300 proposals, full VGG-16 widths, chained end to end on
+    the GPU vs the fp32 oracle, compared per proposal (anchor-keyed) like the 720x600 chain test."""
+    from densecap_b200.model import DenseCapModel
+    H, W = 600, 800
+    cfg = {"rpn_nms_thresh": 0.7, "final_nms_thresh": 0.3, "num_proposals": 300, "seq_length": 15}
+    dims = ModelDims()
+    weights = make_weights(dims, seed=0, box_variant="C")
+    img = make_image(H, W, seed=4)
+    ref = O.densecap_forward_test(img, weights, cfg, return_intermediates=True)
+    m = DenseCapModel({"dims": dims, "max_proposals": 300}, weights=weights, max_image_hw=(800, 800))
+    m.setTestArgs(cfg)
+    try:
+        m.ctx.set_decode_all(True)
+        r = m.forward_device(dev(img))
+        torch.cuda.synchronize()
+        K = int(r["num_proposals"][0]); Kf = int(r["num_final"][0])
+        gidx = r["proposal_idx"][:K].cpu().numpy()
+        oidx = ref["ll"]["idx"]
+        assert K == len(oidx) and set(gidx.tolist()) == set(oidx.tolist()), "proposals differ from the oracle (%d vs %d)" % (K, len(oidx))
+        assert order_within_noise(gidx, ref["ll"]["all_prob"], 4e-6)
+        pos = {int(a): i for i, a in enumerate(gidx.tolist())}
+        perm = np.array([pos[int(a)] for a in oidx.tolist()])
+        e_roi = rel(r["roi_boxes"][:K].cpu().numpy()[perm], ref["roi_boxes"])
+        e_box = rel(r["all_boxes"][:K].cpu().numpy()[perm], ref["pre_nms"]["final_boxes"])
+        e_sc = rel(r["all_scores"][:K].cpu().numpy()[perm], ref["pre_nms"]["obj"][:, 0])
+        tok_diff = int((r["all_seq"][:K].cpu().numpy()[perm] != ref["pre_nms"]["seq"]).any(axis=1).sum())
+        gfin = set(gidx[r["final_idx"][:Kf].cpu().numpy() - 1].tolist())
+        ofin = set(oidx[ref["final_idx"] - 1].tolist())
+        report("C.size_800x600_p300", {"roi_boxes_rel": e_roi, "final_boxes_rel": e_box, "scores_rel": e_sc, "token_rows_differing": tok_diff,
+                                       "num_final": [len(gfin), len(ofin)], "final_in_common": len(gfin & ofin)})
+        assert e_roi < 1e-4 and e_box < 1e-4 and e_sc < 1e-4
+        assert tok_diff == 0
+        assert gfin == ofin
+    finally:
+        m.ctx.close()
