@@ -322,10 +322,16 @@ lm_decode_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 // ==================================================================================================================
 constexpr int WS_NP = 176;                                   // output columns per CTA pair
 constexpr int WS_NC = WS_NP / 2;                             // weight rows resident per CTA
-constexpr int WS_KA = 32;                                    // K extent of one A stage
+#ifndef DC_WS_KA
+#define DC_WS_KA 32
+#endif
+constexpr int WS_KA = DC_WS_KA;                              // K extent of one A stage: 32 (64-byte rows, SWIZZLE_64B) or 16 (32-byte rows, SWIZZLE_32B)
 constexpr uint32_t WS_A_PLANE = BLOCK_M * WS_KA * 2;         // 8 KB
 constexpr uint32_t WS_A_STAGE = 2 * WS_A_PLANE;              // 16 KB (hi + lo)
-constexpr int WS_STAGES = 3;
+// 48 KB of ring beside the resident weights: 3 x 16 KB.  (ncu at batch 4: L2 at 20 % of its peak, tensor pipe 37 % -- the h stream looks bound by
+// the bytes in flight against the L2 latency; a finer ring of 6 x 8 KB SWIZZLE_32B stages, -DDC_WS_KA=16, keeps 40 KB instead of 32 KB on the way
+// but measured no faster: 0.614 vs 0.600 ms per 4-image step.)
+constexpr int WS_STAGES = 49152 / WS_A_STAGE;
 constexpr uint32_t WS_B_PLANE = WS_NC * BLOCK_K * 2;         // 11264 B: 88 rows x 128 B (one 64-wide K block of one plane)
 constexpr uint32_t WS_B_KB = 2 * WS_B_PLANE;                 // hi + lo
 constexpr int WS_MAX_KB = 8;                                 // H <= 512
@@ -461,11 +467,13 @@ lm_decode_ws_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             mbar_wait(full_bar(stage), phase);
             tcgen05_fence_after();
             const uint32_t a_hi = a_ring + stage * WS_A_STAGE, a_lo = a_hi + WS_A_PLANE;
-            const uint32_t b_hi = b_base + (uint32_t)(ks >> 1) * WS_B_KB + (uint32_t)(ks & 1) * 64u, b_lo = b_hi + WS_B_PLANE;
+            constexpr int SPB = BLOCK_K / WS_KA;               // A stages per 64-wide K block of the resident weights
+            const uint32_t b_hi = b_base + (uint32_t)(ks / SPB) * WS_B_KB + (uint32_t)(ks % SPB) * (uint32_t)(WS_KA * 2), b_lo = b_hi + WS_B_PLANE;
 #pragma unroll
             for (int kk = 0; kk < WS_KA / UMMA_K; ++kk) {
               const uint32_t koff = kk * UMMA_K * 2;
-              const uint64_t da_hi = make_kmajor_sw64_desc(a_hi + koff), da_lo = make_kmajor_sw64_desc(a_lo + koff);
+              const uint64_t da_hi = WS_KA == 32 ? make_kmajor_sw64_desc(a_hi + koff) : make_kmajor_sw32_desc(a_hi + koff);
+              const uint64_t da_lo = WS_KA == 32 ? make_kmajor_sw64_desc(a_lo + koff) : make_kmajor_sw32_desc(a_lo + koff);
               const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff), db_lo = make_kmajor_sw128_desc(b_lo + koff);
               const uint32_t acc = (ks | kk) != 0;
               umma2_f16(d_small, da_lo, db_hi, idesc, acc);
@@ -707,13 +715,13 @@ static int launch_lm_decode_ws(dc_ctx* ctx, const LmDecodeArgs& a, cudaStream_t 
     const uint64_t dims[3] = {(uint64_t)a.E, (uint64_t)rows_cap, 2};
     const uint64_t str[2] = {(uint64_t)a.E * 2, (uint64_t)a.x_plane_elems * 2};
     const uint32_t box[3] = {WS_KA, BLOCK_M, 2};
-    if ((rc = encode_map(ctx, &mx, a.x_planes, 3, dims, str, box, 64))) return rc;
+    if ((rc = encode_map(ctx, &mx, a.x_planes, 3, dims, str, box, 2 * WS_KA))) return rc;
   }
   {
     const uint64_t dims[3] = {(uint64_t)a.H, (uint64_t)rows_cap, 2};
     const uint64_t str[2] = {(uint64_t)a.H * 2, (uint64_t)(2 * hbuf) * 2};
     const uint32_t box[3] = {WS_KA, BLOCK_M, 2};
-    if ((rc = encode_map(ctx, &mh, h_hi, 3, dims, str, box, 64))) return rc;
+    if ((rc = encode_map(ctx, &mh, h_hi, 3, dims, str, box, 2 * WS_KA))) return rc;
   }
   {
     const uint64_t dims[3] = {(uint64_t)a.H, (uint64_t)V1, 2};

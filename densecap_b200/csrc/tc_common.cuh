@@ -240,6 +240,15 @@ __device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
   d |= (uint64_t)4 << 61;
   return d;
 }
+// Same for SWIZZLE_32B (32-byte rows: 16 fp16 along K per row, 8-row groups 256 B apart, layout type 6)
+__device__ __forceinline__ uint64_t make_kmajor_sw32_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
 // Instruction descriptor (kind::f16): c_format=F32 (bits 4-5 = 1), a/b format = F16 (0), K-major A and B,
 // n_dim = N>>3 at bits [17,23), m_dim = M>>4 at bits [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
@@ -620,7 +629,8 @@ static int encode_map(dc_ctx* ctx, CUtensorMap* map, const void* base, int rank,
   DC_REQUIRE(ctx, encode != nullptr, DC_E_CUDA, "cuTensorMapEncodeTiled unavailable (tc_init not run)");
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                             : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE)),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DC_REQUIRE(ctx, r == CUDA_SUCCESS, DC_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
